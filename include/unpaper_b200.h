@@ -1,0 +1,232 @@
+/* unpaper_b200.h — C-ABI of the B200-native `--device=cuda` backend for
+ * unpaper's per-sheet processing hot path.
+ *
+ * Three layers, all `extern "C"`, plain pointers and sizes only:
+ *
+ *  (1) the reference's own backend boundary: the vtable symbol `backend_cuda`
+ *      (reference imageprocess/backend.c:86-88 picks it up through
+ *      `extern const ImageBackend backend_cuda`) plus the image residency
+ *      protocol of imageprocess/image.h:32-61 and `image_cuda_release`
+ *      (imageprocess/image.c:13,52);
+ *  (2) host-buffer entry points (`unpaper_b200_host_*`): one vtable op on an
+ *      image that lives in caller memory — upload, op, download.  These are
+ *      what the parity tests and any non-C host (ctypes, cgo, JNI) bind;
+ *  (3) the sheet engine (`unpaper_b200_engine_*`): the reference's
+ *      process_sheet() stage order (src/core/sheet_stages.c:660-672) run for a
+ *      GROUP of independent sheets per launch with every data-dependent
+ *      decision kept on the device — the throughput path bench.py measures.
+ *
+ * Error convention follows the reference (lib/logging.c:129-141): vtable
+ * entry points do not return errors, an unrecoverable CUDA failure prints and
+ * exits.  The layer (2)/(3) entry points return 0 on success and a negative
+ * code on failure instead, so that a foreign host can recover.
+ */
+#pragma once
+
+#include "unpaper_b200_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------
+ * (1) reference boundary
+ * --------------------------------------------------------------------- */
+
+/* replaces reference imageprocess/backend_cuda.c:586-612 */
+extern const ImageBackend backend_cuda;
+
+/* replaces reference imageprocess/image_cuda.c (API: imageprocess/image.h:32-61) */
+void image_ensure_cuda(Image *image);       /* image_cuda.c:135-206 */
+void image_ensure_cuda_alloc(Image *image); /* image_cuda.c:208-267 */
+void image_ensure_cpu(Image *image);        /* image_cuda.c:269-305 */
+void image_mark_cpu_dirty(Image *image);
+void image_mark_cuda_dirty(Image *image);
+Image create_image_from_gpu(void *gpu_ptr, size_t pitch, int width, int height,
+                            int pixel_format, Pixel background,
+                            uint8_t abs_black_threshold, bool owns_memory);
+bool image_is_gpu_resident(Image *image);
+void image_set_gpu_resident(Image *image, bool resident);
+void *image_get_gpu_ptr(Image *image);
+size_t image_get_gpu_pitch(Image *image);
+void image_cuda_release(Image *image);      /* image.c:13,52 */
+
+/* replaces reference imageprocess/cuda_runtime.h (subset used by L3/L4) */
+typedef enum {
+  UNPAPER_CUDA_INIT_OK = 0,
+  UNPAPER_CUDA_INIT_NO_RUNTIME = 1,
+  UNPAPER_CUDA_INIT_NO_DEVICE = 2,
+  UNPAPER_CUDA_INIT_ERROR = 3,
+} UnpaperCudaInitStatus;
+UnpaperCudaInitStatus unpaper_cuda_try_init(void); /* cuda_runtime.c:137-215 */
+const char *unpaper_cuda_init_status_string(UnpaperCudaInitStatus st);
+/* Per-thread current device + stream (reference: thread-local current stream,
+ * cuda_runtime.c:70,616-626; extended here to {device, stream}). */
+int unpaper_b200_set_device(int device);
+int unpaper_b200_get_device(void);
+int unpaper_b200_device_count(void);
+void unpaper_b200_thread_sync(void);
+
+/* ------------------------------------------------------------------------
+ * (2) host-buffer entry points
+ * --------------------------------------------------------------------- */
+
+/* An image in caller memory.  `format` is an AVPixelFormat value
+ * (GRAY8=8, RGB24=2, Y400A=58, MONOWHITE=9, MONOBLACK=10). */
+typedef struct {
+  uint8_t *data;
+  int32_t width;
+  int32_t height;
+  int32_t linesize;
+  int32_t format;
+  Pixel background;
+  uint8_t abs_black_threshold;
+} B200HostImage;
+
+#define B200_FMT_RGB24 2
+#define B200_FMT_GRAY8 8
+#define B200_FMT_MONOWHITE 9
+#define B200_FMT_MONOBLACK 10
+#define B200_FMT_Y400A 58
+
+int unpaper_b200_host_wipe_rectangle(B200HostImage *img, const Rectangle *area, Pixel color);
+int unpaper_b200_host_copy_rectangle(const B200HostImage *src, B200HostImage *dst,
+                                     const Rectangle *src_area, Point target);
+int unpaper_b200_host_center_image(const B200HostImage *src, B200HostImage *dst,
+                                   Point target_origin, RectangleSize target_size);
+/* The four *_and_replace ops allocate their result: `out` must provide a
+ * buffer of out->linesize*out->height bytes; width/height are checked. */
+int unpaper_b200_host_stretch(const B200HostImage *img, B200HostImage *out, int32_t interp);
+int unpaper_b200_host_resize(const B200HostImage *img, B200HostImage *out, int32_t interp);
+int unpaper_b200_host_flip_rotate_90(const B200HostImage *img, B200HostImage *out, int32_t direction);
+int unpaper_b200_host_mirror(B200HostImage *img, Direction direction);
+int unpaper_b200_host_shift(const B200HostImage *img, B200HostImage *out, Delta d);
+
+int unpaper_b200_host_apply_masks(B200HostImage *img, const Rectangle *masks, size_t n, Pixel color);
+int unpaper_b200_host_apply_wipes(B200HostImage *img, const Wipes *wipes, Pixel color);
+int unpaper_b200_host_apply_border(B200HostImage *img, const Border *border, Pixel color);
+/* returns mask count (>=0) or a negative error */
+int unpaper_b200_host_detect_masks(const B200HostImage *img, const MaskDetectionParameters *p,
+                                   const Point *points, size_t n, Rectangle *masks_out);
+int unpaper_b200_host_center_mask(B200HostImage *img, Point center, const Rectangle *area);
+int unpaper_b200_host_align_mask(B200HostImage *img, const Rectangle *inside,
+                                 const Rectangle *outside, const MaskAlignmentParameters *p);
+int unpaper_b200_host_detect_border(const B200HostImage *img, const BorderScanParameters *p,
+                                    const Rectangle *outside, Border *out);
+
+int unpaper_b200_host_blackfilter(B200HostImage *img, const BlackfilterParameters *p);
+int unpaper_b200_host_blurfilter(B200HostImage *img, const BlurfilterParameters *p,
+                                 uint8_t abs_white_threshold);
+int unpaper_b200_host_noisefilter(B200HostImage *img, uint64_t intensity, uint8_t min_white_level);
+int unpaper_b200_host_grayfilter(B200HostImage *img, const GrayfilterParameters *p);
+
+int unpaper_b200_host_detect_rotation(const B200HostImage *img, const Rectangle *mask,
+                                      const DeskewParameters *p, float *radians_out);
+int unpaper_b200_host_deskew(B200HostImage *img, const Rectangle *mask, float radians, int32_t interp);
+
+/* ------------------------------------------------------------------------
+ * (3) sheet engine
+ * --------------------------------------------------------------------- */
+
+/* The part of the reference's `Options` + `SheetProcessConfig`
+ * (lib/options.h:29-119, sheet_process.h:22-37) that process_sheet() reads on
+ * the hot path, flattened to a POD. */
+typedef struct {
+  int32_t layout;       /* Layout */
+  int32_t input_count;  /* pages per sheet on input (1 or 2) */
+  int32_t interpolate_type;
+  Pixel sheet_background;
+  Pixel mask_color;
+  uint8_t abs_black_threshold;
+  uint8_t abs_white_threshold;
+  /* stage switches: options->no_*_multi_index with count -1 ("disable all") */
+  uint8_t no_blackfilter, no_noisefilter, no_blurfilter, no_grayfilter;
+  uint8_t no_mask_scan, no_mask_center, no_deskew, no_wipe, no_border;
+  uint8_t no_border_scan, no_border_align;
+  uint8_t reserved0;
+  uint64_t noisefilter_intensity;
+  BlackfilterParameters blackfilter; /* exclusions_count==0 -> layout default */
+  BlurfilterParameters blurfilter;
+  GrayfilterParameters grayfilter;
+  DeskewParameters deskew;
+  MaskDetectionParameters mask_detection;
+  MaskAlignmentParameters mask_alignment;
+  BorderScanParameters border_scan;
+  Border pre_border, border, post_border;
+  int32_t middle_wipe[2];
+  int32_t point_count;      /* 0 -> layout default points */
+  Point points[8];
+  int32_t pre_mask_count;
+  Rectangle pre_masks[8];
+  int32_t pre_wipe_count, wipe_count, post_wipe_count;
+  Rectangle pre_wipes[8], wipes[8], post_wipes[8];
+} B200SheetConfig;
+
+#define B200_TRACE_MAX_MASKS 8
+
+/* What process_sheet() decided for one sheet (every integer here must be
+ * bit-identical with the reference CPU backend). */
+typedef struct {
+  int32_t status;        /* 0 ok */
+  int32_t sheet_width, sheet_height;
+  int32_t deskew_mask_count;                 /* sheet_stages.c:401-404 */
+  Rectangle deskew_masks[B200_TRACE_MAX_MASKS];
+  float rotation[B200_TRACE_MAX_MASKS];      /* sheet_stages.c:408-409 */
+  int32_t center_mask_count;                 /* sheet_stages.c:433-436 */
+  Rectangle center_masks[B200_TRACE_MAX_MASKS];
+  int32_t centered[B200_TRACE_MAX_MASKS];    /* masks.c:232 took the branch */
+  int32_t border_count;                      /* sheet_stages.c:467-473 */
+  Border borders[MAX_PAGES];
+  Rectangle border_masks[MAX_PAGES];
+  int32_t blackfilter_fills;                 /* flood-filled scan areas */
+  int32_t noise_clusters;                    /* filters.c:342 count */
+  int32_t reserved[6];
+} B200SheetResult;
+
+/* Defaults = options_init() + options_init_filter_defaults() + the CLI's
+ * threshold defaults (lib/options.c:22-170, src/cli/cli_options.c:229-274,
+ * :1108-1109). */
+void unpaper_b200_sheet_config_defaults(B200SheetConfig *cfg);
+
+typedef struct B200Engine B200Engine;
+
+/* One engine = one GPU, `lanes` groups in flight (each lane owns a stream, a
+ * workspace and pinned staging), `group_pages` sheets per group.  All sheets
+ * of an engine share input geometry and configuration. */
+B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device,
+                                       int page_width, int page_height,
+                                       int page_format, int group_pages,
+                                       int lanes);
+void unpaper_b200_engine_destroy(B200Engine *e);
+int unpaper_b200_engine_sheet_width(const B200Engine *e);
+int unpaper_b200_engine_sheet_height(const B200Engine *e);
+/* bytes of one output sheet (format = page format for GRAY8/RGB24 input) */
+size_t unpaper_b200_engine_sheet_bytes(const B200Engine *e);
+
+/* Pages resident in device memory: `pages_dev` holds n_sheets*input_count
+ * tightly packed pages (row stride = width*bpp); `out_dev` receives n_sheets
+ * tightly packed output sheets.  Asynchronous across lanes; returns after all
+ * work has been issued AND completed. `results` may be NULL. */
+int unpaper_b200_engine_process_device(B200Engine *e, const uint8_t *pages_dev,
+                                       uint8_t *out_dev, int n_sheets,
+                                       B200SheetResult *results);
+/* Same through host memory: H2D of every page and D2H of every sheet happen
+ * inside the call (pinned staging, overlapped across lanes). */
+int unpaper_b200_engine_process_host(B200Engine *e, const uint8_t *pages_host,
+                                     uint8_t *out_host, int n_sheets,
+                                     B200SheetResult *results);
+/* Kernel launches issued by the engine since creation (for bench.py). */
+uint64_t unpaper_b200_engine_launch_count(const B200Engine *e);
+/* Device-time (ms) per named kernel family accumulated with CUDA events when
+ * profiling is enabled; returns number of entries written. */
+int unpaper_b200_engine_set_profiling(B200Engine *e, int enabled);
+int unpaper_b200_engine_get_profile(const B200Engine *e, int max_entries,
+                                    const char **names, double *ms,
+                                    uint64_t *launches, double *alg_bytes);
+
+const char *unpaper_b200_last_error(void);
+const char *unpaper_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,489 @@
+/* ref_harness.c — TEST INFRASTRUCTURE (never linked into the product).
+ *
+ * Thin C-ABI over the UNMODIFIED reference CPU backend, compiled by
+ * oracle/Makefile from the sources where they lie under /root/reference into
+ * oracle/_ref/libunpaper_ref.so.  It exists so that tests/ and bench.py's
+ * cpu_baseline / --impl reference legs can drive the reference's own
+ * `*_cpu` functions and its own process_sheet() on in-memory pages.
+ *
+ * Every entry point mirrors the signature of the matching
+ * `unpaper_b200_host_*` / engine call in include/unpaper_b200.h with the
+ * prefix `ref_`, so one ctypes binding serves both.
+ *
+ * Tracing: reference imageprocess/backend.c is compiled with
+ * UNPAPER_WITH_CUDA=1 so that image_backend_select(UNPAPER_DEVICE_CUDA) binds
+ * the symbol `backend_cuda` — provided HERE as a pass-through that forwards
+ * every op to the reference's `*_cpu` function and records what the detectors
+ * returned (masks, rotation, border).  No arithmetic is changed.
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdatomic.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <libavutil/frame.h>
+
+#include "imageprocess/backend.h"
+#include "imageprocess/blit.h"
+#include "imageprocess/image.h"
+#include "imageprocess/masks.h"
+#include "imageprocess/pixel.h"
+#include "lib/logging.h"
+#include "lib/options.h"
+#include "sheet_process.h"
+
+#define UNPAPER_B200_WITH_REFERENCE_HEADERS 1
+#include "unpaper_b200.h"
+
+/* ---- symbols the reference expects from files we do not compile ---------- */
+
+void loadImage(const char *filename, Image *image, Pixel sheet_background,
+               uint8_t abs_black_threshold) {
+  (void)filename; (void)image; (void)sheet_background; (void)abs_black_threshold;
+  errOutput("ref_harness: loadImage is not available (pages are injected)");
+}
+void saveImage(char *filename, Image image, int fmt) {
+  (void)filename; (void)image; (void)fmt;
+}
+int detectPixelFormatFromExtension(const char *filename) {
+  (void)filename;
+  return AV_PIX_FMT_NONE;
+}
+struct EncodeQueue;
+bool encode_queue_gpu_enabled(struct EncodeQueue *q) { (void)q; return false; }
+bool encode_queue_submit_gpu(struct EncodeQueue *q, void *p, size_t pitch, int w,
+                             int h, int c, char **files, int n, int fmt, int j) {
+  (void)q; (void)p; (void)pitch; (void)w; (void)h; (void)c; (void)files; (void)n; (void)fmt; (void)j;
+  return false;
+}
+bool encode_queue_submit(struct EncodeQueue *q, AVFrame *f, char **files, int n,
+                         int fmt, int j, bool pinned) {
+  (void)q; (void)files; (void)n; (void)fmt; (void)j; (void)pinned;
+  av_frame_free(&f);
+  return false;
+}
+
+/* ---- the reference's CPU entry points (imageprocess/backend.c:11-45) ------ */
+
+void wipe_rectangle_cpu(Image image, Rectangle input_area, Pixel color);
+void copy_rectangle_cpu(Image source, Image target, Rectangle source_area, Point target_coords);
+void center_image_cpu(Image source, Image target, Point target_origin, RectangleSize target_size);
+void stretch_and_replace_cpu(Image *pImage, RectangleSize size, Interpolation interpolate_type);
+void resize_and_replace_cpu(Image *pImage, RectangleSize size, Interpolation interpolate_type);
+void flip_rotate_90_cpu(Image *pImage, RotationDirection direction);
+void mirror_cpu(Image image, Direction direction);
+void shift_image_cpu(Image *pImage, Delta d);
+void apply_masks_cpu(Image image, const Rectangle masks[], size_t masks_count, Pixel color);
+void apply_wipes_cpu(Image image, Wipes wipes, Pixel color);
+void apply_border_cpu(Image image, const Border border, Pixel color);
+size_t detect_masks_cpu(Image image, MaskDetectionParameters params, const Point points[],
+                        size_t points_count, Rectangle masks[]);
+void align_mask_cpu(Image image, const Rectangle inside_area, const Rectangle outside,
+                    MaskAlignmentParameters params);
+Border detect_border_cpu(Image image, BorderScanParameters params, const Rectangle outside_mask);
+void blackfilter_cpu(Image image, BlackfilterParameters params);
+void blurfilter_cpu(Image image, BlurfilterParameters params, uint8_t abs_white_threshold);
+void noisefilter_cpu(Image image, uint64_t intensity, uint8_t min_white_level);
+void grayfilter_cpu(Image image, GrayfilterParameters params);
+float detect_rotation_cpu(Image image, Rectangle mask, const DeskewParameters params);
+void deskew_cpu(Image source, Rectangle mask, float radians, Interpolation interpolate_type);
+
+/* ---- tracing pass-through backend --------------------------------------- */
+
+typedef struct {
+  B200SheetResult *res;
+  int detect_masks_calls;
+} Trace;
+static __thread Trace *tls_trace = NULL;
+
+static size_t tr_detect_masks(Image image, MaskDetectionParameters params,
+                              const Point points[], size_t n, Rectangle masks[]) {
+  size_t c = detect_masks_cpu(image, params, points, n, masks);
+  Trace *t = tls_trace;
+  if (t && t->res) {
+    t->detect_masks_calls++;
+    /* call 1: masks stage (result discarded by the reference, sheet_stages.c:368-372)
+     * call 2: deskew stage; call 3: post stage (mask centring). */
+    size_t m = c < B200_TRACE_MAX_MASKS ? c : B200_TRACE_MAX_MASKS;
+    if (t->detect_masks_calls == 2) {
+      t->res->deskew_mask_count = (int32_t)c;
+      memcpy(t->res->deskew_masks, masks, m * sizeof(Rectangle));
+    } else if (t->detect_masks_calls == 3) {
+      t->res->center_mask_count = (int32_t)c;
+      memcpy(t->res->center_masks, masks, m * sizeof(Rectangle));
+    }
+  }
+  return c;
+}
+static float tr_detect_rotation(Image image, Rectangle mask, const DeskewParameters p) {
+  float r = detect_rotation_cpu(image, mask, p);
+  Trace *t = tls_trace;
+  if (t && t->res) {
+    for (int i = 0; i < t->res->deskew_mask_count && i < B200_TRACE_MAX_MASKS; i++) {
+      if (memcmp(&t->res->deskew_masks[i], &mask, sizeof(mask)) == 0) {
+        t->res->rotation[i] = r;
+        break;
+      }
+    }
+  }
+  return r;
+}
+static Border tr_detect_border(Image image, BorderScanParameters p, const Rectangle outside) {
+  Border b = detect_border_cpu(image, p, outside);
+  Trace *t = tls_trace;
+  if (t && t->res && t->res->border_count < MAX_PAGES) {
+    int k = t->res->border_count++;
+    t->res->borders[k] = b;
+    t->res->border_masks[k] = border_to_mask(image, b);
+  }
+  return b;
+}
+
+const ImageBackend backend_cuda = {
+    .name = "cpu-traced",
+    .wipe_rectangle = wipe_rectangle_cpu,
+    .copy_rectangle = copy_rectangle_cpu,
+    .center_image = center_image_cpu,
+    .stretch_and_replace = stretch_and_replace_cpu,
+    .resize_and_replace = resize_and_replace_cpu,
+    .flip_rotate_90 = flip_rotate_90_cpu,
+    .mirror = mirror_cpu,
+    .shift_image = shift_image_cpu,
+    .apply_masks = apply_masks_cpu,
+    .apply_wipes = apply_wipes_cpu,
+    .apply_border = apply_border_cpu,
+    .detect_masks = tr_detect_masks,
+    .align_mask = align_mask_cpu,
+    .detect_border = tr_detect_border,
+    .blackfilter = blackfilter_cpu,
+    .blurfilter = blurfilter_cpu,
+    .noisefilter = noisefilter_cpu,
+    .grayfilter = grayfilter_cpu,
+    .detect_rotation = tr_detect_rotation,
+    .deskew = deskew_cpu,
+};
+
+static pthread_once_t init_once = PTHREAD_ONCE_INIT;
+static void do_init(void) {
+  verbose = VERBOSE_QUIET;
+  image_backend_select(UNPAPER_DEVICE_CUDA); /* = the pass-through above */
+}
+static void ensure_init(void) { pthread_once(&init_once, do_init); }
+
+/* ---- host image <-> reference Image ------------------------------------- */
+
+/* Borrow the caller's buffer: no copy, nothing owned by the frame. */
+static Image wrap(const B200HostImage *h, AVFrame *storage) {
+  memset(storage, 0, sizeof(*storage));
+  storage->data[0] = h->data;
+  storage->linesize[0] = h->linesize;
+  storage->width = h->width;
+  storage->height = h->height;
+  storage->format = h->format;
+  return (Image){.frame = storage, .background = h->background,
+                 .abs_black_threshold = h->abs_black_threshold};
+}
+
+static Image clone_owned(const B200HostImage *h) {
+  Image img = create_image((RectangleSize){h->width, h->height}, h->format, false,
+                           h->background, h->abs_black_threshold);
+  int row = av_shim_row_bytes(h->format, h->width);
+  for (int y = 0; y < h->height; y++)
+    memcpy(img.frame->data[0] + (size_t)y * img.frame->linesize[0],
+           h->data + (size_t)y * h->linesize, (size_t)row);
+  return img;
+}
+
+static int export_owned(Image img, B200HostImage *out) {
+  if (out->width != img.frame->width || out->height != img.frame->height ||
+      out->format != img.frame->format)
+    return -2;
+  int row = av_shim_row_bytes(out->format, out->width);
+  for (int y = 0; y < out->height; y++)
+    memcpy(out->data + (size_t)y * out->linesize,
+           img.frame->data[0] + (size_t)y * img.frame->linesize[0], (size_t)row);
+  return 0;
+}
+
+/* ---- per-op entry points -------------------------------------------------- */
+
+int ref_host_wipe_rectangle(B200HostImage *img, const Rectangle *area, Pixel color) {
+  ensure_init();
+  AVFrame f; wipe_rectangle(wrap(img, &f), *area, color); return 0;
+}
+int ref_host_copy_rectangle(const B200HostImage *src, B200HostImage *dst,
+                            const Rectangle *src_area, Point target) {
+  ensure_init();
+  AVFrame a, b; copy_rectangle(wrap(src, &a), wrap(dst, &b), *src_area, target); return 0;
+}
+int ref_host_center_image(const B200HostImage *src, B200HostImage *dst,
+                          Point target_origin, RectangleSize target_size) {
+  ensure_init();
+  AVFrame a, b; center_image(wrap(src, &a), wrap(dst, &b), target_origin, target_size); return 0;
+}
+int ref_host_stretch(const B200HostImage *img, B200HostImage *out, int32_t interp) {
+  ensure_init();
+  Image w = clone_owned(img);
+  stretch_and_replace(&w, (RectangleSize){out->width, out->height}, (Interpolation)interp);
+  int rc = export_owned(w, out); free_image(&w); return rc;
+}
+int ref_host_resize(const B200HostImage *img, B200HostImage *out, int32_t interp) {
+  ensure_init();
+  Image w = clone_owned(img);
+  resize_and_replace(&w, (RectangleSize){out->width, out->height}, (Interpolation)interp);
+  int rc = export_owned(w, out); free_image(&w); return rc;
+}
+int ref_host_flip_rotate_90(const B200HostImage *img, B200HostImage *out, int32_t direction) {
+  ensure_init();
+  Image w = clone_owned(img);
+  flip_rotate_90(&w, (RotationDirection)direction);
+  int rc = export_owned(w, out); free_image(&w); return rc;
+}
+int ref_host_mirror(B200HostImage *img, Direction direction) {
+  ensure_init();
+  AVFrame f; mirror(wrap(img, &f), direction); return 0;
+}
+int ref_host_shift(const B200HostImage *img, B200HostImage *out, Delta d) {
+  ensure_init();
+  Image w = clone_owned(img);
+  shift_image(&w, d);
+  int rc = export_owned(w, out); free_image(&w); return rc;
+}
+int ref_host_apply_masks(B200HostImage *img, const Rectangle *masks, size_t n, Pixel color) {
+  ensure_init();
+  AVFrame f; apply_masks(wrap(img, &f), masks, n, color); return 0;
+}
+int ref_host_apply_wipes(B200HostImage *img, const Wipes *wipes, Pixel color) {
+  ensure_init();
+  AVFrame f; apply_wipes(wrap(img, &f), *wipes, color); return 0;
+}
+int ref_host_apply_border(B200HostImage *img, const Border *border, Pixel color) {
+  ensure_init();
+  AVFrame f; apply_border(wrap(img, &f), *border, color); return 0;
+}
+int ref_host_detect_masks(const B200HostImage *img, const MaskDetectionParameters *p,
+                          const Point *points, size_t n, Rectangle *masks_out) {
+  ensure_init();
+  AVFrame f; return (int)detect_masks(wrap(img, &f), *p, points, n, masks_out);
+}
+int ref_host_center_mask(B200HostImage *img, Point center, const Rectangle *area) {
+  ensure_init();
+  AVFrame f; center_mask(wrap(img, &f), center, *area); return 0;
+}
+int ref_host_align_mask(B200HostImage *img, const Rectangle *inside, const Rectangle *outside,
+                        const MaskAlignmentParameters *p) {
+  ensure_init();
+  AVFrame f; align_mask(wrap(img, &f), *inside, *outside, *p); return 0;
+}
+int ref_host_detect_border(const B200HostImage *img, const BorderScanParameters *p,
+                           const Rectangle *outside, Border *out) {
+  ensure_init();
+  AVFrame f; *out = detect_border(wrap(img, &f), *p, *outside); return 0;
+}
+int ref_host_blackfilter(B200HostImage *img, const BlackfilterParameters *p) {
+  ensure_init();
+  AVFrame f; blackfilter(wrap(img, &f), *p); return 0;
+}
+int ref_host_blurfilter(B200HostImage *img, const BlurfilterParameters *p, uint8_t abs_white) {
+  ensure_init();
+  AVFrame f; blurfilter(wrap(img, &f), *p, abs_white); return 0;
+}
+int ref_host_noisefilter(B200HostImage *img, uint64_t intensity, uint8_t min_white_level) {
+  ensure_init();
+  AVFrame f; noisefilter(wrap(img, &f), intensity, min_white_level); return 0;
+}
+int ref_host_grayfilter(B200HostImage *img, const GrayfilterParameters *p) {
+  ensure_init();
+  AVFrame f; grayfilter(wrap(img, &f), *p); return 0;
+}
+int ref_host_detect_rotation(const B200HostImage *img, const Rectangle *mask,
+                             const DeskewParameters *p, float *radians_out) {
+  ensure_init();
+  AVFrame f; *radians_out = detect_rotation(wrap(img, &f), *mask, *p); return 0;
+}
+int ref_host_deskew(B200HostImage *img, const Rectangle *mask, float radians, int32_t interp) {
+  ensure_init();
+  AVFrame f; deskew(wrap(img, &f), *mask, radians, (Interpolation)interp); return 0;
+}
+
+/* ---- whole sheets through the reference's own process_sheet() ------------- */
+
+static const struct MultiIndex MI_NONE = {.count = 0, .indexes = NULL};
+static const struct MultiIndex MI_ALL = {.count = -1, .indexes = NULL};
+
+static void options_from_cfg(Options *o, Rectangle *bf_excl, const B200SheetConfig *c) {
+  options_init(o);
+  options_init_filter_defaults(o, bf_excl);
+  o->device = UNPAPER_DEVICE_CPU;
+  o->write_output = false;
+  o->layout = (Layout)c->layout;
+  o->input_count = c->input_count;
+  o->interpolate_type = (Interpolation)c->interpolate_type;
+  o->sheet_background = c->sheet_background;
+  o->mask_color = c->mask_color;
+  o->abs_black_threshold = c->abs_black_threshold;
+  o->abs_white_threshold = c->abs_white_threshold;
+#define SW(flag, field) o->field = (c->flag) ? MI_ALL : MI_NONE
+  SW(no_blackfilter, no_blackfilter_multi_index);
+  SW(no_noisefilter, no_noisefilter_multi_index);
+  SW(no_blurfilter, no_blurfilter_multi_index);
+  SW(no_grayfilter, no_grayfilter_multi_index);
+  SW(no_mask_scan, no_mask_scan_multi_index);
+  SW(no_mask_center, no_mask_center_multi_index);
+  SW(no_deskew, no_deskew_multi_index);
+  SW(no_wipe, no_wipe_multi_index);
+  SW(no_border, no_border_multi_index);
+  SW(no_border_scan, no_border_scan_multi_index);
+  SW(no_border_align, no_border_align_multi_index);
+#undef SW
+  o->noisefilter_intensity = c->noisefilter_intensity;
+  o->blackfilter_parameters = c->blackfilter;
+  o->blackfilter_parameters.exclusions = bf_excl;
+  o->blackfilter_parameters.exclusions_count = 0;
+  for (size_t i = 0; i < c->blackfilter.exclusions_count && i < MAX_MASKS; i++)
+    bf_excl[o->blackfilter_parameters.exclusions_count++] = c->blackfilter.exclusions[i];
+  o->blurfilter_parameters = c->blurfilter;
+  o->grayfilter_parameters = c->grayfilter;
+  o->deskew_parameters = c->deskew;
+  o->mask_detection_parameters = c->mask_detection;
+  o->mask_alignment_parameters = c->mask_alignment;
+  o->border_scan_parameters = c->border_scan;
+  o->pre_border = c->pre_border;
+  o->border = c->border;
+  o->post_border = c->post_border;
+  o->pre_wipes.count = (size_t)c->pre_wipe_count;
+  o->wipes.count = (size_t)c->wipe_count;
+  o->post_wipes.count = (size_t)c->post_wipe_count;
+  for (int i = 0; i < 8; i++) {
+    o->pre_wipes.areas[i] = c->pre_wipes[i];
+    o->wipes.areas[i] = c->wipes[i];
+    o->post_wipes.areas[i] = c->post_wipes[i];
+  }
+}
+
+/* One sheet: pages -> reference process_sheet() -> sheet in the page format. */
+static int run_one_sheet(const B200SheetConfig *cfg, const Options *opt,
+                         const uint8_t *pages, int page_w, int page_h, int page_fmt,
+                         uint8_t *out, B200SheetResult *res) {
+  int row = av_shim_row_bytes(page_fmt, page_w);
+  if (row < 0) return -1;
+  size_t page_bytes = (size_t)row * page_h;
+
+  SheetProcessConfig spc;
+  /* The batch path passes blackfilter_exclude_count = 0 so that layout
+   * defaults apply (image_pipeline.c:377-379); user exclusions already sit in
+   * opt->blackfilter_parameters. */
+  sheet_process_config_init(&spc, opt, cfg->pre_masks, (size_t)cfg->pre_mask_count,
+                            cfg->points, (size_t)cfg->point_count, cfg->middle_wipe,
+                            NULL, opt->blackfilter_parameters.exclusions_count);
+
+  BatchJob job;
+  memset(&job, 0, sizeof(job));
+  job.sheet_nr = 1;
+  job.input_count = cfg->input_count;
+  job.output_count = 1;
+  job.layout_override = -1;
+
+  SheetProcessState st;
+  sheet_process_state_init(&st, &spc, &job);
+  for (int j = 0; j < cfg->input_count; j++) {
+    AVFrame *fr = av_frame_alloc();
+    fr->width = page_w; fr->height = page_h; fr->format = page_fmt;
+    if (av_frame_get_buffer(fr, 8) < 0) return -3;
+    for (int y = 0; y < page_h; y++)
+      memcpy(fr->data[0] + (size_t)y * fr->linesize[0],
+             pages + (size_t)j * page_bytes + (size_t)y * row, (size_t)row);
+    sheet_process_state_set_decoded(&st, fr, j);
+  }
+
+  B200SheetResult local;
+  if (!res) res = &local;
+  memset(res, 0, sizeof(*res));
+  Trace tr = {.res = res, .detect_masks_calls = 0};
+  tls_trace = &tr;
+  bool ok = process_sheet(&st, &spc);
+  tls_trace = NULL;
+  res->status = ok ? 0 : -1;
+  if (ok) {
+    res->sheet_width = st.sheet.frame->width;
+    res->sheet_height = st.sheet.frame->height;
+    if (out) {
+      /* what saveImage() would hand to the writer (file.c:211-262) */
+      B200HostImage o = {.data = out, .width = res->sheet_width, .height = res->sheet_height,
+                         .linesize = av_shim_row_bytes(page_fmt, res->sheet_width),
+                         .format = page_fmt, .background = st.sheet.background,
+                         .abs_black_threshold = st.sheet.abs_black_threshold};
+      AVFrame f;
+      copy_rectangle_cpu(st.sheet, wrap(&o, &f), full_image(st.sheet), POINT_ORIGIN);
+    }
+  }
+  sheet_process_state_cleanup(&st);
+  return ok ? 0 : -1;
+}
+
+typedef struct {
+  const B200SheetConfig *cfg;
+  const Options *opt;
+  const uint8_t *pages;
+  uint8_t *out;
+  B200SheetResult *results;
+  int page_w, page_h, page_fmt, n_sheets;
+  size_t sheet_in_bytes, sheet_out_bytes;
+  atomic_int next;
+  atomic_int failed;
+} Job;
+
+static void *worker(void *arg) {
+  Job *jb = (Job *)arg;
+  for (;;) {
+    int i = atomic_fetch_add(&jb->next, 1);
+    if (i >= jb->n_sheets) break;
+    int rc = run_one_sheet(jb->cfg, jb->opt, jb->pages + (size_t)i * jb->sheet_in_bytes,
+                           jb->page_w, jb->page_h, jb->page_fmt,
+                           jb->out ? jb->out + (size_t)i * jb->sheet_out_bytes : NULL,
+                           jb->results ? &jb->results[i] : NULL);
+    if (rc != 0) atomic_fetch_add(&jb->failed, 1);
+  }
+  return NULL;
+}
+
+/* Reference process_sheet() over n_sheets sheets with `threads` pthreads —
+ * functionally batch_process_parallel() (lib/batch_worker.c:273-296) minus the
+ * codecs.  `pages` holds n_sheets*input_count tightly packed pages; `out`
+ * (may be NULL) receives tightly packed sheets in the page format.
+ * Returns 0 or the number of failed sheets (negative). */
+int ref_process_sheets(const B200SheetConfig *cfg, const uint8_t *pages, int page_w,
+                       int page_h, int page_fmt, int n_sheets, uint8_t *out,
+                       B200SheetResult *results, int threads, int *sheet_w, int *sheet_h) {
+  ensure_init();
+  Options opt;
+  static __thread Rectangle bf_excl[MAX_MASKS];
+  options_from_cfg(&opt, bf_excl, cfg);
+  int row = av_shim_row_bytes(page_fmt, page_w);
+  if (row < 0) return -1;
+  int sw = page_w * cfg->input_count, sh = page_h;
+  if (sheet_w) *sheet_w = sw;
+  if (sheet_h) *sheet_h = sh;
+  Job jb = {.cfg = cfg, .opt = &opt, .pages = pages, .out = out, .results = results,
+            .page_w = page_w, .page_h = page_h, .page_fmt = page_fmt, .n_sheets = n_sheets,
+            .sheet_in_bytes = (size_t)row * page_h * cfg->input_count,
+            .sheet_out_bytes = (size_t)av_shim_row_bytes(page_fmt, sw) * sh};
+  atomic_init(&jb.next, 0);
+  atomic_init(&jb.failed, 0);
+  if (threads <= 1) {
+    worker(&jb);
+  } else {
+    pthread_t *th = calloc((size_t)threads, sizeof(*th));
+    for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, worker, &jb);
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    free(th);
+  }
+  return -atomic_load(&jb.failed);
+}
+
+int ref_online_cpus(void) { return (int)sysconf(_SC_NPROCESSORS_ONLN); }
+const char *ref_version(void) { return "unpaper reference CPU backend (oracle/_ref)"; }
