@@ -1,0 +1,95 @@
+"""Sheet engine (CUDA) vs the reference's own process_sheet() on the CPU backend:
+every decision bit-identical, every pixel identical."""
+import numpy as np
+import pytest
+
+import unpaper_gpu_b200 as U
+from unpaper_gpu_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(cfg, pages, w, h, fmt, ref_lib, group=4, lanes=2):
+    from unpaper_gpu_b200.lib import Engine
+    eng = Engine(cfg, w, h, fmt, group_pages=group, lanes=lanes)
+    out, res = eng.process_numpy(pages)
+    eng.close()
+    rout, rres = U.process_sheets_cpu(ref_lib, "ref_", cfg, pages, w, h, fmt, threads=8)
+    for i, (a, b) in enumerate(zip(res, rres)):
+        assert a.status == 0 and b.status == 0
+        assert a.deskew_mask_count == b.deskew_mask_count, f"sheet {i}"
+        for k in range(a.deskew_mask_count):
+            assert U.rect_tuple(a.deskew_masks[k]) == U.rect_tuple(b.deskew_masks[k]), f"sheet {i} deskew mask {k}"
+            assert a.rotation[k] == b.rotation[k], f"sheet {i} rotation {k}: {a.rotation[k]} vs {b.rotation[k]}"
+        assert a.center_mask_count == b.center_mask_count
+        for k in range(a.center_mask_count):
+            assert U.rect_tuple(a.center_masks[k]) == U.rect_tuple(b.center_masks[k]), f"sheet {i} center mask {k}"
+        assert a.border_count == b.border_count
+        for k in range(a.border_count):
+            assert U.border_tuple(a.borders[k]) == U.border_tuple(b.borders[k]), f"sheet {i} border {k}"
+    diff = out != rout
+    assert not diff.any(), f"{int(diff.sum())} differing bytes; per sheet {diff.reshape(len(res), -1).sum(axis=1)}"
+    return out, res
+
+
+def test_engine_gray_small(ref_lib):
+    w, h = 620, 877
+    pages = np.stack([synth.gray_page(i, w, h) for i in range(6)])
+    _compare(U.default_sheet_config(), pages, w, h, U.FMT_GRAY8, ref_lib, group=4, lanes=2)
+
+
+def test_engine_gray_half_scale(ref_lib):
+    w, h = 1240, 1754
+    pages = np.stack([synth.gray_page(40 + i, w, h) for i in range(3)])
+    _compare(U.default_sheet_config(), pages, w, h, U.FMT_GRAY8, ref_lib, group=2, lanes=2)
+
+
+def test_engine_rgb_small(ref_lib):
+    w, h = 620, 877
+    pages = np.stack([synth.color_page(i, w, h) for i in range(3)])
+    cfg = U.default_sheet_config()
+    cfg.no_blackfilter = cfg.no_noisefilter = 1   # BASELINE config 3: gray/blur filters + cubic deskew
+    _compare(cfg, pages, w, h, U.FMT_RGB24, ref_lib, group=2, lanes=1)
+
+
+def test_engine_double_layout(ref_lib):
+    w, h = 1754, 1240
+    pages = np.stack([synth.double_sheet(i, w, h) for i in range(2)])
+    cfg = U.default_sheet_config()
+    cfg.layout = U.LAYOUT_DOUBLE
+    _compare(cfg, pages, w, h, U.FMT_GRAY8, ref_lib, group=2, lanes=1)
+
+
+def test_engine_stage_switches(ref_lib):
+    w, h = 620, 877
+    pages = np.stack([synth.gray_page(70 + i, w, h) for i in range(2)])
+    for flags in (("no_deskew",), ("no_mask_center", "no_border_align"), ("no_mask_scan",), ("no_border_scan", "no_grayfilter")):
+        cfg = U.default_sheet_config()
+        for f in flags:
+            setattr(cfg, f, 1)
+        _compare(cfg, pages, w, h, U.FMT_GRAY8, ref_lib, group=2, lanes=1)
+
+
+def test_engine_full_a4(ref_lib):
+    """BASELINE config 2 at full size, one sheet (the reference needs ~15 s)."""
+    w, h = synth.A4_W, synth.A4_H
+    pages = synth.gray_page(0, w, h)[None]
+    _compare(U.default_sheet_config(), pages, w, h, U.FMT_GRAY8, ref_lib, group=1, lanes=1)
+
+
+def test_engine_idempotent_and_deterministic():
+    """Size-independent properties at full size: same input twice -> same bytes;
+    a processed page run again detects rotation 0."""
+    from unpaper_gpu_b200.lib import Engine
+    w, h = synth.A4_W, synth.A4_H
+    pages = np.stack([synth.gray_page(i, w, h) for i in range(4)])
+    eng = Engine(U.default_sheet_config(), w, h, U.FMT_GRAY8, group_pages=2, lanes=2)
+    out1, res1 = eng.process_numpy(pages)
+    out2, res2 = eng.process_numpy(pages)
+    assert np.array_equal(out1, out2)
+    out3, res3 = eng.process_numpy(out1)
+    eng.close()
+    for r in res1:
+        assert r.status == 0 and r.deskew_mask_count == 1 and r.rotation[0] != 0.0
+    for r in res3:
+        assert abs(r.rotation[0]) <= np.deg2rad(0.2) + 1e-6

@@ -1,5 +1,5 @@
 /* Minimal stand-in for <libavutil/buffer.h> (reference-counted byte buffers).
- * TEST INFRASTRUCTURE / build shim; see pixfmt.h. */
+ * Build shim for hosts without FFmpeg headers; see pixfmt.h. */
 #pragma once
 #include <stddef.h>
 #include <stdint.h>

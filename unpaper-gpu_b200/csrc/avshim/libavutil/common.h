@@ -1,4 +1,4 @@
-/* stand-in for <libavutil/common.h>; TEST INFRASTRUCTURE / build shim. */
+/* stand-in for <libavutil/common.h>; Build shim for hosts without FFmpeg headers. */
 #pragma once
 #include <stdint.h>
 static inline uint8_t av_clip_uint8(int a) {

@@ -1,6 +1,6 @@
 /* Minimal stand-in for <libavutil/frame.h>: the AVFrame fields and the four
- * allocation calls unpaper's imageprocess/ layer uses. TEST INFRASTRUCTURE /
- * build shim; see pixfmt.h. */
+ * allocation calls unpaper's imageprocess/ layer uses.  Build shim for hosts
+ * without FFmpeg headers; see pixfmt.h. */
 #pragma once
 #include <stddef.h>
 #include <stdint.h>

@@ -1,7 +1,7 @@
 /* Minimal stand-in for <libavutil/pixfmt.h>: only the pixel formats the
- * unpaper sheet path touches. TEST INFRASTRUCTURE (used to build oracle/_ref
- * and, when FFmpeg headers are absent, the B200 backend). Numeric values follow
- * FFmpeg's enum so a binary built against the real header agrees. */
+ * unpaper sheet path touches.  Used when FFmpeg's own headers are absent (this
+ * image has none): by the B200 backend build and by oracle/Makefile.  Numeric
+ * values follow FFmpeg's enum so a binary built against the real header agrees. */
 #pragma once
 enum AVPixelFormat {
   AV_PIX_FMT_NONE = -1,

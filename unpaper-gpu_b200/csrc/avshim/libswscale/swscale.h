@@ -1,6 +1,6 @@
 /* stand-in for <libswscale/swscale.h>: the YUV->RGB conversion branch of the
  * decode stage is outside the hot path; the context is never created here.
- * TEST INFRASTRUCTURE / build shim. */
+ * Build shim for hosts without FFmpeg headers. */
 #pragma once
 #include <stddef.h>
 #include <stdint.h>

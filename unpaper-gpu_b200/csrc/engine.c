@@ -1,0 +1,491 @@
+/* engine.c — the sheet engine: process_sheet()'s stage order
+ * (reference src/core/sheet_stages.c:44-696) for GROUPS of independent sheets.
+ *
+ * Replaces the reference's page scheduler (lib/batch_worker.c:79-296: one
+ * pthread + one stream per sheet, each blocking on dozens of tiny D2H reads)
+ * with asynchronous lanes: a lane owns a stream, a device workspace for
+ * `group_pages` sheets and the job/result records; every kernel covers the
+ * whole group and every data-dependent decision (masks, rotation, centring,
+ * border) stays in the pages' device records.  One host thread keeps all lanes
+ * busy; there is no host round-trip inside a sheet.
+ *
+ * Working-sheet format: the reference always builds an RGB24 sheet
+ * (sheet_stages.c:153-155).  For GRAY8 pages with gray background / mask
+ * colours every RGB24 pixel would carry r=g=b through all stages, so the
+ * engine keeps a 1 byte/pixel sheet instead — same results, a third of the
+ * traffic.  RGB24 pages use an RGB24 sheet.
+ */
+#define _GNU_SOURCE
+#include <libavutil/pixfmt.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "host.h"
+
+enum { STG_DECODE, STG_BLACK, STG_NOISE, STG_BLUR, STG_GRAY, STG_MASKS, STG_ROTDET, STG_DESKEW,
+       STG_CENTER, STG_BORDER, STG_OUTPUT, STG_COUNT };
+static const char *STG_NAME[STG_COUNT] = {"decode", "blackfilter", "noisefilter", "blurfilter", "grayfilter",
+                                          "detect_masks", "detect_rotation", "deskew", "center_mask",
+                                          "border", "output"};
+
+typedef struct {
+  cudaStream_t st;
+  cudaEvent_t done;
+  cudaEvent_t ev[STG_COUNT + 1];
+  int ev_mask;            /* which stage boundaries were recorded */
+  uint8_t *sheets, *aux, *cls;
+  uint32_t *list, *u32;
+  uint64_t *stack;
+  uint8_t *page_stage;    /* device staging for host-mode pages */
+  DPage *pages_dev, *pages_tmpl /* host */, *pages_res /* pinned */;
+  DFillJob *fillA, *fillB, *decode_fill;
+  DCopyJob *copyA, *copyB, *decode_copy, *decode_copy_host_tmpl;
+  DMaskJob *maskJ;
+  DFillJob *static_fill[3];   /* pre / mid / post wipe+border rectangles, per page */
+  int static_fill_n[3];
+  DMaskJob *static_mask[3];
+  DRect *static_mask_rects[3];
+  int busy, first, n;
+  uint8_t *out_host; uint8_t *out_dev;
+  int host_mode;
+} Lane;
+
+struct B200Engine {
+  B200SheetConfig cfg;
+  int device, page_w, page_h, page_fmt, dfmt, bpp;
+  int sheet_w, sheet_h, sheet_pitch, page_row, sheet_row;
+  size_t sheet_stride, page_bytes;
+  int group, nlanes;
+  int npoints, noutside;
+  Point points[D_MAX_MASKS];
+  Rectangle outside[D_MAX_BORDERS];
+  Rectangle bf_excl[MAX_MASKS];
+  BfPlan bf; BlurPlan blur; GrayPlan gray; MaskPlan mask; BorderPlan border; RotPlan rot;
+  ScratchNeed need;
+  Lane *lanes;
+  uint64_t launches;
+  int profiling;
+  int n_static_mask_jobs[3];
+  int bad_sheets;
+  double stage_ms[STG_COUNT];
+  uint64_t stage_groups[STG_COUNT];
+};
+
+static int imax(int a, int b) { return a > b ? a : b; }
+
+int unpaper_b200_engine_sheet_width(const B200Engine *e) { return e->sheet_w; }
+int unpaper_b200_engine_sheet_height(const B200Engine *e) { return e->sheet_h; }
+size_t unpaper_b200_engine_sheet_bytes(const B200Engine *e) { return (size_t)e->sheet_row * e->sheet_h; }
+uint64_t unpaper_b200_engine_launch_count(const B200Engine *e) { return e->launches; }
+int unpaper_b200_engine_set_profiling(B200Engine *e, int enabled) {
+  e->profiling = enabled;
+  memset(e->stage_ms, 0, sizeof(e->stage_ms));
+  memset(e->stage_groups, 0, sizeof(e->stage_groups));
+  return 0;
+}
+int unpaper_b200_engine_get_profile(const B200Engine *e, int max_entries, const char **names, double *ms,
+                                    uint64_t *launches, double *alg_bytes) {
+  int n = 0;
+  for (int s = 0; s < STG_COUNT && n < max_entries; s++) {
+    names[n] = STG_NAME[s]; ms[n] = e->stage_ms[s]; launches[n] = e->stage_groups[s];
+    if (alg_bytes) alg_bytes[n] = 0;
+    n++;
+  }
+  return n;
+}
+
+/* fill rectangles that the reference applies with apply_wipes / apply_border
+ * as static jobs (geometry does not depend on the page contents) */
+static int build_static(B200Engine *e, Lane *ln, int slot, const Rectangle *wipes, int nw, Border border,
+                        const Rectangle *masks, int nm, const Rectangle *extra_wipe) {
+  int P = e->group;
+  int nfill = nw + (extra_wipe ? 1 : 0);
+  ln->static_fill_n[slot] = nfill;
+  ln->static_fill[slot] = NULL; ln->static_mask[slot] = NULL; ln->static_mask_rects[slot] = NULL;
+  if (nfill > 0) {
+    DFillJob *h = (DFillJob *)calloc((size_t)nfill * P, sizeof(DFillJob));
+    for (int k = 0; k < nfill; k++) {
+      Rectangle r = k < nw ? wipes[k] : *extra_wipe;
+      for (int p = 0; p < P; p++) {
+        DFillJob *j = &h[(size_t)k * P + p];
+        j->img = ln->pages_tmpl[p].img;
+        j->r = (DRect){r.vertex[0].x, r.vertex[0].y, r.vertex[1].x, r.vertex[1].y};   /* apply_wipes: as given */
+        j->c[0] = e->cfg.mask_color.r; j->c[1] = e->cfg.mask_color.g; j->c[2] = e->cfg.mask_color.b;
+        j->enabled = 1;
+      }
+    }
+    ln->static_fill[slot] = (DFillJob *)blob_upload(h, (size_t)nfill * P * sizeof(DFillJob));
+    free(h);
+  }
+  bool has_border = border.left || border.top || border.right || border.bottom;
+  int nrect = nm + (has_border ? 1 : 0);
+  if (nrect > 0) {
+    /* apply_masks(pre_masks) and apply_border are separate calls in the
+     * reference; both are "paint outside these rectangles" and run here as two
+     * consecutive jobs when both are present */
+    DRect *hr = (DRect *)calloc((size_t)nrect, sizeof(DRect));
+    for (int k = 0; k < nm; k++) hr[k] = (DRect){masks[k].vertex[0].x, masks[k].vertex[0].y, masks[k].vertex[1].x, masks[k].vertex[1].y};
+    if (has_border) hr[nm] = (DRect){border.left, border.top, e->sheet_w - border.right - 1, e->sheet_h - border.bottom - 1};
+    ln->static_mask_rects[slot] = (DRect *)blob_upload(hr, (size_t)nrect * sizeof(DRect));
+    free(hr);
+    int njob = (nm > 0 ? 1 : 0) + (has_border ? 1 : 0);
+    DMaskJob *hj = (DMaskJob *)calloc((size_t)njob * P, sizeof(DMaskJob));
+    int q = 0;
+    if (nm > 0) { for (int p = 0; p < P; p++) { DMaskJob *j = &hj[(size_t)q * P + p]; j->img = ln->pages_tmpl[p].img; j->rects = ln->static_mask_rects[slot]; j->nrects = nm; j->enabled = 1;
+        j->c[0] = e->cfg.mask_color.r; j->c[1] = e->cfg.mask_color.g; j->c[2] = e->cfg.mask_color.b; } q++; }
+    if (has_border) { for (int p = 0; p < P; p++) { DMaskJob *j = &hj[(size_t)q * P + p]; j->img = ln->pages_tmpl[p].img; j->rects = ln->static_mask_rects[slot] + nm; j->nrects = 1; j->enabled = 1;
+        j->c[0] = e->cfg.mask_color.r; j->c[1] = e->cfg.mask_color.g; j->c[2] = e->cfg.mask_color.b; } q++; }
+    ln->static_mask[slot] = (DMaskJob *)blob_upload(hj, (size_t)njob * P * sizeof(DMaskJob));
+    free(hj);
+    return njob;
+  }
+  return 0;
+}
+
+static void lane_free(Lane *ln) {
+  void *ptrs[] = {ln->sheets, ln->aux, ln->cls, ln->list, ln->u32, ln->stack, ln->page_stage, ln->pages_dev,
+                  ln->fillA, ln->fillB, ln->decode_fill, ln->copyA, ln->copyB, ln->decode_copy, ln->maskJ,
+                  ln->static_fill[0], ln->static_fill[1], ln->static_fill[2], ln->static_mask[0], ln->static_mask[1],
+                  ln->static_mask[2], ln->static_mask_rects[0], ln->static_mask_rects[1], ln->static_mask_rects[2]};
+  for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) b200_dev_free(ptrs[i]);
+  if (ln->pages_res) b200_pinned_free(ln->pages_res);
+  free(ln->pages_tmpl); free(ln->decode_copy_host_tmpl);
+  if (ln->done) cudaEventDestroy(ln->done);
+  for (int i = 0; i <= STG_COUNT; i++) if (ln->ev[i]) cudaEventDestroy(ln->ev[i]);
+  if (ln->st) b200_stream_release(ln->st);
+  memset(ln, 0, sizeof(*ln));
+}
+
+void unpaper_b200_engine_destroy(B200Engine *e) {
+  if (!e) return;
+  unpaper_b200_set_device(e->device);
+  if (e->lanes) { for (int i = 0; i < e->nlanes; i++) lane_free(&e->lanes[i]); free(e->lanes); }
+  bf_plan_free(&e->bf); blur_plan_free(&e->blur); mask_plan_free(&e->mask); border_plan_free(&e->border); rot_plan_free(&e->rot);
+  free(e);
+}
+
+
+B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, int page_w, int page_h,
+                                       int page_format, int group_pages, int lanes) {
+  if (!cfg || page_w <= 0 || page_h <= 0 || group_pages <= 0 || lanes <= 0) { b200_set_error("engine: bad arguments"); return NULL; }
+  if (unpaper_b200_set_device(device)) return NULL;
+  if (page_format != AV_PIX_FMT_GRAY8 && page_format != AV_PIX_FMT_RGB24) { b200_set_error("engine: page format must be GRAY8 or RGB24"); return NULL; }
+  if (cfg->input_count < 1 || cfg->input_count > 2) { b200_set_error("engine: input_count must be 1 or 2"); return NULL; }
+  bool gray_colors = cfg->sheet_background.r == cfg->sheet_background.g && cfg->sheet_background.g == cfg->sheet_background.b &&
+                     cfg->mask_color.r == cfg->mask_color.g && cfg->mask_color.g == cfg->mask_color.b;
+  if (page_format == AV_PIX_FMT_GRAY8 && !gray_colors) { b200_set_error("engine: GRAY8 pages need gray background and mask colours"); return NULL; }
+  B200Engine *e = (B200Engine *)calloc(1, sizeof(*e));
+  e->cfg = *cfg; e->device = device;
+  e->page_w = page_w; e->page_h = page_h; e->page_fmt = page_format; e->dfmt = b200_fmt_to_dev(page_format);
+  e->bpp = page_format == AV_PIX_FMT_GRAY8 ? 1 : 3;
+  e->group = group_pages; e->nlanes = lanes;
+  /* sheet size = input pages side by side (sheet_stages.c:140-145) */
+  e->sheet_w = page_w * cfg->input_count; e->sheet_h = page_h;
+  e->page_row = page_w * e->bpp; e->sheet_row = e->sheet_w * e->bpp;
+  e->sheet_pitch = (e->sheet_row + 15) & ~15;
+  e->sheet_stride = (((size_t)e->sheet_pitch * e->sheet_h + 64) + 255) & ~(size_t)255;
+  e->page_bytes = (size_t)e->page_row * page_h;
+  int W = e->sheet_w, H = e->sheet_h;
+
+  /* layout-derived points, mask maxima, border-scan areas (sheet_stages.c:232-279) */
+  MaskDetectionParameters mp = cfg->mask_detection;
+  e->npoints = cfg->point_count;
+  for (int i = 0; i < e->npoints && i < D_MAX_MASKS; i++) e->points[i] = cfg->points[i];
+  if (cfg->layout == LAYOUT_SINGLE) {
+    if (e->npoints == 0) e->points[e->npoints++] = (Point){W / 2, H / 2};
+    if (mp.maximum_width == -1) mp.maximum_width = W;
+    if (mp.maximum_height == -1) mp.maximum_height = H;
+    e->outside[e->noutside++] = (Rectangle){{{0, 0}, {W - 1, H - 1}}};
+  } else if (cfg->layout == LAYOUT_DOUBLE) {
+    if (e->npoints == 0) { e->points[e->npoints++] = (Point){W / 4, H / 2}; e->points[e->npoints++] = (Point){W - W / 4, H / 2}; }
+    if (mp.maximum_width == -1) mp.maximum_width = W / 2;
+    if (mp.maximum_height == -1) mp.maximum_height = H;
+    e->outside[e->noutside++] = (Rectangle){{{0, 0}, {W / 2, H - 1}}};
+    e->outside[e->noutside++] = (Rectangle){{{W / 2, 0}, {W - 1, H - 1}}};
+  }
+  if (mp.maximum_width == -1) mp.maximum_width = W;
+  if (mp.maximum_height == -1) mp.maximum_height = H;
+
+  /* blackfilter exclusions (sheet_stages.c:298-322) */
+  BlackfilterParameters bfp = cfg->blackfilter;
+  size_t nex = 0;
+  for (size_t i = 0; i < cfg->blackfilter.exclusions_count && i < MAX_MASKS; i++) e->bf_excl[nex++] = cfg->blackfilter.exclusions[i];
+  if (nex == 0 && cfg->layout != LAYOUT_NONE) {
+    if (cfg->layout == LAYOUT_SINGLE) {
+      e->bf_excl[nex++] = (Rectangle){{{W / 4, H / 4}, {W / 4 + W / 2 - 1, H / 4 + H / 2 - 1}}};
+    } else {
+      int fw = W / 4, fh = H / 2, ox = W / 8, oy = H / 4;
+      e->bf_excl[nex++] = (Rectangle){{{ox, oy}, {ox + fw - 1, oy + fh - 1}}};
+      e->bf_excl[nex++] = (Rectangle){{{ox + W / 2, oy}, {ox + W / 2 + fw - 1, oy + fh - 1}}};
+    }
+  }
+  bfp.exclusions = e->bf_excl; bfp.exclusions_count = nex;
+
+  int rc = 0;
+  if (!cfg->no_blackfilter) rc |= bf_plan_build(&e->bf, W, H, &bfp, cfg->abs_black_threshold);
+  if (!cfg->no_blurfilter) rc |= blur_plan_build(&e->blur, W, H, &cfg->blurfilter, cfg->abs_white_threshold);
+  if (!cfg->no_grayfilter) rc |= gray_plan_build(&e->gray, W, H, &cfg->grayfilter, cfg->abs_black_threshold);
+  if (!cfg->no_mask_scan) rc |= mask_plan_build(&e->mask, W, H, &mp, e->points, e->npoints);
+  if (!cfg->no_border_scan) rc |= border_plan_build(&e->border, W, H, &cfg->border_scan, e->outside, e->noutside, cfg->abs_black_threshold);
+  if (!cfg->no_deskew) rc |= rot_plan_build(&e->rot, W, H, &cfg->deskew, imax(e->npoints, 1), true);
+  if (!cfg->no_noisefilter && (H >= 32768 || W >= 65536 || cfg->noisefilter_intensity > 4000)) {
+    b200_set_error("engine: noisefilter limits exceeded"); rc = -1;
+  }
+  if (rc) { unpaper_b200_engine_destroy(e); return NULL; }
+
+  scratch_need_all(&e->need, W, H, e->dfmt);
+  int u32 = 64;
+  u32 = imax(u32, e->bf.u32_need); u32 = imax(u32, e->blur.u32_need); u32 = imax(u32, e->gray.u32_need);
+  u32 = imax(u32, e->mask.u32_need); u32 = imax(u32, e->border.u32_need); u32 = imax(u32, e->rot.u32_need);
+  e->need.u32_cap = (u32 + 63) & ~63;
+
+  int P = group_pages;
+  e->lanes = (Lane *)calloc((size_t)lanes, sizeof(Lane));
+  for (int li = 0; li < lanes; li++) {
+    Lane *ln = &e->lanes[li];
+    ln->st = b200_stream_acquire();
+    CUDA_OK(cudaEventCreateWithFlags(&ln->done, cudaEventDisableTiming));
+    for (int i = 0; i <= STG_COUNT; i++) CUDA_OK(cudaEventCreate(&ln->ev[i]));
+    ln->sheets = (uint8_t *)b200_dev_alloc(e->sheet_stride * P);
+    size_t aux_stride = (e->need.aux_bytes + 255) & ~(size_t)255;
+    size_t cls_stride = (e->need.cls_bytes + 255) & ~(size_t)255;
+    ln->aux = (uint8_t *)b200_dev_alloc(aux_stride * P);
+    ln->cls = (uint8_t *)b200_dev_alloc(cls_stride * P);
+    ln->list = (uint32_t *)b200_dev_alloc((size_t)e->need.list_cap * 4 * P);
+    ln->u32 = (uint32_t *)b200_dev_alloc((size_t)e->need.u32_cap * 4 * P);
+    ln->stack = (uint64_t *)b200_dev_alloc((size_t)e->need.stack_cap * 32 * P);
+    ln->page_stage = (uint8_t *)b200_dev_alloc(e->page_bytes * cfg->input_count * P + 64);
+    ln->pages_dev = (DPage *)b200_dev_alloc(sizeof(DPage) * P);
+    ln->pages_res = (DPage *)b200_pinned_alloc(sizeof(DPage) * P);
+    ln->pages_tmpl = (DPage *)calloc((size_t)P, sizeof(DPage));
+    ln->fillA = (DFillJob *)b200_dev_alloc(sizeof(DFillJob) * P);
+    ln->fillB = (DFillJob *)b200_dev_alloc(sizeof(DFillJob) * P);
+    ln->copyA = (DCopyJob *)b200_dev_alloc(sizeof(DCopyJob) * P);
+    ln->copyB = (DCopyJob *)b200_dev_alloc(sizeof(DCopyJob) * P);
+    ln->maskJ = (DMaskJob *)b200_dev_alloc(sizeof(DMaskJob) * P);
+    ln->decode_fill = (DFillJob *)b200_dev_alloc(sizeof(DFillJob) * P);
+    ln->decode_copy = (DCopyJob *)b200_dev_alloc(sizeof(DCopyJob) * P * cfg->input_count);
+    ln->decode_copy_host_tmpl = (DCopyJob *)calloc((size_t)P * cfg->input_count, sizeof(DCopyJob));
+    DFillJob *dfill = (DFillJob *)calloc((size_t)P, sizeof(DFillJob));
+    for (int p = 0; p < P; p++) {
+      DPage *pg = &ln->pages_tmpl[p];
+      pg->img = (DImg){ln->sheets + e->sheet_stride * p, W, H, e->sheet_pitch, e->dfmt, cfg->abs_black_threshold,
+                       {cfg->sheet_background.r, cfg->sheet_background.g, cfg->sheet_background.b}};
+      pg->aux = pg->img;
+      pg->aux.data = ln->aux + aux_stride * p; pg->aux.pitch = e->need.aux_pitch; pg->aux.h = e->need.aux_h; pg->aux.w = W + 64;
+      pg->cls = ln->cls + cls_stride * p;
+      pg->list = ln->list + (size_t)e->need.list_cap * p; pg->list_cap = e->need.list_cap;
+      pg->u32 = ln->u32 + (size_t)e->need.u32_cap * p; pg->u32_cap = e->need.u32_cap;
+      pg->stack = ln->stack + (size_t)e->need.stack_cap * 4 * p; pg->stack_cap = e->need.stack_cap;
+      pg->point_count = e->npoints;
+      for (int i = 0; i < e->npoints; i++) { pg->px[i] = e->points[i].x; pg->py[i] = e->points[i].y; }
+      pg->outside_count = e->noutside;
+      for (int i = 0; i < e->noutside; i++)
+        pg->outside[i] = (DRect){e->outside[i].vertex[0].x, e->outside[i].vertex[0].y, e->outside[i].vertex[1].x, e->outside[i].vertex[1].y};
+      for (int i = 0; i < D_MAX_MASKS; i++) pg->rot_cos[i] = 1.0f;
+      /* decode: create_image(fill) + center_image per input (sheet_stages.c:150-165).
+       * Pages have the slot's size here, so center_image never wipes and the
+       * fill is only needed when the sheet pitch has padding columns (none read). */
+      dfill[p].img = pg->img; dfill[p].r = (DRect){0, 0, W - 1, H - 1};
+      dfill[p].c[0] = cfg->sheet_background.r; dfill[p].c[1] = cfg->sheet_background.g; dfill[p].c[2] = cfg->sheet_background.b;
+      dfill[p].enabled = 0;
+      for (int j = 0; j < cfg->input_count; j++) {
+        DCopyJob *cj = &ln->decode_copy_host_tmpl[(size_t)p * cfg->input_count + j];
+        cj->src = (DImg){NULL, page_w, page_h, e->page_row, e->dfmt, cfg->abs_black_threshold, {255, 255, 255}};
+        cj->dst = pg->img;
+        cj->area = (DRect){0, 0, page_w - 1, page_h - 1};
+        cj->tx = W * j / cfg->input_count; cj->ty = 0;
+        cj->enabled = 1;
+      }
+    }
+    CUDA_OK(cudaMemcpy(ln->pages_dev, ln->pages_tmpl, sizeof(DPage) * P, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(ln->decode_fill, dfill, sizeof(DFillJob) * P, cudaMemcpyHostToDevice));
+    free(dfill);
+    /* static wipes / borders at the three points where the reference applies them */
+    Rectangle mid = {{{W / 2 - cfg->middle_wipe[0], 0}, {W / 2 + cfg->middle_wipe[1], H - 1}}};
+    bool use_mid = cfg->layout == LAYOUT_DOUBLE && (cfg->middle_wipe[0] > 0 || cfg->middle_wipe[1] > 0);
+    Border none = {0, 0, 0, 0};
+    e->n_static_mask_jobs[0] = build_static(e, ln, 0, cfg->pre_wipes, cfg->no_wipe ? 0 : cfg->pre_wipe_count,
+                                         cfg->no_border ? none : cfg->pre_border, cfg->pre_masks, cfg->pre_mask_count, NULL);
+    e->n_static_mask_jobs[1] = build_static(e, ln, 1, cfg->wipes, cfg->no_wipe ? 0 : cfg->wipe_count,
+                                         cfg->no_border ? none : cfg->border, NULL, 0, (use_mid && !cfg->no_wipe) ? &mid : NULL);
+    e->n_static_mask_jobs[2] = build_static(e, ln, 2, cfg->post_wipes, cfg->no_wipe ? 0 : cfg->post_wipe_count,
+                                         cfg->no_border ? none : cfg->post_border, NULL, 0, NULL);
+  }
+  return e;
+}
+
+static void mark(B200Engine *e, Lane *ln, int stage_boundary) {
+  if (!e->profiling) return;
+  CUDA_OK(cudaEventRecord(ln->ev[stage_boundary], ln->st));
+  ln->ev_mask |= 1 << stage_boundary;
+}
+
+/* apply pre-masks first (sheet_stages.c:211-214), then wipes (:282-285), then
+ * border (:288-291) — same order for the mid and post slots */
+static void run_static(B200Engine *e, Lane *ln, StageCtx *c, int slot, int n) {
+  int P = e->group;
+  int q = 0;
+  bool has_masks = slot == 0 && e->cfg.pre_mask_count > 0;
+  if (has_masks) { b200k_apply_masks(c->st, ln->static_mask[slot] + (size_t)q * P, n, e->sheet_w, e->sheet_h); q++; c->launches++; }
+  for (int k = 0; k < ln->static_fill_n[slot]; k++) { b200k_fill_jobs(c->st, ln->static_fill[slot] + (size_t)k * P, n, e->sheet_w, e->sheet_h); c->launches++; }
+  if (q < e->n_static_mask_jobs[slot]) { b200k_apply_masks(c->st, ln->static_mask[slot] + (size_t)q * P, n, e->sheet_w, e->sheet_h); c->launches++; }
+}
+
+static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, int n) {
+  const B200SheetConfig *cfg = &e->cfg;
+  StageCtx c;
+  memset(&c, 0, sizeof(c));
+  c.st = ln->st; c.npages = n; c.pages = ln->pages_dev; c.w = e->sheet_w; c.h = e->sheet_h; c.fmt = e->dfmt;
+  c.fillA = ln->fillA; c.fillB = ln->fillB; c.copyA = ln->copyA; c.copyB = ln->copyB; c.maskJ = ln->maskJ;
+  ln->ev_mask = 0;
+  int ic = cfg->input_count;
+
+  mark(e, ln, STG_DECODE);
+  b200k_page_reset(c.st, c.pages, n);
+  /* decode stage: page(s) -> sheet */
+  for (int p = 0; p < n; p++)
+    for (int j = 0; j < ic; j++)
+      ln->decode_copy_host_tmpl[(size_t)p * ic + j].src.data = (uint8_t *)pages_dev_in + e->page_bytes * ((size_t)p * ic + j);
+  /* job records are tiny; one pageable H2D per group */
+  CUDA_OK(cudaMemcpyAsync(ln->decode_copy, ln->decode_copy_host_tmpl, sizeof(DCopyJob) * n * ic, cudaMemcpyHostToDevice, c.st));
+  b200k_copy_jobs(c.st, ln->decode_copy, n * ic, e->page_row, e->page_h);
+  c.launches += 2;
+  run_static(e, ln, &c, 0, n);
+
+  mark(e, ln, STG_BLACK);
+  if (!cfg->no_blackfilter) stage_blackfilter(&c, &e->bf);
+  mark(e, ln, STG_NOISE);
+  if (!cfg->no_noisefilter) stage_noisefilter(&c, cfg->noisefilter_intensity, cfg->abs_white_threshold);
+  mark(e, ln, STG_BLUR);
+  if (!cfg->no_blurfilter) stage_blurfilter(&c, &e->blur);
+  mark(e, ln, STG_GRAY);
+  /* masks stage: the reference's first detect_masks() result is discarded
+   * (sheet_stages.c:368-372) and has no side effect -> not run */
+  if (!cfg->no_grayfilter) stage_grayfilter(&c, &e->gray);
+  mark(e, ln, STG_MASKS);
+  int nm = e->npoints;
+  if (!cfg->no_deskew) {
+    if (!cfg->no_mask_scan) stage_detect_masks(&c, &e->mask);
+    mark(e, ln, STG_ROTDET);
+    stage_detect_rotation(&c, &e->rot, nm);
+    mark(e, ln, STG_DESKEW);
+    stage_deskew(&c, cfg->interpolate_type, nm);
+  } else { mark(e, ln, STG_ROTDET); mark(e, ln, STG_DESKEW); }
+  mark(e, ln, STG_CENTER);
+  if (!cfg->no_mask_center) {
+    if (!cfg->no_mask_scan) stage_detect_masks(&c, &e->mask);
+    stage_center_masks(&c, nm);
+  }
+  run_static(e, ln, &c, 1, n);
+  mark(e, ln, STG_BORDER);
+  if (!cfg->no_border_scan) {
+    stage_detect_border(&c, &e->border);
+    stage_apply_border_masks(&c, cfg->mask_color);
+    if (!cfg->no_border_align) stage_align_masks(&c, &cfg->mask_alignment, e->noutside);
+  }
+  run_static(e, ln, &c, 2, n);
+  mark(e, ln, STG_OUTPUT);
+  /* output stage: sheet -> caller (tight rows) + the decisions */
+  if (ln->host_mode) {
+    CUDA_OK(cudaMemcpy2DAsync(ln->out_host, (size_t)e->sheet_row, ln->sheets, (size_t)e->sheet_pitch, (size_t)e->sheet_row,
+                              (size_t)e->sheet_h * 1, cudaMemcpyDeviceToHost, c.st));
+    for (int p = 1; p < n; p++)
+      CUDA_OK(cudaMemcpy2DAsync(ln->out_host + (size_t)e->sheet_row * e->sheet_h * p, (size_t)e->sheet_row,
+                                ln->sheets + e->sheet_stride * p, (size_t)e->sheet_pitch, (size_t)e->sheet_row,
+                                (size_t)e->sheet_h, cudaMemcpyDeviceToHost, c.st));
+  } else {
+    b200k_pack_rows(c.st, ln->sheets, e->sheet_pitch, ln->out_dev, e->sheet_row, e->sheet_row, e->sheet_h, n,
+                    e->sheet_stride, (size_t)e->sheet_row * e->sheet_h);
+    c.launches++;
+  }
+  CUDA_OK(cudaMemcpyAsync(ln->pages_res, ln->pages_dev, sizeof(DPage) * n, cudaMemcpyDeviceToHost, c.st));
+  mark(e, ln, STG_COUNT);
+  CUDA_OK(cudaEventRecord(ln->done, c.st));
+  e->launches += c.launches;
+}
+
+static void collect(B200Engine *e, Lane *ln, B200SheetResult *results) {
+  if (!ln->busy) return;
+  CUDA_OK(cudaEventSynchronize(ln->done));
+  if (e->profiling) {
+    for (int s = 0; s < STG_COUNT; s++) {
+      float ms = 0;
+      if ((ln->ev_mask >> s & 1) && (ln->ev_mask >> (s + 1) & 1) &&
+          cudaEventElapsedTime(&ms, ln->ev[s], ln->ev[s + 1]) == cudaSuccess) {
+        e->stage_ms[s] += ms; e->stage_groups[s] += 1;
+      }
+    }
+  }
+  for (int p = 0; p < ln->n; p++) if (ln->pages_res[p].error) e->bad_sheets++;
+  if (results) {
+    for (int p = 0; p < ln->n; p++) {
+      const DPage *pg = &ln->pages_res[p];
+      B200SheetResult *r = &results[ln->first + p];
+      memset(r, 0, sizeof(*r));
+      r->status = pg->error ? -(int)pg->error : 0;
+      r->sheet_width = e->sheet_w; r->sheet_height = e->sheet_h;
+      int nm = pg->mask_count < B200_TRACE_MAX_MASKS ? pg->mask_count : B200_TRACE_MAX_MASKS;
+      /* the deskew-stage masks are overwritten by the post-stage detection in
+       * the device record; rotation[] belongs to the former, masks[] to the latter */
+      r->center_mask_count = e->cfg.no_mask_center || e->cfg.no_mask_scan ? 0 : pg->mask_count;
+      r->deskew_mask_count = e->cfg.no_deskew || e->cfg.no_mask_scan ? 0 : pg->mask_count_deskew;
+      for (int i = 0; i < nm; i++) {
+        r->center_masks[i] = (Rectangle){{{pg->masks[i].x0, pg->masks[i].y0}, {pg->masks[i].x1, pg->masks[i].y1}}};
+        r->centered[i] = pg->centered[i];
+      }
+      for (int i = 0; i < r->deskew_mask_count && i < B200_TRACE_MAX_MASKS; i++) {
+        r->deskew_masks[i] = (Rectangle){{{pg->masks_deskew[i].x0, pg->masks_deskew[i].y0}, {pg->masks_deskew[i].x1, pg->masks_deskew[i].y1}}};
+        r->rotation[i] = pg->rotation[i];
+      }
+      r->border_count = e->cfg.no_border_scan ? 0 : pg->outside_count;
+      for (int i = 0; i < r->border_count && i < MAX_PAGES; i++) {
+        r->borders[i] = (Border){pg->border[i].left, pg->border[i].top, pg->border[i].right, pg->border[i].bottom};
+        r->border_masks[i] = (Rectangle){{{pg->border_mask[i].x0, pg->border_mask[i].y0}, {pg->border_mask[i].x1, pg->border_mask[i].y1}}};
+      }
+      r->blackfilter_fills = (int32_t)pg->bf_fills;
+      r->noise_clusters = (int32_t)pg->nf_clusters;
+    }
+  }
+  ln->busy = 0;
+}
+
+static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_sheets, B200SheetResult *results, int host_mode) {
+  if (!e || !pages || !out || n_sheets < 0) { b200_set_error("engine: bad arguments"); return -1; }
+  unpaper_b200_set_device(e->device);
+  int P = e->group, ic = e->cfg.input_count;
+  size_t out_sheet = (size_t)e->sheet_row * e->sheet_h;
+  int g = 0;
+  for (int first = 0; first < n_sheets; first += P, g++) {
+    Lane *ln = &e->lanes[g % e->nlanes];
+    collect(e, ln, results);
+    int n = n_sheets - first < P ? n_sheets - first : P;
+    ln->first = first; ln->n = n; ln->host_mode = host_mode;
+    const uint8_t *src = pages + e->page_bytes * ic * (size_t)first;
+    if (host_mode) {
+      CUDA_OK(cudaMemcpyAsync(ln->page_stage, src, e->page_bytes * ic * (size_t)n, cudaMemcpyHostToDevice, ln->st));
+      ln->out_host = out + out_sheet * first;
+      issue_group(e, ln, ln->page_stage, n);
+    } else {
+      ln->out_dev = out + out_sheet * first;
+      issue_group(e, ln, src, n);
+    }
+    ln->busy = 1;
+  }
+  for (int i = 0; i < e->nlanes; i++) collect(e, &e->lanes[(g + i) % e->nlanes], results);
+  CUDA_OK(cudaGetLastError());
+  int bad = e->bad_sheets;
+  e->bad_sheets = 0;
+  if (bad) b200_set_error("engine: %d sheet(s) reported device-side failure flags", bad);
+  return bad ? -2 : 0;
+}
+
+int unpaper_b200_engine_process_device(B200Engine *e, const uint8_t *pages_dev, uint8_t *out_dev, int n_sheets,
+                                       B200SheetResult *results) {
+  return process(e, pages_dev, out_dev, n_sheets, results, 0);
+}
+int unpaper_b200_engine_process_host(B200Engine *e, const uint8_t *pages_host, uint8_t *out_host, int n_sheets,
+                                     B200SheetResult *results) {
+  return process(e, pages_host, out_host, n_sheets, results, 1);
+}

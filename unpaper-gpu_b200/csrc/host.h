@@ -1,0 +1,117 @@
+/* host.h — internal declarations of the C host layer. */
+#pragma once
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "dev.h"
+#include "launch.h"
+#include "rt.h"
+#include "unpaper_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int b200_fmt_to_dev(int av_pix_fmt);            /* -1 if unsupported */
+int b200_fmt_row_bytes(int av_pix_fmt, int width);
+bool b200_image_view(Image *image, DImg *out);  /* image_res.c */
+
+/* ---- plans: static, geometry-dependent tables in device memory ----------- */
+
+typedef struct {
+  int npos, njobs, sums_len, flag_off, u32_need;
+  DBfPos *pos_dev;
+  DLineJob *jobs_host, *jobs_dev;
+  int abs_threshold, mask_hi;
+  long long intensity;
+} BfPlan;
+
+typedef struct {
+  int n, nrows, bw, bh, nrects;
+  DRect *rects_dev;
+  int cnt_off, state_off, flag_off, u32_need;
+  unsigned long long T;
+  float intensity;
+  int white;
+} BlurPlan;
+
+typedef struct {
+  int gp[18];
+  int white_off, u32_need;
+  int dark_max;
+  int ok;
+} GrayPlan;
+
+typedef struct {
+  int njobs, stride, u32_need, max_points;
+  DLineJob *jobs_host, *jobs_dev;
+  MaskDetectionParameters p;
+} MaskPlan;
+
+typedef struct {
+  int njobs, stride, u32_need, oob_dark, abt;
+  DLineJob *jobs_host, *jobs_dev;
+  BorderScanParameters p;
+} BorderPlan;
+
+typedef struct {
+  int nangles;
+  float *rot_host, *tan_host;      /* the reference's angle sequence (deskew.c:156-160) */
+  float *rot_dev, *tan_dev;
+  float *pair_dev;                 /* optional [2n][2n][4] table: rotation, sin, cos of -rotation */
+  int edges[4];
+  int peak_off, u32_need, scan_cap;
+  DeskewParameters p;
+} RotPlan;
+
+int bf_plan_build(BfPlan *pl, int w, int h, const BlackfilterParameters *p, int abs_black_threshold);
+void bf_plan_free(BfPlan *pl);
+int blur_plan_build(BlurPlan *pl, int w, int h, const BlurfilterParameters *p, int abs_white);
+void blur_plan_free(BlurPlan *pl);
+int gray_plan_build(GrayPlan *pl, int w, int h, const GrayfilterParameters *p, int abs_black_threshold);
+int mask_plan_build(MaskPlan *pl, int w, int h, const MaskDetectionParameters *p, const Point *pts, int npts);
+void mask_plan_free(MaskPlan *pl);
+int border_plan_build(BorderPlan *pl, int w, int h, const BorderScanParameters *p,
+                      const Rectangle *outside, int n, int abs_black_threshold);
+void border_plan_free(BorderPlan *pl);
+int rot_plan_build(RotPlan *pl, int w, int h, const DeskewParameters *p, int max_masks, bool with_pair_table);
+void rot_plan_free(RotPlan *pl);
+/* detect_rotation_cpu's float tail (deskew.c:218-240) on host */
+float rot_finalize_host(const RotPlan *pl, const int angle_idx[4]);
+
+/* ---- stages: enqueue one pipeline step for a group of pages -------------- */
+
+typedef struct {
+  cudaStream_t st;
+  int npages;
+  DPage *pages;               /* device array */
+  int w, h, fmt;              /* geometry shared by the group (device fmt code) */
+  DFillJob *fillA, *fillB;    /* device job arrays, npages each */
+  DCopyJob *copyA, *copyB;
+  DMaskJob *maskJ;
+  uint64_t launches;
+} StageCtx;
+
+void stage_blackfilter(StageCtx *c, const BfPlan *pl);
+int stage_noisefilter(StageCtx *c, uint64_t intensity, int white);
+void stage_blurfilter(StageCtx *c, const BlurPlan *pl);
+int stage_grayfilter(StageCtx *c, const GrayPlan *pl);
+void stage_detect_masks(StageCtx *c, const MaskPlan *pl);
+int stage_detect_rotation(StageCtx *c, const RotPlan *pl, int max_masks);
+void stage_deskew(StageCtx *c, int interp, int max_masks);
+void stage_center_masks(StageCtx *c, int max_masks);
+void stage_detect_border(StageCtx *c, const BorderPlan *pl);
+void stage_apply_border_masks(StageCtx *c, Pixel color);
+void stage_align_masks(StageCtx *c, const MaskAlignmentParameters *p, int n_outside);
+
+/* scratch sizing for one page of w x h in device format fmt */
+typedef struct { size_t aux_bytes; int aux_pitch, aux_h; size_t cls_bytes; int list_cap, u32_cap, stack_cap; } ScratchNeed;
+void scratch_need_all(ScratchNeed *n, int w, int h, int fmt);
+
+void *blob_upload(const void *host, size_t bytes);   /* synchronous H2D into cached device memory */
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,132 @@
+// k_blit.cu — rectangle fill / copy / mask painting / mirror / quarter turns.
+// Replaces reference imageprocess/cuda_kernels_blit.cu and the OpenCV calls of
+// imageprocess/opencv_ops.cpp:91-367 with the CPU backend's exact semantics
+// (imageprocess/blit.c:20-85, :291-354; masks.c:311-347).
+#include "common.cuh"
+#include "launch.h"
+
+// ---- fill ---------------------------------------------------------------
+// One job = one rectangle [x0..x1]x[y0..y1] (empty when inverted), clipped to
+// the image here.  blockIdx.z = job.
+__global__ void k_fill_jobs(const DFillJob *jobs) {
+  const DFillJob &j = jobs[blockIdx.z];
+  if (!j.enabled) return;
+  const DImg &im = j.img;
+  int x0 = max(j.r.x0, 0), x1 = min(j.r.x1, im.w - 1);
+  int y0 = max(j.r.y0, 0), y1 = min(j.r.y1, im.h - 1);
+  int y = y0 + blockIdx.y;
+  if (y > y1) return;
+  int r = j.c[0], g = j.c[1], b = j.c[2];
+  if (im.fmt == DF_GRAY8) {
+    // byte-addressed rows: 4 pixels per thread
+    uint8_t v = (uint8_t)((r + g + b) / 3);
+    uint8_t *row = im.data + (size_t)y * im.pitch;
+    for (int x = x0 + (blockIdx.x * blockDim.x + threadIdx.x) * 4; x <= x1; x += gridDim.x * blockDim.x * 4) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) if (x + k <= x1) row[x + k] = v;
+    }
+    return;
+  }
+  for (int x = x0 + blockIdx.x * blockDim.x + threadIdx.x; x <= x1; x += gridDim.x * blockDim.x)
+    px_store(im, x, y, r, g, b);
+}
+
+// ---- copy (imageprocess/blit.c:30-80) -------------------------------------
+__global__ void k_copy_jobs(const DCopyJob *jobs) {
+  const DCopyJob &j = jobs[blockIdx.z];
+  if (!j.enabled) return;
+  const DImg &s = j.src, &d = j.dst;
+  // clip_rectangle(source, area): normalise, then clip to the source image
+  int ax0 = max(min(j.area.x0, j.area.x1), 0), ax1 = min(max(j.area.x0, j.area.x1), s.w - 1);
+  int ay0 = max(min(j.area.y0, j.area.y1), 0), ay1 = min(max(j.area.y0, j.area.y1), s.h - 1);
+  int width = ax1 - ax0 + 1, height = ay1 - ay0 + 1;
+  int sy = ay0 + blockIdx.y;
+  if (sy > ay1 || width <= 0) return;
+  int ty = j.ty + blockIdx.y;
+  int bpp = bytes_pp(s.fmt);
+  bool raw = s.fmt == d.fmt && bpp > 0 && height > 0 && j.tx >= 0 && j.ty >= 0 &&
+             j.tx + width <= d.w && j.ty + height <= d.h;
+  if (raw) {
+    const uint8_t *sp = s.data + (size_t)sy * s.pitch + (size_t)ax0 * bpp;
+    uint8_t *dp = d.data + (size_t)ty * d.pitch + (size_t)j.tx * bpp;
+    int n = width * bpp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dp[i] = sp[i];
+    return;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < width; i += gridDim.x * blockDim.x) {
+    Px p = px_load(s, ax0 + i, sy);
+    px_set(d, j.tx + i, ty, p.r, p.g, p.b);
+  }
+}
+
+// ---- apply_masks (masks.c:311-325): paint what no rectangle covers ---------
+__global__ void k_apply_masks(const DMaskJob *jobs) {
+  const DMaskJob &j = jobs[blockIdx.z];
+  if (!j.enabled || j.nrects <= 0) return;
+  const DImg &im = j.img;
+  int y = blockIdx.y;
+  if (y >= im.h) return;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < im.w; x += gridDim.x * blockDim.x) {
+    bool inside = false;
+    for (int k = 0; k < j.nrects && !inside; k++) inside = pt_in_rect(x, y, j.rects[k]);
+    if (!inside) px_store(im, x, y, j.c[0], j.c[1], j.c[2]);
+  }
+}
+
+// ---- mirror (blit.c:320-354): disjoint pixel pairs swapped in place --------
+__global__ void k_mirror(DImg im, int dir_h, int dir_v) {
+  int y = blockIdx.y;
+  int ymax = dir_v ? (im.h - 1) / 2 : im.h - 1;
+  if (y > ymax) return;
+  int yy = dir_v ? im.h - y - 1 : y;
+  int xmax = im.w - 1;
+  if (dir_h && (!dir_v || y == yy)) xmax = (im.w - 1) / 2;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x <= xmax; x += gridDim.x * blockDim.x) {
+    int xx = dir_h ? im.w - x - 1 : x;
+    Px p1 = px_load(im, x, y), p2 = px_load(im, xx, yy);
+    px_store(im, x, y, p2.r, p2.g, p2.b);
+    px_store(im, xx, yy, p1.r, p1.g, p1.b);
+  }
+}
+
+// ---- flip_rotate_90 (blit.c:291-314) -------------------------------------
+__global__ void k_rotate90(DImg src, DImg dst, int dir) {
+  int y = blockIdx.y;
+  if (y >= src.h) return;
+  int xx = ((dir > 0) ? src.h - 1 : 0) - y * dir;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < src.w; x += gridDim.x * blockDim.x) {
+    int yy = ((dir < 0) ? src.w - 1 : 0) + x * dir;
+    Px p = px_load(src, x, y);
+    px_set(dst, xx, yy, p.r, p.g, p.b);
+  }
+}
+
+static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+extern "C" {
+void b200k_fill_jobs(cudaStream_t st, const DFillJob *jobs, int njobs, int maxw, int maxh) {
+  if (njobs <= 0 || maxw <= 0 || maxh <= 0) return;
+  dim3 g(min(cdiv(maxw, 256 * 4), 64u), maxh, njobs);
+  k_fill_jobs<<<g, 256, 0, st>>>(jobs);
+}
+void b200k_copy_jobs(cudaStream_t st, const DCopyJob *jobs, int njobs, int maxw_bytes, int maxh) {
+  if (njobs <= 0 || maxw_bytes <= 0 || maxh <= 0) return;
+  dim3 g(min(cdiv(maxw_bytes, 256), 64u), maxh, njobs);
+  k_copy_jobs<<<g, 256, 0, st>>>(jobs);
+}
+void b200k_apply_masks(cudaStream_t st, const DMaskJob *jobs, int njobs, int maxw, int maxh) {
+  if (njobs <= 0 || maxw <= 0 || maxh <= 0) return;
+  dim3 g(min(cdiv(maxw, 256), 64u), maxh, njobs);
+  k_apply_masks<<<g, 256, 0, st>>>(jobs);
+}
+void b200k_mirror(cudaStream_t st, DImg im, int dir_h, int dir_v) {
+  if (im.w <= 0 || im.h <= 0) return;
+  dim3 g(min(cdiv(im.w, 256), 64u), im.h, 1);
+  k_mirror<<<g, 256, 0, st>>>(im, dir_h, dir_v);
+}
+void b200k_rotate90(cudaStream_t st, DImg src, DImg dst, int dir) {
+  if (src.w <= 0 || src.h <= 0) return;
+  dim3 g(min(cdiv(src.w, 256), 64u), src.h, 1);
+  k_rotate90<<<g, 256, 0, st>>>(src, dst, dir);
+}
+}

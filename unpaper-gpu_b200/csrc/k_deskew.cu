@@ -1,0 +1,315 @@
+// k_deskew.cu — rotation detection and interpolated resampling.
+// CPU semantics: reference imageprocess/deskew.c:48-290 and
+// imageprocess/interpolate.c:13-129 (including its quirks: bicubic truncates
+// toward zero, bilinear uses the wrong fractional coordinate in its two
+// degenerate branches).  Compiled with --fmad=false so that every float
+// expression rounds exactly like the C code (reference meson.build:243).
+// Replaces backend_cuda_deskew.c + cuda_kernels_deskew.cu:13-200 and the
+// cv::cuda::warpAffine path (opencv_ops.cpp:552).
+#include "common.cuh"
+#include "launch.h"
+
+static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+#define ROT_CHUNK 32
+
+struct RotParams {
+  int scan_size;        // params.deskewScanSize (may be -1)
+  float scan_depth;     // params.deskewScanDepth
+  int nangles;
+  int edges[4];         // left, top, right, bottom enabled
+  int peak_off;         // u32 offset: peaks[mask][edge][angle]
+};
+
+// detect_edge_rotation_peak (deskew.c:48-142) for one (page, mask, edge, angle)
+__global__ void k_rot_peaks(DPage *pages, const float *tan_tab, RotParams rp) {
+  extern __shared__ int2 pts[];
+  __shared__ int s_red[8][ROT_CHUNK];
+  __shared__ int s_done, s_max, s_dep;
+  DPage &pg = pages[blockIdx.z];
+  int a = blockIdx.x, mi = blockIdx.y >> 2, e = blockIdx.y & 3;
+  if (mi >= pg.mask_count || !rp.edges[e]) return;
+  const DImg &im = pg.img;
+  DRect mask = pg.masks[mi];
+  float m = tan_tab[a];
+  int sw = abs(mask.x0 - mask.x1) + 1, sh = abs(mask.y0 - mask.y1) + 1;
+  // edge -> shift: left = rightward, top = downward, right = leftward, bottom = upward
+  int shx = e == 0 ? 1 : e == 2 ? -1 : 0;
+  int shy = e == 1 ? 1 : e == 3 ? -1 : 0;
+  int scan = rp.scan_size, maxDepth;
+  float X, Y, stepX, stepY;
+  if (shy == 0) {
+    if (scan == -1) scan = sh;
+    scan = min(scan, min(10000, sh));
+    maxDepth = sw / 2;
+    int half = scan / 2;
+    int outer = (int)(fabsf(m) * half);
+    int mid = sh / 2;
+    int side = shx > 0 ? mask.x0 - outer : mask.x1 + outer;
+    X = side + half * m;
+    Y = mask.y0 + mid - half;
+    stepX = -m; stepY = 1.0f;
+  } else {
+    if (scan == -1) scan = sw;
+    scan = min(scan, min(10000, sw));
+    maxDepth = sh / 2;
+    int half = scan / 2;
+    int outer = (int)(fabsf(m) * half);
+    int mid = sw / 2;
+    int side = shy > 0 ? mask.x0 - outer : mask.x1 + outer;   // deskew.c:96-97 uses .x here
+    X = mask.x0 + mid - half;
+    Y = side - (half * m);
+    stepX = 1.0f; stepY = -m;
+  }
+  int maxAbs = (int)(255 * rp.scan_size * rp.scan_depth);   // deskew.c:67
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < scan; k++) {   // deskew.c:108-113: sequential float accumulation
+      pts[k] = make_int2((int)X, (int)Y);
+      X += stepX; Y += stepY;
+    }
+    s_done = 0; s_max = 0; s_dep = 0;
+  }
+  __syncthreads();
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int last = 0, maxDiff = 0, acc = 0, dep = 0;   // thread 0's copies are authoritative
+  int mx0 = min(mask.x0, mask.x1), mx1 = max(mask.x0, mask.x1), my0 = min(mask.y0, mask.y1), my1 = max(mask.y0, mask.y1);
+  for (int base = 0; base < maxDepth; base += ROT_CHUNK) {
+    int part[ROT_CHUNK];
+#pragma unroll
+    for (int d = 0; d < ROT_CHUNK; d++) part[d] = 0;
+    for (int k = threadIdx.x; k < scan; k += blockDim.x) {
+      int2 p = pts[k];
+#pragma unroll
+      for (int d = 0; d < ROT_CHUNK; d++) {
+        int x = p.x + (base + d) * shx, y = p.y + (base + d) * shy;
+        if (x >= mx0 && x <= mx1 && y >= my0 && y <= my1 && in_img(im, x, y))
+          part[d] += 255 - px_darkinv(px_load(im, x, y));
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < ROT_CHUNK; d++) {
+      int v = warp_sum_i32(part[d]);
+      if (lane == 0) s_red[warp][d] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int d = 0; d < ROT_CHUNK; d++) {
+        if (!((acc < maxAbs) && (dep < maxDepth))) { s_done = 1; break; }   // deskew.c:119
+        int blackness = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) blackness += s_red[w][d];
+        int diff = blackness - last;
+        last = blackness;
+        if (diff >= maxDiff) maxDiff = diff;
+        acc += blackness;
+        dep++;
+      }
+      if (!((acc < maxAbs) && (dep < maxDepth))) s_done = 1;
+      s_max = maxDiff; s_dep = dep;
+    }
+    __syncthreads();
+    if (s_done) break;
+  }
+  if (threadIdx.x == 0) {
+    int peak = (s_dep < maxDepth) ? s_max : 0;   // deskew.c:137-141
+    pg.u32[rp.peak_off + ((size_t)mi * 4 + e) * rp.nangles + a] = (unsigned)peak;
+  }
+}
+
+struct RotFinalParams {
+  int nangles;
+  int edges[4];
+  int peak_off;
+  float deviation;
+  int use_table;         // 1: pair table indexed [vi][vj], v = sign*nangles + angle
+};
+
+// detect_edge_rotation's argmax (deskew.c:156-168) + detect_rotation_cpu's
+// average / deviation test (deskew.c:218-240)
+__global__ void k_rot_finalize(DPage *pages, int npages, const float *rot_tab, const float *pair_tab, RotFinalParams fp) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int p = t / D_MAX_MASKS, mi = t % D_MAX_MASKS;
+  if (p >= npages) return;
+  DPage &pg = pages[p];
+  if (mi == 0) pg.mask_count_deskew = pg.mask_count;
+  if (mi >= pg.mask_count) return;
+  pg.masks_deskew[mi] = pg.masks[mi];
+  float rot[4];
+  int vidx[4];
+  int count = 0;
+  for (int e = 0; e < 4; e++) {
+    if (!fp.edges[e]) { pg.rot_angle_idx[mi][e] = -2; continue; }
+    const unsigned *pk = pg.u32 + fp.peak_off + ((size_t)mi * 4 + e) * fp.nangles;
+    int best = 0, besti = -1;
+    for (int a = 0; a < fp.nangles; a++) {
+      int v = (int)pk[a];
+      if (v > best) { best = v; besti = a; }
+    }
+    pg.rot_angle_idx[mi][e] = besti;
+    float r = besti >= 0 ? rot_tab[besti] : 0.0f;
+    bool neg = (e == 1 || e == 3);   // top / bottom results are negated (deskew.c:204,222)
+    rot[count] = neg ? -r : r;
+    // table coordinate: angle index (no winner = angle 0, rotation 0.0) and sign
+    vidx[count] = (neg ? fp.nangles : 0) + (besti >= 0 ? besti : 0);
+    count++;
+  }
+  float result = 0.0f, s = 0.0f, c = 1.0f;
+  if (count > 0) {
+    if (fp.use_table && count <= 2) {
+      int i = vidx[0], j = count == 2 ? vidx[1] : vidx[0];
+      const float *en = pair_tab + ((size_t)i * (2 * fp.nangles) + j) * 4 + (count == 2 ? 0 : 0);
+      // entry = {rotation(count=2), sin, cos, rotation(count=1 uses i==j which is identical)}
+      result = en[0]; s = en[1]; c = en[2];
+    } else {
+      float total = 0.0f;
+      for (int i = 0; i < count; i++) total += rot[i];
+      float average = total / count;
+      total = 0.0f;
+      for (int i = 0; i < count; i++) { float d = rot[i] - average; total += d * d; }
+      float deviation = sqrtf(total);
+      result = (deviation <= fp.deviation) ? average : 0.0f;
+      // no host libm here: double-precision evaluation rounded once (may differ
+      // from glibc sinf/cosf by 1 ulp; only reachable with 3-4 scan edges)
+      s = (float)sin(-(double)result); c = (float)cos(-(double)result);
+    }
+  }
+  pg.rotation[mi] = result;
+  pg.rot_sin[mi] = s; pg.rot_cos[mi] = c;
+  pg.rot_apply[mi] = result != 0.0f;
+}
+
+// ---- interpolation (interpolate.c:13-129) ----------------------------------
+__device__ __forceinline__ int clip_u8(int a) { return a < 0 ? 0 : a > 255 ? 255 : a; }
+
+__device__ __forceinline__ int cubic_scale(float f, int a, int b, int c, int d) {   // interpolate.c:24-32
+  int result = (int)(b + 0.5f * f * (c - a + f * (2.0f * a - 5.0f * b + 4.0f * c - d + f * (3.0f * (b - c) + d - a))));
+  return clip_u8(result);
+}
+__device__ __forceinline__ int linear_scale(float x, int a, int b) {   // interpolate.c:62-64
+  return (int)(uint8_t)(int)((1.0f - x) * a + x * b);
+}
+
+template <bool GRAY>
+__device__ __forceinline__ Px interp_cubic(const DImg &im, float fx, float fy) {
+  int px = (int)fx, py = (int)fy;
+  float ffx = fx - px, ffy = fy - py;
+  int rr[4], gg[4], bb[4];
+#pragma unroll
+  for (int i = -1; i < 3; i++) {
+    Px q0 = px_get(im, px - 1, py + i), q1 = px_get(im, px, py + i), q2 = px_get(im, px + 1, py + i), q3 = px_get(im, px + 2, py + i);
+    rr[i + 1] = cubic_scale(ffx, q0.r, q1.r, q2.r, q3.r);
+    if (!GRAY) {
+      gg[i + 1] = cubic_scale(ffx, q0.g, q1.g, q2.g, q3.g);
+      bb[i + 1] = cubic_scale(ffx, q0.b, q1.b, q2.b, q3.b);
+    }
+  }
+  Px o;
+  o.r = cubic_scale(ffy, rr[0], rr[1], rr[2], rr[3]);
+  if (GRAY) { o.g = o.r; o.b = o.r; }
+  else { o.g = cubic_scale(ffy, gg[0], gg[1], gg[2], gg[3]); o.b = cubic_scale(ffy, bb[0], bb[1], bb[2], bb[3]); }
+  return o;
+}
+
+__device__ __forceinline__ Px lin_px(float f, Px a, Px b) {
+  return Px{linear_scale(f, a.r, b.r), linear_scale(f, a.g, b.g), linear_scale(f, a.b, b.b)};
+}
+
+__device__ Px interp_linear(const DImg &im, float fx, float fy) {   // interpolate.c:76-117
+  int p1x = (int)floorf(fx), p1y = (int)floorf(fy);
+  int p2x = (int)ceil((double)fx), p2y = (int)ceilf(fy);
+  if (!in_img(im, p2x, p2y)) return px_get(im, p1x, p1y);
+  if (p1x == p2x && p1y == p2y) return px_get(im, p1x, p1y);
+  if (p1x == p2x) return lin_px(fx - p1x, px_get(im, p1x, p1y), px_get(im, p2x, p2y));
+  if (p1y == p2y) return lin_px(fy - p1y, px_get(im, p1x, p1y), px_get(im, p2x, p2y));
+  Px a = px_get(im, p1x, p1y), b = px_get(im, p2x, p1y), c = px_get(im, p1x, p2y), d = px_get(im, p2x, p2y);
+  Px h1 = lin_px(fx - p1x, a, b), h2 = lin_px(fx - p1x, c, d);
+  return lin_px(fy - p1y, h1, h2);
+}
+
+__device__ __forceinline__ Px interp_any(const DImg &im, float fx, float fy, int type, bool gray) {
+  if (type == 0) return px_get(im, (int)roundf(fx), (int)roundf(fy));   // interpolate.c:13-18
+  if (type == 1) return interp_linear(im, fx, fy);
+  return gray ? interp_cubic<true>(im, fx, fy) : interp_cubic<false>(im, fx, fy);
+}
+
+// rotate() (deskew.c:253-274) of mask `mi` into aux (mask-sized); the copy
+// back is a DCopyJob prepared here.
+__global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) {
+  DPage &pg = pages[blockIdx.z];
+  bool active = mi < pg.mask_count && pg.rot_apply[mi];
+  DRect mask = pg.masks[mi];
+  int w = abs(mask.x0 - mask.x1) + 1, h = abs(mask.y0 - mask.y1) + 1;
+  DImg aux = pg.aux;
+  int bpp = bytes_pp(aux.fmt);
+  int pitch = bpp ? ((w * bpp + 15) & ~15) : (((w + 7) / 8 + 15) & ~15);
+  if ((long long)pitch * h > (long long)aux.pitch * aux.h) { active = false; if (mi < pg.mask_count && pg.rot_apply[mi] && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) atomicOr(&pg.error, DERR_UNSUPPORTED); }
+  aux.w = w; aux.h = h; aux.pitch = pitch;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    DCopyJob j; j.src = aux; j.dst = pg.img; j.area = DRect{0, 0, w - 1, h - 1};
+    j.tx = mask.x0; j.ty = mask.y0; j.enabled = active; j.pad = 0;
+    back_jobs[blockIdx.z] = j;
+  }
+  if (!active) return;
+  const DImg &im = pg.img;
+  int y = blockIdx.y;
+  if (y >= h) return;
+  // center_of_rectangle (primitives.c:136-145) of the (normalised) mask / target
+  int nx0 = min(mask.x0, mask.x1), ny0 = min(mask.y0, mask.y1);
+  float scx = nx0 + w / 2.0f, scy = ny0 + h / 2.0f;
+  float tcx = 0 + w / 2.0f, tcy = 0 + h / 2.0f;
+  float sinval = pg.rot_sin[mi], cosval = pg.rot_cos[mi];
+  bool gray = im.fmt != DF_RGB24;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) {
+    float srcX = scx + (x - tcx) * cosval + (y - tcy) * sinval;
+    float srcY = scy + (y - tcy) * cosval - (x - tcx) * sinval;
+    Px o = interp_any(im, srcX, srcY, interp, gray);
+    px_store(aux, x, y, o.r, o.g, o.b);
+  }
+}
+
+// stretch_frame (blit.c:209-228)
+__global__ void k_stretch(DImg src, DImg dst, float hr, float vr, int interp) {
+  int y = blockIdx.y;
+  if (y >= dst.h) return;
+  bool gray = src.fmt != DF_RGB24;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < dst.w; x += gridDim.x * blockDim.x) {
+    Px o = interp_any(src, x * hr, y * vr, interp, gray);
+    px_store(dst, x, y, o.r, o.g, o.b);
+  }
+}
+
+extern "C" {
+int b200k_rot_peaks(cudaStream_t st, DPage *pages, int npages, int max_masks, const float *tan_tab_dev,
+                    int nangles, int scan_size_param, float scan_depth, const int edges[4],
+                    int peak_off, int scan_cap) {
+  if (npages <= 0 || max_masks <= 0 || nangles <= 0) return 0;
+  RotParams rp;
+  rp.scan_size = scan_size_param; rp.scan_depth = scan_depth; rp.nangles = nangles; rp.peak_off = peak_off;
+  for (int i = 0; i < 4; i++) rp.edges[i] = edges[i];
+  size_t sm = (size_t)scan_cap * sizeof(int2);
+  if (sm > 200 * 1024) return -1;
+  if (sm > 40 * 1024) cudaFuncSetAttribute(k_rot_peaks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  dim3 g(nangles, max_masks * 4, npages);
+  k_rot_peaks<<<g, 256, sm, st>>>(pages, tan_tab_dev, rp);
+  return 0;
+}
+void b200k_rot_finalize(cudaStream_t st, DPage *pages, int npages, const float *rot_tab_dev,
+                        const float *pair_tab_dev, int nangles, const int edges[4], int peak_off,
+                        float deviation) {
+  if (npages <= 0) return;
+  RotFinalParams fp;
+  fp.nangles = nangles; fp.peak_off = peak_off; fp.deviation = deviation; fp.use_table = pair_tab_dev != NULL;
+  for (int i = 0; i < 4; i++) fp.edges[i] = edges[i];
+  k_rot_finalize<<<cdiv(npages * D_MAX_MASKS, 64), 64, 0, st>>>(pages, npages, rot_tab_dev, pair_tab_dev, fp);
+}
+void b200k_rotate(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int maxw, int maxh,
+                  DCopyJob *back_jobs) {
+  if (npages <= 0 || maxw <= 0 || maxh <= 0) return;
+  dim3 g(min(cdiv(maxw, 128), 64u), maxh, npages);
+  k_rotate<<<g, 128, 0, st>>>(pages, mi, interp, back_jobs);
+}
+void b200k_stretch(cudaStream_t st, DImg src, DImg dst, float hr, float vr, int interp) {
+  if (dst.w <= 0 || dst.h <= 0) return;
+  dim3 g(min(cdiv(dst.w, 128), 64u), dst.h, 1);
+  k_stretch<<<g, 128, 0, st>>>(src, dst, hr, vr, interp);
+}
+}

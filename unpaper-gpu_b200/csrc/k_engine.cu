@@ -1,0 +1,53 @@
+// k_engine.cu — small helpers of the sheet engine.
+#include "common.cuh"
+#include "launch.h"
+
+static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+// zero the per-sheet counters and results of every page of a group
+__global__ void k_page_reset(DPage *pages, int npages) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npages) return;
+  DPage &pg = pages[p];
+  pg.list_n = 0; pg.nf_clusters = 0; pg.bf_fills = 0; pg.error = 0;
+  pg.mask_count = 0; pg.mask_count_deskew = 0;
+  for (int i = 0; i < D_MAX_MASKS; i++) {
+    pg.rotation[i] = 0.0f; pg.rot_sin[i] = 0.0f; pg.rot_cos[i] = 1.0f; pg.rot_apply[i] = 0; pg.centered[i] = 0;
+    pg.mask_valid[i] = 0;
+    for (int e = 0; e < 4; e++) { pg.edge_count[i][e] = 0; pg.rot_angle_idx[i][e] = -1; }
+  }
+}
+
+// Strided row copy between packed host-layout images and pitched device
+// images, 16 bytes per thread where alignment allows.
+__global__ void k_pack_rows(const uint8_t *src, int src_pitch, uint8_t *dst, int dst_pitch,
+                            int row_bytes, int rows, size_t src_stride, size_t dst_stride) {
+  const uint8_t *s = src + (size_t)blockIdx.z * src_stride;
+  uint8_t *d = dst + (size_t)blockIdx.z * dst_stride;
+  for (int y = blockIdx.y; y < rows; y += gridDim.y) {
+    const uint8_t *sr = s + (size_t)y * src_pitch;
+    uint8_t *dr = d + (size_t)y * dst_pitch;
+    bool vec = ((((uintptr_t)sr) | ((uintptr_t)dr)) & 15) == 0;
+    if (vec) {
+      int n16 = row_bytes >> 4;
+      const uint4 *s4 = (const uint4 *)sr; uint4 *d4 = (uint4 *)dr;
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) d4[i] = s4[i];
+      for (int i = (n16 << 4) + blockIdx.x * blockDim.x + threadIdx.x; i < row_bytes; i += gridDim.x * blockDim.x) dr[i] = sr[i];
+    } else {
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_bytes; i += gridDim.x * blockDim.x) dr[i] = sr[i];
+    }
+  }
+}
+
+extern "C" {
+void b200k_page_reset(cudaStream_t st, DPage *pages, int npages) {
+  if (npages <= 0) return;
+  k_page_reset<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages);
+}
+void b200k_pack_rows(cudaStream_t st, const uint8_t *src, int src_pitch, uint8_t *dst, int dst_pitch,
+                     int row_bytes, int rows, int nimages, size_t src_stride, size_t dst_stride) {
+  if (nimages <= 0 || rows <= 0 || row_bytes <= 0) return;
+  dim3 g(min(cdiv(row_bytes, 16 * 256), 8u), min((unsigned)rows, 1024u), nimages);
+  k_pack_rows<<<g, 256, 0, st>>>(src, src_pitch, dst, dst_pitch, row_bytes, rows, src_stride, dst_stride);
+}
+}

@@ -1,0 +1,575 @@
+// k_filters.cu — blackfilter, noisefilter, blurfilter, grayfilter with the
+// reference CPU backend's sequential semantics reproduced exactly
+// (reference imageprocess/filters.c:49-402, imageprocess/fill.c:16-107).
+// Replaces backend_cuda_filters.c + cuda_kernels_filters.cu + the OpenCV CCL /
+// NPP-integral paths of opencv_bridge.cpp (which are NOT CPU-exact).
+#include "common.cuh"
+#include "launch.h"
+
+static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+/* =========================================================================
+ * blackfilter
+ *
+ * The scan positions (filters.c:60-103) depend only on geometry, so the host
+ * enumerates them once, in order, dropping excluded ones.  Flood fills only
+ * ever whiten pixels, so an area's darkness can only fall while the filter
+ * runs: "hit on the untouched image" is a superset of the true hits.  One
+ * warp per page walks that candidate list in order, re-measures a candidate
+ * exactly if any fill ran before it, and emulates flood_fill()'s recursion
+ * (fill.c:81-107) with an explicit frame stack so that the painted set —
+ * including fill_line's overruns — matches the CPU order-dependent result.
+ * ====================================================================== */
+
+__device__ __forceinline__ bool ff_match(const DImg &im, int x, int y, int lo, int hi) {
+  int g = px_gray(px_get(im, x, y));
+  return g >= lo && g <= hi;
+}
+
+// fill_line (fill.c:16-43): returns painted distance.  Warp-cooperative.
+__device__ int ff_fill_line(const DImg &im, int px, int py, int dx, int dy, int lo, int hi,
+                            unsigned long long intensity, int lane) {
+  int distance = 0;
+  unsigned long long cnt = 1;
+  for (;;) {
+    int qx = px + (distance + lane + 1) * dx, qy = py + (distance + lane + 1) * dy;
+    bool inb = in_img(im, qx, qy);
+    bool m = ff_match(im, qx, qy, lo, hi);
+    unsigned M = __ballot_sync(0xffffffffu, m), I = __ballot_sync(0xffffffffu, inb);
+    int painted = 32;
+    if ((M & I) == 0xffffffffu) {
+      cnt = intensity;
+      if (cnt == 0) painted = 0;   // degenerate intensity 0: stops on the first pixel
+    } else {
+      painted = 32;
+      for (int i = 0; i < 32; i++) {
+        if ((M >> i) & 1u) cnt = intensity; else cnt--;
+        if (cnt == 0 || !((I >> i) & 1u)) { painted = i; break; }
+      }
+    }
+    if (lane < painted) px_store(im, qx, qy, 255, 255, 255);
+    __syncwarp();
+    distance += painted;
+    if (painted < 32) return distance;
+  }
+}
+
+struct FFFrame { int cx, cy; int L, T, R, B; unsigned cursor; };
+
+__device__ __forceinline__ void ff_cand(const FFFrame &f, unsigned idx, int &x, int &y) {
+  unsigned d = (idx >> 1) + 1u, sub = idx & 1u;
+  unsigned nL = 2u * f.L, nT = 2u * f.T, nR = 2u * f.R;
+  if (idx < nL) { x = f.cx - (int)d; y = f.cy + (sub ? -1 : 1); return; }
+  idx -= nL; d = (idx >> 1) + 1u;
+  if (idx < nT) { x = f.cx + (sub ? -1 : 1); y = f.cy - (int)d; return; }
+  idx -= nT; d = (idx >> 1) + 1u;
+  if (idx < nR) { x = f.cx + (int)d; y = f.cy + (sub ? -1 : 1); return; }
+  idx -= nR; d = (idx >> 1) + 1u;
+  x = f.cx + (sub ? -1 : 1); y = f.cy + (int)d;
+}
+
+// flood_fill(p) for a p that is known to match: paint the cross and push.
+__device__ bool ff_open(DPage &pg, const DImg &im, int x, int y, int lo, int hi,
+                        unsigned long long intensity, int lane, int &sp, FFFrame &top) {
+  if (sp >= pg.stack_cap) { if (lane == 0) atomicOr(&pg.error, DERR_STACK_OVERFLOW); return false; }
+  if (sp > 0 && lane == 0) {   // spill the current top
+    unsigned long long *s = (unsigned long long *)pg.stack + (size_t)(sp - 1) * 4;
+    s[0] = (unsigned)top.cx | ((unsigned long long)(unsigned)top.cy << 32);
+    s[1] = (unsigned long long)(unsigned)top.L | ((unsigned long long)(unsigned)top.T << 32);
+    s[2] = (unsigned long long)(unsigned)top.R | ((unsigned long long)(unsigned)top.B << 32);
+    s[3] = top.cursor;
+  }
+  if (lane == 0) px_store(im, x, y, 255, 255, 255);
+  __syncwarp();
+  top.cx = x; top.cy = y;
+  top.L = ff_fill_line(im, x, y, -1, 0, lo, hi, intensity, lane);
+  top.T = ff_fill_line(im, x, y, 0, -1, lo, hi, intensity, lane);
+  top.R = ff_fill_line(im, x, y, 1, 0, lo, hi, intensity, lane);
+  top.B = ff_fill_line(im, x, y, 0, 1, lo, hi, intensity, lane);
+  top.cursor = 0;
+  sp++;
+  return true;
+}
+
+// Runs the recursion to completion starting from an already-open frame.
+__device__ void ff_run(DPage &pg, const DImg &im, int lo, int hi, unsigned long long intensity,
+                       int lane, int &sp, FFFrame &top) {
+  while (sp > 0) {
+    unsigned total = 2u * ((unsigned)top.L + top.T + top.R + top.B);
+    bool opened = false;
+    while (top.cursor < total) {
+      unsigned idx = top.cursor + lane;
+      int x = 0, y = 0;
+      bool m = false;
+      if (idx < total) { ff_cand(top, idx, x, y); m = in_img(im, x, y) && ff_match(im, x, y, lo, hi); }
+      unsigned M = __ballot_sync(0xffffffffu, m);
+      if (M) {
+        int first = __ffs(M) - 1;
+        top.cursor += first + 1;
+        int fx = __shfl_sync(0xffffffffu, x, first), fy = __shfl_sync(0xffffffffu, y, first);
+        if (!ff_open(pg, im, fx, fy, lo, hi, intensity, lane, sp, top)) { sp = 0; return; }
+        opened = true;
+        break;
+      }
+      top.cursor += 32;
+    }
+    if (opened) continue;
+    sp--;   // frame exhausted: return to the caller's frame
+    if (sp > 0) {
+      const unsigned long long *s = (const unsigned long long *)pg.stack + (size_t)(sp - 1) * 4;
+      unsigned long long a = s[0], b = s[1], c = s[2], d = s[3];
+      top.cx = (int)(unsigned)a; top.cy = (int)(unsigned)(a >> 32);
+      top.L = (int)(unsigned)b; top.T = (int)(unsigned)(b >> 32);
+      top.R = (int)(unsigned)c; top.B = (int)(unsigned)(c >> 32);
+      top.cursor = (unsigned)d;
+    }
+  }
+}
+
+__device__ unsigned long long warp_rect_maxch_sum(const DImg &im, int x0, int y0, int x1, int y1, int lane) {
+  unsigned long long s = 0;
+  if (x0 <= x1 && y0 <= y1) {
+    int w = x1 - x0 + 1, n = w * (y1 - y0 + 1);
+    for (int i = lane; i < n; i += 32) s += (unsigned)px_darkinv(px_load(im, x0 + i % w, y0 + i / w));
+  }
+  return warp_sum_u64(s);
+}
+
+__global__ void k_bf_scan(DPage *pages, const DBfPos *pos, int npos, int abs_threshold,
+                          unsigned long long intensity, int mask_lo, int mask_hi, int flag_off) {
+  DPage &pg = pages[blockIdx.x];
+  const DImg im = pg.img;
+  int lane = threadIdx.x;
+  uint8_t *cand = (uint8_t *)(pg.u32 + flag_off);
+  // phase 1: darkness of every position on the untouched image (blit.c:131-146)
+  for (int k = lane; k < npos; k += 32) {
+    DBfPos q = pos[k];
+    int x0 = max(q.r.x0, 0), x1 = min(q.r.x1, im.w - 1), y0 = max(q.r.y0, 0), y1 = min(q.r.y1, im.h - 1);
+    unsigned long long cnt = (unsigned long long)(abs(x0 - x1) + 1) * (unsigned long long)(abs(y0 - y1) + 1);
+    unsigned long long s = 0;
+    if (x0 <= x1 && y0 <= y1) {
+      const unsigned *b = pg.u32 + q.sum_off;
+      if (q.axis == 0) for (int x = x0; x <= x1; x++) s += b[x];
+      else for (int y = y0; y <= y1; y++) s += b[y];
+    }
+    int darkness = (int)(uint8_t)(0xFF - (s / cnt));
+    cand[k] = darkness >= abs_threshold ? 1 : 0;
+  }
+  __syncwarp();
+  // phase 2: candidates in scan order
+  bool dirty = false;
+  unsigned fills = 0;
+  for (int base = 0; base < npos; base += 32) {
+    int k = base + lane;
+    unsigned C = __ballot_sync(0xffffffffu, k < npos && cand[k]);
+    while (C) {
+      int b = __ffs(C) - 1;
+      C &= C - 1;
+      DBfPos q = pos[base + b];
+      int x0 = max(q.r.x0, 0), x1 = min(q.r.x1, im.w - 1), y0 = max(q.r.y0, 0), y1 = min(q.r.y1, im.h - 1);
+      if (dirty) {
+        unsigned long long cnt = (unsigned long long)(abs(x0 - x1) + 1) * (unsigned long long)(abs(y0 - y1) + 1);
+        unsigned long long s = warp_rect_maxch_sum(im, x0, y0, x1, y1, lane);
+        int darkness = (int)(uint8_t)(0xFF - (s / cnt));
+        if (darkness < abs_threshold) continue;
+      }
+      dirty = true;
+      fills++;
+      // flood_fill from every pixel of the (unclipped) area in raster order
+      // (filters.c:86-89); pixels outside the image never match.
+      int w = x1 - x0 + 1, n = (x0 <= x1 && y0 <= y1) ? w * (y1 - y0 + 1) : 0;
+      int sp = 0;
+      FFFrame top;
+      for (int rb = 0; rb < n;) {
+        int i = rb + lane;
+        int x = x0 + i % w, y = y0 + i / w;
+        bool m = i < n && ff_match(im, x, y, mask_lo, mask_hi);
+        unsigned M = __ballot_sync(0xffffffffu, m);
+        if (!M) { rb += 32; continue; }
+        int first = __ffs(M) - 1;
+        int fx = __shfl_sync(0xffffffffu, x, first), fy = __shfl_sync(0xffffffffu, y, first);
+        rb += first + 1;
+        if (ff_open(pg, im, fx, fy, mask_lo, mask_hi, intensity, lane, sp, top))
+          ff_run(pg, im, mask_lo, mask_hi, intensity, lane, sp, top);
+        sp = 0;
+      }
+    }
+  }
+  if (lane == 0) pg.bf_fills = fills;
+}
+
+/* =========================================================================
+ * noisefilter (filters.c:243-348)
+ *
+ * NOT a component-size filter: pixels are visited in raster order, and a
+ * dark pixel whose ring-neighbourhood count is <= intensity clears itself and
+ * the rings up to the first empty one, which changes what later pixels see.
+ * Exact parallel form:
+ *   (1) classify: a pixel of an 8-connected set of >intensity "ring-dark"
+ *       pixels (min channel < white) that lies outside the left/top band where
+ *       the reference's unsigned ring walk is truncated can never be cleared
+ *       -> PERMANENT.  Found with a bounded union walk inside a shared-memory
+ *       tile (component size only matters up to intensity+1).
+ *   (2) everything else that is trigger-dark (max channel < white) is MUTABLE
+ *       and decided in raster order; two mutable pixels farther apart than
+ *       R = 2*intensity cannot see each other's effects, so every round
+ *       decides, in parallel, each undecided pixel that has no undecided
+ *       raster-earlier pixel within R.
+ * ====================================================================== */
+
+#define NF_LIVE 1u
+#define NF_MUT 2u
+#define NF_UNDEC 4u
+#define NF_TRIG 8u
+#define NF_TW 64
+#define NF_TH 16
+#define NF_MAXI 15
+
+__global__ void k_nf_classify(DPage *pages, int intensity, int white, int all_mutable) {
+  extern __shared__ uint8_t tile[];
+  DPage &pg = pages[blockIdx.z];
+  const DImg &im = pg.img;
+  int halo = all_mutable ? 0 : intensity + 1;
+  int tw = NF_TW + 2 * halo, th = NF_TH + 2 * halo;
+  int bx = blockIdx.x * NF_TW, by = blockIdx.y * NF_TH;
+  if (bx >= im.w || by >= im.h) return;
+  int band = 2 * intensity;
+  for (int i = threadIdx.x; i < tw * th; i += blockDim.x) {
+    int x = bx - halo + i % tw, y = by - halo + i / tw;
+    uint8_t v = 0;
+    if (in_img(im, x, y)) {
+      Px p = px_load(im, x, y);
+      if (px_light(p) < white) v = 1 | ((x < band || y < band) ? 2 : 0) | (px_darkinv(p) < white ? 4 : 0);
+    }
+    tile[i] = v;
+  }
+  __syncthreads();
+  int need = intensity + 1;
+  for (int i = threadIdx.x; i < NF_TW * NF_TH; i += blockDim.x) {
+    int lx = i % NF_TW, ly = i / NF_TW;
+    int x = bx + lx, y = by + ly;
+    if (x >= im.w || y >= im.h) continue;
+    uint8_t v = tile[(ly + halo) * tw + lx + halo];
+    uint8_t c = 0;
+    if (v & 1) {
+      bool mut = all_mutable || (v & 2);
+      if (!mut) {
+        // bounded walk over 8-connected ring-dark pixels outside the band
+        short vx[NF_MAXI + 1], vy[NF_MAXI + 1];
+        int n = 1, head = 0;
+        vx[0] = (short)(lx + halo); vy[0] = (short)(ly + halo);
+        while (head < n && n < need) {
+          int cx = vx[head], cy = vy[head]; head++;
+          for (int dy = -1; dy <= 1 && n < need; dy++)
+            for (int dx = -1; dx <= 1 && n < need; dx++) {
+              if (!dx && !dy) continue;
+              int nx = cx + dx, ny = cy + dy;
+              if (nx < 0 || ny < 0 || nx >= tw || ny >= th) continue;
+              if ((tile[ny * tw + nx] & 3) != 1) continue;
+              bool seen = false;
+              for (int k = 0; k < n; k++) seen |= (vx[k] == nx && vy[k] == ny);
+              if (!seen) { vx[n] = (short)nx; vy[n] = (short)ny; n++; }
+            }
+        }
+        mut = n < need;
+      }
+      c = NF_LIVE | ((v & 4) ? NF_TRIG : 0);
+      if (mut) {
+        c |= NF_MUT;
+        if (v & 4) {
+          c |= NF_UNDEC;
+          unsigned idx = atomicAdd(&pg.list_n, 1u);
+          if (idx < (unsigned)pg.list_cap) pg.list[idx] = ((unsigned)y << 16) | (unsigned)x;
+          else atomicOr(&pg.error, DERR_LIST_OVERFLOW);
+        }
+      }
+    }
+    pg.cls[(size_t)y * im.w + x] = c;
+  }
+}
+
+__device__ __forceinline__ bool nf_live(const uint8_t *cls, int w, int h, int x, int y) {
+  return (unsigned)x < (unsigned)w && (unsigned)y < (unsigned)h && (cls[(size_t)y * w + x] & NF_LIVE);
+}
+// noisefilter_compare_and_clear (filters.c:243-254) on the class map
+__device__ __forceinline__ unsigned nf_cc(DPage &pg, uint8_t *cls, int x, int y, bool clear) {
+  const DImg &im = pg.img;
+  if (!nf_live(cls, im.w, im.h, x, y)) return 0;
+  if (clear) {
+    uint8_t c = cls[(size_t)y * im.w + x];
+    if (!(c & NF_MUT)) atomicOr(&pg.error, DERR_UNSUPPORTED);  // permanence proof violated
+    cls[(size_t)y * im.w + x] = 0;
+    px_store(im, x, y, 255, 255, 255);
+  }
+  return 1;
+}
+// noisefilter_count_pixel_neighbors_level (filters.c:256-285) incl. the
+// unsigned-compare truncation near the left/top edge
+__device__ unsigned nf_ring(DPage &pg, uint8_t *cls, int px, int py, int level, bool clear) {
+  unsigned count = 0;
+  if (px >= level)
+    for (int xx = px - level; xx <= px + level; xx++) {
+      count += nf_cc(pg, cls, xx, py - level, clear);
+      count += nf_cc(pg, cls, xx, py + level, clear);
+    }
+  if (py >= level - 1)
+    for (int yy = py - (level - 1); yy <= py + (level - 1); yy++) {
+      count += nf_cc(pg, cls, px - level, yy, clear);
+      count += nf_cc(pg, cls, px + level, yy, clear);
+    }
+  return count;
+}
+
+__global__ void k_nf_resolve(DPage *pages, int intensity) {
+  DPage &pg = pages[blockIdx.x];
+  const DImg &im = pg.img;
+  uint8_t *cls = pg.cls;
+  int n = (int)min(pg.list_n, (unsigned)pg.list_cap);
+  int R = 2 * intensity;
+  __shared__ unsigned s_clusters;
+  if (threadIdx.x == 0) s_clusters = 0;
+  __syncthreads();
+  for (;;) {
+    // phase A: readiness against the state at the start of the round
+    int pending = 0;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      unsigned v = pg.list[e];
+      int x = v & 0xFFFF, y = (v >> 16) & 0x7FFF;
+      if (!(cls[(size_t)y * im.w + x] & NF_UNDEC)) continue;
+      pending = 1;
+      bool ready = true;
+      int ya = max(y - R, 0), xa = max(x - R, 0), xb = min(x + R, im.w - 1);
+      for (int yy = ya; yy <= y && ready; yy++) {
+        const uint8_t *row = cls + (size_t)yy * im.w;
+        int xe = (yy == y) ? x - 1 : xb;
+        for (int xx = xa; xx <= xe; xx++)
+          if (row[xx] & NF_UNDEC) { ready = false; break; }
+      }
+      if (ready) pg.list[e] = v | 0x80000000u;
+    }
+    if (!__syncthreads_or(pending)) break;
+    // phase B: ready pixels are pairwise farther apart than R -> independent
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      unsigned v = pg.list[e];
+      if (!(v & 0x80000000u)) continue;
+      pg.list[e] = v & 0x7FFFFFFFu;
+      int x = v & 0xFFFF, y = (v >> 16) & 0x7FFF;
+      size_t o = (size_t)y * im.w + x;
+      uint8_t c = cls[o];
+      if (c & NF_LIVE) {
+        unsigned long long count = 1;   // filters.c:287-302
+        unsigned l;
+        int level = 1;
+        do { l = nf_ring(pg, cls, x, y, level, false); count += l; level++; } while (l != 0 && level <= intensity);
+        if (count <= (unsigned long long)intensity) {   // filters.c:304-317
+          cls[o] = 0;
+          px_store(im, x, y, 255, 255, 255);
+          level = 1;
+          do { l = nf_ring(pg, cls, x, y, level, true); level++; } while (l != 0);
+          atomicAdd(&s_clusters, 1u);
+          c = 0;
+        }
+      }
+      if (c) cls[o] = c & ~NF_UNDEC;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) pg.nf_clusters = s_clusters;
+}
+
+/* =========================================================================
+ * blurfilter (filters.c:149-232)
+ *
+ * Every count the CPU loop reads is taken strictly below / right of what it
+ * has wiped so far, i.e. on the untouched image: count them all in parallel
+ * (k_rect_count), replay the scalar state machine — INCLUDING the reference's
+ * aliased prev/cur/next pointers into one zero-initialised buffer
+ * (filters.c:160-167) — and wipe the flagged blocks.
+ * layout in u32: [c0: n][h: nrows*(n+1)][state: 3*(n+2)][flags: nrows*n]
+ * ====================================================================== */
+__global__ void k_blur_decide(DPage *pages, int npages, int n, int nrows, unsigned long long T,
+                              float intensity, int cnt_off, int state_off, int flag_off) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npages) return;
+  DPage &pg = pages[p];
+  const unsigned *c0 = pg.u32 + cnt_off;
+  const unsigned *h = c0 + n;
+  unsigned *flat = pg.u32 + state_off;
+  unsigned *flag = pg.u32 + flag_off;
+  unsigned Tu = (unsigned)T;
+  for (int i = 0; i < 3 * (n + 2); i++) flat[i] = 0;
+  int prev = 0, cur = 1, next = 2;
+  flat[cur + 0] = Tu; flat[cur + n] = Tu; flat[next + 0] = Tu; flat[next + n] = Tu;
+  for (int b = 0; b < n; b++) flat[cur + 1 + b] = c0[b];
+  for (int r = 0; r < nrows; r++) {
+    flat[next + 0] = h[(size_t)r * (n + 1) + 0];
+    for (int b = 0, block = 1; b < n; b++, block++) {
+      flat[next + block + 1] = h[(size_t)r * (n + 1) + block];
+      unsigned m1 = max(flat[prev + block - 1], max(flat[prev + block + 1], flat[cur + block]));
+      unsigned m = max(flat[next + block - 1], max(flat[next + block + 1], m1));
+      bool wipe = ((float)(unsigned long long)m / (float)T) <= intensity;
+      flag[(size_t)r * n + b] = wipe ? 1u : 0u;
+      if (wipe) flat[cur + block] = Tu;
+    }
+    int tmp = prev; prev = cur; cur = next; next = tmp;
+  }
+}
+
+__global__ void k_blur_wipe(DPage *pages, int n, int bw, int bh, int flag_off) {
+  DPage &pg = pages[blockIdx.z];
+  int b = blockIdx.x, r = blockIdx.y;
+  if (!pg.u32[flag_off + (size_t)r * n + b]) return;
+  const DImg &im = pg.img;
+  int x0 = b * bw, y0 = r * bh;
+  for (int i = threadIdx.x; i < bw * bh; i += blockDim.x) {
+    int x = x0 + i % bw, y = y0 + i / bw;
+    px_set(im, x, y, 255, 255, 255);
+  }
+}
+
+/* =========================================================================
+ * grayfilter (filters.c:370-402)
+ *
+ * Windows are visited in raster order and a wiped window raises the lightness
+ * of every later window it overlaps, so decisions cascade.  A wiped window
+ * had zero dark pixels, hence dark counts never change: keep per-cell
+ * (gx x gy, g = gcd(size, step)) dark counts and lightness sums, and run the
+ * cascade as a skewed wavefront (window (i,j) only depends on windows with a
+ * smaller j + skew*i) inside one CTA per page.
+ * layout in u32: [dark: nc][light: nc][wiped: nc]   nc = ncx*ncy
+ * ====================================================================== */
+struct GrayParams {
+  int gx, gy, ncx, ncy;       // cell size / grid
+  int wcx, wcy, scx, scy;     // window size / step in cells
+  int nwx, nwy, skew;
+  int size_w, size_h, step_h, step_v;
+  int abs_threshold, oob_dark;
+  int off;
+};
+
+__global__ void k_gray_cascade(DPage *pages, GrayParams gp) {
+  DPage &pg = pages[blockIdx.x];
+  const DImg &im = pg.img;
+  int nc = gp.ncx * gp.ncy;
+  const unsigned *dark = pg.u32 + gp.off;
+  unsigned *light = pg.u32 + gp.off + nc;
+  unsigned *wiped = pg.u32 + gp.off + 2 * nc;
+  for (int i = threadIdx.x; i < nc; i += blockDim.x) wiped[i] = 0;
+  __syncthreads();
+  int nwave = gp.nwx + gp.skew * (gp.nwy - 1);
+  for (int t = 0; t < nwave; t++) {
+    for (int i = threadIdx.x; i < gp.nwy; i += blockDim.x) {
+      int j = t - gp.skew * i;
+      if (j < 0 || j >= gp.nwx) continue;
+      int x0 = j * gp.step_h, y0 = i * gp.step_v;
+      int x1 = x0 + gp.size_w - 1, y1 = y0 + gp.size_h - 1;
+      int x0c = max(x0, 0), x1c = min(x1, im.w - 1), y0c = max(y0, 0), y1c = min(y1, im.h - 1);
+      bool inside = x0c <= x1c && y0c <= y1c;
+      unsigned long long d = 0, l = 0;
+      int cx0 = j * gp.scx, cy0 = i * gp.scy;
+      for (int cy = cy0; cy < cy0 + gp.wcy; cy++)
+        for (int cx = cx0; cx < cx0 + gp.wcx; cx++) {
+          d += dark[cy * gp.ncx + cx];
+          l += light[cy * gp.ncx + cx];
+        }
+      long long area_in = inside ? (long long)(x1c - x0c + 1) * (y1c - y0c + 1) : 0;
+      if (gp.oob_dark) d += (unsigned long long)((long long)gp.size_w * gp.size_h - area_in);
+      if (d != 0) continue;
+      // inverse_lightness_rect (blit.c:111-126): clipped count with abs(); an
+      // inverted clip scans nothing and yields 255
+      unsigned long long cnt = (unsigned long long)(abs(x0c - x1c) + 1) * (unsigned long long)(abs(y0c - y1c) + 1);
+      unsigned long long sum = inside ? l : 0;
+      int lightness = (int)(uint8_t)(0xFF - (sum / cnt));
+      if (lightness < gp.abs_threshold) {
+        for (int cy = cy0; cy < cy0 + gp.wcy; cy++)
+          for (int cx = cx0; cx < cx0 + gp.wcx; cx++) {
+            int ax0 = cx * gp.gx, ay0 = cy * gp.gy;
+            int w = max(0, min(ax0 + gp.gx, im.w) - ax0), h = max(0, min(ay0 + gp.gy, im.h) - ay0);
+            light[cy * gp.ncx + cx] = 255u * (unsigned)(w * h);
+            wiped[cy * gp.ncx + cx] = 1;
+          }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Snapshot which cells were already pure white before the cascade
+// (light == 255*npix) so that the wipe pass can skip them.
+__global__ void k_gray_prewhite(DPage *pages, GrayParams gp, int white_off) {
+  DPage &pg = pages[blockIdx.y];
+  const DImg &im = pg.img;
+  int nc = gp.ncx * gp.ncy;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+    int cx = c % gp.ncx, cy = c / gp.ncx;
+    int ax0 = cx * gp.gx, ay0 = cy * gp.gy;
+    int w = max(0, min(ax0 + gp.gx, im.w) - ax0), h = max(0, min(ay0 + gp.gy, im.h) - ay0);
+    pg.u32[white_off + c] = (pg.u32[gp.off + nc + c] == 255u * (unsigned)(w * h)) ? 1u : 0u;
+  }
+}
+
+__global__ void k_gray_wipe(DPage *pages, GrayParams gp, int white_off) {
+  DPage &pg = pages[blockIdx.y];
+  const DImg &im = pg.img;
+  int nc = gp.ncx * gp.ncy;
+  int cy = blockIdx.x;
+  const unsigned *wiped = pg.u32 + gp.off + 2 * nc + (size_t)cy * gp.ncx;
+  const unsigned *white = pg.u32 + white_off + (size_t)cy * gp.ncx;
+  bool skip_white = im.fmt != DF_Y400A;
+  int y0 = cy * gp.gy, y1 = min(y0 + gp.gy - 1, im.h - 1);
+  for (int x = threadIdx.x; x < im.w; x += blockDim.x) {
+    int cx = x / gp.gx;
+    if (cx >= gp.ncx || !wiped[cx] || (skip_white && white[cx])) continue;
+    for (int y = y0; y <= y1; y++) px_store(im, x, y, 255, 255, 255);
+  }
+}
+
+extern "C" {
+
+void b200k_bf_scan(cudaStream_t st, DPage *pages, int npages, const DBfPos *pos_dev, int npos,
+                   int abs_threshold, long long intensity, int mask_lo, int mask_hi, int flag_off) {
+  if (npages <= 0 || npos <= 0) return;
+  k_bf_scan<<<npages, 32, 0, st>>>(pages, pos_dev, npos, abs_threshold, (unsigned long long)intensity,
+                                  mask_lo, mask_hi, flag_off);
+}
+
+int b200k_noisefilter(cudaStream_t st, DPage *pages, int npages, int maxw, int maxh,
+                      unsigned long long intensity, int white) {
+  if (npages <= 0 || intensity == 0) return 0;
+  if (intensity > 4000) return -1;
+  int I = (int)intensity;
+  int all_mut = I > NF_MAXI;
+  int halo = all_mut ? 0 : I + 1;
+  size_t sm = (size_t)(NF_TW + 2 * halo) * (NF_TH + 2 * halo);
+  dim3 g(cdiv(maxw, NF_TW), cdiv(maxh, NF_TH), npages);
+  k_nf_classify<<<g, 256, sm, st>>>(pages, I, white, all_mut);
+  k_nf_resolve<<<npages, 256, 0, st>>>(pages, I);
+  return 0;
+}
+
+void b200k_blur_decide(cudaStream_t st, DPage *pages, int npages, int n, int nrows,
+                       unsigned long long T, float intensity, int cnt_off, int state_off, int flag_off) {
+  if (npages <= 0) return;
+  k_blur_decide<<<cdiv(npages, 32), 32, 0, st>>>(pages, npages, n, nrows, T, intensity, cnt_off, state_off, flag_off);
+}
+void b200k_blur_wipe(cudaStream_t st, DPage *pages, int npages, int n, int nrows, int bw, int bh, int flag_off) {
+  if (npages <= 0 || n <= 0 || nrows <= 0) return;
+  dim3 g(n, nrows, npages);
+  k_blur_wipe<<<g, 256, 0, st>>>(pages, n, bw, bh, flag_off);
+}
+
+void b200k_gray_cascade(cudaStream_t st, DPage *pages, int npages, const int *gpi, int white_off) {
+  if (npages <= 0) return;
+  GrayParams gp;
+  gp.gx = gpi[0]; gp.gy = gpi[1]; gp.ncx = gpi[2]; gp.ncy = gpi[3]; gp.wcx = gpi[4]; gp.wcy = gpi[5];
+  gp.scx = gpi[6]; gp.scy = gpi[7]; gp.nwx = gpi[8]; gp.nwy = gpi[9]; gp.skew = gpi[10];
+  gp.size_w = gpi[11]; gp.size_h = gpi[12]; gp.step_h = gpi[13]; gp.step_v = gpi[14];
+  gp.abs_threshold = gpi[15]; gp.oob_dark = gpi[16]; gp.off = gpi[17];
+  int nc = gp.ncx * gp.ncy;
+  dim3 g1(min(cdiv(nc, 256), 128u), npages);
+  k_gray_prewhite<<<g1, 256, 0, st>>>(pages, gp, white_off);
+  k_gray_cascade<<<npages, 256, 0, st>>>(pages, gp);
+  dim3 g2(gp.ncy, npages);
+  k_gray_wipe<<<g2, 256, 0, st>>>(pages, gp, white_off);
+}
+}

@@ -1,0 +1,168 @@
+// k_stats.cu — one-pass image statistics every detector consumes:
+//   * band line sums (column sums over a row band / row sums over a column
+//     band) of gray, max-channel or "gray in [lo,hi]" indicators — feeds
+//     detect_masks (masks.c:54-100 via blit.c:91-106), detect_border
+//     (masks.c:410-448 via blit.c:148-167) and the blackfilter scan
+//     (filters.c:49-104 via blit.c:131-146);
+//   * rectangle counts for blurfilter (filters.c:176-205);
+//   * g x g cell statistics for grayfilter (filters.c:377-389).
+// Replaces reference cuda_kernels_masks.cu:13-158 (one 64-bit atomic per pixel)
+// and the NPP integral images (npp_integral.c).
+#include "common.cuh"
+#include "launch.h"
+
+__device__ __forceinline__ unsigned stat_of(Px p, int stat, int lo, int hi) {
+  if (stat == ST_GRAY) return (unsigned)px_gray(p);
+  if (stat == ST_MAXCH) return (unsigned)px_darkinv(p);
+  int g = px_gray(p);
+  return (g >= lo && g <= hi) ? 1u : 0u;
+}
+
+__global__ void k_zero_u32(DPage *pages, int off, int n) {
+  unsigned *p = pages[blockIdx.y].u32 + off;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0u;
+}
+
+// Column sums: thread = column, block = 256 columns x ROWS rows; partial sums
+// merged with one atomic per (block, column).  blockIdx.z = page*njobs + job.
+#define LS_ROWS 128
+__global__ void k_linesum_cols(DPage *pages, const DLineJob *jobs, int njobs, int stat, int lo, int hi) {
+  int page = blockIdx.z / njobs, job = blockIdx.z % njobs;
+  const DLineJob j = jobs[job];
+  if (j.axis != 0 || j.xa > j.xb || j.ya > j.yb) return;
+  const DImg &im = pages[page].img;
+  int x = j.xa + blockIdx.x * blockDim.x + threadIdx.x;
+  int y0 = j.ya + blockIdx.y * LS_ROWS;
+  if (x > j.xb || y0 > j.yb) return;
+  int y1 = min(y0 + LS_ROWS - 1, j.yb);
+  unsigned acc = 0;
+  if (im.fmt == DF_GRAY8 && stat != ST_COUNT_GRAY_RANGE) {
+    const uint8_t *p = im.data + (size_t)y0 * im.pitch + x;
+    for (int y = y0; y <= y1; y++, p += im.pitch) acc += *p;
+  } else {
+    for (int y = y0; y <= y1; y++) acc += stat_of(px_load(im, x, y), stat, lo, hi);
+  }
+  atomicAdd(pages[page].u32 + j.out_off + (x - j.xa), acc);
+}
+
+// Row sums: one warp per row.
+__global__ void k_linesum_rows(DPage *pages, const DLineJob *jobs, int njobs, int stat, int lo, int hi) {
+  int page = blockIdx.z / njobs, job = blockIdx.z % njobs;
+  const DLineJob j = jobs[job];
+  if (j.axis != 1 || j.xa > j.xb || j.ya > j.yb) return;
+  const DImg &im = pages[page].img;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int y = j.ya + blockIdx.y * (blockDim.x >> 5) + warp;
+  if (y > j.yb) return;
+  unsigned acc = 0;
+  for (int x = j.xa + lane; x <= j.xb; x += 32) acc += stat_of(px_load(im, x, y), stat, lo, hi);
+  acc = warp_sum_u32(acc);
+  if (lane == 0) pages[page].u32[j.out_off + (y - j.ya)] = acc;
+}
+
+// Count of pixels with gray in [lo,hi] inside rect k of a static list; pixels
+// outside the image read as white (blit.c:148-167 does not clip).  One warp per
+// rectangle.  out = pages[p].u32 + out_off + k.
+__global__ void k_rect_count(DPage *pages, const DRect *rects, int nrects, int lo, int hi, int out_off) {
+  int page = blockIdx.y;
+  int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (k >= nrects) return;
+  const DImg &im = pages[page].img;
+  DRect r = rects[k];
+  long long total = (r.x1 >= r.x0 && r.y1 >= r.y0) ? (long long)(r.x1 - r.x0 + 1) * (r.y1 - r.y0 + 1) : 0;
+  int x0 = max(r.x0, 0), x1 = min(r.x1, im.w - 1), y0 = max(r.y0, 0), y1 = min(r.y1, im.h - 1);
+  unsigned cnt = 0;
+  long long inside = 0;
+  if (x0 <= x1 && y0 <= y1 && total > 0) {
+    inside = (long long)(x1 - x0 + 1) * (y1 - y0 + 1);
+    int w = x1 - x0 + 1;
+    int n = w * (y1 - y0 + 1);
+    for (int i = lane; i < n; i += 32) {
+      int yy = y0 + i / w, xx = x0 + i % w;
+      int g = px_gray(px_load(im, xx, yy));
+      cnt += (g >= lo && g <= hi) ? 1u : 0u;
+    }
+  }
+  cnt = warp_sum_u32(cnt);
+  if (lane == 0) {
+    if (255 >= lo && 255 <= hi) cnt += (unsigned)(total - inside);
+    pages[page].u32[out_off + k] = cnt;
+  }
+}
+
+// gx x gy cell statistics over a grid of ncx x ncy cells anchored at (0,0):
+//   dark[c]  = #pixels (in image) with gray <= dark_max
+//   light[c] = sum of min-channel over the in-image pixels
+// One block per cell row; columns accumulate in registers over the g rows and
+// merge into shared per-cell counters.  Layout in u32: [dark ncx*ncy][light ncx*ncy].
+__global__ void k_cellstats(DPage *pages, int gx, int gy, int ncx, int ncy, int dark_max, int out_off) {
+  extern __shared__ unsigned sm[];
+  unsigned *sd = sm, *sl = sm + ncx;
+  int page = blockIdx.y, cy = blockIdx.x;
+  const DImg &im = pages[page].img;
+  for (int i = threadIdx.x; i < 2 * ncx; i += blockDim.x) sm[i] = 0;
+  __syncthreads();
+  int y0 = cy * gy, y1 = min(y0 + gy - 1, im.h - 1);
+  int xlim = min(ncx * gx, im.w);
+  for (int x = threadIdx.x; x < xlim; x += blockDim.x) {
+    unsigned d = 0, l = 0;
+    for (int y = y0; y <= y1; y++) {
+      Px p = px_load(im, x, y);
+      d += (px_gray(p) <= dark_max) ? 1u : 0u;
+      l += (unsigned)px_light(p);
+    }
+    int c = x / gx;
+    if (d) atomicAdd(&sd[c], d);
+    atomicAdd(&sl[c], l);
+  }
+  __syncthreads();
+  unsigned *od = pages[page].u32 + out_off + (size_t)cy * ncx;
+  unsigned *ol = od + (size_t)ncx * ncy;
+  for (int i = threadIdx.x; i < ncx; i += blockDim.x) { od[i] = sd[i]; ol[i] = sl[i]; }
+}
+
+static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+extern "C" {
+void b200k_zero_u32(cudaStream_t st, DPage *pages, int npages, int off, int n) {
+  if (n <= 0 || npages <= 0) return;
+  dim3 g(min(cdiv(n, 256), 256u), npages);
+  k_zero_u32<<<g, 256, 0, st>>>(pages, off, n);
+}
+void b200k_linesums(cudaStream_t st, DPage *pages, int npages, const DLineJob *jobs_dev,
+                    const DLineJob *jobs_host, int njobs, int stat, int lo, int hi) {
+  if (njobs <= 0 || npages <= 0) return;
+  int maxc = 0, maxr = 0, rows_len = 0, rows_any = 0, cols_any = 0;
+  for (int i = 0; i < njobs; i++) {
+    const DLineJob *j = &jobs_host[i];
+    if (j->xa > j->xb || j->ya > j->yb) continue;
+    if (j->axis == 0) { cols_any = 1; maxc = max(maxc, j->xb - j->xa + 1); maxr = max(maxr, j->yb - j->ya + 1); }
+    else { rows_any = 1; rows_len = max(rows_len, j->yb - j->ya + 1); }
+  }
+  if (cols_any) {
+    dim3 g(cdiv(maxc, 256), cdiv(maxr, LS_ROWS), npages * njobs);
+    k_linesum_cols<<<g, 256, 0, st>>>(pages, jobs_dev, njobs, stat, lo, hi);
+  }
+  if (rows_any) {
+    dim3 g(1, cdiv(rows_len, 8), npages * njobs);
+    k_linesum_rows<<<g, 256, 0, st>>>(pages, jobs_dev, njobs, stat, lo, hi);
+  }
+}
+void b200k_rect_count(cudaStream_t st, DPage *pages, int npages, const DRect *rects_dev, int nrects,
+                      int lo, int hi, int out_off) {
+  if (nrects <= 0 || npages <= 0) return;
+  dim3 g(cdiv(nrects, 8), npages);
+  k_rect_count<<<g, 256, 0, st>>>(pages, rects_dev, nrects, lo, hi, out_off);
+}
+int b200k_cellstats(cudaStream_t st, DPage *pages, int npages, int gx, int gy, int ncx, int ncy,
+                    int dark_max, int out_off) {
+  if (npages <= 0 || ncx <= 0 || ncy <= 0) return 0;
+  size_t sm = (size_t)ncx * 2 * sizeof(unsigned);
+  if (sm > 200 * 1024) return -1;
+  if (sm > 48 * 1024) cudaFuncSetAttribute(k_cellstats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  dim3 gr(ncy, npages);
+  k_cellstats<<<gr, 256, sm, st>>>(pages, gx, gy, ncx, ncy, dark_max, out_off);
+  return 0;
+}
+}

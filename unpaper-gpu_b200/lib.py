@@ -1,0 +1,116 @@
+"""Loader and thin wrappers for libunpaper_b200.so (the CUDA product).
+
+There is no CPU fallback: if the shared library is missing, or no GPU is
+present when an op is called, this fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .abi import (HostOps, SheetConfig, SheetResult, bytes_per_row)
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libunpaper_b200.so")
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(the B200 backend has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.unpaper_b200_last_error.restype = C.c_char_p
+    lib.unpaper_b200_version.restype = C.c_char_p
+    lib.unpaper_cuda_try_init.restype = C.c_int
+    lib.unpaper_b200_device_count.restype = C.c_int
+    lib.unpaper_b200_set_device.argtypes = [C.c_int]
+    lib.unpaper_b200_sheet_config_defaults.argtypes = [C.POINTER(SheetConfig)]
+    lib.unpaper_b200_engine_create.argtypes = [C.POINTER(SheetConfig), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.unpaper_b200_engine_create.restype = C.c_void_p
+    lib.unpaper_b200_engine_destroy.argtypes = [C.c_void_p]
+    lib.unpaper_b200_engine_sheet_width.argtypes = [C.c_void_p]
+    lib.unpaper_b200_engine_sheet_height.argtypes = [C.c_void_p]
+    lib.unpaper_b200_engine_sheet_bytes.argtypes = [C.c_void_p]
+    lib.unpaper_b200_engine_sheet_bytes.restype = C.c_size_t
+    for name in ("unpaper_b200_engine_process_device", "unpaper_b200_engine_process_host"):
+        f = getattr(lib, name)
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(SheetResult)]
+        f.restype = C.c_int
+    lib.unpaper_b200_engine_launch_count.argtypes = [C.c_void_p]
+    lib.unpaper_b200_engine_launch_count.restype = C.c_uint64
+    lib.unpaper_b200_engine_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    lib.unpaper_b200_engine_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
+                                                    C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+    _lib = lib
+    return lib
+
+
+def host_ops():
+    """The 21 `unpaper_b200_host_*` entry points (CUDA)."""
+    return HostOps(load(), "unpaper_b200_host_")
+
+
+def last_error():
+    return load().unpaper_b200_last_error().decode()
+
+
+class Engine:
+    """Python face of the sheet engine (include/unpaper_b200.h layer 3)."""
+
+    def __init__(self, cfg, page_w, page_h, fmt, group_pages=32, lanes=2, device=0):
+        self.lib = load()
+        self.cfg = cfg
+        self.h = self.lib.unpaper_b200_engine_create(C.byref(cfg), device, page_w, page_h, fmt, group_pages, lanes)
+        if not self.h:
+            raise RuntimeError("engine_create failed: " + last_error())
+        self.page_w, self.page_h, self.fmt = page_w, page_h, fmt
+        self.sheet_w = self.lib.unpaper_b200_engine_sheet_width(self.h)
+        self.sheet_h = self.lib.unpaper_b200_engine_sheet_height(self.h)
+        self.sheet_bytes = self.lib.unpaper_b200_engine_sheet_bytes(self.h)
+        self.page_bytes = bytes_per_row(fmt, page_w) * page_h
+        self.sheet_in_bytes = self.page_bytes * cfg.input_count
+
+    def close(self):
+        if self.h:
+            self.lib.unpaper_b200_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process_ptr(self, in_ptr, out_ptr, n, host, results=None):
+        fn = self.lib.unpaper_b200_engine_process_host if host else self.lib.unpaper_b200_engine_process_device
+        rc = fn(self.h, in_ptr, out_ptr, n, results)
+        if rc != 0:
+            raise RuntimeError(f"engine process failed ({rc}): {last_error()}")
+
+    def process_numpy(self, pages):
+        """pages: uint8 array with n*input_count tightly packed pages (host).
+        Returns (out [n, sheet_h, row_bytes], [SheetResult])."""
+        pages = np.ascontiguousarray(pages, dtype=np.uint8).reshape(-1)
+        n = pages.size // self.sheet_in_bytes
+        out = np.empty((n, self.sheet_h, self.sheet_bytes // self.sheet_h), dtype=np.uint8)
+        res = (SheetResult * n)()
+        self.process_ptr(pages.ctypes.data, out.ctypes.data, n, True, res)
+        return out, list(res)
+
+    def launch_count(self):
+        return int(self.lib.unpaper_b200_engine_launch_count(self.h))
+
+    def set_profiling(self, on):
+        self.lib.unpaper_b200_engine_set_profiling(self.h, 1 if on else 0)
+
+    def profile(self):
+        names = (C.c_char_p * 32)()
+        ms = (C.c_double * 32)()
+        cnt = (C.c_uint64 * 32)()
+        n = self.lib.unpaper_b200_engine_get_profile(self.h, 32, names, ms, cnt, None)
+        return {names[i].decode(): (ms[i], int(cnt[i])) for i in range(n)}
