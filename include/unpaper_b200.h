@@ -217,6 +217,9 @@ int unpaper_b200_engine_process_host(B200Engine *e, const uint8_t *pages_host,
                                      B200SheetResult *results);
 /* Kernel launches issued by the engine since creation (for bench.py). */
 uint64_t unpaper_b200_engine_launch_count(const B200Engine *e);
+/* Device time of the last process_* call: CUDA events from the first enqueue on
+ * the first lane's stream to the last lane's completion, in ms. */
+double unpaper_b200_engine_last_device_ms(const B200Engine *e);
 /* Device-time (ms) per named kernel family accumulated with CUDA events when
  * profiling is enabled; returns number of entries written. */
 int unpaper_b200_engine_set_profiling(B200Engine *e, int enabled);

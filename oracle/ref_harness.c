@@ -97,6 +97,7 @@ void deskew_cpu(Image source, Rectangle mask, float radians, Interpolation inter
 typedef struct {
   B200SheetResult *res;
   int detect_masks_calls;
+  int no_deskew;   /* the deskew stage (and its detect_masks call) is skipped */
 } Trace;
 static __thread Trace *tls_trace = NULL;
 
@@ -109,10 +110,11 @@ static size_t tr_detect_masks(Image image, MaskDetectionParameters params,
     /* call 1: masks stage (result discarded by the reference, sheet_stages.c:368-372)
      * call 2: deskew stage; call 3: post stage (mask centring). */
     size_t m = c < B200_TRACE_MAX_MASKS ? c : B200_TRACE_MAX_MASKS;
-    if (t->detect_masks_calls == 2) {
+    int deskew_call = t->no_deskew ? -1 : 2, center_call = t->no_deskew ? 2 : 3;
+    if (t->detect_masks_calls == deskew_call) {
       t->res->deskew_mask_count = (int32_t)c;
       memcpy(t->res->deskew_masks, masks, m * sizeof(Rectangle));
-    } else if (t->detect_masks_calls == 3) {
+    } else if (t->detect_masks_calls == center_call) {
       t->res->center_mask_count = (int32_t)c;
       memcpy(t->res->center_masks, masks, m * sizeof(Rectangle));
     }
@@ -403,7 +405,7 @@ static int run_one_sheet(const B200SheetConfig *cfg, const Options *opt,
   B200SheetResult local;
   if (!res) res = &local;
   memset(res, 0, sizeof(*res));
-  Trace tr = {.res = res, .detect_masks_calls = 0};
+  Trace tr = {.res = res, .detect_masks_calls = 0, .no_deskew = cfg->no_deskew};
   tls_trace = &tr;
   bool ok = process_sheet(&st, &spc);
   tls_trace = NULL;

@@ -32,6 +32,8 @@ static const char *STG_NAME[STG_COUNT] = {"decode", "blackfilter", "noisefilter"
 typedef struct {
   cudaStream_t st;
   cudaEvent_t done;
+  cudaEvent_t done_t;     /* timing-enabled twin of `done` */
+  int ran;
   cudaEvent_t ev[STG_COUNT + 1];
   int ev_mask;            /* which stage boundaries were recorded */
   uint8_t *sheets, *aux, *cls;
@@ -67,7 +69,10 @@ struct B200Engine {
   uint64_t launches;
   int profiling;
   int n_static_mask_jobs[3];
-  int bad_sheets;
+  int bad_sheets, bad_first;
+  unsigned bad_flags;
+  cudaEvent_t ev_begin;
+  double last_device_ms;
   double stage_ms[STG_COUNT];
   uint64_t stage_groups[STG_COUNT];
 };
@@ -78,6 +83,7 @@ int unpaper_b200_engine_sheet_width(const B200Engine *e) { return e->sheet_w; }
 int unpaper_b200_engine_sheet_height(const B200Engine *e) { return e->sheet_h; }
 size_t unpaper_b200_engine_sheet_bytes(const B200Engine *e) { return (size_t)e->sheet_row * e->sheet_h; }
 uint64_t unpaper_b200_engine_launch_count(const B200Engine *e) { return e->launches; }
+double unpaper_b200_engine_last_device_ms(const B200Engine *e) { return e->last_device_ms; }
 int unpaper_b200_engine_set_profiling(B200Engine *e, int enabled) {
   e->profiling = enabled;
   memset(e->stage_ms, 0, sizeof(e->stage_ms));
@@ -152,6 +158,7 @@ static void lane_free(Lane *ln) {
   if (ln->pages_res) b200_pinned_free(ln->pages_res);
   free(ln->pages_tmpl); free(ln->decode_copy_host_tmpl);
   if (ln->done) cudaEventDestroy(ln->done);
+  if (ln->done_t) cudaEventDestroy(ln->done_t);
   for (int i = 0; i <= STG_COUNT; i++) if (ln->ev[i]) cudaEventDestroy(ln->ev[i]);
   if (ln->st) b200_stream_release(ln->st);
   memset(ln, 0, sizeof(*ln));
@@ -161,6 +168,7 @@ void unpaper_b200_engine_destroy(B200Engine *e) {
   if (!e) return;
   unpaper_b200_set_device(e->device);
   if (e->lanes) { for (int i = 0; i < e->nlanes; i++) lane_free(&e->lanes[i]); free(e->lanes); }
+  if (e->ev_begin) cudaEventDestroy(e->ev_begin);
   bf_plan_free(&e->bf); blur_plan_free(&e->blur); mask_plan_free(&e->mask); border_plan_free(&e->border); rot_plan_free(&e->rot);
   free(e);
 }
@@ -246,6 +254,7 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
     Lane *ln = &e->lanes[li];
     ln->st = b200_stream_acquire();
     CUDA_OK(cudaEventCreateWithFlags(&ln->done, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreate(&ln->done_t));
     for (int i = 0; i <= STG_COUNT; i++) CUDA_OK(cudaEventCreate(&ln->ev[i]));
     ln->sheets = (uint8_t *)b200_dev_alloc(e->sheet_stride * P);
     size_t aux_stride = (e->need.aux_bytes + 255) & ~(size_t)255;
@@ -402,7 +411,9 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
   }
   CUDA_OK(cudaMemcpyAsync(ln->pages_res, ln->pages_dev, sizeof(DPage) * n, cudaMemcpyDeviceToHost, c.st));
   mark(e, ln, STG_COUNT);
+  CUDA_OK(cudaEventRecord(ln->done_t, c.st));
   CUDA_OK(cudaEventRecord(ln->done, c.st));
+  ln->ran = 1;
   e->launches += c.launches;
 }
 
@@ -418,7 +429,8 @@ static void collect(B200Engine *e, Lane *ln, B200SheetResult *results) {
       }
     }
   }
-  for (int p = 0; p < ln->n; p++) if (ln->pages_res[p].error) e->bad_sheets++;
+  for (int p = 0; p < ln->n; p++)
+    if (ln->pages_res[p].error) { e->bad_sheets++; e->bad_flags |= ln->pages_res[p].error; e->bad_first = ln->first + p; }
   if (results) {
     for (int p = 0; p < ln->n; p++) {
       const DPage *pg = &ln->pages_res[p];
@@ -457,6 +469,10 @@ static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_shee
   int P = e->group, ic = e->cfg.input_count;
   size_t out_sheet = (size_t)e->sheet_row * e->sheet_h;
   int g = 0;
+  for (int i = 0; i < e->nlanes; i++) e->lanes[i].ran = 0;
+  /* every lane is idle here, so an event on lane 0 marks the start of device work */
+  if (!e->ev_begin) CUDA_OK(cudaEventCreate(&e->ev_begin));
+  CUDA_OK(cudaEventRecord(e->ev_begin, e->lanes[0].st));
   for (int first = 0; first < n_sheets; first += P, g++) {
     Lane *ln = &e->lanes[g % e->nlanes];
     collect(e, ln, results);
@@ -475,9 +491,16 @@ static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_shee
   }
   for (int i = 0; i < e->nlanes; i++) collect(e, &e->lanes[(g + i) % e->nlanes], results);
   CUDA_OK(cudaGetLastError());
+  e->last_device_ms = 0.0;
+  for (int i = 0; i < e->nlanes; i++) {
+    float ms = 0;
+    if (e->lanes[i].ran && cudaEventElapsedTime(&ms, e->ev_begin, e->lanes[i].done_t) == cudaSuccess && ms > e->last_device_ms)
+      e->last_device_ms = ms;
+  }
   int bad = e->bad_sheets;
   e->bad_sheets = 0;
-  if (bad) b200_set_error("engine: %d sheet(s) reported device-side failure flags", bad);
+  if (bad) b200_set_error("engine: %d sheet(s) reported device-side failure flags 0x%x (e.g. sheet %d)", bad, e->bad_flags, e->bad_first);
+  e->bad_flags = 0;
   return bad ? -2 : 0;
 }
 

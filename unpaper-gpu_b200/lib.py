@@ -43,6 +43,8 @@ def load():
         f.restype = C.c_int
     lib.unpaper_b200_engine_launch_count.argtypes = [C.c_void_p]
     lib.unpaper_b200_engine_launch_count.restype = C.c_uint64
+    lib.unpaper_b200_engine_last_device_ms.argtypes = [C.c_void_p]
+    lib.unpaper_b200_engine_last_device_ms.restype = C.c_double
     lib.unpaper_b200_engine_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.unpaper_b200_engine_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                                     C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
@@ -104,6 +106,9 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.unpaper_b200_engine_launch_count(self.h))
+
+    def last_device_ms(self):
+        return float(self.lib.unpaper_b200_engine_last_device_ms(self.h))
 
     def set_profiling(self, on):
         self.lib.unpaper_b200_engine_set_profiling(self.h, 1 if on else 0)

@@ -73,12 +73,12 @@ def _rotate_into(page, block, theta, cx, cy):
 
 
 def gray_page(index, width=A4_W, height=A4_H, max_skew_deg=5.0, speckle=1.0 / 5000,
-              dark_edges=True):
+              dark_edges=True, box=(0.76, 0.80)):
     """BASELINE config 2 ("C2"): GRAY8 page, text box +-5 deg, speckle, dark edges."""
     rng = _rng(index)
     scale = width / float(A4_W)
     page = np.full((height, width), 255, dtype=np.uint8)
-    bw, bh = int(width * 0.76), int(height * 0.80)
+    bw, bh = int(width * box[0]), int(height * box[1])
     block = _text_block(rng, bw, bh, scale)
     theta = np.deg2rad(rng.uniform(-max_skew_deg, max_skew_deg))
     _rotate_into(page, block, theta, width / 2.0, height / 2.0)
@@ -86,7 +86,10 @@ def gray_page(index, width=A4_W, height=A4_H, max_skew_deg=5.0, speckle=1.0 / 50
         n = rng.binomial(width * height, speckle)
         page[rng.integers(0, height, n), rng.integers(0, width, n)] = 0
     if dark_edges:
-        le, re = max(2, int(round(40 * scale))), max(2, int(round(30 * scale)))
+        # never narrower than the blackfilter's 20-px scan bar, or the filter
+        # leaves them in and detect_edge() runs off the sheet (it never returns
+        # in the reference: masks.c:88-97)
+        le, re = max(24, int(round(40 * scale))), max(22, int(round(30 * scale)))
         page[:, :le] = 10
         page[:, width - re:] = 10
     return page
