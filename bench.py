@@ -34,6 +34,7 @@ import numpy as np  # noqa: E402
 
 import unpaper_gpu_b200 as U  # noqa: E402
 from unpaper_gpu_b200 import synth  # noqa: E402
+from oracle import checker  # test infrastructure: the CPU checkers
 
 W, H = synth.A4_W, synth.A4_H
 WORKLOAD = ("BASELINE config 2: synthetic A4 300-dpi GRAY8 2480x3508, +-5 deg skew, speckle 1/5000, "
@@ -100,11 +101,11 @@ def run_reference(args, rank, world):
     """The reference's CPU path on the host cores (rank 0 only)."""
     if rank != 0:
         return
-    lib = U.load_ref()
+    lib = checker.load_ref()
     kind = "reference"
     prefix = "ref_"
     if lib is None:
-        lib, kind, prefix = U.load_oracle(), "port", "orc_"
+        lib, kind, prefix = checker.load_oracle(), "port", "orc_"
     if lib is None:
         print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref nor oracle/liboracle.so is built"}))
         return
@@ -118,7 +119,7 @@ def run_reference(args, rank, world):
     times = []
     for i in range(min(args.warmup, 1) + args.steps):
         t0 = time.time()
-        U.process_sheets_cpu(lib, prefix, cfg, pages, W, H, U.FMT_GRAY8, threads=cores, want_out=False)
+        checker.process_sheets_cpu(lib, prefix, cfg, pages, W, H, U.FMT_GRAY8, threads=cores, want_out=False)
         dt = time.time() - t0
         if i >= min(args.warmup, 1):
             times.append(dt)
@@ -268,17 +269,17 @@ def main():
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "stages": per_stage,
                 "failed_sheets": bad}
         if world == 1 and not args.no_cpu_baseline:
-            lib = U.load_ref()
+            lib = checker.load_ref()
             kind, prefix = "reference", "ref_"
             if lib is None:
-                lib, kind, prefix = U.load_oracle(), "port", "orc_"
+                lib, kind, prefix = checker.load_oracle(), "port", "orc_"
             if lib is not None and hasattr(lib, prefix + "process_sheets"):
                 cores = os.cpu_count() or 1
                 sample = host_np[:min(cores, args.pages)]
                 if len(sample) < cores:
                     sample = np.concatenate([sample] * ((cores + len(sample) - 1) // len(sample)))[:cores]
                 t0 = time.time()
-                U.process_sheets_cpu(lib, prefix, cfg, sample, W, H, U.FMT_GRAY8, threads=cores, want_out=False)
+                checker.process_sheets_cpu(lib, prefix, cfg, sample, W, H, U.FMT_GRAY8, threads=cores, want_out=False)
                 dt = time.time() - t0
                 line["cpu_baseline"] = {"value": len(sample) / dt, "unit": UNIT, "cores": cores, "kind": kind,
                                         "sample": f"{len(sample)} pages of the same workload, {cores} threads, one pass ({dt:.1f} s)"}

@@ -16,7 +16,8 @@ def pytest_configure(config):
 def ref_ops():
     """Reference CPU backend (oracle/_ref) as the checker; None if not built."""
     import unpaper_gpu_b200 as U
-    lib = U.load_ref()
+    from oracle import checker
+    lib = checker.load_ref()
     if lib is None:
         pytest.skip("oracle/_ref/libunpaper_ref.so not built")
     return U.HostOps(lib, "ref_host_")
@@ -25,7 +26,8 @@ def ref_ops():
 @pytest.fixture(scope="session")
 def ref_lib():
     import unpaper_gpu_b200 as U
-    lib = U.load_ref()
+    from oracle import checker
+    lib = checker.load_ref()
     if lib is None:
         pytest.skip("oracle/_ref/libunpaper_ref.so not built")
     return lib

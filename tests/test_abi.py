@@ -1,0 +1,67 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/*.h declares;
+struct layouts agree between C and the ctypes mirror; no compute calls."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import unpaper_gpu_b200 as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "unpaper_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set(re.findall(r"\b((?:unpaper_b200_|unpaper_cuda_|image_|create_image_from_gpu)\w*)\s*\(", text))
+    names.add("backend_cuda")
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol():
+    from unpaper_gpu_b200 import lib as L
+    handle = L.load()
+    missing = [n for n in _declared_symbols() if not hasattr(handle, n)]
+    assert not missing, missing
+    assert len(_declared_symbols()) > 50
+
+
+def test_backend_vtable_shape():
+    """`backend_cuda` = name + 20 function pointers (reference backend.h:19-57)."""
+    from unpaper_gpu_b200 import lib as L
+    handle = L.load()
+    tab = (C.c_void_p * 21).in_dll(handle, "backend_cuda")
+    assert C.cast(tab[0], C.c_char_p).value == b"cuda"
+    assert all(tab[i] for i in range(1, 21))
+
+
+def test_struct_layouts_match_c(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "unpaper_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(B200SheetConfig),sizeof(B200SheetResult),sizeof(B200HostImage),sizeof(BlackfilterParameters),'
+                   'sizeof(MaskDetectionParameters),offsetof(B200SheetConfig,deskew),offsetof(B200SheetResult,borders));}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(U.SheetConfig), C.sizeof(U.SheetResult), C.sizeof(U.HostImage), C.sizeof(U.BlackfilterParameters),
+            C.sizeof(U.MaskDetectionParameters), U.SheetConfig.deskew.offset, U.SheetResult.borders.offset]
+    assert got == want
+
+
+def test_defaults_match_c():
+    from unpaper_gpu_b200 import lib as L
+    c = U.SheetConfig()
+    L.load().unpaper_b200_sheet_config_defaults(C.byref(c))
+    p = U.default_sheet_config()
+    assert bytes(c) == bytes(p)
+
+
+def test_product_does_not_touch_oracle():
+    """The product tree must not reference anything under oracle/."""
+    bad = []
+    for dp, _, files in os.walk(os.path.join(ROOT, "unpaper-gpu_b200")):
+        for f in files:
+            if f.endswith((".c", ".h", ".cu", ".cuh", ".py")) or f == "Makefile":
+                if "oracle" in open(os.path.join(dp, f), errors="ignore").read().lower().replace("oracle/makefile", ""):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad

@@ -5,6 +5,7 @@ import pytest
 
 import unpaper_gpu_b200 as U
 from unpaper_gpu_b200 import synth
+from oracle import checker  # test infrastructure: the CPU checkers
 
 pytestmark = pytest.mark.gpu
 
@@ -17,7 +18,7 @@ def _compare(cfg, pages, w, h, fmt, ref_lib, group=4, lanes=2):
     eng = Engine(cfg, w, h, fmt, group_pages=group, lanes=lanes)
     out, res = eng.process_numpy(pages)
     eng.close()
-    rout, rres = U.process_sheets_cpu(ref_lib, "ref_", cfg, pages, w, h, fmt, threads=8)
+    rout, rres = checker.process_sheets_cpu(ref_lib, "ref_", cfg, pages, w, h, fmt, threads=8)
     for i, (a, b) in enumerate(zip(res, rres)):
         assert a.status == 0 and b.status == 0
         assert a.deskew_mask_count == b.deskew_mask_count, f"sheet {i}"

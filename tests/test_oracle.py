@@ -1,0 +1,118 @@
+"""CPU-only: pins the oracle restatement (oracle/liboracle.so).
+
+ * against the unmodified reference compiled into oracle/_ref (when present —
+   it is in the build container and it travels to the GPU box as a prebuilt
+   .so): every op bit-exact on seeded inputs, and the whole process_sheet()
+   pipeline on small synthetic sheets;
+ * against tests/golden/golden_vectors.json, which records what the reference
+   produced (incl. its own goldenA1 end-to-end case) — works without oracle/_ref.
+"""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import unpaper_gpu_b200 as U
+from unpaper_gpu_b200 import synth
+from oracle import checker  # test infrastructure: the CPU checkers
+import golden_cases as G
+import test_gpu_blit as B
+import test_gpu_filters as F
+from util import FMTS_ALL, FMTS_BYTE
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_vectors.json")))
+
+
+@pytest.fixture(scope="module")
+def orc_lib():
+    lib = checker.load_oracle()
+    if lib is None or not hasattr(lib, "orc_process_sheets"):
+        pytest.fail("oracle/liboracle.so not built: run __graft_entry__.build()")
+    return lib
+
+
+@pytest.fixture(scope="module")
+def orc_ops(orc_lib):
+    return U.HostOps(orc_lib, "orc_host_")
+
+
+def test_golden_a1_record_is_sane():
+    """oracle/_ref reproduced the reference's goldenA1.pbm when the vectors were made."""
+    a1 = GOLD["A1"]
+    assert a1 is not None and a1["golden_diff_ratio_thr170"] < 1e-4
+    assert a1["result"]["center_masks"] == [[670, 0, 2265, 3506]]
+    assert a1["result"]["borders"] == [[0, 315, 1, 741]]
+
+
+@pytest.mark.parametrize("name", sorted(GOLD["ops"].keys()))
+def test_oracle_ops_match_golden(orc_ops, name):
+    got = G.op_cases()[name](orc_ops)
+    assert got == GOLD["ops"][name]
+
+
+@pytest.mark.parametrize("name", ["gray_620", "color_620"])
+def test_oracle_sheets_match_golden(orc_lib, name):
+    cfg, pages, w, h, fmt = G.sheet_cases()[name]
+    out, res = checker.process_sheets_cpu(orc_lib, "orc_", cfg, pages, w, h, fmt, threads=4)
+    want = GOLD["sheets"][name]
+    assert [G.result_dict(r) for r in res] == want["results"]
+    assert [hashlib.sha256(x.tobytes()).hexdigest() for x in out] == want["output_sha256"]
+
+
+def test_ref_still_matches_golden(ref_lib):
+    """The prebuilt reference library agrees with the committed vectors."""
+    cfg, pages, w, h, fmt = G.sheet_cases()["gray_620"]
+    out, res = checker.process_sheets_cpu(ref_lib, "ref_", cfg, pages[:1], w, h, fmt)
+    assert G.result_dict(res[0]) == GOLD["sheets"]["gray_620"]["results"][0]
+    assert hashlib.sha256(out[0].tobytes()).hexdigest() == GOLD["sheets"]["gray_620"]["output_sha256"][0]
+
+
+# ---- op-by-op against the live reference (same bodies as the GPU parity tests) ----
+
+@pytest.mark.parametrize("fmt", FMTS_ALL)
+def test_orc_blit_ops(orc_ops, ref_ops, fmt):
+    B.test_wipe_rectangle(orc_ops, ref_ops, fmt, 37, 29)
+    B.test_mirror(orc_ops, ref_ops, fmt, 37, 29)
+    B.test_flip_rotate_90(orc_ops, ref_ops, fmt)
+    B.test_shift(orc_ops, ref_ops, fmt)
+    B.test_apply_masks_wipes_border(orc_ops, ref_ops, fmt)
+    B.test_center_and_align_mask(orc_ops, ref_ops, fmt)
+
+
+def test_orc_copy_center(orc_ops, ref_ops):
+    for s, d in ((U.FMT_GRAY8, U.FMT_RGB24), (U.FMT_RGB24, U.FMT_GRAY8), (U.FMT_Y400A, U.FMT_Y400A),
+                 (U.FMT_MONOWHITE, U.FMT_RGB24), (U.FMT_RGB24, U.FMT_MONOBLACK)):
+        B.test_copy_rectangle(orc_ops, ref_ops, s, d)
+    B.test_center_image(orc_ops, ref_ops, U.FMT_RGB24)
+
+
+@pytest.mark.parametrize("interp", [U.INTERP_NN, U.INTERP_LINEAR, U.INTERP_CUBIC])
+def test_orc_stretch_deskew(orc_ops, ref_ops, interp):
+    B.test_stretch_resize(orc_ops, ref_ops, U.FMT_RGB24, interp)
+    F.test_deskew(orc_ops, ref_ops, U.FMT_GRAY8, interp)
+
+
+@pytest.mark.parametrize("fmt", FMTS_BYTE)
+def test_orc_filters(orc_ops, ref_ops, fmt):
+    F.test_noisefilter_random(orc_ops, ref_ops, fmt, 4)
+    F.test_noisefilter_random(orc_ops, ref_ops, fmt, 7)
+    F.test_blackfilter_blobs(orc_ops, ref_ops, fmt, 20)
+    F.test_blurfilter(orc_ops, ref_ops, fmt)
+    F.test_grayfilter(orc_ops, ref_ops, fmt)
+
+
+def test_orc_detectors(orc_ops, ref_ops):
+    F.test_detect_masks(orc_ops, ref_ops, U.FMT_GRAY8)
+    F.test_detect_border(orc_ops, ref_ops, U.FMT_RGB24)
+    F.test_detect_rotation(orc_ops, ref_ops, U.FMT_GRAY8)
+
+
+def test_orc_sheet_vs_ref(orc_lib, ref_lib):
+    cfg, pages, w, h, fmt = G.sheet_cases()["double_1754"]
+    a, ra = checker.process_sheets_cpu(orc_lib, "orc_", cfg, pages, w, h, fmt)
+    b, rb = checker.process_sheets_cpu(ref_lib, "ref_", cfg, pages, w, h, fmt)
+    assert [G.result_dict(r) for r in ra] == [G.result_dict(r) for r in rb]
+    assert np.array_equal(a, b)

@@ -1,13 +1,8 @@
 """ctypes mirror of include/unpaper_b200.h / unpaper_b200_types.h.
 
-One binding serves three libraries that export the same entry points under
-different prefixes:
-
-  * ``unpaper_b200_host_*`` — the CUDA product (libunpaper_b200.so);
-  * ``ref_host_*``          — the unmodified reference CPU backend
-                               (oracle/_ref/libunpaper_ref.so, test infra);
-  * ``orc_host_*``          — this repo's CPU restatement
-                               (oracle/liboracle.so, test infra).
+``HostOps`` binds the 21 host-buffer entry points of any library that exports
+them under a common prefix (``unpaper_b200_host_*`` for the CUDA product; the
+test suite binds its CPU checkers through the same class).
 """
 import ctypes as C
 import os
@@ -135,7 +130,8 @@ def default_sheet_config():
     bf.abs_threshold = int(np.float32(255) * np.float32(0.95)); bf.intensity = 20
     c.blurfilter = BlurfilterParameters(RectangleSize(100, 100), Delta(50, 50), 0.01)
     c.grayfilter = GrayfilterParameters(RectangleSize(50, 50), Delta(20, 20), int(255 * 0.5))
-    d2r = lambda d: float(np.float32(np.float32(d) * np.pi / 180.0))  # deskew.c:23
+    # deskew.c:23: `float d` promoted to double, multiplied, rounded to float once
+    d2r = lambda d: float(np.float32(float(np.float32(d)) * np.pi / 180.0))
     c.deskew = DeskewParameters(d2r(5.0), d2r(0.1), d2r(1.0), 1500, 0.5, Edges(True, False, True, False))
     c.mask_detection = MaskDetectionParameters(
         RectangleSize(50, 50), Delta(5, 5), _I2(-1, -1), Direction(True, False),
@@ -202,52 +198,3 @@ class HostOps:
 
     def call(self, name, *args):
         return self._chk(self.fn[name](*args), name)
-
-
-def load_ref():
-    """oracle/_ref/libunpaper_ref.so (the reference CPU backend) or None."""
-    p = os.path.join(ROOT, "oracle", "_ref", "libunpaper_ref.so")
-    if not os.path.exists(p):
-        return None
-    lib = C.CDLL(p)
-    lib.ref_process_sheets.argtypes = [
-        C.POINTER(SheetConfig), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-        C.POINTER(SheetResult), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    lib.ref_process_sheets.restype = C.c_int
-    lib.ref_online_cpus.restype = C.c_int
-    return lib
-
-
-def load_oracle():
-    """oracle/liboracle.so (this repo's CPU restatement) or None."""
-    p = os.path.join(ROOT, "oracle", "liboracle.so")
-    if not os.path.exists(p):
-        return None
-    lib = C.CDLL(p)
-    if hasattr(lib, "orc_process_sheets"):
-        lib.orc_process_sheets.argtypes = [
-            C.POINTER(SheetConfig), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-            C.POINTER(SheetResult), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-        lib.orc_process_sheets.restype = C.c_int
-    return lib
-
-
-def process_sheets_cpu(lib, prefix, cfg, pages, page_w, page_h, fmt, threads=1, want_out=True):
-    """Run ``n`` sheets through a CPU library's process_sheet() equivalent.
-
-    ``pages``: uint8 array holding n*input_count tightly packed pages.
-    Returns (out array [n, sheet_h, sheet_row_bytes] or None, list of SheetResult)."""
-    row = bytes_per_row(fmt, page_w)
-    per_sheet = row * page_h * cfg.input_count
-    pages = np.ascontiguousarray(pages, dtype=np.uint8).reshape(-1)
-    n = pages.size // per_sheet
-    sw, sh = page_w * cfg.input_count, page_h
-    out = np.empty((n, sh, bytes_per_row(fmt, sw)), dtype=np.uint8) if want_out else None
-    res = (SheetResult * n)()
-    w, h = C.c_int(), C.c_int()
-    rc = getattr(lib, prefix + "process_sheets")(
-        C.byref(cfg), pages.ctypes.data, page_w, page_h, fmt, n,
-        out.ctypes.data if want_out else None, res, threads, C.byref(w), C.byref(h))
-    if rc != 0:
-        raise RuntimeError(f"{prefix}process_sheets: {rc}")
-    return out, list(res)

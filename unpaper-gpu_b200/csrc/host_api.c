@@ -1,7 +1,6 @@
 /* host_api.c — layer (2) of include/unpaper_b200.h: one backend op on an image
  * that lives in caller memory.  Upload, run the `backend_cuda` entry point,
- * download.  This is what the parity tests bind (the oracle harness exports
- * the same signatures over the reference's CPU backend). */
+ * download.  This is what the parity tests and foreign-language hosts bind. */
 #define _GNU_SOURCE
 #include <libavutil/frame.h>
 #include <math.h>
