@@ -8,27 +8,75 @@
 // ---- fill ---------------------------------------------------------------
 // One job = one rectangle [x0..x1]x[y0..y1] (empty when inverted), clipped to
 // the image here.  blockIdx.z = job.
+// byte-run helpers: 16-byte stores on an aligned body, bytes on head and tail
+__device__ __forceinline__ void fill_run(uint8_t *dst, int n, const uint8_t pat[3], int phase, int tid, int nthreads) {
+  // writes dst[i] = pat[(phase + i) % 3] for i in [0, n)
+  int head = (int)((16u - ((unsigned)(uintptr_t)dst & 15u)) & 15u);
+  if (head > n) head = n;
+  for (int i = tid; i < head; i += nthreads) dst[i] = pat[(phase + i) % 3];
+  int nvec = (n - head) >> 4;
+  uint4 *d4 = (uint4 *)(dst + head);
+  if (nvec > 0) {
+    unsigned w[3][4];   // the three possible 16-byte vectors of a 3-periodic pattern
+#pragma unroll
+    for (int v = 0; v < 3; v++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        int o = phase + head + 16 * v + 4 * k;
+        w[v][k] = (unsigned)pat[o % 3] | ((unsigned)pat[(o + 1) % 3] << 8) | ((unsigned)pat[(o + 2) % 3] << 16) | ((unsigned)pat[(o + 3) % 3] << 24);
+      }
+    for (int i = tid; i < nvec; i += nthreads) {
+      int v = i % 3;
+      d4[i] = v == 0 ? make_uint4(w[0][0], w[0][1], w[0][2], w[0][3]) : v == 1 ? make_uint4(w[1][0], w[1][1], w[1][2], w[1][3]) : make_uint4(w[2][0], w[2][1], w[2][2], w[2][3]);
+    }
+  }
+  for (int i = head + (nvec << 4) + tid; i < n; i += nthreads) dst[i] = pat[(phase + i) % 3];
+}
+
+__device__ __forceinline__ void copy_run(uint8_t *dst, const uint8_t *src, int n, int tid, int nthreads) {
+  int head = (int)((16u - ((unsigned)(uintptr_t)dst & 15u)) & 15u);
+  if (head > n) head = n;
+  for (int i = tid; i < head; i += nthreads) dst[i] = src[i];
+  int nvec = (n - head) >> 4;
+  uint4 *d4 = (uint4 *)(dst + head);
+  const uint8_t *sb = src + head;
+  unsigned mis = (unsigned)(uintptr_t)sb & 3u;
+  if (((uintptr_t)sb & 15u) == 0) {
+    const uint4 *s4 = (const uint4 *)sb;
+    for (int i = tid; i < nvec; i += nthreads) d4[i] = s4[i];
+  } else if (mis == 0) {
+    const unsigned *sw = (const unsigned *)sb;
+    for (int i = tid; i < nvec; i += nthreads) d4[i] = make_uint4(sw[4 * i], sw[4 * i + 1], sw[4 * i + 2], sw[4 * i + 3]);
+  } else {
+    const unsigned *sw = (const unsigned *)(sb - mis);   // aligned words straddling the source bytes
+    unsigned sh = mis * 8;
+    for (int i = tid; i < nvec; i += nthreads) {
+      unsigned a = sw[4 * i], b = sw[4 * i + 1], c = sw[4 * i + 2], d = sw[4 * i + 3], e = sw[4 * i + 4];
+      d4[i] = make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh), __funnelshift_r(c, d, sh), __funnelshift_r(d, e, sh));
+    }
+  }
+  for (int i = head + (nvec << 4) + tid; i < n; i += nthreads) dst[i] = src[i];
+}
+
 __global__ void k_fill_jobs(const DFillJob *jobs) {
   const DFillJob &j = jobs[blockIdx.z];
   if (!j.enabled) return;
   const DImg &im = j.img;
   int x0 = max(j.r.x0, 0), x1 = min(j.r.x1, im.w - 1);
   int y0 = max(j.r.y0, 0), y1 = min(j.r.y1, im.h - 1);
-  int y = y0 + blockIdx.y;
-  if (y > y1) return;
+  if (x0 > x1) return;
   int r = j.c[0], g = j.c[1], b = j.c[2];
-  if (im.fmt == DF_GRAY8) {
-    // byte-addressed rows: 4 pixels per thread
+  int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  if (im.fmt == DF_GRAY8 || im.fmt == DF_RGB24) {
     uint8_t v = (uint8_t)((r + g + b) / 3);
-    uint8_t *row = im.data + (size_t)y * im.pitch;
-    for (int x = x0 + (blockIdx.x * blockDim.x + threadIdx.x) * 4; x <= x1; x += gridDim.x * blockDim.x * 4) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) if (x + k <= x1) row[x + k] = v;
-    }
+    uint8_t pat[3] = {im.fmt == DF_GRAY8 ? v : (uint8_t)r, im.fmt == DF_GRAY8 ? v : (uint8_t)g, im.fmt == DF_GRAY8 ? v : (uint8_t)b};
+    int bpp = im.fmt == DF_GRAY8 ? 1 : 3;
+    for (int y = y0 + blockIdx.y; y <= y1; y += gridDim.y)
+      fill_run(im.data + (size_t)y * im.pitch + (size_t)x0 * bpp, (x1 - x0 + 1) * bpp, pat, 0, tid, nth);
     return;
   }
-  for (int x = x0 + blockIdx.x * blockDim.x + threadIdx.x; x <= x1; x += gridDim.x * blockDim.x)
-    px_store(im, x, y, r, g, b);
+  for (int y = y0 + blockIdx.y; y <= y1; y += gridDim.y)
+    for (int x = x0 + tid; x <= x1; x += nth) px_store(im, x, y, r, g, b);
 }
 
 // ---- copy (imageprocess/blit.c:30-80) -------------------------------------
@@ -49,8 +97,7 @@ __global__ void k_copy_jobs(const DCopyJob *jobs) {
   if (raw) {
     const uint8_t *sp = s.data + (size_t)sy * s.pitch + (size_t)ax0 * bpp;
     uint8_t *dp = d.data + (size_t)ty * d.pitch + (size_t)j.tx * bpp;
-    int n = width * bpp;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dp[i] = sp[i];
+    copy_run(dp, sp, width * bpp, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
     return;
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < width; i += gridDim.x * blockDim.x) {
@@ -106,13 +153,13 @@ static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 extern "C" {
 void b200k_fill_jobs(cudaStream_t st, const DFillJob *jobs, int njobs, int maxw, int maxh) {
   if (njobs <= 0 || maxw <= 0 || maxh <= 0) return;
-  dim3 g(min(cdiv(maxw, 256 * 4), 64u), maxh, njobs);
-  k_fill_jobs<<<g, 256, 0, st>>>(jobs);
+  dim3 g(min(cdiv(maxw * 3, 128 * 16), 8u), min((unsigned)maxh, 2048u), njobs);
+  k_fill_jobs<<<g, 128, 0, st>>>(jobs);
 }
 void b200k_copy_jobs(cudaStream_t st, const DCopyJob *jobs, int njobs, int maxw_bytes, int maxh) {
   if (njobs <= 0 || maxw_bytes <= 0 || maxh <= 0) return;
-  dim3 g(min(cdiv(maxw_bytes, 256), 64u), maxh, njobs);
-  k_copy_jobs<<<g, 256, 0, st>>>(jobs);
+  dim3 g(min(cdiv(maxw_bytes, 128 * 16), 8u), maxh, njobs);
+  k_copy_jobs<<<g, 128, 0, st>>>(jobs);
 }
 void b200k_apply_masks(cudaStream_t st, const DMaskJob *jobs, int njobs, int maxw, int maxh) {
   if (njobs <= 0 || maxw <= 0 || maxh <= 0) return;

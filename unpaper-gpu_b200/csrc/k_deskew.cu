@@ -62,41 +62,42 @@ __global__ void k_rot_peaks(DPage *pages, const float *tan_tab, RotParams rp) {
     stepX = 1.0f; stepY = -m;
   }
   int maxAbs = (int)(255 * rp.scan_size * rp.scan_depth);   // deskew.c:67
+  // deskew.c:108-113: sequential float accumulation; X and Y are independent
+  // chains, so two threads (of different warps) run one each
   if (threadIdx.x == 0) {
-    for (int k = 0; k < scan; k++) {   // deskew.c:108-113: sequential float accumulation
-      pts[k] = make_int2((int)X, (int)Y);
-      X += stepX; Y += stepY;
-    }
+    for (int k = 0; k < scan; k++) { pts[k].x = (int)X; X += stepX; }
     s_done = 0; s_max = 0; s_dep = 0;
+  } else if (threadIdx.x == 32) {
+    for (int k = 0; k < scan; k++) { pts[k].y = (int)Y; Y += stepY; }
   }
   __syncthreads();
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   int last = 0, maxDiff = 0, acc = 0, dep = 0;   // thread 0's copies are authoritative
   int mx0 = min(mask.x0, mask.x1), mx1 = max(mask.x0, mask.x1), my0 = min(mask.y0, mask.y1), my1 = max(mask.y0, mask.y1);
+  // a sample only counts inside the mask AND inside the image (outside reads white = 0)
+  int vx0 = max(mx0, 0), vx1 = min(mx1, im.w - 1), vy0 = max(my0, 0), vy1 = min(my1, im.h - 1);
+  bool gray8 = im.fmt == DF_GRAY8;
   for (int base = 0; base < maxDepth; base += ROT_CHUNK) {
-    int part[ROT_CHUNK];
-#pragma unroll
-    for (int d = 0; d < ROT_CHUNK; d++) part[d] = 0;
-    for (int k = threadIdx.x; k < scan; k += blockDim.x) {
+    // lane = depth (base + lane): with a horizontal shift the 32 lanes read 32
+    // consecutive bytes of one row per sample point
+    int d = base + lane;
+    int part = 0;
+    int ox = d * shx, oy = d * shy;
+    for (int k = warp; k < scan; k += nwarp) {
       int2 p = pts[k];
-#pragma unroll
-      for (int d = 0; d < ROT_CHUNK; d++) {
-        int x = p.x + (base + d) * shx, y = p.y + (base + d) * shy;
-        if (x >= mx0 && x <= mx1 && y >= my0 && y <= my1 && in_img(im, x, y))
-          part[d] += 255 - px_darkinv(px_load(im, x, y));
+      int x = p.x + ox, y = p.y + oy;
+      if (x >= vx0 && x <= vx1 && y >= vy0 && y <= vy1) {
+        int v = gray8 ? (int)im.data[(size_t)y * im.pitch + x] : px_darkinv(px_load(im, x, y));
+        part += 255 - v;
       }
     }
-#pragma unroll
-    for (int d = 0; d < ROT_CHUNK; d++) {
-      int v = warp_sum_i32(part[d]);
-      if (lane == 0) s_red[warp][d] = v;
-    }
+    s_red[warp][lane] = part;
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int d = 0; d < ROT_CHUNK; d++) {
+      for (int dd = 0; dd < ROT_CHUNK; dd++) {
         if (!((acc < maxAbs) && (dep < maxDepth))) { s_done = 1; break; }   // deskew.c:119
         int blackness = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) blackness += s_red[w][d];
+        for (int w = 0; w < nwarp; w++) blackness += s_red[w][dd];
         int diff = blackness - last;
         last = blackness;
         if (diff >= maxDiff) maxDiff = diff;
@@ -258,9 +259,40 @@ __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) 
   float tcx = 0 + w / 2.0f, tcy = 0 + h / 2.0f;
   float sinval = pg.rot_sin[mi], cosval = pg.rot_cos[mi];
   bool gray = im.fmt != DF_RGB24;
+  bool fast = im.fmt == DF_GRAY8 && interp == 2;
+  uint8_t *orow = aux.data + (size_t)y * aux.pitch;
   for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) {
     float srcX = scx + (x - tcx) * cosval + (y - tcy) * sinval;
     float srcY = scy + (y - tcy) * cosval - (x - tcx) * sinval;
+    if (fast) {
+      int px = (int)srcX, py = (int)srcY;
+      if (px >= 1 && py >= 1 && px + 2 < im.w && py + 2 < im.h) {
+        // the 4x4 taps as four packed words (two aligned loads + funnel shift per row)
+        const uint8_t *p0 = im.data + (size_t)(py - 1) * im.pitch + (px - 1);
+        unsigned rw[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint8_t *pr = p0 + (size_t)i * im.pitch;
+          const unsigned *wp = (const unsigned *)((uintptr_t)pr & ~(uintptr_t)3);
+          unsigned sh = ((unsigned)(uintptr_t)pr & 3u) * 8u;
+          rw[i] = sh ? __funnelshift_r(wp[0], wp[1], sh) : wp[0];
+        }
+        unsigned v0 = rw[0] & 0xFFu;
+        int o;
+        if (rw[0] == v0 * 0x01010101u && rw[1] == rw[0] && rw[2] == rw[0] && rw[3] == rw[0]) {
+          o = (int)v0;   // all 16 taps equal: every cubic term cancels exactly
+        } else {
+          float fx = srcX - px, fy = srcY - py;
+          int r4[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            r4[i] = cubic_scale(fx, (int)(rw[i] & 0xFF), (int)((rw[i] >> 8) & 0xFF), (int)((rw[i] >> 16) & 0xFF), (int)(rw[i] >> 24));
+          o = cubic_scale(fy, r4[0], r4[1], r4[2], r4[3]);
+        }
+        orow[x] = (uint8_t)o;
+        continue;
+      }
+    }
     Px o = interp_any(im, srcX, srcY, interp, gray);
     px_store(aux, x, y, o.r, o.g, o.b);
   }

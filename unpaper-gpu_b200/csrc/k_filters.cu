@@ -26,31 +26,50 @@ __device__ __forceinline__ bool ff_match(const DImg &im, int x, int y, int lo, i
   return g >= lo && g <= hi;
 }
 
-// fill_line (fill.c:16-43): returns painted distance.  Warp-cooperative.
+// fill_line (fill.c:16-43): returns painted distance.  Warp-cooperative; FF_U
+// chunks of 32 pixels are fetched per round so that the (latency-bound) walk
+// along a column keeps several loads in flight.
+#define FF_U 4
 __device__ int ff_fill_line(const DImg &im, int px, int py, int dx, int dy, int lo, int hi,
                             unsigned long long intensity, int lane) {
   int distance = 0;
   unsigned long long cnt = 1;
   for (;;) {
-    int qx = px + (distance + lane + 1) * dx, qy = py + (distance + lane + 1) * dy;
-    bool inb = in_img(im, qx, qy);
-    bool m = ff_match(im, qx, qy, lo, hi);
-    unsigned M = __ballot_sync(0xffffffffu, m), I = __ballot_sync(0xffffffffu, inb);
-    int painted = 32;
-    if ((M & I) == 0xffffffffu) {
-      cnt = intensity;
-      if (cnt == 0) painted = 0;   // degenerate intensity 0: stops on the first pixel
-    } else {
-      painted = 32;
-      for (int i = 0; i < 32; i++) {
-        if ((M >> i) & 1u) cnt = intensity; else cnt--;
-        if (cnt == 0 || !((I >> i) & 1u)) { painted = i; break; }
-      }
+    unsigned M[FF_U], I[FF_U];
+#pragma unroll
+    for (int u = 0; u < FF_U; u++) {
+      int s = distance + u * 32 + lane + 1;
+      int qx = px + s * dx, qy = py + s * dy;
+      bool inb = in_img(im, qx, qy);
+      bool m = ff_match(im, qx, qy, lo, hi);
+      M[u] = __ballot_sync(0xffffffffu, m);
+      I[u] = __ballot_sync(0xffffffffu, inb);
     }
-    if (lane < painted) px_store(im, qx, qy, 255, 255, 255);
+    int total = 0;
+    bool stop = false;
+#pragma unroll
+    for (int u = 0; u < FF_U; u++) {
+      if (stop) break;
+      int painted = 32;
+      if ((M[u] & I[u]) == 0xffffffffu) {
+        cnt = intensity;
+        if (cnt == 0) painted = 0;   // degenerate intensity 0: stops on the first pixel
+      } else {
+        for (int i = 0; i < 32; i++) {
+          if ((M[u] >> i) & 1u) cnt = intensity; else cnt--;
+          if (cnt == 0 || !((I[u] >> i) & 1u)) { painted = i; break; }
+        }
+      }
+      if (lane < painted) {
+        int s = distance + u * 32 + lane + 1;
+        px_store(im, px + s * dx, py + s * dy, 255, 255, 255);
+      }
+      total += painted;
+      if (painted < 32) stop = true;
+    }
     __syncwarp();
-    distance += painted;
-    if (painted < 32) return distance;
+    distance += total;
+    if (stop) return distance;
   }
 }
 
@@ -98,20 +117,30 @@ __device__ void ff_run(DPage &pg, const DImg &im, int lo, int hi, unsigned long 
     unsigned total = 2u * ((unsigned)top.L + top.T + top.R + top.B);
     bool opened = false;
     while (top.cursor < total) {
-      unsigned idx = top.cursor + lane;
-      int x = 0, y = 0;
-      bool m = false;
-      if (idx < total) { ff_cand(top, idx, x, y); m = in_img(im, x, y) && ff_match(im, x, y, lo, hi); }
-      unsigned M = __ballot_sync(0xffffffffu, m);
-      if (M) {
-        int first = __ffs(M) - 1;
-        top.cursor += first + 1;
-        int fx = __shfl_sync(0xffffffffu, x, first), fy = __shfl_sync(0xffffffffu, y, first);
+      int x[FF_U], y[FF_U];
+      unsigned M[FF_U];
+#pragma unroll
+      for (int u = 0; u < FF_U; u++) {
+        unsigned idx = top.cursor + u * 32 + lane;
+        x[u] = 0; y[u] = 0;
+        bool m = false;
+        if (idx < total) { ff_cand(top, idx, x[u], y[u]); m = in_img(im, x[u], y[u]) && ff_match(im, x[u], y[u], lo, hi); }
+        M[u] = __ballot_sync(0xffffffffu, m);
+      }
+      int hit = -1;
+#pragma unroll
+      for (int u = 0; u < FF_U; u++) if (hit < 0 && M[u]) hit = u;
+      if (hit >= 0) {
+        int first = __ffs(M[hit]) - 1;
+        int fx = 0, fy = 0;
+#pragma unroll
+        for (int u = 0; u < FF_U; u++) if (u == hit) { fx = __shfl_sync(0xffffffffu, x[u], first); fy = __shfl_sync(0xffffffffu, y[u], first); }
+        top.cursor += hit * 32 + first + 1;
         if (!ff_open(pg, im, fx, fy, lo, hi, intensity, lane, sp, top)) { sp = 0; return; }
         opened = true;
         break;
       }
-      top.cursor += 32;
+      top.cursor += 32 * FF_U;
     }
     if (opened) continue;
     sp--;   // frame exhausted: return to the caller's frame
@@ -181,14 +210,24 @@ __global__ void k_bf_scan(DPage *pages, const DBfPos *pos, int npos, int abs_thr
       int sp = 0;
       FFFrame top;
       for (int rb = 0; rb < n;) {
-        int i = rb + lane;
-        int x = x0 + i % w, y = y0 + i / w;
-        bool m = i < n && ff_match(im, x, y, mask_lo, mask_hi);
-        unsigned M = __ballot_sync(0xffffffffu, m);
-        if (!M) { rb += 32; continue; }
-        int first = __ffs(M) - 1;
-        int fx = __shfl_sync(0xffffffffu, x, first), fy = __shfl_sync(0xffffffffu, y, first);
-        rb += first + 1;
+        int x[FF_U], y[FF_U];
+        unsigned M[FF_U];
+#pragma unroll
+        for (int u = 0; u < FF_U; u++) {
+          int i = rb + u * 32 + lane;
+          x[u] = x0 + i % w; y[u] = y0 + i / w;
+          bool m = i < n && ff_match(im, x[u], y[u], mask_lo, mask_hi);
+          M[u] = __ballot_sync(0xffffffffu, m);
+        }
+        int hit = -1;
+#pragma unroll
+        for (int u = 0; u < FF_U; u++) if (hit < 0 && M[u]) hit = u;
+        if (hit < 0) { rb += 32 * FF_U; continue; }
+        int first = __ffs(M[hit]) - 1;
+        int fx = 0, fy = 0;
+#pragma unroll
+        for (int u = 0; u < FF_U; u++) if (u == hit) { fx = __shfl_sync(0xffffffffu, x[u], first); fy = __shfl_sync(0xffffffffu, y[u], first); }
+        rb += hit * 32 + first + 1;
         if (ff_open(pg, im, fx, fy, mask_lo, mask_hi, intensity, lane, sp, top))
           ff_run(pg, im, mask_lo, mask_hi, intensity, lane, sp, top);
         sp = 0;
@@ -253,6 +292,17 @@ __global__ void k_nf_classify(DPage *pages, int intensity, int white, int all_mu
     uint8_t c = 0;
     if (v & 1) {
       bool mut = all_mutable || (v & 2);
+      if (!mut && need <= 9) {
+        // >= need ring-dark pixels in the 3x3 block: all of them touch this
+        // pixel, so its component already has need members
+        int c9 = 0;
+        const uint8_t *t0 = tile + (ly + halo - 1) * tw + (lx + halo - 1);
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+          for (int dx = 0; dx < 3; dx++) c9 += ((t0[dy * tw + dx] & 3) == 1);
+        if (c9 >= need) goto classified;
+      }
       if (!mut) {
         // bounded walk over 8-connected ring-dark pixels outside the band
         short vx[NF_MAXI + 1], vy[NF_MAXI + 1];
@@ -273,6 +323,7 @@ __global__ void k_nf_classify(DPage *pages, int intensity, int white, int all_mu
         }
         mut = n < need;
       }
+    classified:
       c = NF_LIVE | ((v & 4) ? NF_TRIG : 0);
       if (mut) {
         c |= NF_MUT;
