@@ -5,6 +5,8 @@
 #include "common.cuh"
 #include "launch.h"
 
+#define COPY_ROWS 8
+
 // ---- fill ---------------------------------------------------------------
 // One job = one rectangle [x0..x1]x[y0..y1] (empty when inverted), clipped to
 // the image here.  blockIdx.z = job.
@@ -67,6 +69,7 @@ __global__ void k_fill_jobs(const DFillJob *jobs) {
   if (x0 > x1) return;
   int r = j.c[0], g = j.c[1], b = j.c[2];
   int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  if (y0 + (int)blockIdx.y > y1) return;
   if (im.fmt == DF_GRAY8 || im.fmt == DF_RGB24) {
     uint8_t v = (uint8_t)((r + g + b) / 3);
     uint8_t pat[3] = {im.fmt == DF_GRAY8 ? v : (uint8_t)r, im.fmt == DF_GRAY8 ? v : (uint8_t)g, im.fmt == DF_GRAY8 ? v : (uint8_t)b};
@@ -88,21 +91,23 @@ __global__ void k_copy_jobs(const DCopyJob *jobs) {
   int ax0 = max(min(j.area.x0, j.area.x1), 0), ax1 = min(max(j.area.x0, j.area.x1), s.w - 1);
   int ay0 = max(min(j.area.y0, j.area.y1), 0), ay1 = min(max(j.area.y0, j.area.y1), s.h - 1);
   int width = ax1 - ax0 + 1, height = ay1 - ay0 + 1;
-  int sy = ay0 + blockIdx.y;
-  if (sy > ay1 || width <= 0) return;
-  int ty = j.ty + blockIdx.y;
+  if (width <= 0 || height <= 0) return;
   int bpp = bytes_pp(s.fmt);
-  bool raw = s.fmt == d.fmt && bpp > 0 && height > 0 && j.tx >= 0 && j.ty >= 0 &&
+  bool raw = s.fmt == d.fmt && bpp > 0 && j.tx >= 0 && j.ty >= 0 &&
              j.tx + width <= d.w && j.ty + height <= d.h;
-  if (raw) {
-    const uint8_t *sp = s.data + (size_t)sy * s.pitch + (size_t)ax0 * bpp;
-    uint8_t *dp = d.data + (size_t)ty * d.pitch + (size_t)j.tx * bpp;
-    copy_run(dp, sp, width * bpp, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
-    return;
-  }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < width; i += gridDim.x * blockDim.x) {
-    Px p = px_load(s, ax0 + i, sy);
-    px_set(d, j.tx + i, ty, p.r, p.g, p.b);
+  // one block per COPY_ROWS rows; all its threads stride across each row
+  for (int r = blockIdx.y * COPY_ROWS; r < min(height, (int)(blockIdx.y + 1) * COPY_ROWS); r++) {
+    int sy = ay0 + r, ty = j.ty + r;
+    if (raw) {
+      const uint8_t *sp = s.data + (size_t)sy * s.pitch + (size_t)ax0 * bpp;
+      uint8_t *dp = d.data + (size_t)ty * d.pitch + (size_t)j.tx * bpp;
+      copy_run(dp, sp, width * bpp, threadIdx.x, blockDim.x);
+    } else {
+      for (int i = threadIdx.x; i < width; i += blockDim.x) {
+        Px p = px_load(s, ax0 + i, sy);
+        px_set(d, j.tx + i, ty, p.r, p.g, p.b);
+      }
+    }
   }
 }
 
@@ -111,12 +116,35 @@ __global__ void k_apply_masks(const DMaskJob *jobs) {
   const DMaskJob &j = jobs[blockIdx.z];
   if (!j.enabled || j.nrects <= 0) return;
   const DImg &im = j.img;
-  int y = blockIdx.y;
-  if (y >= im.h) return;
-  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < im.w; x += gridDim.x * blockDim.x) {
-    bool inside = false;
-    for (int k = 0; k < j.nrects && !inside; k++) inside = pt_in_rect(x, y, j.rects[k]);
-    if (!inside) px_store(im, x, y, j.c[0], j.c[1], j.c[2]);
+  bool bytes = im.fmt == DF_GRAY8 || im.fmt == DF_RGB24;
+  int bpp = im.fmt == DF_RGB24 ? 3 : 1;
+  uint8_t gv = (uint8_t)((j.c[0] + j.c[1] + j.c[2]) / 3);
+  uint8_t pat[3] = {im.fmt == DF_GRAY8 ? gv : j.c[0], im.fmt == DF_GRAY8 ? gv : j.c[1], im.fmt == DF_GRAY8 ? gv : j.c[2]};
+  const int SPAN = 64;
+  int nspan = (im.w + SPAN - 1) / SPAN;
+  for (int y = blockIdx.y; y < im.h; y += gridDim.y) {
+    for (int sp = threadIdx.x; sp < nspan; sp += blockDim.x) {
+      int xa = sp * SPAN, xb = min(xa + SPAN, im.w) - 1;
+      // classify the span against every rectangle (normalised like point_in_rectangle)
+      bool inside_one = false, touches = false;
+      for (int k = 0; k < j.nrects; k++) {
+        DRect r = j.rects[k];
+        int ax = min(r.x0, r.x1), bx = max(r.x0, r.x1), ay = min(r.y0, r.y1), by = max(r.y0, r.y1);
+        if (y < ay || y > by || xb < ax || xa > bx) continue;
+        touches = true;
+        if (xa >= ax && xb <= bx) { inside_one = true; break; }
+      }
+      if (inside_one) continue;
+      if (!touches && bytes) {
+        fill_run(im.data + (size_t)y * im.pitch + (size_t)xa * bpp, (xb - xa + 1) * bpp, pat, 0, 0, 1);
+        continue;
+      }
+      for (int x = xa; x <= xb; x++) {
+        bool inside = false;
+        for (int k = 0; k < j.nrects && !inside; k++) inside = pt_in_rect(x, y, j.rects[k]);
+        if (!inside) px_store(im, x, y, j.c[0], j.c[1], j.c[2]);
+      }
+    }
   }
 }
 
@@ -153,18 +181,20 @@ static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 extern "C" {
 void b200k_fill_jobs(cudaStream_t st, const DFillJob *jobs, int njobs, int maxw, int maxh) {
   if (njobs <= 0 || maxw <= 0 || maxh <= 0) return;
-  dim3 g(min(cdiv(maxw * 3, 128 * 16), 8u), min((unsigned)maxh, 2048u), njobs);
-  k_fill_jobs<<<g, 128, 0, st>>>(jobs);
+  // one 256-thread block covers a row (16 B per thread per step); ~8 rows per block
+  dim3 g(1, min(cdiv((unsigned)maxh, 8u), 1024u), njobs);
+  k_fill_jobs<<<g, 256, 0, st>>>(jobs);
 }
 void b200k_copy_jobs(cudaStream_t st, const DCopyJob *jobs, int njobs, int maxw_bytes, int maxh) {
   if (njobs <= 0 || maxw_bytes <= 0 || maxh <= 0) return;
-  dim3 g(min(cdiv(maxw_bytes, 128 * 16), 8u), maxh, njobs);
-  k_copy_jobs<<<g, 128, 0, st>>>(jobs);
+  (void)maxw_bytes;
+  dim3 g(1, cdiv(maxh, COPY_ROWS), njobs);
+  k_copy_jobs<<<g, 256, 0, st>>>(jobs);
 }
 void b200k_apply_masks(cudaStream_t st, const DMaskJob *jobs, int njobs, int maxw, int maxh) {
   if (njobs <= 0 || maxw <= 0 || maxh <= 0) return;
-  dim3 g(min(cdiv(maxw, 256), 64u), maxh, njobs);
-  k_apply_masks<<<g, 256, 0, st>>>(jobs);
+  dim3 g(1, min(cdiv((unsigned)maxh, 4u), 1024u), njobs);
+  k_apply_masks<<<g, 64, 0, st>>>(jobs);
 }
 void b200k_mirror(cudaStream_t st, DImg im, int dir_h, int dir_v) {
   if (im.w <= 0 || im.h <= 0) return;

@@ -12,6 +12,7 @@
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
 #define ROT_CHUNK 32
+#define ROT_ROWS 16
 
 struct RotParams {
   int scan_size;        // params.deskewScanSize (may be -1)
@@ -185,6 +186,16 @@ __device__ __forceinline__ int cubic_scale(float f, int a, int b, int c, int d) 
   int result = (int)(b + 0.5f * f * (c - a + f * (2.0f * a - 5.0f * b + 4.0f * c - d + f * (3.0f * (b - c) + d - a))));
   return clip_u8(result);
 }
+
+// exact uint8/small-int -> float without the (slow) conversion pipe: 2^23 + b has b in its mantissa
+__device__ __forceinline__ float u8f(unsigned b) { return __int_as_float(0x4B000000u | b) - 8388608.0f; }
+// cubic_scale on operands that are already floats holding the same integers:
+// (float)(c - a) == fc - fa and (float)(b - c) == fb - fc exactly, so every
+// rounding step of interpolate.c:24-32 is reproduced
+__device__ __forceinline__ unsigned cubic_scale_f(float f, float a, float b, float c, float d) {
+  int result = __float2int_rz(b + 0.5f * f * ((c - a) + f * (2.0f * a - 5.0f * b + 4.0f * c - d + f * (3.0f * (b - c) + d - a))));
+  return (unsigned)clip_u8(result);
+}
 __device__ __forceinline__ int linear_scale(float x, int a, int b) {   // interpolate.c:62-64
   return (int)(uint8_t)(int)((1.0f - x) * a + x * b);
 }
@@ -251,8 +262,6 @@ __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) 
   }
   if (!active) return;
   const DImg &im = pg.img;
-  int y = blockIdx.y;
-  if (y >= h) return;
   // center_of_rectangle (primitives.c:136-145) of the (normalised) mask / target
   int nx0 = min(mask.x0, mask.x1), ny0 = min(mask.y0, mask.y1);
   float scx = nx0 + w / 2.0f, scy = ny0 + h / 2.0f;
@@ -260,34 +269,43 @@ __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) 
   float sinval = pg.rot_sin[mi], cosval = pg.rot_cos[mi];
   bool gray = im.fmt != DF_RGB24;
   bool fast = im.fmt == DF_GRAY8 && interp == 2;
+  bool pitch4 = ((im.pitch & 3) == 0);
+  // a block owns ROT_ROWS consecutive target rows x 128 columns (one block per
+  // row would be launch-bound: ~70 k blocks per A4 page)
+  for (int y = blockIdx.y * ROT_ROWS; y < min(h, (int)(blockIdx.y + 1) * ROT_ROWS); y++) {
   uint8_t *orow = aux.data + (size_t)y * aux.pitch;
   for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) {
     float srcX = scx + (x - tcx) * cosval + (y - tcy) * sinval;
     float srcY = scy + (y - tcy) * cosval - (x - tcx) * sinval;
     if (fast) {
       int px = (int)srcX, py = (int)srcY;
-      if (px >= 1 && py >= 1 && px + 2 < im.w && py + 2 < im.h) {
+      if ((unsigned)(px - 1) < (unsigned)(im.w - 3) && (unsigned)(py - 1) < (unsigned)(im.h - 3)) {
         // the 4x4 taps as four packed words (two aligned loads + funnel shift per row)
         const uint8_t *p0 = im.data + (size_t)(py - 1) * im.pitch + (px - 1);
         unsigned rw[4];
+        if (pitch4) {   // rows share their alignment
+          const unsigned *wp = (const unsigned *)((uintptr_t)p0 & ~(uintptr_t)3);
+          unsigned sh = ((unsigned)(uintptr_t)p0 & 3u) * 8u;
+          int wpitch = im.pitch >> 2;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const uint8_t *pr = p0 + (size_t)i * im.pitch;
-          const unsigned *wp = (const unsigned *)((uintptr_t)pr & ~(uintptr_t)3);
-          unsigned sh = ((unsigned)(uintptr_t)pr & 3u) * 8u;
-          rw[i] = sh ? __funnelshift_r(wp[0], wp[1], sh) : wp[0];
-        }
-        unsigned v0 = rw[0] & 0xFFu;
-        int o;
-        if (rw[0] == v0 * 0x01010101u && rw[1] == rw[0] && rw[2] == rw[0] && rw[3] == rw[0]) {
-          o = (int)v0;   // all 16 taps equal: every cubic term cancels exactly
+          for (int i = 0; i < 4; i++) rw[i] = __funnelshift_r(wp[i * wpitch], wp[i * wpitch + 1], sh);
         } else {
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const uint8_t *pr = p0 + (size_t)i * im.pitch;
+            const unsigned *wp = (const unsigned *)((uintptr_t)pr & ~(uintptr_t)3);
+            rw[i] = __funnelshift_r(wp[0], wp[1], ((unsigned)(uintptr_t)pr & 3u) * 8u);
+          }
+        }
+        unsigned o = rw[0] & 0xFFu;
+        // all 16 taps equal: every cubic term cancels exactly and the result is that value
+        if (!(rw[0] == o * 0x01010101u && rw[1] == rw[0] && rw[2] == rw[0] && rw[3] == rw[0])) {
           float fx = srcX - px, fy = srcY - py;
-          int r4[4];
+          float r4[4];
 #pragma unroll
           for (int i = 0; i < 4; i++)
-            r4[i] = cubic_scale(fx, (int)(rw[i] & 0xFF), (int)((rw[i] >> 8) & 0xFF), (int)((rw[i] >> 16) & 0xFF), (int)(rw[i] >> 24));
-          o = cubic_scale(fy, r4[0], r4[1], r4[2], r4[3]);
+            r4[i] = u8f(cubic_scale_f(fx, u8f(rw[i] & 0xFFu), u8f((rw[i] >> 8) & 0xFFu), u8f((rw[i] >> 16) & 0xFFu), u8f(rw[i] >> 24)));
+          o = cubic_scale_f(fy, r4[0], r4[1], r4[2], r4[3]);
         }
         orow[x] = (uint8_t)o;
         continue;
@@ -295,6 +313,7 @@ __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) 
     }
     Px o = interp_any(im, srcX, srcY, interp, gray);
     px_store(aux, x, y, o.r, o.g, o.b);
+  }
   }
 }
 
@@ -336,7 +355,7 @@ void b200k_rot_finalize(cudaStream_t st, DPage *pages, int npages, const float *
 void b200k_rotate(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int maxw, int maxh,
                   DCopyJob *back_jobs) {
   if (npages <= 0 || maxw <= 0 || maxh <= 0) return;
-  dim3 g(min(cdiv(maxw, 128), 64u), maxh, npages);
+  dim3 g(min(cdiv(maxw, 128), 64u), cdiv(maxh, ROT_ROWS), npages);
   k_rotate<<<g, 128, 0, st>>>(pages, mi, interp, back_jobs);
 }
 void b200k_stretch(cudaStream_t st, DImg src, DImg dst, float hr, float vr, int interp) {

@@ -21,8 +21,19 @@ static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
  * including fill_line's overruns — matches the CPU order-dependent result.
  * ====================================================================== */
 
+// The flood fill is one warp of serial work: code size matters more than
+// inlining (the fully inlined kernel was ~22 k SASS instructions and ran out of
+// the instruction caches), so pixel access goes through two small calls.
+__device__ __noinline__ int ff_gray_at(const DImg &im, int x, int y) {
+  if (im.fmt == DF_GRAY8) return in_img(im, x, y) ? (int)im.data[(size_t)y * im.pitch + x] : 255;
+  return px_gray(px_get(im, x, y));
+}
+__device__ __noinline__ void ff_paint(const DImg &im, int x, int y) {
+  if (im.fmt == DF_GRAY8) { im.data[(size_t)y * im.pitch + x] = 255; return; }
+  px_store(im, x, y, 255, 255, 255);
+}
 __device__ __forceinline__ bool ff_match(const DImg &im, int x, int y, int lo, int hi) {
-  int g = px_gray(px_get(im, x, y));
+  int g = ff_gray_at(im, x, y);
   return g >= lo && g <= hi;
 }
 
@@ -30,7 +41,7 @@ __device__ __forceinline__ bool ff_match(const DImg &im, int x, int y, int lo, i
 // chunks of 32 pixels are fetched per round so that the (latency-bound) walk
 // along a column keeps several loads in flight.
 #define FF_U 4
-__device__ int ff_fill_line(const DImg &im, int px, int py, int dx, int dy, int lo, int hi,
+__device__ __noinline__ int ff_fill_line(const DImg &im, int px, int py, int dx, int dy, int lo, int hi,
                             unsigned long long intensity, int lane) {
   int distance = 0;
   unsigned long long cnt = 1;
@@ -62,7 +73,7 @@ __device__ int ff_fill_line(const DImg &im, int px, int py, int dx, int dy, int 
       }
       if (lane < painted) {
         int s = distance + u * 32 + lane + 1;
-        px_store(im, px + s * dx, py + s * dy, 255, 255, 255);
+        ff_paint(im, px + s * dx, py + s * dy);
       }
       total += painted;
       if (painted < 32) stop = true;
@@ -88,7 +99,7 @@ __device__ __forceinline__ void ff_cand(const FFFrame &f, unsigned idx, int &x, 
 }
 
 // flood_fill(p) for a p that is known to match: paint the cross and push.
-__device__ bool ff_open(DPage &pg, const DImg &im, int x, int y, int lo, int hi,
+__device__ __noinline__ bool ff_open(DPage &pg, const DImg &im, int x, int y, int lo, int hi,
                         unsigned long long intensity, int lane, int &sp, FFFrame &top) {
   if (sp >= pg.stack_cap) { if (lane == 0) atomicOr(&pg.error, DERR_STACK_OVERFLOW); return false; }
   if (sp > 0 && lane == 0) {   // spill the current top
@@ -98,7 +109,7 @@ __device__ bool ff_open(DPage &pg, const DImg &im, int x, int y, int lo, int hi,
     s[2] = (unsigned long long)(unsigned)top.R | ((unsigned long long)(unsigned)top.B << 32);
     s[3] = top.cursor;
   }
-  if (lane == 0) px_store(im, x, y, 255, 255, 255);
+  if (lane == 0) ff_paint(im, x, y);
   __syncwarp();
   top.cx = x; top.cy = y;
   top.L = ff_fill_line(im, x, y, -1, 0, lo, hi, intensity, lane);
@@ -111,7 +122,7 @@ __device__ bool ff_open(DPage &pg, const DImg &im, int x, int y, int lo, int hi,
 }
 
 // Runs the recursion to completion starting from an already-open frame.
-__device__ void ff_run(DPage &pg, const DImg &im, int lo, int hi, unsigned long long intensity,
+__device__ __noinline__ void ff_run(DPage &pg, const DImg &im, int lo, int hi, unsigned long long intensity,
                        int lane, int &sp, FFFrame &top) {
   while (sp > 0) {
     unsigned total = 2u * ((unsigned)top.L + top.T + top.R + top.B);
@@ -155,7 +166,7 @@ __device__ void ff_run(DPage &pg, const DImg &im, int lo, int hi, unsigned long 
   }
 }
 
-__device__ unsigned long long warp_rect_maxch_sum(const DImg &im, int x0, int y0, int x1, int y1, int lane) {
+__device__ __noinline__ unsigned long long warp_rect_maxch_sum(const DImg &im, int x0, int y0, int x1, int y1, int lane) {
   unsigned long long s = 0;
   if (x0 <= x1 && y0 <= y1) {
     int w = x1 - x0 + 1, n = w * (y1 - y0 + 1);
@@ -264,6 +275,32 @@ __global__ void k_bf_scan(DPage *pages, const DBfPos *pos, int npos, int abs_thr
 #define NF_TH 16
 #define NF_MAXI 15
 
+// Bounded walk over 8-connected ring-dark, out-of-band pixels ((code & 3) == 1) of
+// a shared-memory tile: true when fewer than `need` pixels are reachable from
+// (tx, ty).  Kept out of line: inlined and unrolled it dwarfs the kernels.
+__device__ __noinline__ bool nf_small_component(const uint8_t *tile, int tw, int th, int tx, int ty, int need) {
+  short vx[NF_MAXI + 1], vy[NF_MAXI + 1];
+  int n = 1, head = 0;
+  vx[0] = (short)tx; vy[0] = (short)ty;
+  while (head < n && n < need) {
+    int cx = vx[head], cy = vy[head]; head++;
+#pragma unroll 1
+    for (int dy = -1; dy <= 1 && n < need; dy++)
+#pragma unroll 1
+      for (int dx = -1; dx <= 1 && n < need; dx++) {
+        if (!dx && !dy) continue;
+        int nx = cx + dx, ny = cy + dy;
+        if (nx < 0 || ny < 0 || nx >= tw || ny >= th) continue;
+        if ((tile[ny * tw + nx] & 3) != 1) continue;
+        bool seen = false;
+#pragma unroll 1
+        for (int k = 0; k < n; k++) seen |= (vx[k] == nx && vy[k] == ny);
+        if (!seen) { vx[n] = (short)nx; vy[n] = (short)ny; n++; }
+      }
+  }
+  return n < need;
+}
+
 __global__ void k_nf_classify(DPage *pages, int intensity, int white, int all_mutable) {
   extern __shared__ uint8_t tile[];
   DPage &pg = pages[blockIdx.z];
@@ -303,26 +340,7 @@ __global__ void k_nf_classify(DPage *pages, int intensity, int white, int all_mu
           for (int dx = 0; dx < 3; dx++) c9 += ((t0[dy * tw + dx] & 3) == 1);
         if (c9 >= need) goto classified;
       }
-      if (!mut) {
-        // bounded walk over 8-connected ring-dark pixels outside the band
-        short vx[NF_MAXI + 1], vy[NF_MAXI + 1];
-        int n = 1, head = 0;
-        vx[0] = (short)(lx + halo); vy[0] = (short)(ly + halo);
-        while (head < n && n < need) {
-          int cx = vx[head], cy = vy[head]; head++;
-          for (int dy = -1; dy <= 1 && n < need; dy++)
-            for (int dx = -1; dx <= 1 && n < need; dx++) {
-              if (!dx && !dy) continue;
-              int nx = cx + dx, ny = cy + dy;
-              if (nx < 0 || ny < 0 || nx >= tw || ny >= th) continue;
-              if ((tile[ny * tw + nx] & 3) != 1) continue;
-              bool seen = false;
-              for (int k = 0; k < n; k++) seen |= (vx[k] == nx && vy[k] == ny);
-              if (!seen) { vx[n] = (short)nx; vy[n] = (short)ny; n++; }
-            }
-        }
-        mut = n < need;
-      }
+      if (!mut) mut = nf_small_component(tile, tw, th, lx + halo, ly + halo, need);
     classified:
       c = NF_LIVE | ((v & 4) ? NF_TRIG : 0);
       if (mut) {
@@ -337,6 +355,86 @@ __global__ void k_nf_classify(DPage *pages, int intensity, int white, int all_mu
     }
     pg.cls[(size_t)y * im.w + x] = c;
   }
+}
+
+// GRAY8 specialisation (intensity <= 7): 4 pixels per 32-bit load, tile x-halo
+// fixed at 8 so that every tile word is 4-byte aligned, 4 classes per store.
+#define NF_G8_HX 8
+#define NF_G8_TWB (NF_TW + 2 * NF_G8_HX)
+__global__ void k_nf_classify_g8(DPage *pages, int intensity, int white) {
+  extern __shared__ uint8_t tile[];
+  DPage &pg = pages[blockIdx.z];
+  const DImg &im = pg.img;
+  int halo = intensity + 1;
+  int th = NF_TH + 2 * halo;
+  int bx = blockIdx.x * NF_TW, by = blockIdx.y * NF_TH;
+  if (bx >= im.w || by >= im.h) return;
+  int band = 2 * intensity;
+  bool aligned = ((im.pitch & 3) == 0) && (((uintptr_t)im.data & 3) == 0);
+  const int WPR = NF_G8_TWB / 4;
+  for (int i = threadIdx.x; i < WPR * th; i += blockDim.x) {
+    int r = i / WPR, c = i % WPR;
+    int y = by - halo + r, x = bx - NF_G8_HX + 4 * c;
+    unsigned codes = 0;
+    if (y >= 0 && y < im.h && x + 3 >= 0 && x < im.w) {
+      const uint8_t *rp = im.data + (size_t)y * im.pitch;
+      unsigned v;
+      if (aligned && x >= 0 && x + 3 < im.w) v = *(const unsigned *)(rp + x);
+      else {
+        v = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (x + k >= 0 && x + k < im.w) v = (v & ~(0xFFu << (8 * k))) | ((unsigned)rp[x + k] << (8 * k));
+      }
+      bool yb = y < band;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        unsigned b = (v >> (8 * k)) & 0xFFu;
+        bool ok = x + k >= 0 && x + k < im.w && (int)b < white;
+        unsigned code = ok ? (5u | ((yb || x + k < band) ? 2u : 0u)) : 0u;
+        codes |= code << (8 * k);
+      }
+    }
+    ((unsigned *)tile)[i] = codes;
+  }
+  __syncthreads();
+  int need = intensity + 1;
+  int t = threadIdx.x;
+  int ly = t / (NF_TW / 4), lx0 = 4 * (t % (NF_TW / 4));
+  int y = by + ly;
+  if (y >= im.h) return;
+  unsigned out = 0;
+  const int tw = NF_G8_TWB;
+#pragma unroll 1
+  for (int q = 0; q < 4; q++) {
+    int lx = lx0 + q, x = bx + lx;
+    if (x >= im.w) break;
+    int tx = lx + NF_G8_HX, ty = ly + halo;
+    uint8_t v = tile[ty * tw + tx];
+    uint8_t c = 0;
+    if (v & 1) {
+      bool mut = (v & 2) != 0;
+      if (!mut) {
+        int c9 = 0;
+        const uint8_t *t0 = tile + (ty - 1) * tw + (tx - 1);
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+          for (int dx = 0; dx < 3; dx++) c9 += ((t0[dy * tw + dx] & 3) == 1);
+        if (c9 < need) mut = nf_small_component(tile, tw, th, tx, ty, need);
+      }
+      c = NF_LIVE | NF_TRIG;
+      if (mut) {
+        c |= NF_MUT | NF_UNDEC;
+        unsigned idx = atomicAdd(&pg.list_n, 1u);
+        if (idx < (unsigned)pg.list_cap) pg.list[idx] = ((unsigned)y << 16) | (unsigned)x;
+        else atomicOr(&pg.error, DERR_LIST_OVERFLOW);
+      }
+    }
+    out |= (unsigned)c << (8 * q);
+  }
+  size_t o = (size_t)y * im.w + bx + lx0;
+  if ((im.w & 3) == 0 && bx + lx0 + 3 < im.w && ((uintptr_t)pg.cls & 3) == 0) *(unsigned *)(pg.cls + o) = out;
+  else for (int q = 0; q < 4 && bx + lx0 + q < im.w; q++) pg.cls[o + q] = (uint8_t)(out >> (8 * q));
 }
 
 __device__ __forceinline__ bool nf_live(const uint8_t *cls, int w, int h, int x, int y) {
@@ -498,39 +596,67 @@ struct GrayParams {
   int off;
 };
 
-__global__ void k_gray_cascade(DPage *pages, GrayParams gp) {
-  DPage &pg = pages[blockIdx.x];
+// Per window, before the cascade: a window with a dark pixel is never wiped, and
+// wiping a window whose cells are all pure white changes nothing; only the rest
+// ("live" windows) can alter the sheet.  Marks them and the wavefronts that hold one.
+__global__ void k_gray_windows(DPage *pages, GrayParams gp, int white_off, int wflag_off, int wave_off) {
+  DPage &pg = pages[blockIdx.y];
   const DImg &im = pg.img;
   int nc = gp.ncx * gp.ncy;
   const unsigned *dark = pg.u32 + gp.off;
+  const unsigned *white = pg.u32 + white_off;
+  unsigned *wflag = pg.u32 + wflag_off;
+  unsigned *wave = pg.u32 + wave_off;
+  int nw = gp.nwx * gp.nwy;
+  for (int wi = blockIdx.x * blockDim.x + threadIdx.x; wi < nw; wi += gridDim.x * blockDim.x) {
+    int i = wi / gp.nwx, j = wi % gp.nwx;
+    int x0 = j * gp.step_h, y0 = i * gp.step_v;
+    int x1 = x0 + gp.size_w - 1, y1 = y0 + gp.size_h - 1;
+    int x0c = max(x0, 0), x1c = min(x1, im.w - 1), y0c = max(y0, 0), y1c = min(y1, im.h - 1);
+    bool inside = x0c <= x1c && y0c <= y1c;
+    unsigned long long d = 0;
+    bool allwhite = true;
+    int cx0 = j * gp.scx, cy0 = i * gp.scy;
+    for (int cy = cy0; cy < cy0 + gp.wcy; cy++)
+      for (int cx = cx0; cx < cx0 + gp.wcx; cx++) {
+        d += dark[cy * gp.ncx + cx];
+        allwhite = allwhite && white[cy * gp.ncx + cx];
+      }
+    long long area_in = inside ? (long long)(x1c - x0c + 1) * (y1c - y0c + 1) : 0;
+    if (gp.oob_dark) d += (unsigned long long)((long long)gp.size_w * gp.size_h - area_in);
+    // Y400A: a wipe also rewrites alpha, so an all-white window is not a no-op there
+    if (im.fmt == DF_Y400A) allwhite = false;
+    unsigned live = (d == 0 && !allwhite && inside) ? 1u : 0u;
+    wflag[wi] = live;
+    if (live) wave[j + gp.skew * i] = 1u;
+  }
+  (void)nc;
+}
+
+__global__ void k_gray_cascade(DPage *pages, GrayParams gp, int wflag_off, int wave_off) {
+  DPage &pg = pages[blockIdx.x];
+  const DImg &im = pg.img;
+  int nc = gp.ncx * gp.ncy;
   unsigned *light = pg.u32 + gp.off + nc;
   unsigned *wiped = pg.u32 + gp.off + 2 * nc;
-  for (int i = threadIdx.x; i < nc; i += blockDim.x) wiped[i] = 0;
-  __syncthreads();
+  const unsigned *wflag = pg.u32 + wflag_off;
+  const unsigned *wave = pg.u32 + wave_off;
   int nwave = gp.nwx + gp.skew * (gp.nwy - 1);
   for (int t = 0; t < nwave; t++) {
+    if (!wave[t]) continue;   // block-uniform: no live window on this wavefront
     for (int i = threadIdx.x; i < gp.nwy; i += blockDim.x) {
       int j = t - gp.skew * i;
-      if (j < 0 || j >= gp.nwx) continue;
+      if (j < 0 || j >= gp.nwx || !wflag[i * gp.nwx + j]) continue;
       int x0 = j * gp.step_h, y0 = i * gp.step_v;
       int x1 = x0 + gp.size_w - 1, y1 = y0 + gp.size_h - 1;
       int x0c = max(x0, 0), x1c = min(x1, im.w - 1), y0c = max(y0, 0), y1c = min(y1, im.h - 1);
-      bool inside = x0c <= x1c && y0c <= y1c;
-      unsigned long long d = 0, l = 0;
+      unsigned long long l = 0;
       int cx0 = j * gp.scx, cy0 = i * gp.scy;
       for (int cy = cy0; cy < cy0 + gp.wcy; cy++)
-        for (int cx = cx0; cx < cx0 + gp.wcx; cx++) {
-          d += dark[cy * gp.ncx + cx];
-          l += light[cy * gp.ncx + cx];
-        }
-      long long area_in = inside ? (long long)(x1c - x0c + 1) * (y1c - y0c + 1) : 0;
-      if (gp.oob_dark) d += (unsigned long long)((long long)gp.size_w * gp.size_h - area_in);
-      if (d != 0) continue;
-      // inverse_lightness_rect (blit.c:111-126): clipped count with abs(); an
-      // inverted clip scans nothing and yields 255
+        for (int cx = cx0; cx < cx0 + gp.wcx; cx++) l += light[cy * gp.ncx + cx];
+      // inverse_lightness_rect (blit.c:111-126) on the clipped window (live windows intersect the image)
       unsigned long long cnt = (unsigned long long)(abs(x0c - x1c) + 1) * (unsigned long long)(abs(y0c - y1c) + 1);
-      unsigned long long sum = inside ? l : 0;
-      int lightness = (int)(uint8_t)(0xFF - (sum / cnt));
+      int lightness = (int)(uint8_t)(0xFF - (l / cnt));
       if (lightness < gp.abs_threshold) {
         for (int cy = cy0; cy < cy0 + gp.wcy; cy++)
           for (int cx = cx0; cx < cx0 + gp.wcx; cx++) {
@@ -542,6 +668,13 @@ __global__ void k_gray_cascade(DPage *pages, GrayParams gp) {
       }
     }
     __syncthreads();
+  }
+}
+
+__global__ void k_zero_range(DPage *pages, int off_a, int na, int off_b, int nb) {
+  unsigned *u = pages[blockIdx.y].u32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += gridDim.x * blockDim.x) {
+    if (i < na) u[off_a + i] = 0u; else u[off_b + (i - na)] = 0u;
   }
 }
 
@@ -584,7 +717,7 @@ void b200k_bf_scan(cudaStream_t st, DPage *pages, int npages, const DBfPos *pos_
                                   mask_lo, mask_hi, flag_off);
 }
 
-int b200k_noisefilter(cudaStream_t st, DPage *pages, int npages, int maxw, int maxh,
+int b200k_noisefilter(cudaStream_t st, DPage *pages, int npages, int maxw, int maxh, int fmt,
                       unsigned long long intensity, int white) {
   if (npages <= 0 || intensity == 0) return 0;
   if (intensity > 4000) return -1;
@@ -593,7 +726,11 @@ int b200k_noisefilter(cudaStream_t st, DPage *pages, int npages, int maxw, int m
   int halo = all_mut ? 0 : I + 1;
   size_t sm = (size_t)(NF_TW + 2 * halo) * (NF_TH + 2 * halo);
   dim3 g(cdiv(maxw, NF_TW), cdiv(maxh, NF_TH), npages);
-  k_nf_classify<<<g, 256, sm, st>>>(pages, I, white, all_mut);
+  if (fmt == DF_GRAY8 && I <= 7) {
+    size_t smg = (size_t)NF_G8_TWB * (NF_TH + 2 * (I + 1));
+    k_nf_classify_g8<<<g, 256, smg, st>>>(pages, I, white);
+  } else
+    k_nf_classify<<<g, 256, sm, st>>>(pages, I, white, all_mut);
   k_nf_resolve<<<npages, 256, 0, st>>>(pages, I);
   return 0;
 }
@@ -617,9 +754,14 @@ void b200k_gray_cascade(cudaStream_t st, DPage *pages, int npages, const int *gp
   gp.size_w = gpi[11]; gp.size_h = gpi[12]; gp.step_h = gpi[13]; gp.step_v = gpi[14];
   gp.abs_threshold = gpi[15]; gp.oob_dark = gpi[16]; gp.off = gpi[17];
   int nc = gp.ncx * gp.ncy;
+  int nw = gp.nwx * gp.nwy, nwave = gp.nwx + gp.skew * (gp.nwy - 1);
+  int wflag_off = white_off + nc, wave_off = wflag_off + nw;
   dim3 g1(min(cdiv(nc, 256), 128u), npages);
   k_gray_prewhite<<<g1, 256, 0, st>>>(pages, gp, white_off);
-  k_gray_cascade<<<npages, 256, 0, st>>>(pages, gp);
+  // clear wiped[] and the wavefront marks, then classify windows
+  k_zero_range<<<dim3(min(cdiv(nc + nwave, 256), 128u), npages), 256, 0, st>>>(pages, gp.off + 2 * nc, nc, wave_off, nwave);
+  k_gray_windows<<<dim3(min(cdiv(nw, 128), 256u), npages), 128, 0, st>>>(pages, gp, white_off, wflag_off, wave_off);
+  k_gray_cascade<<<npages, 256, 0, st>>>(pages, gp, wflag_off, wave_off);
   dim3 g2(gp.ncy, npages);
   k_gray_wipe<<<g2, 256, 0, st>>>(pages, gp, white_off);
 }

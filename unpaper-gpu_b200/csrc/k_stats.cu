@@ -18,6 +18,32 @@ __device__ __forceinline__ unsigned stat_of(Px p, int stat, int lo, int hi) {
   return (g >= lo && g <= hi) ? 1u : 0u;
 }
 
+
+// ---- GRAY8 helpers: four pixels per 32-bit word ---------------------------------
+__device__ __forceinline__ unsigned sum4(unsigned w) { return __vsadu4(w, 0u); }          // b0+b1+b2+b3
+// number of bytes of w that lie in [lo, hi] (0 <= lo <= hi <= 255)
+__device__ __forceinline__ unsigned count4_range(unsigned w, unsigned lo4, unsigned hi4) {
+  unsigned ge = __vcmpgeu4(w, lo4), le = __vcmpleu4(w, hi4);
+  return (unsigned)__popc(ge & le) >> 3;
+}
+// Applies f(word, nvalid_mask) over the bytes [p, p+n): aligned 32-bit loads,
+// `keep` has 0xFF in the byte lanes that belong to the run.
+template <typename F>
+__device__ __forceinline__ void for_words(const uint8_t *p, int n, int lane, int nlanes, F f) {
+  if (n <= 0) return;
+  uintptr_t a = (uintptr_t)p;
+  const unsigned *w0 = (const unsigned *)(a & ~(uintptr_t)3);
+  int lead = (int)(a & 3);                  // bytes of the first word that precede the run
+  int nw = (lead + n + 3) >> 2;
+  for (int i = lane; i < nw; i += nlanes) {
+    unsigned keep = 0xFFFFFFFFu;
+    if (i == 0 && lead) keep &= 0xFFFFFFFFu << (8 * lead);
+    int end = lead + n - 4 * i;             // valid bytes of this word counted from its start
+    if (end < 4) keep &= 0xFFFFFFFFu >> (8 * (4 - end));
+    f(w0[i], keep);
+  }
+}
+
 __global__ void k_zero_u32(DPage *pages, int off, int n) {
   unsigned *p = pages[blockIdx.y].u32 + off;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0u;
@@ -55,7 +81,22 @@ __global__ void k_linesum_rows(DPage *pages, const DLineJob *jobs, int njobs, in
   int y = j.ya + blockIdx.y * (blockDim.x >> 5) + warp;
   if (y > j.yb) return;
   unsigned acc = 0;
-  for (int x = j.xa + lane; x <= j.xb; x += 32) acc += stat_of(px_load(im, x, y), stat, lo, hi);
+  if (im.fmt == DF_GRAY8) {
+    const uint8_t *row = im.data + (size_t)y * im.pitch + j.xa;
+    int n = j.xb - j.xa + 1;
+    if (stat == ST_COUNT_GRAY_RANGE) {
+      unsigned lo4 = (unsigned)lo * 0x01010101u, hi4 = (unsigned)hi * 0x01010101u;
+      // bytes outside the run are forced to a value outside [lo,hi] when one exists; otherwise subtracted
+      for_words(row, n, lane, 32, [&](unsigned w, unsigned keep) {
+        unsigned c = __vcmpgeu4(w, lo4) & __vcmpleu4(w, hi4) & keep;
+        acc += (unsigned)__popc(c) >> 3;
+      });
+    } else {
+      for_words(row, n, lane, 32, [&](unsigned w, unsigned keep) { acc += sum4(w & keep); });
+    }
+  } else {
+    for (int x = j.xa + lane; x <= j.xb; x += 32) acc += stat_of(px_load(im, x, y), stat, lo, hi);
+  }
   acc = warp_sum_u32(acc);
   if (lane == 0) pages[page].u32[j.out_off + (y - j.ya)] = acc;
 }
@@ -77,11 +118,19 @@ __global__ void k_rect_count(DPage *pages, const DRect *rects, int nrects, int l
   if (x0 <= x1 && y0 <= y1 && total > 0) {
     inside = (long long)(x1 - x0 + 1) * (y1 - y0 + 1);
     int w = x1 - x0 + 1;
-    int n = w * (y1 - y0 + 1);
-    for (int i = lane; i < n; i += 32) {
-      int yy = y0 + i / w, xx = x0 + i % w;
-      int g = px_gray(px_load(im, xx, yy));
-      cnt += (g >= lo && g <= hi) ? 1u : 0u;
+    if (im.fmt == DF_GRAY8) {
+      unsigned lo4 = (unsigned)lo * 0x01010101u, hi4 = (unsigned)hi * 0x01010101u;
+      for (int yy = y0; yy <= y1; yy++)
+        for_words(im.data + (size_t)yy * im.pitch + x0, w, lane, 32, [&](unsigned wd, unsigned keep) {
+          unsigned c = __vcmpgeu4(wd, lo4) & __vcmpleu4(wd, hi4) & keep;
+          cnt += (unsigned)__popc(c) >> 3;
+        });
+    } else {
+      for (int yy = y0; yy <= y1; yy++)
+        for (int xx = x0 + lane; xx <= x1; xx += 32) {
+          int g = px_gray(px_load(im, xx, yy));
+          cnt += (g >= lo && g <= hi) ? 1u : 0u;
+        }
     }
   }
   cnt = warp_sum_u32(cnt);
@@ -105,6 +154,23 @@ __global__ void k_cellstats(DPage *pages, int gx, int gy, int ncx, int ncy, int 
   __syncthreads();
   int y0 = cy * gy, y1 = min(y0 + gy - 1, im.h - 1);
   int xlim = min(ncx * gx, im.w);
+  if (im.fmt == DF_GRAY8 && (gx & 1) == 0 && (im.pitch & 1) == 0 && ((uintptr_t)im.data & 1) == 0) {
+    // two pixels per 16-bit load: a pixel pair never straddles a cell when gx is even
+    unsigned dm = (unsigned)dark_max;
+    for (int x = 2 * threadIdx.x; x < xlim; x += 2 * blockDim.x) {
+      unsigned d = 0, l = 0;
+      bool two = x + 1 < xlim;
+      for (int y = y0; y <= y1; y++) {
+        unsigned v = *(const unsigned short *)(im.data + (size_t)y * im.pitch + x);
+        unsigned a = v & 0xFFu, b = v >> 8;
+        d += (a <= dm); l += a;
+        if (two) { d += (b <= dm); l += b; }
+      }
+      int c = x / gx;
+      if (d) atomicAdd(&sd[c], d);
+      atomicAdd(&sl[c], l);
+    }
+  } else
   for (int x = threadIdx.x; x < xlim; x += blockDim.x) {
     unsigned d = 0, l = 0;
     for (int y = y0; y <= y1; y++) {

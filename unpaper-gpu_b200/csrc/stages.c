@@ -201,7 +201,8 @@ int gray_plan_build(GrayPlan *pl, int w, int h, const GrayfilterParameters *p, i
   long long nc = (long long)ncx * ncy;
   if (nc * 4 > 0x7fffffffLL / 2) { b200_set_error("grayfilter: cell grid too large"); return -1; }
   pl->white_off = (int)(3 * nc);
-  pl->u32_need = (int)(4 * nc) + 1;
+  /* [dark][light][wiped][white][window flags][wavefront marks] */
+  pl->u32_need = (int)(4 * nc) + nwx * nwy + nwx + skew * (nwy - 1) + 4;
   pl->dark_max = abt;
   pl->ok = 1;
   return 0;
@@ -362,7 +363,7 @@ void stage_blackfilter(StageCtx *c, const BfPlan *pl) {
 
 int stage_noisefilter(StageCtx *c, uint64_t intensity, int white) {
   if (c->h >= 32768 || c->w >= 65536) { b200_set_error("noisefilter: image too large"); return -1; }
-  int rc = b200k_noisefilter(c->st, c->pages, c->npages, c->w, c->h, intensity, white);
+  int rc = b200k_noisefilter(c->st, c->pages, c->npages, c->w, c->h, c->fmt, intensity, white);
   if (rc) b200_set_error("noisefilter: unsupported intensity");
   c->launches += 2;
   return rc;
@@ -382,7 +383,7 @@ int stage_grayfilter(StageCtx *c, const GrayPlan *pl) {
   int rc = b200k_cellstats(c->st, c->pages, c->npages, g[0], g[1], g[2], g[3], pl->dark_max, 0);
   if (rc) { b200_set_error("grayfilter: cell row too wide"); return rc; }
   b200k_gray_cascade(c->st, c->pages, c->npages, pl->gp, pl->white_off);
-  c->launches += 4;
+  c->launches += 6;
   return 0;
 }
 
