@@ -41,7 +41,7 @@ typedef struct {
   uint64_t *stack;
   uint8_t *page_stage;    /* device staging for host-mode pages */
   DPage *pages_dev, *pages_tmpl /* host */, *pages_res /* pinned */;
-  DFillJob *fillA, *fillB, *decode_fill;
+  DFillJob *fillA, *fillB, *fillC, *decode_fill;
   DCopyJob *copyA, *copyB, *decode_copy, *decode_copy_host_tmpl;
   DMaskJob *maskJ;
   DFillJob *static_fill[3];   /* pre / mid / post wipe+border rectangles, per page */
@@ -151,7 +151,7 @@ static int build_static(B200Engine *e, Lane *ln, int slot, const Rectangle *wipe
 
 static void lane_free(Lane *ln) {
   void *ptrs[] = {ln->sheets, ln->aux, ln->cls, ln->list, ln->u32, ln->stack, ln->page_stage, ln->pages_dev,
-                  ln->fillA, ln->fillB, ln->decode_fill, ln->copyA, ln->copyB, ln->decode_copy, ln->maskJ,
+                  ln->fillA, ln->fillB, ln->fillC, ln->decode_fill, ln->copyA, ln->copyB, ln->decode_copy, ln->maskJ,
                   ln->static_fill[0], ln->static_fill[1], ln->static_fill[2], ln->static_mask[0], ln->static_mask[1],
                   ln->static_mask[2], ln->static_mask_rects[0], ln->static_mask_rects[1], ln->static_mask_rects[2]};
   for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) b200_dev_free(ptrs[i]);
@@ -270,6 +270,7 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
     ln->pages_tmpl = (DPage *)calloc((size_t)P, sizeof(DPage));
     ln->fillA = (DFillJob *)b200_dev_alloc(sizeof(DFillJob) * P);
     ln->fillB = (DFillJob *)b200_dev_alloc(sizeof(DFillJob) * P);
+    ln->fillC = (DFillJob *)b200_dev_alloc(sizeof(DFillJob) * P);
     ln->copyA = (DCopyJob *)b200_dev_alloc(sizeof(DCopyJob) * P);
     ln->copyB = (DCopyJob *)b200_dev_alloc(sizeof(DCopyJob) * P);
     ln->maskJ = (DMaskJob *)b200_dev_alloc(sizeof(DMaskJob) * P);
@@ -347,7 +348,7 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
   StageCtx c;
   memset(&c, 0, sizeof(c));
   c.st = ln->st; c.npages = n; c.pages = ln->pages_dev; c.w = e->sheet_w; c.h = e->sheet_h; c.fmt = e->dfmt;
-  c.fillA = ln->fillA; c.fillB = ln->fillB; c.copyA = ln->copyA; c.copyB = ln->copyB; c.maskJ = ln->maskJ;
+  c.fillA = ln->fillA; c.fillB = ln->fillB; c.fillC = ln->fillC; c.copyA = ln->copyA; c.copyB = ln->copyB; c.maskJ = ln->maskJ;
   ln->ev_mask = 0;
   int ic = cfg->input_count;
 

@@ -88,7 +88,7 @@ typedef struct {
   int npages;
   DPage *pages;               /* device array */
   int w, h, fmt;              /* geometry shared by the group (device fmt code) */
-  DFillJob *fillA, *fillB;    /* device job arrays, npages each */
+  DFillJob *fillA, *fillB, *fillC; /* device job arrays, npages each */
   DCopyJob *copyA, *copyB;
   DMaskJob *maskJ;
   uint64_t launches;

@@ -24,11 +24,11 @@ static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 // The flood fill is one warp of serial work: code size matters more than
 // inlining (the fully inlined kernel was ~22 k SASS instructions and ran out of
 // the instruction caches), so pixel access goes through two small calls.
-__device__ __noinline__ int ff_gray_at(const DImg &im, int x, int y) {
+__device__ __forceinline__ int ff_gray_at(const DImg &im, int x, int y) {
   if (im.fmt == DF_GRAY8) return in_img(im, x, y) ? (int)im.data[(size_t)y * im.pitch + x] : 255;
   return px_gray(px_get(im, x, y));
 }
-__device__ __noinline__ void ff_paint(const DImg &im, int x, int y) {
+__device__ __forceinline__ void ff_paint(const DImg &im, int x, int y) {
   if (im.fmt == DF_GRAY8) { im.data[(size_t)y * im.pitch + x] = 255; return; }
   px_store(im, x, y, 255, 255, 255);
 }
@@ -372,26 +372,29 @@ __global__ void k_nf_classify_g8(DPage *pages, int intensity, int white) {
   int band = 2 * intensity;
   bool aligned = ((im.pitch & 3) == 0) && (((uintptr_t)im.data & 3) == 0);
   const int WPR = NF_G8_TWB / 4;
+  unsigned white4 = (unsigned)min(max(white, 0), 255) * 0x01010101u;
+  if (white > 255) white4 = 0xFFFFFFFFu;
   for (int i = threadIdx.x; i < WPR * th; i += blockDim.x) {
     int r = i / WPR, c = i % WPR;
     int y = by - halo + r, x = bx - NF_G8_HX + 4 * c;
     unsigned codes = 0;
     if (y >= 0 && y < im.h && x + 3 >= 0 && x < im.w) {
       const uint8_t *rp = im.data + (size_t)y * im.pitch;
-      unsigned v;
+      unsigned v, inimg = 0xFFFFFFFFu;
       if (aligned && x >= 0 && x + 3 < im.w) v = *(const unsigned *)(rp + x);
       else {
-        v = 0xFFFFFFFFu;
+        v = 0xFFFFFFFFu; inimg = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) if (x + k >= 0 && x + k < im.w) v = (v & ~(0xFFu << (8 * k))) | ((unsigned)rp[x + k] << (8 * k));
+        for (int k = 0; k < 4; k++) if (x + k >= 0 && x + k < im.w) { v = (v & ~(0xFFu << (8 * k))) | ((unsigned)rp[x + k] << (8 * k)); inimg |= 0xFFu << (8 * k); }
       }
-      bool yb = y < band;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        unsigned b = (v >> (8 * k)) & 0xFFu;
-        bool ok = x + k >= 0 && x + k < im.w && (int)b < white;
-        unsigned code = ok ? (5u | ((yb || x + k < band) ? 2u : 0u)) : 0u;
-        codes |= code << (8 * k);
+      // 0xFF in every byte lane whose pixel is ring-dark (value < white)
+      unsigned dark = __vcmpltu4(v, white4) & inimg;
+      if (dark) {
+        unsigned inband;
+        if (y < band || x + 3 < band) inband = 0xFFFFFFFFu;
+        else if (x >= band) inband = 0u;
+        else { inband = 0; for (int k = 0; k < 4; k++) if (x + k < band) inband |= 0xFFu << (8 * k); }
+        codes = (dark & 0x05050505u) | (dark & inband & 0x02020202u);
       }
     }
     ((unsigned *)tile)[i] = codes;
@@ -404,8 +407,10 @@ __global__ void k_nf_classify_g8(DPage *pages, int intensity, int white) {
   if (y >= im.h) return;
   unsigned out = 0;
   const int tw = NF_G8_TWB;
+  // four white pixels (the common case): one shared-memory word, nothing to classify
+  bool any = *(const unsigned *)(tile + (ly + halo) * tw + lx0 + NF_G8_HX) != 0u;
 #pragma unroll 1
-  for (int q = 0; q < 4; q++) {
+  for (int q = 0; any && q < 4; q++) {
     int lx = lx0 + q, x = bx + lx;
     if (x >= im.w) break;
     int tx = lx + NF_G8_HX, ty = ly + halo;

@@ -194,7 +194,7 @@ __global__ void k_border_to_mask(DPage *pages, int npages) {
 }
 
 // ---- move preparation ----------------------------------------------------
-struct MoveJobs { DFillJob *fill_aux; DCopyJob *copy_out; DFillJob *wipe; DCopyJob *copy_in; };
+struct MoveJobs { DFillJob *fill_aux; DCopyJob *copy_out; DFillJob *wipe; DCopyJob *copy_in; DFillJob *wipe2; };
 
 __device__ void emit_move(DPage &pg, MoveJobs mj, int p, DRect area, int tx, int ty, int enabled) {
   int w = abs(area.x0 - area.x1) + 1, h = abs(area.y0 - area.y1) + 1;
@@ -204,14 +204,37 @@ __device__ void emit_move(DPage &pg, MoveJobs mj, int p, DRect area, int tx, int
   // capacity check: aux was allocated for aux.pitch * aux.h bytes
   if ((long long)pitch * h > (long long)aux.pitch * aux.h) { enabled = 0; atomicOr(&pg.error, DERR_UNSUPPORTED); }
   aux.w = w; aux.h = h; aux.pitch = pitch;
-  DFillJob f; f.img = aux; f.r = DRect{0, 0, w - 1, h - 1}; f.c[0] = aux.bg[0]; f.c[1] = aux.bg[1]; f.c[2] = aux.bg[2]; f.pad = 0; f.enabled = enabled;
+  // normalised area, and its part inside the image (what copy_rectangle really copies)
+  DRect na = DRect{min(area.x0, area.x1), min(area.y0, area.y1), max(area.x0, area.x1), max(area.y0, area.y1)};
+  bool area_inside = na.x0 >= 0 && na.y0 >= 0 && na.x1 < pg.img.w && na.y1 < pg.img.h;
+  // the temp only needs its background where the copy below leaves holes
+  DFillJob f; f.img = aux; f.r = DRect{0, 0, w - 1, h - 1}; f.c[0] = aux.bg[0]; f.c[1] = aux.bg[1]; f.c[2] = aux.bg[2]; f.pad = 0;
+  f.enabled = enabled && !area_inside;
   mj.fill_aux[p] = f;
   DCopyJob c; c.src = pg.img; c.dst = aux; c.area = area; c.tx = 0; c.ty = 0; c.enabled = enabled; c.pad = 0;
   mj.copy_out[p] = c;
-  DFillJob wj; wj.img = pg.img;
-  wj.r = DRect{min(area.x0, area.x1), min(area.y0, area.y1), max(area.x0, area.x1), max(area.y0, area.y1)};
-  wj.c[0] = pg.img.bg[0]; wj.c[1] = pg.img.bg[1]; wj.c[2] = pg.img.bg[2]; wj.pad = 0; wj.enabled = enabled;
+  // wipe_rectangle(area) followed by the paste of T = [tx,tx+w) x [ty,ty+h): what the
+  // paste overwrites need not be wiped first.  area \ T is an L shape (T is the area
+  // shifted): a full-width horizontal strip plus a vertical strip beside T.
+  DFillJob wj; wj.img = pg.img; wj.c[0] = pg.img.bg[0]; wj.c[1] = pg.img.bg[1]; wj.c[2] = pg.img.bg[2]; wj.pad = 0;
+  DFillJob w2 = wj;
+  int dxs = tx - na.x0, dys = ty - na.y0;
+  bool overlap = abs(dxs) < w && abs(dys) < h;
+  if (!overlap) {
+    wj.r = na; wj.enabled = enabled; w2.r = na; w2.enabled = 0;
+  } else {
+    // rows of the area outside T's row range
+    if (dys > 0) wj.r = DRect{na.x0, na.y0, na.x1, ty - 1};
+    else wj.r = DRect{na.x0, ty + h, na.x1, na.y1};          // empty when dys == 0
+    wj.enabled = enabled && dys != 0;
+    // remaining rows (those shared with T): columns of the area outside T's column range
+    int ry0 = max(na.y0, ty), ry1 = min(na.y1, ty + h - 1);
+    if (dxs > 0) w2.r = DRect{na.x0, ry0, tx - 1, ry1};
+    else w2.r = DRect{tx + w, ry0, na.x1, ry1};               // empty when dxs == 0
+    w2.enabled = enabled && dxs != 0;
+  }
   mj.wipe[p] = wj;
+  mj.wipe2[p] = w2;
   DCopyJob ci; ci.src = aux; ci.dst = pg.img; ci.area = DRect{0, 0, w - 1, h - 1}; ci.tx = tx; ci.ty = ty; ci.enabled = enabled; ci.pad = 0;
   mj.copy_in[p] = ci;
 }
@@ -294,14 +317,14 @@ void b200k_detect_border(cudaStream_t st, DPage *pages, int npages, int size_w, 
   k_border_to_mask<<<cdiv(npages * 2, 64), 64, 0, st>>>(pages, npages);
 }
 void b200k_prep_center(cudaStream_t st, DPage *pages, int npages, int i, DFillJob *fill_aux,
-                       DCopyJob *copy_out, DFillJob *wipe, DCopyJob *copy_in) {
-  MoveJobs mj = {fill_aux, copy_out, wipe, copy_in};
+                       DCopyJob *copy_out, DFillJob *wipe, DCopyJob *copy_in, DFillJob *wipe2) {
+  MoveJobs mj = {fill_aux, copy_out, wipe, copy_in, wipe2};
   k_prep_center<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages, i, mj);
 }
 void b200k_prep_align(cudaStream_t st, DPage *pages, int npages, int i, int left, int top, int right,
                       int bottom, int margin_h, int margin_v, DFillJob *fill_aux, DCopyJob *copy_out,
-                      DFillJob *wipe, DCopyJob *copy_in) {
-  MoveJobs mj = {fill_aux, copy_out, wipe, copy_in};
+                      DFillJob *wipe, DCopyJob *copy_in, DFillJob *wipe2) {
+  MoveJobs mj = {fill_aux, copy_out, wipe, copy_in, wipe2};
   AlignParams ap = {left, top, right, bottom, margin_h, margin_v};
   k_prep_align<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages, i, ap, mj);
 }

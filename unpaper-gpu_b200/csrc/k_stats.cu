@@ -118,7 +118,27 @@ __global__ void k_rect_count(DPage *pages, const DRect *rects, int nrects, int l
   if (x0 <= x1 && y0 <= y1 && total > 0) {
     inside = (long long)(x1 - x0 + 1) * (y1 - y0 + 1);
     int w = x1 - x0 + 1;
-    if (im.fmt == DF_GRAY8) {
+    if (im.fmt == DF_GRAY8 && (im.pitch & 3) == 0 && ((uintptr_t)im.data & 3) == 0) {
+      // every row of the rectangle has the same word alignment: a lane owns one
+      // word column and walks down the rows
+      unsigned lo4 = (unsigned)lo * 0x01010101u, hi4 = (unsigned)hi * 0x01010101u;
+      int lead = x0 & 3, nw = (lead + w + 3) >> 2;
+      const unsigned *base = (const unsigned *)(im.data + (size_t)y0 * im.pitch + (x0 - lead));
+      int wpitch = im.pitch >> 2, rows = y1 - y0 + 1;
+      for (int i = lane; i < nw; i += 32) {
+        unsigned keep = 0xFFFFFFFFu;
+        if (i == 0 && lead) keep &= 0xFFFFFFFFu << (8 * lead);
+        int end = lead + w - 4 * i;
+        if (end < 4) keep &= 0xFFFFFFFFu >> (8 * (4 - end));
+        const unsigned *p = base + i;
+        unsigned acc = 0;
+        for (int r = 0; r < rows; r++, p += wpitch) {
+          unsigned wd = *p;
+          acc += (unsigned)__popc(__vcmpgeu4(wd, lo4) & __vcmpleu4(wd, hi4) & keep);
+        }
+        cnt += acc >> 3;
+      }
+    } else if (im.fmt == DF_GRAY8) {
       unsigned lo4 = (unsigned)lo * 0x01010101u, hi4 = (unsigned)hi * 0x01010101u;
       for (int yy = y0; yy <= y1; yy++)
         for_words(im.data + (size_t)yy * im.pitch + x0, w, lane, 32, [&](unsigned wd, unsigned keep) {

@@ -36,10 +36,10 @@ void b200k_detect_border(cudaStream_t st, DPage *pages, int npages, int size_w, 
                          int step_v, int thr_h, int thr_v, int dir_h, int dir_v, int sum_off,
                          int sum_stride, int oob_dark);
 void b200k_prep_center(cudaStream_t st, DPage *pages, int npages, int i, DFillJob *fill_aux,
-                       DCopyJob *copy_out, DFillJob *wipe, DCopyJob *copy_in);
+                       DCopyJob *copy_out, DFillJob *wipe, DCopyJob *copy_in, DFillJob *wipe2);
 void b200k_prep_align(cudaStream_t st, DPage *pages, int npages, int i, int left, int top, int right,
                       int bottom, int margin_h, int margin_v, DFillJob *fill_aux, DCopyJob *copy_out,
-                      DFillJob *wipe, DCopyJob *copy_in);
+                      DFillJob *wipe, DCopyJob *copy_in, DFillJob *wipe2);
 void b200k_prep_border_maskjob(cudaStream_t st, DPage *pages, int npages, DMaskJob *jobs, int r, int g, int b);
 
 /* k_filters.cu */

@@ -428,13 +428,14 @@ static void run_move(StageCtx *c) {
   b200k_fill_jobs(c->st, c->fillA, c->npages, aw, ah);
   b200k_copy_jobs(c->st, c->copyA, c->npages, aw * bppf(c->fmt), ah);
   b200k_fill_jobs(c->st, c->fillB, c->npages, aw, ah);
+  b200k_fill_jobs(c->st, c->fillC, c->npages, aw, ah);
   b200k_copy_jobs(c->st, c->copyB, c->npages, aw * bppf(c->fmt), ah);
-  c->launches += 4;
+  c->launches += 5;
 }
 
 void stage_center_masks(StageCtx *c, int max_masks) {
   for (int i = 0; i < max_masks; i++) {
-    b200k_prep_center(c->st, c->pages, c->npages, i, c->fillA, c->copyA, c->fillB, c->copyB);
+    b200k_prep_center(c->st, c->pages, c->npages, i, c->fillA, c->copyA, c->fillB, c->copyB, c->fillC);
     c->launches += 1;
     run_move(c);
   }
@@ -464,7 +465,7 @@ void stage_align_masks(StageCtx *c, const MaskAlignmentParameters *p, int n_outs
   for (int i = 0; i < n_outside; i++) {
     b200k_prep_align(c->st, c->pages, c->npages, i, p->alignment.left, p->alignment.top, p->alignment.right,
                      p->alignment.bottom, p->margin.horizontal, p->margin.vertical, c->fillA, c->copyA,
-                     c->fillB, c->copyB);
+                     c->fillB, c->copyB, c->fillC);
     c->launches += 1;
     run_move(c);
   }
