@@ -22,7 +22,7 @@ typedef struct {
   StageCtx sc;
   DPage hp;            /* host copy of the page record */
   DPage *dp;           /* device record */
-  void *aux, *cls, *list, *u32, *stack, *jobs;
+  void *aux, *cls, *list, *u32, *stack, *jobs, *pre;
 } Op;
 
 static void op_begin(Op *o, Image *image, int need_aux, int need_nf, int u32_need, int need_stack) {
@@ -85,6 +85,7 @@ static void op_end(Op *o, Image *image, bool modified) {
   if (o->u32) b200_dev_free(o->u32);
   if (o->stack) b200_dev_free(o->stack);
   if (o->jobs) b200_dev_free(o->jobs);
+  if (o->pre) b200_dev_free(o->pre);
 }
 static void op_check(const Op *o, const char *what) {
   if (o->hp.error) b200_fatal("%s: device-side failure flags 0x%x", what, o->hp.error);
@@ -435,6 +436,8 @@ static float detect_rotation_b200(Image image, Rectangle mask, const DeskewParam
   if (rot_plan_build(&pl, image.frame->width, image.frame->height, &params, 1, false))
     b200_fatal("%s", unpaper_b200_last_error());
   Op o; op_begin(&o, &image, 0, 0, pl.u32_need, 0);
+  o.pre = b200_dev_alloc((size_t)pl.pre_need * 4);
+  o.hp.pre = (uint32_t *)o.pre; o.hp.pre_cap = pl.pre_need;
   o.hp.mask_count = 1;
   o.hp.masks[0] = drect(mask);
   op_push(&o);

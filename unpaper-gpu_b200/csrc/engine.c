@@ -31,16 +31,26 @@ static const char *STG_NAME[STG_COUNT] = {"decode", "blackfilter", "noisefilter"
 
 typedef struct {
   cudaStream_t st;
-  cudaEvent_t done;
-  cudaEvent_t done_t;     /* timing-enabled twin of `done` */
+  /* up to QD groups are queued on a lane's stream, so the stream never runs dry
+   * while the host is busy with another lane; the device workspace is shared
+   * (stream order protects it), only the result records are per flight */
+  struct Flight {
+    cudaEvent_t done;
+    cudaEvent_t done_t;   /* timing-enabled twin of `done` */
+    cudaEvent_t ev[STG_COUNT + 1];
+    int ev_mask;          /* which stage boundaries were recorded */
+    DPage *pages_res;     /* pinned */
+    int busy, first, n;
+  } fl[2];
+  int slot;               /* flight being issued / collected */
   int ran;
-  cudaEvent_t ev[STG_COUNT + 1];
-  int ev_mask;            /* which stage boundaries were recorded */
+  cudaEvent_t last_done_t;
   uint8_t *sheets, *aux, *cls;
   uint32_t *list, *u32;
   uint64_t *stack;
+  uint32_t *pre;
   uint8_t *page_stage;    /* device staging for host-mode pages */
-  DPage *pages_dev, *pages_tmpl /* host */, *pages_res /* pinned */;
+  DPage *pages_dev, *pages_tmpl /* host */;
   DFillJob *fillA, *fillB, *fillC, *decode_fill;
   DCopyJob *copyA, *copyB, *decode_copy, *decode_copy_host_tmpl;
   DMaskJob *maskJ;
@@ -48,7 +58,6 @@ typedef struct {
   int static_fill_n[3];
   DMaskJob *static_mask[3];
   DRect *static_mask_rects[3];
-  int busy, first, n;
   uint8_t *out_host; uint8_t *out_dev;
   int host_mode;
 } Lane;
@@ -150,16 +159,18 @@ static int build_static(B200Engine *e, Lane *ln, int slot, const Rectangle *wipe
 }
 
 static void lane_free(Lane *ln) {
-  void *ptrs[] = {ln->sheets, ln->aux, ln->cls, ln->list, ln->u32, ln->stack, ln->page_stage, ln->pages_dev,
+  void *ptrs[] = {ln->sheets, ln->aux, ln->cls, ln->list, ln->u32, ln->stack, ln->pre, ln->page_stage, ln->pages_dev,
                   ln->fillA, ln->fillB, ln->fillC, ln->decode_fill, ln->copyA, ln->copyB, ln->decode_copy, ln->maskJ,
                   ln->static_fill[0], ln->static_fill[1], ln->static_fill[2], ln->static_mask[0], ln->static_mask[1],
                   ln->static_mask[2], ln->static_mask_rects[0], ln->static_mask_rects[1], ln->static_mask_rects[2]};
   for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) b200_dev_free(ptrs[i]);
-  if (ln->pages_res) b200_pinned_free(ln->pages_res);
   free(ln->pages_tmpl); free(ln->decode_copy_host_tmpl);
-  if (ln->done) cudaEventDestroy(ln->done);
-  if (ln->done_t) cudaEventDestroy(ln->done_t);
-  for (int i = 0; i <= STG_COUNT; i++) if (ln->ev[i]) cudaEventDestroy(ln->ev[i]);
+  for (ln->slot = 0; ln->slot < 2; ln->slot++) {
+    if (ln->fl[ln->slot].pages_res) b200_pinned_free(ln->fl[ln->slot].pages_res);
+    if (ln->fl[ln->slot].done) cudaEventDestroy(ln->fl[ln->slot].done);
+    if (ln->fl[ln->slot].done_t) cudaEventDestroy(ln->fl[ln->slot].done_t);
+    for (int i = 0; i <= STG_COUNT; i++) if (ln->fl[ln->slot].ev[i]) cudaEventDestroy(ln->fl[ln->slot].ev[i]);
+  }
   if (ln->st) b200_stream_release(ln->st);
   memset(ln, 0, sizeof(*ln));
 }
@@ -247,15 +258,20 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
   u32 = imax(u32, e->bf.u32_need); u32 = imax(u32, e->blur.u32_need); u32 = imax(u32, e->gray.u32_need);
   u32 = imax(u32, e->mask.u32_need); u32 = imax(u32, e->border.u32_need); u32 = imax(u32, e->rot.u32_need);
   e->need.u32_cap = (u32 + 63) & ~63;
+  e->need.pre_cap = cfg->no_deskew ? 0 : (e->rot.pre_need + 63) & ~63LL;
 
   int P = group_pages;
   e->lanes = (Lane *)calloc((size_t)lanes, sizeof(Lane));
   for (int li = 0; li < lanes; li++) {
     Lane *ln = &e->lanes[li];
     ln->st = b200_stream_acquire();
-    CUDA_OK(cudaEventCreateWithFlags(&ln->done, cudaEventDisableTiming));
-    CUDA_OK(cudaEventCreate(&ln->done_t));
-    for (int i = 0; i <= STG_COUNT; i++) CUDA_OK(cudaEventCreate(&ln->ev[i]));
+    for (ln->slot = 0; ln->slot < 2; ln->slot++) {
+      CUDA_OK(cudaEventCreateWithFlags(&ln->fl[ln->slot].done, cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreate(&ln->fl[ln->slot].done_t));
+      for (int i = 0; i <= STG_COUNT; i++) CUDA_OK(cudaEventCreate(&ln->fl[ln->slot].ev[i]));
+      ln->fl[ln->slot].pages_res = (DPage *)b200_pinned_alloc(sizeof(DPage) * P);
+    }
+    ln->slot = 0;
     ln->sheets = (uint8_t *)b200_dev_alloc(e->sheet_stride * P);
     size_t aux_stride = (e->need.aux_bytes + 255) & ~(size_t)255;
     size_t cls_stride = (e->need.cls_bytes + 255) & ~(size_t)255;
@@ -264,9 +280,9 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
     ln->list = (uint32_t *)b200_dev_alloc((size_t)e->need.list_cap * 4 * P);
     ln->u32 = (uint32_t *)b200_dev_alloc((size_t)e->need.u32_cap * 4 * P);
     ln->stack = (uint64_t *)b200_dev_alloc((size_t)e->need.stack_cap * 32 * P);
+    if (e->need.pre_cap > 0) ln->pre = (uint32_t *)b200_dev_alloc((size_t)e->need.pre_cap * 4 * P);
     ln->page_stage = (uint8_t *)b200_dev_alloc(e->page_bytes * cfg->input_count * P + 64);
     ln->pages_dev = (DPage *)b200_dev_alloc(sizeof(DPage) * P);
-    ln->pages_res = (DPage *)b200_pinned_alloc(sizeof(DPage) * P);
     ln->pages_tmpl = (DPage *)calloc((size_t)P, sizeof(DPage));
     ln->fillA = (DFillJob *)b200_dev_alloc(sizeof(DFillJob) * P);
     ln->fillB = (DFillJob *)b200_dev_alloc(sizeof(DFillJob) * P);
@@ -288,6 +304,7 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
       pg->list = ln->list + (size_t)e->need.list_cap * p; pg->list_cap = e->need.list_cap;
       pg->u32 = ln->u32 + (size_t)e->need.u32_cap * p; pg->u32_cap = e->need.u32_cap;
       pg->stack = ln->stack + (size_t)e->need.stack_cap * 4 * p; pg->stack_cap = e->need.stack_cap;
+      if (ln->pre) { pg->pre = ln->pre + (size_t)e->need.pre_cap * p; pg->pre_cap = e->need.pre_cap; }
       pg->point_count = e->npoints;
       for (int i = 0; i < e->npoints; i++) { pg->px[i] = e->points[i].x; pg->py[i] = e->points[i].y; }
       pg->outside_count = e->noutside;
@@ -328,8 +345,8 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
 
 static void mark(B200Engine *e, Lane *ln, int stage_boundary) {
   if (!e->profiling) return;
-  CUDA_OK(cudaEventRecord(ln->ev[stage_boundary], ln->st));
-  ln->ev_mask |= 1 << stage_boundary;
+  CUDA_OK(cudaEventRecord(ln->fl[ln->slot].ev[stage_boundary], ln->st));
+  ln->fl[ln->slot].ev_mask |= 1 << stage_boundary;
 }
 
 /* apply pre-masks first (sheet_stages.c:211-214), then wipes (:282-285), then
@@ -349,7 +366,7 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
   memset(&c, 0, sizeof(c));
   c.st = ln->st; c.npages = n; c.pages = ln->pages_dev; c.w = e->sheet_w; c.h = e->sheet_h; c.fmt = e->dfmt;
   c.fillA = ln->fillA; c.fillB = ln->fillB; c.fillC = ln->fillC; c.copyA = ln->copyA; c.copyB = ln->copyB; c.maskJ = ln->maskJ;
-  ln->ev_mask = 0;
+  ln->fl[ln->slot].ev_mask = 0;
   int ic = cfg->input_count;
 
   mark(e, ln, STG_DECODE);
@@ -399,43 +416,49 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
   mark(e, ln, STG_OUTPUT);
   /* output stage: sheet -> caller (tight rows) + the decisions */
   if (ln->host_mode) {
-    CUDA_OK(cudaMemcpy2DAsync(ln->out_host, (size_t)e->sheet_row, ln->sheets, (size_t)e->sheet_pitch, (size_t)e->sheet_row,
-                              (size_t)e->sheet_h * 1, cudaMemcpyDeviceToHost, c.st));
-    for (int p = 1; p < n; p++)
-      CUDA_OK(cudaMemcpy2DAsync(ln->out_host + (size_t)e->sheet_row * e->sheet_h * p, (size_t)e->sheet_row,
-                                ln->sheets + e->sheet_stride * p, (size_t)e->sheet_pitch, (size_t)e->sheet_row,
-                                (size_t)e->sheet_h, cudaMemcpyDeviceToHost, c.st));
+    size_t sheet_bytes = (size_t)e->sheet_row * e->sheet_h;
+    if (e->sheet_pitch == e->sheet_row) {
+      /* rows are tight, sheets are `sheet_stride` apart: one 2-D copy with one "row" per sheet */
+      CUDA_OK(cudaMemcpy2DAsync(ln->out_host, sheet_bytes, ln->sheets, e->sheet_stride, sheet_bytes, (size_t)n,
+                                cudaMemcpyDeviceToHost, c.st));
+    } else {
+      for (int p = 0; p < n; p++)
+        CUDA_OK(cudaMemcpy2DAsync(ln->out_host + sheet_bytes * p, (size_t)e->sheet_row,
+                                  ln->sheets + e->sheet_stride * p, (size_t)e->sheet_pitch, (size_t)e->sheet_row,
+                                  (size_t)e->sheet_h, cudaMemcpyDeviceToHost, c.st));
+    }
   } else {
     b200k_pack_rows(c.st, ln->sheets, e->sheet_pitch, ln->out_dev, e->sheet_row, e->sheet_row, e->sheet_h, n,
                     e->sheet_stride, (size_t)e->sheet_row * e->sheet_h);
     c.launches++;
   }
-  CUDA_OK(cudaMemcpyAsync(ln->pages_res, ln->pages_dev, sizeof(DPage) * n, cudaMemcpyDeviceToHost, c.st));
+  CUDA_OK(cudaMemcpyAsync(ln->fl[ln->slot].pages_res, ln->pages_dev, sizeof(DPage) * n, cudaMemcpyDeviceToHost, c.st));
   mark(e, ln, STG_COUNT);
-  CUDA_OK(cudaEventRecord(ln->done_t, c.st));
-  CUDA_OK(cudaEventRecord(ln->done, c.st));
+  CUDA_OK(cudaEventRecord(ln->fl[ln->slot].done_t, c.st));
+  CUDA_OK(cudaEventRecord(ln->fl[ln->slot].done, c.st));
   ln->ran = 1;
+  ln->last_done_t = ln->fl[ln->slot].done_t;
   e->launches += c.launches;
 }
 
 static void collect(B200Engine *e, Lane *ln, B200SheetResult *results) {
-  if (!ln->busy) return;
-  CUDA_OK(cudaEventSynchronize(ln->done));
+  if (!ln->fl[ln->slot].busy) return;
+  CUDA_OK(cudaEventSynchronize(ln->fl[ln->slot].done));
   if (e->profiling) {
     for (int s = 0; s < STG_COUNT; s++) {
       float ms = 0;
-      if ((ln->ev_mask >> s & 1) && (ln->ev_mask >> (s + 1) & 1) &&
-          cudaEventElapsedTime(&ms, ln->ev[s], ln->ev[s + 1]) == cudaSuccess) {
+      if ((ln->fl[ln->slot].ev_mask >> s & 1) && (ln->fl[ln->slot].ev_mask >> (s + 1) & 1) &&
+          cudaEventElapsedTime(&ms, ln->fl[ln->slot].ev[s], ln->fl[ln->slot].ev[s + 1]) == cudaSuccess) {
         e->stage_ms[s] += ms; e->stage_groups[s] += 1;
       }
     }
   }
-  for (int p = 0; p < ln->n; p++)
-    if (ln->pages_res[p].error) { e->bad_sheets++; e->bad_flags |= ln->pages_res[p].error; e->bad_first = ln->first + p; }
+  for (int p = 0; p < ln->fl[ln->slot].n; p++)
+    if (ln->fl[ln->slot].pages_res[p].error) { e->bad_sheets++; e->bad_flags |= ln->fl[ln->slot].pages_res[p].error; e->bad_first = ln->fl[ln->slot].first + p; }
   if (results) {
-    for (int p = 0; p < ln->n; p++) {
-      const DPage *pg = &ln->pages_res[p];
-      B200SheetResult *r = &results[ln->first + p];
+    for (int p = 0; p < ln->fl[ln->slot].n; p++) {
+      const DPage *pg = &ln->fl[ln->slot].pages_res[p];
+      B200SheetResult *r = &results[ln->fl[ln->slot].first + p];
       memset(r, 0, sizeof(*r));
       r->status = pg->error ? -(int)pg->error : 0;
       r->sheet_width = e->sheet_w; r->sheet_height = e->sheet_h;
@@ -461,7 +484,7 @@ static void collect(B200Engine *e, Lane *ln, B200SheetResult *results) {
       r->noise_clusters = (int32_t)pg->nf_clusters;
     }
   }
-  ln->busy = 0;
+  ln->fl[ln->slot].busy = 0;
 }
 
 static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_sheets, B200SheetResult *results, int host_mode) {
@@ -476,9 +499,10 @@ static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_shee
   CUDA_OK(cudaEventRecord(e->ev_begin, e->lanes[0].st));
   for (int first = 0; first < n_sheets; first += P, g++) {
     Lane *ln = &e->lanes[g % e->nlanes];
-    collect(e, ln, results);
+    ln->slot = (g / e->nlanes) & 1;
+    collect(e, ln, results);          /* the flight issued two rounds ago on this lane */
     int n = n_sheets - first < P ? n_sheets - first : P;
-    ln->first = first; ln->n = n; ln->host_mode = host_mode;
+    ln->fl[ln->slot].first = first; ln->fl[ln->slot].n = n; ln->host_mode = host_mode;
     const uint8_t *src = pages + e->page_bytes * ic * (size_t)first;
     if (host_mode) {
       CUDA_OK(cudaMemcpyAsync(ln->page_stage, src, e->page_bytes * ic * (size_t)n, cudaMemcpyHostToDevice, ln->st));
@@ -488,14 +512,20 @@ static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_shee
       ln->out_dev = out + out_sheet * first;
       issue_group(e, ln, src, n);
     }
-    ln->busy = 1;
+    ln->fl[ln->slot].busy = 1;
   }
-  for (int i = 0; i < e->nlanes; i++) collect(e, &e->lanes[(g + i) % e->nlanes], results);
+  /* drain in issue order */
+  int total_groups = g;
+  for (int k = (total_groups > 2 * e->nlanes ? total_groups - 2 * e->nlanes : 0); k < total_groups; k++) {
+    Lane *ln = &e->lanes[k % e->nlanes];
+    ln->slot = (k / e->nlanes) & 1;
+    collect(e, ln, results);
+  }
   CUDA_OK(cudaGetLastError());
   e->last_device_ms = 0.0;
   for (int i = 0; i < e->nlanes; i++) {
     float ms = 0;
-    if (e->lanes[i].ran && cudaEventElapsedTime(&ms, e->ev_begin, e->lanes[i].done_t) == cudaSuccess && ms > e->last_device_ms)
+    if (e->lanes[i].ran && cudaEventElapsedTime(&ms, e->ev_begin, e->lanes[i].last_done_t) == cudaSuccess && ms > e->last_device_ms)
       e->last_device_ms = ms;
   }
   int bad = e->bad_sheets;

@@ -63,6 +63,7 @@ typedef struct {
   float *pair_dev;                 /* optional [2n][2n][4] table: rotation, sin, cos of -rotation */
   int edges[4];
   int peak_off, u32_need, scan_cap;
+  long long pre_need;              /* u32 elements of column-prefix scratch per page */
   DeskewParameters p;
 } RotPlan;
 
@@ -107,7 +108,7 @@ void stage_apply_border_masks(StageCtx *c, Pixel color);
 void stage_align_masks(StageCtx *c, const MaskAlignmentParameters *p, int n_outside);
 
 /* scratch sizing for one page of w x h in device format fmt */
-typedef struct { size_t aux_bytes; int aux_pitch, aux_h; size_t cls_bytes; int list_cap, u32_cap, stack_cap; } ScratchNeed;
+typedef struct { size_t aux_bytes; int aux_pitch, aux_h; size_t cls_bytes; int list_cap, u32_cap, stack_cap; long long pre_cap; } ScratchNeed;
 void scratch_need_all(ScratchNeed *n, int w, int h, int fmt);
 
 void *blob_upload(const void *host, size_t bytes);   /* synchronous H2D into cached device memory */

@@ -117,6 +117,143 @@ __global__ void k_rot_peaks(DPage *pages, const float *tan_tab, RotParams rp) {
   }
 }
 
+
+/* --------------------------------------------------------------------------
+ * Horizontal-edge fast path (left / right edges, the default).
+ *
+ * For these edges the scan line visits consecutive rows Y0, Y0+1, ... and its
+ * x coordinate (int)X changes only every ~1/|tan| rows, i.e. the line is a
+ * staircase of vertical runs.  With a column prefix sum
+ *     C[r][x] = sum_{r' < r} (255 - max channel)(x, Y0 + r')      (rows outside
+ *     mask /\ image contribute 0)
+ * the blackness of the line at depth d is a sum over RUNS of
+ *     C[k_end][x_run + d] - C[k_start][x_run + d]
+ * — the same integer as the reference's per-sample sum (deskew.c:121-129), with
+ * ~scan*|tan| loads instead of `scan`.  Lanes own consecutive depths, so a warp
+ * reads 32 consecutive prefix entries per run.
+ * ------------------------------------------------------------------------ */
+#define RP_SEG 8
+
+__device__ __forceinline__ void rot_line_geometry(const DRect &mask, int scan_param, int &scan, int &Y0) {
+  int sh = abs(mask.y0 - mask.y1) + 1;
+  scan = scan_param;
+  if (scan == -1) scan = sh;
+  scan = min(scan, min(10000, sh));
+  int half = scan / 2, mid = sh / 2;
+  Y0 = mask.y0 + mid - half;
+}
+
+__global__ void k_rot_colprefix(DPage *pages, int mi, int scan_param) {
+  __shared__ unsigned tot[RP_SEG][32];
+  DPage &pg = pages[blockIdx.y];
+  if (mi >= pg.mask_count) return;
+  const DImg &im = pg.img;
+  DRect mask = pg.masks[mi];
+  int scan, Y0;
+  rot_line_geometry(mask, scan_param, scan, Y0);
+  if (scan <= 0) return;
+  if ((long long)(scan + 1) * im.w > pg.pre_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&pg.error, DERR_UNSUPPORTED); return; }
+  int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  int x = blockIdx.x * 32 + lane;
+  int my0 = min(mask.y0, mask.y1), my1 = max(mask.y0, mask.y1);
+  int vy0 = max(my0, 0), vy1 = min(my1, im.h - 1);
+  int per = (scan + RP_SEG - 1) / RP_SEG;
+  int r0 = seg * per, r1 = min(r0 + per, scan);
+  bool col = x < im.w;
+  bool gray8 = im.fmt == DF_GRAY8;
+  unsigned t = 0;
+  if (col)
+    for (int r = r0; r < r1; r++) {
+      int y = Y0 + r;
+      if (y >= vy0 && y <= vy1) t += 255u - (unsigned)(gray8 ? (int)im.data[(size_t)y * im.pitch + x] : px_darkinv(px_load(im, x, y)));
+    }
+  tot[seg][lane] = t;
+  __syncthreads();
+  if (!col) return;
+  unsigned run = 0;
+  for (int s = 0; s < seg; s++) run += tot[s][lane];
+  unsigned *C = pg.pre;
+  for (int r = r0; r < r1; r++) {
+    C[(size_t)r * im.w + x] = run;
+    int y = Y0 + r;
+    if (y >= vy0 && y <= vy1) run += 255u - (unsigned)(gray8 ? (int)im.data[(size_t)y * im.pitch + x] : px_darkinv(px_load(im, x, y)));
+  }
+  if (r1 == scan && r0 < r1) C[(size_t)scan * im.w + x] = run;
+}
+
+__global__ void k_rot_peaks_h(DPage *pages, const float *tan_tab, RotParams rp, int mi) {
+  extern __shared__ int2 runs[];   // {x of the run, first k of the run}
+  __shared__ int s_red[8][ROT_CHUNK];
+  __shared__ int s_done, s_max, s_dep, s_nruns;
+  DPage &pg = pages[blockIdx.z];
+  int a = blockIdx.x, e = blockIdx.y ? 2 : 0;
+  if (mi >= pg.mask_count || !rp.edges[e]) return;
+  const DImg &im = pg.img;
+  DRect mask = pg.masks[mi];
+  float m = tan_tab[a];
+  int sw = abs(mask.x0 - mask.x1) + 1;
+  int shx = e == 0 ? 1 : -1;
+  int scan, Y0;
+  rot_line_geometry(mask, rp.scan_size, scan, Y0);
+  int maxDepth = sw / 2;
+  int half = scan / 2;
+  int outer = (int)(fabsf(m) * half);
+  int side = shx > 0 ? mask.x0 - outer : mask.x1 + outer;
+  float X = side + half * m;          // deskew.c:88
+  float stepX = -m;
+  int maxAbs = (int)(255 * rp.scan_size * rp.scan_depth);
+  if (threadIdx.x == 0) {
+    int n = 0, prev = 0;
+    for (int k = 0; k < scan; k++) {   // deskew.c:108-113, sequential float accumulation
+      int xi = (int)X;
+      if (k == 0 || xi != prev) { runs[n++] = make_int2(xi, k); prev = xi; }
+      X += stepX;
+    }
+    s_nruns = n; s_done = 0; s_max = 0; s_dep = 0;
+  }
+  __syncthreads();
+  int nruns = s_nruns;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  int last = 0, maxDiff = 0, acc = 0, dep = 0;
+  int mx0 = min(mask.x0, mask.x1), mx1 = max(mask.x0, mask.x1);
+  int vx0 = max(mx0, 0), vx1 = min(mx1, im.w - 1);
+  const unsigned *C = pg.pre;
+  bool have = (long long)(scan + 1) * im.w <= pg.pre_cap && scan > 0;
+  for (int base = 0; base < maxDepth; base += ROT_CHUNK) {
+    int ox = (base + lane) * shx;
+    int part = 0;
+    if (have)
+      for (int r = warp; r < nruns; r += nwarp) {
+        int2 rn = runs[r];
+        int kend = (r + 1 < nruns) ? runs[r + 1].y : scan;
+        int x = rn.x + ox;
+        if (x >= vx0 && x <= vx1) part += (int)(C[(size_t)kend * im.w + x] - C[(size_t)rn.y * im.w + x]);
+      }
+    s_red[warp][lane] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int dd = 0; dd < ROT_CHUNK; dd++) {
+        if (!((acc < maxAbs) && (dep < maxDepth))) { s_done = 1; break; }   // deskew.c:119
+        int blackness = 0;
+        for (int w = 0; w < nwarp; w++) blackness += s_red[w][dd];
+        int diff = blackness - last;
+        last = blackness;
+        if (diff >= maxDiff) maxDiff = diff;
+        acc += blackness;
+        dep++;
+      }
+      if (!((acc < maxAbs) && (dep < maxDepth))) s_done = 1;
+      s_max = maxDiff; s_dep = dep;
+    }
+    __syncthreads();
+    if (s_done) break;
+  }
+  if (threadIdx.x == 0) {
+    int peak = (s_dep < maxDepth) ? s_max : 0;
+    pg.u32[rp.peak_off + ((size_t)mi * 4 + e) * rp.nangles + a] = (unsigned)peak;
+  }
+}
+
 struct RotFinalParams {
   int nangles;
   int edges[4];
@@ -303,8 +440,13 @@ __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) 
           float fx = srcX - px, fy = srcY - py;
           float r4[4];
 #pragma unroll
-          for (int i = 0; i < 4; i++)
-            r4[i] = u8f(cubic_scale_f(fx, u8f(rw[i] & 0xFFu), u8f((rw[i] >> 8) & 0xFFu), u8f((rw[i] >> 16) & 0xFFu), u8f(rw[i] >> 24)));
+          for (int i = 0; i < 4; i++) {
+            unsigned b0 = rw[i] & 0xFFu;
+            // a row of four equal taps interpolates to that value exactly
+            r4[i] = (rw[i] == b0 * 0x01010101u)
+                        ? u8f(b0)
+                        : u8f(cubic_scale_f(fx, u8f(b0), u8f((rw[i] >> 8) & 0xFFu), u8f((rw[i] >> 16) & 0xFFu), u8f(rw[i] >> 24)));
+          }
           o = cubic_scale_f(fy, r4[0], r4[1], r4[2], r4[3]);
         }
         orow[x] = (uint8_t)o;
@@ -331,16 +473,29 @@ __global__ void k_stretch(DImg src, DImg dst, float hr, float vr, int interp) {
 extern "C" {
 int b200k_rot_peaks(cudaStream_t st, DPage *pages, int npages, int max_masks, const float *tan_tab_dev,
                     int nangles, int scan_size_param, float scan_depth, const int edges[4],
-                    int peak_off, int scan_cap) {
+                    int peak_off, int scan_cap, int maxw, int use_prefix) {
   if (npages <= 0 || max_masks <= 0 || nangles <= 0) return 0;
   RotParams rp;
   rp.scan_size = scan_size_param; rp.scan_depth = scan_depth; rp.nangles = nangles; rp.peak_off = peak_off;
   for (int i = 0; i < 4; i++) rp.edges[i] = edges[i];
   size_t sm = (size_t)scan_cap * sizeof(int2);
   if (sm > 200 * 1024) return -1;
-  if (sm > 40 * 1024) cudaFuncSetAttribute(k_rot_peaks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  dim3 g(nangles, max_masks * 4, npages);
-  k_rot_peaks<<<g, 256, sm, st>>>(pages, tan_tab_dev, rp);
+  if (sm > 40 * 1024) {
+    cudaFuncSetAttribute(k_rot_peaks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_rot_peaks_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  }
+  bool horiz = edges[0] || edges[2], vert = edges[1] || edges[3];
+  if (use_prefix && horiz) {
+    for (int mi = 0; mi < max_masks; mi++) {
+      k_rot_colprefix<<<dim3(cdiv(maxw, 32), npages), 32 * RP_SEG, 0, st>>>(pages, mi, scan_size_param);
+      k_rot_peaks_h<<<dim3(nangles, 2, npages), 256, sm, st>>>(pages, tan_tab_dev, rp, mi);
+    }
+    rp.edges[0] = 0; rp.edges[2] = 0;   // the sampling kernel below only does what is left
+  }
+  if ((!use_prefix && horiz) || vert) {
+    dim3 g(nangles, max_masks * 4, npages);
+    k_rot_peaks<<<g, 256, sm, st>>>(pages, tan_tab_dev, rp);
+  }
   return 0;
 }
 void b200k_rot_finalize(cudaStream_t st, DPage *pages, int npages, const float *rot_tab_dev,

@@ -51,7 +51,7 @@ void scratch_need_all(ScratchNeed *n, int w, int h, int fmt) {
   n->aux_h = ah;
   n->aux_bytes = (size_t)n->aux_pitch * ah + 64;
   n->cls_bytes = (size_t)w * h + 64;
-  n->list_cap = imax(4096, (w * h) / 4);
+  n->list_cap = imax(4096, (w * h) / 8);
   n->u32_cap = 0;
   n->stack_cap = 1 << 16;
 }
@@ -302,6 +302,8 @@ int rot_plan_build(RotPlan *pl, int w, int h, const DeskewParameters *p, int max
   pl->u32_need = max_masks * 4 * n + 1;
   int sc = p->deskewScanSize == -1 ? imax(w, h) : p->deskewScanSize;
   pl->scan_cap = imax(1, imin(sc, 10000));
+  /* rows of the column-prefix table: the scan length is at most the mask height (<= h + 1) */
+  pl->pre_need = (long long)(imin(pl->scan_cap, h + 1) + 2) * w;
   if (with_pair && n <= 512) {
     int m = 2 * n;
     float *t = (float *)malloc(sizeof(float) * 4 * (size_t)m * m);
@@ -406,11 +408,12 @@ void stage_detect_masks(StageCtx *c, const MaskPlan *pl) {
 
 int stage_detect_rotation(StageCtx *c, const RotPlan *pl, int max_masks) {
   int rc = b200k_rot_peaks(c->st, c->pages, c->npages, max_masks, pl->tan_dev, pl->nangles,
-                           pl->p.deskewScanSize, pl->p.deskewScanDepth, pl->edges, pl->peak_off, pl->scan_cap);
+                           pl->p.deskewScanSize, pl->p.deskewScanDepth, pl->edges, pl->peak_off, pl->scan_cap,
+                           c->w, 1);
   if (rc) { b200_set_error("deskew: scan size too large"); return rc; }
   b200k_rot_finalize(c->st, c->pages, c->npages, pl->rot_dev, pl->pair_dev, pl->nangles, pl->edges,
                      pl->peak_off, pl->p.deskewScanDeviationRad);
-  c->launches += 2;
+  c->launches += 2 + 2 * max_masks;
   return 0;
 }
 
