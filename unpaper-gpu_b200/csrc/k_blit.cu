@@ -122,6 +122,19 @@ __global__ void k_apply_masks(const DMaskJob *jobs) {
   uint8_t pat[3] = {im.fmt == DF_GRAY8 ? gv : j.c[0], im.fmt == DF_GRAY8 ? gv : j.c[1], im.fmt == DF_GRAY8 ? gv : j.c[2]};
   const int SPAN = 64;
   int nspan = (im.w + SPAN - 1) / SPAN;
+  if (j.nrects == 1 && bytes) {
+    // one rectangle (apply_border / single-page border mask): per row, the part
+    // left of it, right of it, or the whole row
+    DRect r = j.rects[0];
+    int ax = max(min(r.x0, r.x1), 0), bx = min(max(r.x0, r.x1), im.w - 1), ay = min(r.y0, r.y1), by = max(r.y0, r.y1);
+    for (int y = blockIdx.y; y < im.h; y += gridDim.y) {
+      uint8_t *row = im.data + (size_t)y * im.pitch;
+      if (y < ay || y > by || ax > bx) { fill_run(row, im.w * bpp, pat, 0, threadIdx.x, blockDim.x); continue; }
+      if (ax > 0) fill_run(row, ax * bpp, pat, 0, threadIdx.x, blockDim.x);
+      if (bx < im.w - 1) fill_run(row + (size_t)(bx + 1) * bpp, (im.w - 1 - bx) * bpp, pat, 0, threadIdx.x, blockDim.x);
+    }
+    return;
+  }
   for (int y = blockIdx.y; y < im.h; y += gridDim.y) {
     for (int sp = threadIdx.x; sp < nspan; sp += blockDim.x) {
       int xa = sp * SPAN, xb = min(xa + SPAN, im.w) - 1;

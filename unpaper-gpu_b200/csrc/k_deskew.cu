@@ -132,7 +132,7 @@ __global__ void k_rot_peaks(DPage *pages, const float *tan_tab, RotParams rp) {
  * ~scan*|tan| loads instead of `scan`.  Lanes own consecutive depths, so a warp
  * reads 32 consecutive prefix entries per run.
  * ------------------------------------------------------------------------ */
-#define RP_SEG 8
+#define RP_SEG 32
 
 __device__ __forceinline__ void rot_line_geometry(const DRect &mask, int scan_param, int &scan, int &Y0) {
   int sh = abs(mask.y0 - mask.y1) + 1;
@@ -144,7 +144,9 @@ __device__ __forceinline__ void rot_line_geometry(const DRect &mask, int scan_pa
 }
 
 __global__ void k_rot_colprefix(DPage *pages, int mi, int scan_param) {
-  __shared__ unsigned tot[RP_SEG][32];
+  // block = 32 lanes x RP_SEG row segments; a lane owns 4 adjacent columns (one
+  // 32-bit load per row, one 16-byte store of four running sums)
+  __shared__ uint4 tot[RP_SEG][32];
   DPage &pg = pages[blockIdx.y];
   if (mi >= pg.mask_count) return;
   const DImg &im = pg.img;
@@ -154,31 +156,52 @@ __global__ void k_rot_colprefix(DPage *pages, int mi, int scan_param) {
   if (scan <= 0) return;
   if ((long long)(scan + 1) * im.w > pg.pre_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&pg.error, DERR_UNSUPPORTED); return; }
   int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
-  int x = blockIdx.x * 32 + lane;
+  int x = (blockIdx.x * 32 + lane) * 4;
   int my0 = min(mask.y0, mask.y1), my1 = max(mask.y0, mask.y1);
   int vy0 = max(my0, 0), vy1 = min(my1, im.h - 1);
   int per = (scan + RP_SEG - 1) / RP_SEG;
   int r0 = seg * per, r1 = min(r0 + per, scan);
-  bool col = x < im.w;
-  bool gray8 = im.fmt == DF_GRAY8;
-  unsigned t = 0;
-  if (col)
+  bool fast = im.fmt == DF_GRAY8 && (im.pitch & 3) == 0 && ((uintptr_t)im.data & 3) == 0 && (im.w & 3) == 0 &&
+              ((uintptr_t)pg.pre & 15) == 0;
+  int ncol = min(4, im.w - x);          // columns this lane really owns (<= 0: none)
+  uint4 t = make_uint4(0, 0, 0, 0);
+  if (ncol > 0)
     for (int r = r0; r < r1; r++) {
       int y = Y0 + r;
-      if (y >= vy0 && y <= vy1) t += 255u - (unsigned)(gray8 ? (int)im.data[(size_t)y * im.pitch + x] : px_darkinv(px_load(im, x, y)));
+      if (y < vy0 || y > vy1) continue;
+      if (fast) {
+        unsigned w = ~*(const unsigned *)(im.data + (size_t)y * im.pitch + x);   // 255 - v per byte
+        t.x += w & 0xFFu; t.y += (w >> 8) & 0xFFu; t.z += (w >> 16) & 0xFFu; t.w += w >> 24;
+      } else {
+        unsigned v[4] = {0, 0, 0, 0};
+        for (int k = 0; k < ncol; k++) v[k] = 255u - (unsigned)px_darkinv(px_load(im, x + k, y));
+        t.x += v[0]; t.y += v[1]; t.z += v[2]; t.w += v[3];
+      }
     }
   tot[seg][lane] = t;
   __syncthreads();
-  if (!col) return;
-  unsigned run = 0;
-  for (int s = 0; s < seg; s++) run += tot[s][lane];
+  if (ncol <= 0) return;
+  uint4 run = make_uint4(0, 0, 0, 0);
+  for (int s = 0; s < seg; s++) { uint4 q = tot[s][lane]; run.x += q.x; run.y += q.y; run.z += q.z; run.w += q.w; }
   unsigned *C = pg.pre;
-  for (int r = r0; r < r1; r++) {
-    C[(size_t)r * im.w + x] = run;
+  for (int r = r0; r <= r1; r++) {
+    if (r == r1 && r1 != scan) break;   // row `scan` (the grand total) is written by the last segment only
+    if (r0 >= r1) break;
+    unsigned *dst = C + (size_t)r * im.w + x;
+    if (fast) *(uint4 *)dst = run;
+    else { unsigned rv[4] = {run.x, run.y, run.z, run.w}; for (int k = 0; k < ncol; k++) dst[k] = rv[k]; }
+    if (r == r1) break;
     int y = Y0 + r;
-    if (y >= vy0 && y <= vy1) run += 255u - (unsigned)(gray8 ? (int)im.data[(size_t)y * im.pitch + x] : px_darkinv(px_load(im, x, y)));
+    if (y < vy0 || y > vy1) continue;
+    if (fast) {
+      unsigned w = ~*(const unsigned *)(im.data + (size_t)y * im.pitch + x);
+      run.x += w & 0xFFu; run.y += (w >> 8) & 0xFFu; run.z += (w >> 16) & 0xFFu; run.w += w >> 24;
+    } else {
+      unsigned v[4] = {0, 0, 0, 0};
+      for (int k = 0; k < ncol; k++) v[k] = 255u - (unsigned)px_darkinv(px_load(im, x + k, y));
+      run.x += v[0]; run.y += v[1]; run.z += v[2]; run.w += v[3];
+    }
   }
-  if (r1 == scan && r0 < r1) C[(size_t)scan * im.w + x] = run;
 }
 
 __global__ void k_rot_peaks_h(DPage *pages, const float *tan_tab, RotParams rp, int mi) {
@@ -487,8 +510,8 @@ int b200k_rot_peaks(cudaStream_t st, DPage *pages, int npages, int max_masks, co
   bool horiz = edges[0] || edges[2], vert = edges[1] || edges[3];
   if (use_prefix && horiz) {
     for (int mi = 0; mi < max_masks; mi++) {
-      k_rot_colprefix<<<dim3(cdiv(maxw, 32), npages), 32 * RP_SEG, 0, st>>>(pages, mi, scan_size_param);
-      k_rot_peaks_h<<<dim3(nangles, 2, npages), 256, sm, st>>>(pages, tan_tab_dev, rp, mi);
+      k_rot_colprefix<<<dim3(cdiv(maxw, 128), npages), 32 * RP_SEG, 0, st>>>(pages, mi, scan_size_param);
+      k_rot_peaks_h<<<dim3(nangles, 2, npages), 64, sm, st>>>(pages, tan_tab_dev, rp, mi);
     }
     rp.edges[0] = 0; rp.edges[2] = 0;   // the sampling kernel below only does what is left
   }

@@ -275,6 +275,31 @@ __global__ void k_bf_scan(DPage *pages, const DBfPos *pos, int npos, int abs_thr
 #define NF_TH 16
 #define NF_MAXI 15
 
+// number of ring-dark, out-of-band pixels in the 3x3 block centred on (tx, ty)
+__device__ __forceinline__ int nf_count9(const uint8_t *tile, int tw, int tx, int ty) {
+  const uint8_t *t0 = tile + (ty - 1) * tw + (tx - 1);
+  int c = 0;
+#pragma unroll
+  for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+    for (int dx = 0; dx < 3; dx++) c += ((t0[dy * tw + dx] & 3) == 1);
+  return c;
+}
+// Cheap sufficient test for "component has >= need pixels": the 3x3 block around
+// the pixel, or around one of its dark neighbours, already holds that many (all
+// of them touch that centre, which touches the pixel).  Needs a 2-pixel halo.
+__device__ __forceinline__ bool nf_obviously_big(const uint8_t *tile, int tw, int tx, int ty, int need) {
+  if (need > 9) return false;
+  if (nf_count9(tile, tw, tx, ty) >= need) return true;
+#pragma unroll 1
+  for (int k = 0; k < 9; k++) {
+    if (k == 4) continue;
+    int nx = tx + k % 3 - 1, ny = ty + k / 3 - 1;
+    if ((tile[ny * tw + nx] & 3) == 1 && nf_count9(tile, tw, nx, ny) >= need) return true;
+  }
+  return false;
+}
+
 // Bounded walk over 8-connected ring-dark, out-of-band pixels ((code & 3) == 1) of
 // a shared-memory tile: true when fewer than `need` pixels are reachable from
 // (tx, ty).  Kept out of line: inlined and unrolled it dwarfs the kernels.
@@ -329,17 +354,7 @@ __global__ void k_nf_classify(DPage *pages, int intensity, int white, int all_mu
     uint8_t c = 0;
     if (v & 1) {
       bool mut = all_mutable || (v & 2);
-      if (!mut && need <= 9) {
-        // >= need ring-dark pixels in the 3x3 block: all of them touch this
-        // pixel, so its component already has need members
-        int c9 = 0;
-        const uint8_t *t0 = tile + (ly + halo - 1) * tw + (lx + halo - 1);
-#pragma unroll
-        for (int dy = 0; dy < 3; dy++)
-#pragma unroll
-          for (int dx = 0; dx < 3; dx++) c9 += ((t0[dy * tw + dx] & 3) == 1);
-        if (c9 >= need) goto classified;
-      }
+      if (!mut && halo >= 2 && nf_obviously_big(tile, tw, lx + halo, ly + halo, need)) goto classified;
       if (!mut) mut = nf_small_component(tile, tw, th, lx + halo, ly + halo, need);
     classified:
       c = NF_LIVE | ((v & 4) ? NF_TRIG : 0);
@@ -418,15 +433,7 @@ __global__ void k_nf_classify_g8(DPage *pages, int intensity, int white) {
     uint8_t c = 0;
     if (v & 1) {
       bool mut = (v & 2) != 0;
-      if (!mut) {
-        int c9 = 0;
-        const uint8_t *t0 = tile + (ty - 1) * tw + (tx - 1);
-#pragma unroll
-        for (int dy = 0; dy < 3; dy++)
-#pragma unroll
-          for (int dx = 0; dx < 3; dx++) c9 += ((t0[dy * tw + dx] & 3) == 1);
-        if (c9 < need) mut = nf_small_component(tile, tw, th, tx, ty, need);
-      }
+      if (!mut && !nf_obviously_big(tile, tw, tx, ty, need)) mut = nf_small_component(tile, tw, th, tx, ty, need);
       c = NF_LIVE | NF_TRIG;
       if (mut) {
         c |= NF_MUT | NF_UNDEC;
@@ -478,12 +485,16 @@ __global__ void k_nf_resolve(DPage *pages, int intensity) {
   DPage &pg = pages[blockIdx.x];
   const DImg &im = pg.img;
   uint8_t *cls = pg.cls;
-  int n = (int)min(pg.list_n, (unsigned)pg.list_cap);
+  // a truncated list would leave undecided pixels that nobody owns: refuse (the
+  // caller sees DERR_LIST_OVERFLOW) instead of spinning
+  if (pg.list_n > (unsigned)pg.list_cap) return;
+  int n = (int)pg.list_n;
   int R = 2 * intensity;
   __shared__ unsigned s_clusters;
   if (threadIdx.x == 0) s_clusters = 0;
   __syncthreads();
-  for (;;) {
+  // every round decides at least the raster-first undecided pixel
+  for (int round = 0; round <= n; round++) {
     // phase A: readiness against the state at the start of the round
     int pending = 0;
     for (int e = threadIdx.x; e < n; e += blockDim.x) {

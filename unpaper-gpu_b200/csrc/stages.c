@@ -51,7 +51,7 @@ void scratch_need_all(ScratchNeed *n, int w, int h, int fmt) {
   n->aux_h = ah;
   n->aux_bytes = (size_t)n->aux_pitch * ah + 64;
   n->cls_bytes = (size_t)w * h + 64;
-  n->list_cap = imax(4096, (w * h) / 8);
+  n->list_cap = imax(4096, (w * h) / 4);
   n->u32_cap = 0;
   n->stack_cap = 1 << 16;
 }
