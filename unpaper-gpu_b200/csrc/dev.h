@@ -54,6 +54,8 @@ typedef struct DPage {
   uint32_t *list;        /* noisefilter mutable list */
   uint32_t *u32;         /* general u32 scratch */
   uint64_t *stack;       /* flood-fill frame stack (4 x u64 per frame) */
+  uint8_t *ink;          /* 16x16-pixel cells: 1 = every pixel of the cell is pure white */
+  int32_t ink_ncx, ink_ncy, ink_ok, ink_cap;
   uint32_t *pre;         /* column prefix sums for the rotation scan: [rows+1][img.w] */
   int64_t pre_cap;       /* capacity of `pre` in u32 elements */
   int32_t list_cap, u32_cap, stack_cap, pad0;

@@ -49,6 +49,7 @@ typedef struct {
   uint32_t *list, *u32;
   uint64_t *stack;
   uint32_t *pre;
+  uint8_t *ink;
   uint8_t *page_stage;    /* device staging for host-mode pages */
   DPage *pages_dev, *pages_tmpl /* host */;
   DFillJob *fillA, *fillB, *fillC, *decode_fill;
@@ -159,7 +160,7 @@ static int build_static(B200Engine *e, Lane *ln, int slot, const Rectangle *wipe
 }
 
 static void lane_free(Lane *ln) {
-  void *ptrs[] = {ln->sheets, ln->aux, ln->cls, ln->list, ln->u32, ln->stack, ln->pre, ln->page_stage, ln->pages_dev,
+  void *ptrs[] = {ln->sheets, ln->aux, ln->cls, ln->list, ln->u32, ln->stack, ln->pre, ln->ink, ln->page_stage, ln->pages_dev,
                   ln->fillA, ln->fillB, ln->fillC, ln->decode_fill, ln->copyA, ln->copyB, ln->decode_copy, ln->maskJ,
                   ln->static_fill[0], ln->static_fill[1], ln->static_fill[2], ln->static_mask[0], ln->static_mask[1],
                   ln->static_mask[2], ln->static_mask_rects[0], ln->static_mask_rects[1], ln->static_mask_rects[2]};
@@ -281,6 +282,9 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
     ln->u32 = (uint32_t *)b200_dev_alloc((size_t)e->need.u32_cap * 4 * P);
     ln->stack = (uint64_t *)b200_dev_alloc((size_t)e->need.stack_cap * 32 * P);
     if (e->need.pre_cap > 0) ln->pre = (uint32_t *)b200_dev_alloc((size_t)e->need.pre_cap * 4 * P);
+    int ink_cells = ((W + 15) / 16) * ((H + 15) / 16);
+    size_t ink_stride = ((size_t)ink_cells + 255) & ~(size_t)255;
+    ln->ink = (uint8_t *)b200_dev_alloc(ink_stride * P);
     ln->page_stage = (uint8_t *)b200_dev_alloc(e->page_bytes * cfg->input_count * P + 64);
     ln->pages_dev = (DPage *)b200_dev_alloc(sizeof(DPage) * P);
     ln->pages_tmpl = (DPage *)calloc((size_t)P, sizeof(DPage));
@@ -305,6 +309,7 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
       pg->u32 = ln->u32 + (size_t)e->need.u32_cap * p; pg->u32_cap = e->need.u32_cap;
       pg->stack = ln->stack + (size_t)e->need.stack_cap * 4 * p; pg->stack_cap = e->need.stack_cap;
       if (ln->pre) { pg->pre = ln->pre + (size_t)e->need.pre_cap * p; pg->pre_cap = e->need.pre_cap; }
+      pg->ink = ln->ink + ink_stride * p; pg->ink_cap = ink_cells;
       pg->point_count = e->npoints;
       for (int i = 0; i < e->npoints; i++) { pg->px[i] = e->points[i].x; pg->py[i] = e->points[i].y; }
       pg->outside_count = e->noutside;

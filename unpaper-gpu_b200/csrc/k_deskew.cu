@@ -13,6 +13,7 @@ static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
 #define ROT_CHUNK 32
 #define ROT_ROWS 16
+#define ROT_TILE 8
 
 struct RotParams {
   int scan_size;        // params.deskewScanSize (may be -1)
@@ -403,6 +404,68 @@ __device__ __forceinline__ Px interp_any(const DImg &im, float fx, float fy, int
   return gray ? interp_cubic<true>(im, fx, fy) : interp_cubic<false>(im, fx, fy);
 }
 
+
+/* Ink map: which 16x16 cells of the image are pure white.  A target tile whose
+ * source footprint (plus the interpolation taps) only touches white cells — or
+ * lies outside the image, which reads as white — is white after bicubic
+ * interpolation (all 16 taps equal => every term of interpolate.c:24-32 cancels
+ * exactly), so rotate() can write it without touching a pixel. */
+#define INK_CELL 16
+__global__ void k_inkmap(DPage *pages) {
+  DPage &pg = pages[blockIdx.y];
+  const DImg &im = pg.img;
+  int ncx = (im.w + INK_CELL - 1) / INK_CELL, ncy = (im.h + INK_CELL - 1) / INK_CELL;
+  int bpp = im.fmt == DF_GRAY8 ? 1 : im.fmt == DF_RGB24 ? 3 : 0;
+  bool ok = bpp && (im.pitch & 15) == 0 && ((uintptr_t)im.data & 15) == 0 && ncx * ncy <= pg.ink_cap && pg.ink;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { pg.ink_ncx = ncx; pg.ink_ncy = ncy; pg.ink_ok = ok; }
+  if (!ok) return;
+  for (int cy = blockIdx.x; cy < ncy; cy += gridDim.x) {
+    int y0 = cy * INK_CELL, y1 = min(y0 + INK_CELL, im.h);
+    for (int c = threadIdx.x; c < ncx; c += blockDim.x) {
+      bool white = true;
+      int x0 = c * INK_CELL;
+      if (x0 + INK_CELL <= im.w) {
+        for (int y = y0; y < y1 && white; y++) {
+          const uint4 *q = (const uint4 *)(im.data + (size_t)y * im.pitch + (size_t)x0 * bpp);
+          for (int v = 0; v < bpp; v++) { uint4 t = q[v]; white = white && ((t.x & t.y & t.z & t.w) == 0xFFFFFFFFu); }
+        }
+      } else {
+        for (int y = y0; y < y1 && white; y++)
+          for (int x = x0; x < im.w && white; x++) { Px p = px_load(im, x, y); white = (p.r & p.g & p.b) == 255; }
+      }
+      pg.ink[cy * ncx + c] = white ? 1 : 0;
+    }
+  }
+}
+
+// warp-collective: true when the source footprint of the target tile
+// [xa..xb] x [ya..yb] (mask-local coordinates) is entirely white
+__device__ bool rot_tile_white(const DPage &pg, const DImg &im, int xa, int xb, int ya, int yb, float scx, float scy,
+                               float tcx, float tcy, float sinval, float cosval, int lane) {
+  int cxp = (lane & 1) ? xb : xa, cyp = (lane & 2) ? yb : ya;
+  float sx = scx + (cxp - tcx) * cosval + (cyp - tcy) * sinval;
+  float sy = scy + (cyp - tcy) * cosval - (cxp - tcx) * sinval;
+  float mnx = sx, mxx = sx, mny = sy, mxy = sy;
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  mnx = __shfl_sync(0xffffffffu, mnx, 0); mxx = __shfl_sync(0xffffffffu, mxx, 0);
+  mny = __shfl_sync(0xffffffffu, mny, 0); mxy = __shfl_sync(0xffffffffu, mxy, 0);
+  if (!(fabsf(mnx) < 1e7f && fabsf(mxx) < 1e7f && fabsf(mny) < 1e7f && fabsf(mxy) < 1e7f)) return false;
+  // taps reach from (int)src - 1 to (int)src + 2; two pixels of slack for rounding
+  int bx0 = (int)floorf(mnx) - 3, bx1 = (int)floorf(mxx) + 4, by0 = (int)floorf(mny) - 3, by1 = (int)floorf(mxy) + 4;
+  if (bx1 < 0 || by1 < 0 || bx0 >= im.w || by0 >= im.h) return true;   // entirely outside: reads as white
+  int cx0 = max(bx0, 0) / INK_CELL, cx1 = min(bx1, im.w - 1) / INK_CELL;
+  int cy0 = max(by0, 0) / INK_CELL, cy1 = min(by1, im.h - 1) / INK_CELL;
+  int nx = cx1 - cx0 + 1, n = nx * (cy1 - cy0 + 1);
+  if (n > 32) return false;
+  bool w = true;
+  if (lane < n) w = pg.ink[(cy0 + lane / nx) * pg.ink_ncx + cx0 + lane % nx] != 0;
+  return __all_sync(0xffffffffu, w);
+}
+
 // rotate() (deskew.c:253-274) of mask `mi` into aux (mask-sized); the copy
 // back is a DCopyJob prepared here.
 __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) {
@@ -431,10 +494,30 @@ __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) 
   bool fast = im.fmt == DF_GRAY8 && interp == 2;
   bool pitch4 = ((im.pitch & 3) == 0);
   // a block owns ROT_ROWS consecutive target rows x 128 columns (one block per
-  // row would be launch-bound: ~70 k blocks per A4 page)
-  for (int y = blockIdx.y * ROT_ROWS; y < min(h, (int)(blockIdx.y + 1) * ROT_ROWS); y++) {
+  // row would be launch-bound: ~70 k blocks per A4 page); each warp first tries to
+  // dispose of its 32 x ROT_TILE tile through the ink map
+  bool can_skip = pg.ink_ok && interp == 2 && (im.fmt == DF_GRAY8 || im.fmt == DF_RGB24) && (aux.fmt == im.fmt);
+  int lane = threadIdx.x & 31;
+  int yblock = blockIdx.y * ROT_ROWS, yend = min(h, yblock + ROT_ROWS);
+  for (int xs = blockIdx.x * blockDim.x; xs < w; xs += gridDim.x * blockDim.x) {
+  int x = xs + threadIdx.x;
+  int xwa = xs + (threadIdx.x & ~31), xwb = min(xwa + 31, w - 1);   // this warp's columns
+  for (int yt = yblock; yt < yend; yt += ROT_TILE) {
+  int yte = min(yt + ROT_TILE, yend);
+  if (can_skip && xwa < w && rot_tile_white(pg, im, xwa, xwb, yt, yte - 1, scx, scy, tcx, tcy, sinval, cosval, lane)) {
+    if (x < w) {
+      int nb = aux.fmt == DF_RGB24 ? 3 : 1;
+      for (int y = yt; y < yte; y++) {
+        uint8_t *o = aux.data + (size_t)y * aux.pitch + (size_t)x * nb;
+        o[0] = 255; if (nb == 3) { o[1] = 255; o[2] = 255; }
+      }
+    }
+    continue;
+  }
+  if (x >= w) continue;
+  for (int y = yt; y < yte; y++) {
   uint8_t *orow = aux.data + (size_t)y * aux.pitch;
-  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) {
+  {
     float srcX = scx + (x - tcx) * cosval + (y - tcy) * sinval;
     float srcY = scy + (y - tcy) * cosval - (x - tcx) * sinval;
     if (fast) {
@@ -478,6 +561,8 @@ __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) 
     }
     Px o = interp_any(im, srcX, srcY, interp, gray);
     px_store(aux, x, y, o.r, o.g, o.b);
+  }
+  }
   }
   }
 }
@@ -533,6 +618,7 @@ void b200k_rot_finalize(cudaStream_t st, DPage *pages, int npages, const float *
 void b200k_rotate(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int maxw, int maxh,
                   DCopyJob *back_jobs) {
   if (npages <= 0 || maxw <= 0 || maxh <= 0) return;
+  if (interp == 2) k_inkmap<<<dim3(min(cdiv(maxh, INK_CELL), 256u), npages), 128, 0, st>>>(pages);
   dim3 g(min(cdiv(maxw, 128), 64u), cdiv(maxh, ROT_ROWS), npages);
   k_rotate<<<g, 128, 0, st>>>(pages, mi, interp, back_jobs);
 }
