@@ -29,12 +29,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# one hardware queue per engine lane (the default of 8 makes lanes share queues)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np  # noqa: E402
 
 import unpaper_gpu_b200 as U  # noqa: E402
 from unpaper_gpu_b200 import synth  # noqa: E402
-from oracle import checker  # test infrastructure: the CPU checkers
+from unpaper_gpu_b200 import shard  # noqa: E402
+from oracle import checker  # noqa: E402  test infrastructure: the CPU checkers
 
 W, H = synth.A4_W, synth.A4_H
 WORKLOAD = ("BASELINE config 2: synthetic A4 300-dpi GRAY8 2480x3508, +-5 deg skew, speckle 1/5000, "
@@ -153,9 +156,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--pages", type=int, default=int(os.environ.get("BENCH_PAGES", "128")), help="sheets per rank per step")
-    ap.add_argument("--group", type=int, default=int(os.environ.get("BENCH_GROUP", "16")))
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("BENCH_LANES", "4")))
+    ap.add_argument("--pages", type=int, default=int(os.environ.get("BENCH_PAGES", "1024")), help="sheets per rank per step (HBM-resident arm)")
+    ap.add_argument("--e2e-pages", type=int, default=int(os.environ.get("BENCH_E2E_PAGES", "1024")), help="sheets per rank per step (host-buffer arm)")
+    ap.add_argument("--group", type=int, default=int(os.environ.get("BENCH_GROUP", "32")))
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("BENCH_LANES", "8")))
     ap.add_argument("--distinct", type=int, default=int(os.environ.get("BENCH_DISTINCT", "8")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -185,18 +189,32 @@ def main():
     distinct = make_pages(args.distinct, rank)
     reps = (args.pages + args.distinct - 1) // args.distinct
     host_np = np.concatenate([distinct] * reps)[:args.pages]
-    host_in = torch.from_numpy(host_np).pin_memory()
-    host_out = torch.empty((args.pages, H, W), dtype=torch.uint8).pin_memory()
-    dev_in = host_in.to(f"cuda:{local}")
+    e2e_pages = min(args.e2e_pages, args.pages)
+    host_in = torch.from_numpy(host_np[:e2e_pages]).pin_memory()
+    host_out = torch.empty((e2e_pages, H, W), dtype=torch.uint8).pin_memory()
+    dev_in = torch.from_numpy(distinct).to(f"cuda:{local}").repeat((reps, 1, 1))[:args.pages].contiguous()
     dev_out = torch.empty((args.pages, H, W), dtype=torch.uint8, device=f"cuda:{local}")
     res = (U.SheetResult * args.pages)()
+
+    def pcie_gbs():
+        """Raw pinned-memory copy bandwidth of this box: the ceiling of the e2e arm."""
+        n = min(e2e_pages, 64)
+        t_h2d = t_d2h = 1e9
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); dev_out[:n].copy_(host_in[:n], non_blocking=True); b.record(); b.synchronize()
+            t_h2d = min(t_h2d, a.elapsed_time(b))
+            a.record(); host_out[:n].copy_(dev_out[:n], non_blocking=True); b.record(); b.synchronize()
+            t_d2h = min(t_d2h, a.elapsed_time(b))
+        gb = n * W * H / 1e9
+        return round(gb / (t_h2d / 1e3), 1), round(gb / (t_d2h / 1e3), 1)
 
     def step_device():
         eng.process_ptr(dev_in.data_ptr(), dev_out.data_ptr(), args.pages, False, res)
         return eng.last_device_ms()
 
     def step_host():
-        eng.process_ptr(host_in.data_ptr(), host_out.data_ptr(), args.pages, True, res)
+        eng.process_ptr(host_in.data_ptr(), host_out.data_ptr(), e2e_pages, True, res)
         return eng.last_device_ms()
 
     def timed(fn, steps, warmup, profile=False):
@@ -211,10 +229,8 @@ def main():
             dev_ms += fn()          # CUDA events on the engine's own streams, summed over steps
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1000.0
-        t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), eng.launch_count() - l0
+        t = shard.max_over_ranks([dev_ms, wall_ms], device=f"cuda:{local}")
+        return t[0], t[1], eng.launch_count() - l0
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -224,36 +240,67 @@ def main():
     eng.set_profiling(False)
     e2e_ms, e2e_wall_ms, _ = timed(step_host, args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
+    h2d_gbs, d2h_gbs = pcie_gbs()
 
     # correctness guard: every sheet deskewed and flagged ok
     bad = sum(1 for r in res if r.status != 0)
     total_pages = args.pages * world
     value = total_pages * args.steps / (dev_ms / 1000.0)
-    e2e_value = total_pages * args.steps / (e2e_ms / 1000.0)
+    e2e_value = e2e_pages * world * args.steps / (e2e_ms / 1000.0)
+
+    # Per-stage durations with nothing else on the GPU: a second, single-lane engine runs
+    # two groups with CUDA events around every stage (rank 0 only; the lanes of the main
+    # engine are idle by now).  This is "the kernel's own launch duration"; the numbers
+    # taken inside the timed region (all lanes competing for the SMs) are reported too.
+    iso = None
+    if rank == 0:
+        ie = Engine(cfg, W, H, U.FMT_GRAY8, group_pages=min(args.group, 64), lanes=1, device=local)
+        n_iso = min(args.group, 64)
+        for _ in range(2):
+            ie.process_ptr(dev_in.data_ptr(), dev_out.data_ptr(), n_iso, False, None)
+        ie.set_profiling(True)
+        for _ in range(3):
+            ie.process_ptr(dev_in.data_ptr(), dev_out.data_ptr(), n_iso, False, None)
+        iso = (ie.profile(), n_iso)
+        ie.close()
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
         S = W * H
         M = S * 0.82        # typical detected mask share of the sheet on these pages
         sb = stage_bytes(S, M)
-        groups = {k: v[1] for k, v in prof.items()}
-        per_stage = {}
-        dom, dom_ms = None, 0.0
-        for k, (ms, cnt) in prof.items():
-            if cnt == 0:
-                continue
-            avg_ms = ms / cnt                       # one launch sequence = one group of `group` sheets
-            gbs = sb.get(k, 0) * args.group / (avg_ms / 1000.0) / 1e9 if avg_ms > 0 else 0.0
-            per_stage[k] = {"ms_per_group": round(avg_ms, 4), "alg_gbs": round(gbs, 1)}
-            if ms > dom_ms:
-                dom, dom_ms = k, ms
-        roof = None
-        if dom:
-            a = per_stage[dom]["alg_gbs"]
-            roof = {"bound": "hbm", "kernel": dom, "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": round(a / peaks["hbm_gbs"], 4), "traffic": None, "peak_source": peak_src,
-                    "note": "stage-level CUDA-event timing inside the timed region with all lanes running "
-                            "concurrently; algorithmic bytes per SURVEY 8(d) with 1 B/px working sheet"}
+
+        def table(profile, pages_per_group):
+            out, dom, dom_ms = {}, None, 0.0
+            for k, (ms, cnt) in profile.items():
+                if cnt == 0:
+                    continue
+                avg_ms = ms / cnt                   # one launch sequence = one group of sheets
+                gbs = sb.get(k, 0) * pages_per_group / (avg_ms / 1000.0) / 1e9 if avg_ms > 0 else 0.0
+                out[k] = {"ms_per_group": round(avg_ms, 4), "alg_gbs": round(gbs, 1),
+                          "us_per_page": round(1000.0 * avg_ms / pages_per_group, 2)}
+                if ms > dom_ms:
+                    dom, dom_ms = k, ms
+            return out, dom
+
+        per_stage, dom_conc = table(prof, args.group)
+        iso_stage, dom = table(iso[0], iso[1])
+        traffic = None
+        tj = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tj):
+            with open(tj) as f:
+                traffic = json.load(f).get(dom)
+        a = iso_stage[dom]["alg_gbs"]
+        roof = {"bound": "hbm", "kernel": dom, "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(a / peaks["hbm_gbs"], 4), "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": sb.get(dom, 0) * iso[1],
+                "launch": f"one stage launch sequence over a group of {iso[1]} sheets, timed alone with CUDA events "
+                          "on the launching stream",
+                "concurrent": {"kernel": dom_conc, "achieved": per_stage[dom_conc]["alg_gbs"],
+                               "frac": round(per_stage[dom_conc]["alg_gbs"] / peaks["hbm_gbs"], 4),
+                               "note": "same stage timed inside the timed region with all lanes competing"},
+                "note": "algorithmic bytes per SURVEY 8(d) with the 1 B/px working sheet; the dominant stage is "
+                        "the one with the largest share of the isolated per-sheet time"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -263,10 +310,13 @@ def main():
                            "parallelism": f"page-sharded x{world}, no collective",
                            "timing": "CUDA events on the engine's streams (first enqueue -> last lane done), max over ranks",
                            "wall_ms_per_step": dev_wall_ms / args.steps},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": args.pages * S * world,
-                        "d2h_bytes_per_step": args.pages * S * world, "ms_per_step": e2e_ms / args.steps,
-                        "wall_ms_per_step": e2e_wall_ms / args.steps},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_pages * S * world,
+                        "d2h_bytes_per_step": e2e_pages * S * world, "ms_per_step": e2e_ms / args.steps,
+                        "wall_ms_per_step": e2e_wall_ms / args.steps, "pages_per_step_per_gpu": e2e_pages,
+                        "pcie_h2d_gbs": h2d_gbs, "pcie_d2h_gbs": d2h_gbs,
+                        "pcie_bound_pages_per_sec_per_gpu": round(min(h2d_gbs, d2h_gbs) * 1e9 / S, 1)},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "stages": per_stage,
+                "stages_isolated": iso_stage,
                 "failed_sheets": bad}
         if world == 1 and not args.no_cpu_baseline:
             lib = checker.load_ref()

@@ -37,48 +37,68 @@ __device__ __forceinline__ bool ff_match(const DImg &im, int x, int y, int lo, i
   return g >= lo && g <= hi;
 }
 
-// fill_line (fill.c:16-43): returns painted distance.  Warp-cooperative; FF_U
-// chunks of 32 pixels are fetched per round so that the (latency-bound) walk
-// along a column keeps several loads in flight.
+// ---- block-cooperative emulation --------------------------------------------------
+// One CTA of BF_WARPS warps per page.  Every step of the (inherently serial)
+// recursion is made as wide as possible: a round looks at BF_ROUND consecutive
+// pixels of a line / candidates of a frame at once (each warp FF_U chunks of 32),
+// the per-chunk ballots meet in shared memory and every thread replays the same
+// scalar decision, so the recursion state stays uniform across the block.
 #define FF_U 4
+#define BF_WARPS 8
+#define BF_THREADS (BF_WARPS * 32)
+#define BF_CH (BF_WARPS * FF_U)
+#define BF_ROUND (BF_CH * 32)
+
+struct BfShared {
+  unsigned M[BF_CH];
+  unsigned I[BF_CH];
+  unsigned long long red[BF_WARPS];
+};
+
+// fill_line (fill.c:16-43): returns the painted distance
 __device__ __noinline__ int ff_fill_line(const DImg &im, int px, int py, int dx, int dy, int lo, int hi,
-                            unsigned long long intensity, int lane) {
+                                         unsigned long long intensity, BfShared &sh) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int distance = 0;
   unsigned long long cnt = 1;
   for (;;) {
-    unsigned M[FF_U], I[FF_U];
 #pragma unroll
     for (int u = 0; u < FF_U; u++) {
-      int s = distance + u * 32 + lane + 1;
+      int c = warp * FF_U + u;
+      int s = distance + c * 32 + lane + 1;
       int qx = px + s * dx, qy = py + s * dy;
       bool inb = in_img(im, qx, qy);
       bool m = ff_match(im, qx, qy, lo, hi);
-      M[u] = __ballot_sync(0xffffffffu, m);
-      I[u] = __ballot_sync(0xffffffffu, inb);
+      unsigned M = __ballot_sync(0xffffffffu, m), I = __ballot_sync(0xffffffffu, inb);
+      if (lane == 0) { sh.M[c] = M; sh.I[c] = I; }
     }
+    __syncthreads();
     int total = 0;
     bool stop = false;
-#pragma unroll
-    for (int u = 0; u < FF_U; u++) {
-      if (stop) break;
+    for (int c = 0; c < BF_CH && !stop; c++) {
+      unsigned M = sh.M[c], I = sh.I[c];
       int painted = 32;
-      if ((M[u] & I[u]) == 0xffffffffu) {
+      if ((M & I) == 0xffffffffu) {
         cnt = intensity;
         if (cnt == 0) painted = 0;   // degenerate intensity 0: stops on the first pixel
       } else {
         for (int i = 0; i < 32; i++) {
-          if ((M[u] >> i) & 1u) cnt = intensity; else cnt--;
-          if (cnt == 0 || !((I[u] >> i) & 1u)) { painted = i; break; }
+          if ((M >> i) & 1u) cnt = intensity; else cnt--;
+          if (cnt == 0 || !((I >> i) & 1u)) { painted = i; break; }
         }
-      }
-      if (lane < painted) {
-        int s = distance + u * 32 + lane + 1;
-        ff_paint(im, px + s * dx, py + s * dy);
       }
       total += painted;
       if (painted < 32) stop = true;
     }
-    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < FF_U; u++) {
+      int idx = (warp * FF_U + u) * 32 + lane;
+      if (idx < total) {
+        int s = distance + idx + 1;
+        ff_paint(im, px + s * dx, py + s * dy);
+      }
+    }
+    __syncthreads();
     distance += total;
     if (stop) return distance;
   }
@@ -100,22 +120,22 @@ __device__ __forceinline__ void ff_cand(const FFFrame &f, unsigned idx, int &x, 
 
 // flood_fill(p) for a p that is known to match: paint the cross and push.
 __device__ __noinline__ bool ff_open(DPage &pg, const DImg &im, int x, int y, int lo, int hi,
-                        unsigned long long intensity, int lane, int &sp, FFFrame &top) {
-  if (sp >= pg.stack_cap) { if (lane == 0) atomicOr(&pg.error, DERR_STACK_OVERFLOW); return false; }
-  if (sp > 0 && lane == 0) {   // spill the current top
+                                     unsigned long long intensity, BfShared &sh, int &sp, FFFrame &top) {
+  if (sp >= pg.stack_cap) { if (threadIdx.x == 0) atomicOr(&pg.error, DERR_STACK_OVERFLOW); return false; }
+  if (sp > 0 && threadIdx.x == 0) {   // spill the current top
     unsigned long long *s = (unsigned long long *)pg.stack + (size_t)(sp - 1) * 4;
     s[0] = (unsigned)top.cx | ((unsigned long long)(unsigned)top.cy << 32);
     s[1] = (unsigned long long)(unsigned)top.L | ((unsigned long long)(unsigned)top.T << 32);
     s[2] = (unsigned long long)(unsigned)top.R | ((unsigned long long)(unsigned)top.B << 32);
     s[3] = top.cursor;
   }
-  if (lane == 0) ff_paint(im, x, y);
-  __syncwarp();
+  if (threadIdx.x == 0) ff_paint(im, x, y);
+  __syncthreads();
   top.cx = x; top.cy = y;
-  top.L = ff_fill_line(im, x, y, -1, 0, lo, hi, intensity, lane);
-  top.T = ff_fill_line(im, x, y, 0, -1, lo, hi, intensity, lane);
-  top.R = ff_fill_line(im, x, y, 1, 0, lo, hi, intensity, lane);
-  top.B = ff_fill_line(im, x, y, 0, 1, lo, hi, intensity, lane);
+  top.L = ff_fill_line(im, x, y, -1, 0, lo, hi, intensity, sh);
+  top.T = ff_fill_line(im, x, y, 0, -1, lo, hi, intensity, sh);
+  top.R = ff_fill_line(im, x, y, 1, 0, lo, hi, intensity, sh);
+  top.B = ff_fill_line(im, x, y, 0, 1, lo, hi, intensity, sh);
   top.cursor = 0;
   sp++;
   return true;
@@ -123,35 +143,37 @@ __device__ __noinline__ bool ff_open(DPage &pg, const DImg &im, int x, int y, in
 
 // Runs the recursion to completion starting from an already-open frame.
 __device__ __noinline__ void ff_run(DPage &pg, const DImg &im, int lo, int hi, unsigned long long intensity,
-                       int lane, int &sp, FFFrame &top) {
+                                    BfShared &sh, int &sp, FFFrame &top) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   while (sp > 0) {
     unsigned total = 2u * ((unsigned)top.L + top.T + top.R + top.B);
     bool opened = false;
     while (top.cursor < total) {
-      int x[FF_U], y[FF_U];
-      unsigned M[FF_U];
 #pragma unroll
       for (int u = 0; u < FF_U; u++) {
-        unsigned idx = top.cursor + u * 32 + lane;
-        x[u] = 0; y[u] = 0;
+        int c = warp * FF_U + u;
+        unsigned idx = top.cursor + c * 32 + lane;
+        int x = 0, y = 0;
         bool m = false;
-        if (idx < total) { ff_cand(top, idx, x[u], y[u]); m = in_img(im, x[u], y[u]) && ff_match(im, x[u], y[u], lo, hi); }
-        M[u] = __ballot_sync(0xffffffffu, m);
+        if (idx < total) { ff_cand(top, idx, x, y); m = in_img(im, x, y) && ff_match(im, x, y, lo, hi); }
+        unsigned M = __ballot_sync(0xffffffffu, m);
+        if (lane == 0) sh.M[c] = M;
       }
+      __syncthreads();
       int hit = -1;
-#pragma unroll
-      for (int u = 0; u < FF_U; u++) if (hit < 0 && M[u]) hit = u;
+      unsigned Mh = 0;
+      for (int c = 0; c < BF_CH; c++) { unsigned M = sh.M[c]; if (M) { hit = c; Mh = M; break; } }
+      __syncthreads();   // sh.M is rewritten by the next round / by ff_open
       if (hit >= 0) {
-        int first = __ffs(M[hit]) - 1;
-        int fx = 0, fy = 0;
-#pragma unroll
-        for (int u = 0; u < FF_U; u++) if (u == hit) { fx = __shfl_sync(0xffffffffu, x[u], first); fy = __shfl_sync(0xffffffffu, y[u], first); }
-        top.cursor += hit * 32 + first + 1;
-        if (!ff_open(pg, im, fx, fy, lo, hi, intensity, lane, sp, top)) { sp = 0; return; }
+        unsigned idx = top.cursor + hit * 32 + (__ffs(Mh) - 1);
+        int fx, fy;
+        ff_cand(top, idx, fx, fy);
+        top.cursor = idx + 1;
+        if (!ff_open(pg, im, fx, fy, lo, hi, intensity, sh, sp, top)) { sp = 0; return; }
         opened = true;
         break;
       }
-      top.cursor += 32 * FF_U;
+      top.cursor += BF_ROUND;
     }
     if (opened) continue;
     sp--;   // frame exhausted: return to the caller's frame
@@ -166,23 +188,30 @@ __device__ __noinline__ void ff_run(DPage &pg, const DImg &im, int lo, int hi, u
   }
 }
 
-__device__ __noinline__ unsigned long long warp_rect_maxch_sum(const DImg &im, int x0, int y0, int x1, int y1, int lane) {
+__device__ __noinline__ unsigned long long block_rect_maxch_sum(const DImg &im, int x0, int y0, int x1, int y1, BfShared &sh) {
   unsigned long long s = 0;
   if (x0 <= x1 && y0 <= y1) {
     int w = x1 - x0 + 1, n = w * (y1 - y0 + 1);
-    for (int i = lane; i < n; i += 32) s += (unsigned)px_darkinv(px_load(im, x0 + i % w, y0 + i / w));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += (unsigned)px_darkinv(px_load(im, x0 + i % w, y0 + i / w));
   }
-  return warp_sum_u64(s);
+  s = warp_sum_u64(s);
+  if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  unsigned long long t = 0;
+  for (int w = 0; w < BF_WARPS; w++) t += sh.red[w];
+  __syncthreads();
+  return t;
 }
 
-__global__ void k_bf_scan(DPage *pages, const DBfPos *pos, int npos, int abs_threshold,
+__global__ void __launch_bounds__(BF_THREADS) k_bf_scan(DPage *pages, const DBfPos *pos, int npos, int abs_threshold,
                           unsigned long long intensity, int mask_lo, int mask_hi, int flag_off) {
+  __shared__ BfShared sh;
   DPage &pg = pages[blockIdx.x];
   const DImg im = pg.img;
-  int lane = threadIdx.x;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t *cand = (uint8_t *)(pg.u32 + flag_off);
   // phase 1: darkness of every position on the untouched image (blit.c:131-146)
-  for (int k = lane; k < npos; k += 32) {
+  for (int k = threadIdx.x; k < npos; k += blockDim.x) {
     DBfPos q = pos[k];
     int x0 = max(q.r.x0, 0), x1 = min(q.r.x1, im.w - 1), y0 = max(q.r.y0, 0), y1 = min(q.r.y1, im.h - 1);
     unsigned long long cnt = (unsigned long long)(abs(x0 - x1) + 1) * (unsigned long long)(abs(y0 - y1) + 1);
@@ -195,57 +224,50 @@ __global__ void k_bf_scan(DPage *pages, const DBfPos *pos, int npos, int abs_thr
     int darkness = (int)(uint8_t)(0xFF - (s / cnt));
     cand[k] = darkness >= abs_threshold ? 1 : 0;
   }
-  __syncwarp();
-  // phase 2: candidates in scan order
+  __syncthreads();
+  // phase 2: candidates in scan order (every thread walks the same list)
   bool dirty = false;
   unsigned fills = 0;
-  for (int base = 0; base < npos; base += 32) {
-    int k = base + lane;
-    unsigned C = __ballot_sync(0xffffffffu, k < npos && cand[k]);
-    while (C) {
-      int b = __ffs(C) - 1;
-      C &= C - 1;
-      DBfPos q = pos[base + b];
-      int x0 = max(q.r.x0, 0), x1 = min(q.r.x1, im.w - 1), y0 = max(q.r.y0, 0), y1 = min(q.r.y1, im.h - 1);
-      if (dirty) {
-        unsigned long long cnt = (unsigned long long)(abs(x0 - x1) + 1) * (unsigned long long)(abs(y0 - y1) + 1);
-        unsigned long long s = warp_rect_maxch_sum(im, x0, y0, x1, y1, lane);
-        int darkness = (int)(uint8_t)(0xFF - (s / cnt));
-        if (darkness < abs_threshold) continue;
+  for (int k = 0; k < npos; k++) {
+    if (!cand[k]) continue;
+    DBfPos q = pos[k];
+    int x0 = max(q.r.x0, 0), x1 = min(q.r.x1, im.w - 1), y0 = max(q.r.y0, 0), y1 = min(q.r.y1, im.h - 1);
+    if (dirty) {
+      unsigned long long cnt = (unsigned long long)(abs(x0 - x1) + 1) * (unsigned long long)(abs(y0 - y1) + 1);
+      unsigned long long s = block_rect_maxch_sum(im, x0, y0, x1, y1, sh);
+      int darkness = (int)(uint8_t)(0xFF - (s / cnt));
+      if (darkness < abs_threshold) continue;
+    }
+    dirty = true;
+    fills++;
+    // flood_fill from every pixel of the area in raster order (filters.c:86-89);
+    // pixels outside the image never match
+    int w = x1 - x0 + 1, n = (x0 <= x1 && y0 <= y1) ? w * (y1 - y0 + 1) : 0;
+    int sp = 0;
+    FFFrame top;
+    for (int rb = 0; rb < n;) {
+#pragma unroll
+      for (int u = 0; u < FF_U; u++) {
+        int c = warp * FF_U + u;
+        int i = rb + c * 32 + lane;
+        bool m = i < n && ff_match(im, x0 + i % w, y0 + i / w, mask_lo, mask_hi);
+        unsigned M = __ballot_sync(0xffffffffu, m);
+        if (lane == 0) sh.M[c] = M;
       }
-      dirty = true;
-      fills++;
-      // flood_fill from every pixel of the (unclipped) area in raster order
-      // (filters.c:86-89); pixels outside the image never match.
-      int w = x1 - x0 + 1, n = (x0 <= x1 && y0 <= y1) ? w * (y1 - y0 + 1) : 0;
-      int sp = 0;
-      FFFrame top;
-      for (int rb = 0; rb < n;) {
-        int x[FF_U], y[FF_U];
-        unsigned M[FF_U];
-#pragma unroll
-        for (int u = 0; u < FF_U; u++) {
-          int i = rb + u * 32 + lane;
-          x[u] = x0 + i % w; y[u] = y0 + i / w;
-          bool m = i < n && ff_match(im, x[u], y[u], mask_lo, mask_hi);
-          M[u] = __ballot_sync(0xffffffffu, m);
-        }
-        int hit = -1;
-#pragma unroll
-        for (int u = 0; u < FF_U; u++) if (hit < 0 && M[u]) hit = u;
-        if (hit < 0) { rb += 32 * FF_U; continue; }
-        int first = __ffs(M[hit]) - 1;
-        int fx = 0, fy = 0;
-#pragma unroll
-        for (int u = 0; u < FF_U; u++) if (u == hit) { fx = __shfl_sync(0xffffffffu, x[u], first); fy = __shfl_sync(0xffffffffu, y[u], first); }
-        rb += hit * 32 + first + 1;
-        if (ff_open(pg, im, fx, fy, mask_lo, mask_hi, intensity, lane, sp, top))
-          ff_run(pg, im, mask_lo, mask_hi, intensity, lane, sp, top);
-        sp = 0;
-      }
+      __syncthreads();
+      int hit = -1;
+      unsigned Mh = 0;
+      for (int c = 0; c < BF_CH; c++) { unsigned M = sh.M[c]; if (M) { hit = c; Mh = M; break; } }
+      __syncthreads();
+      if (hit < 0) { rb += BF_ROUND; continue; }
+      int i = rb + hit * 32 + (__ffs(Mh) - 1);
+      rb = i + 1;
+      if (ff_open(pg, im, x0 + i % w, y0 + i / w, mask_lo, mask_hi, intensity, sh, sp, top))
+        ff_run(pg, im, mask_lo, mask_hi, intensity, sh, sp, top);
+      sp = 0;
     }
   }
-  if (lane == 0) pg.bf_fills = fills;
+  if (threadIdx.x == 0) pg.bf_fills = fills;
 }
 
 /* =========================================================================
@@ -729,7 +751,7 @@ extern "C" {
 void b200k_bf_scan(cudaStream_t st, DPage *pages, int npages, const DBfPos *pos_dev, int npos,
                    int abs_threshold, long long intensity, int mask_lo, int mask_hi, int flag_off) {
   if (npages <= 0 || npos <= 0) return;
-  k_bf_scan<<<npages, 32, 0, st>>>(pages, pos_dev, npos, abs_threshold, (unsigned long long)intensity,
+  k_bf_scan<<<npages, BF_THREADS, 0, st>>>(pages, pos_dev, npos, abs_threshold, (unsigned long long)intensity,
                                   mask_lo, mask_hi, flag_off);
 }
 
