@@ -97,3 +97,50 @@ def test_engine_idempotent_and_deterministic():
         assert r.status == 0 and r.deskew_mask_count == 1 and r.rotation[0] != 0.0
     for r in res3:
         assert abs(r.rotation[0]) <= np.deg2rad(0.2) + 1e-6
+
+
+# ---- BASELINE.json configs 3 and 4 at full size -------------------------------------
+# The reference needs minutes per sheet here, so full-size runs are held to
+# size-independent properties; the same configurations are compared bit for bit
+# with the reference at reduced size above (test_engine_rgb_small, _double_layout).
+
+def test_engine_color_a4_full_size(ref_lib):
+    """Config 3: A4 RGB24, grayfilter + blurfilter + cubic deskew — one sheet against
+    the reference (about 40 s of CPU), then determinism on a second run."""
+    from unpaper_gpu_b200.lib import Engine
+    w, h = synth.A4_W, synth.A4_H
+    pages = synth.color_page(1, w, h)[None]
+    cfg = U.default_sheet_config()
+    cfg.no_blackfilter = cfg.no_noisefilter = 1
+    out, res = _compare(cfg, pages, w, h, U.FMT_RGB24, ref_lib, group=1, lanes=1)
+    eng = Engine(cfg, w, h, U.FMT_RGB24, group_pages=1, lanes=1)
+    out2, _ = eng.process_numpy(pages)
+    eng.close()
+    assert np.array_equal(out, out2)
+
+
+def test_engine_double_600dpi_properties():
+    """Config 4: 7016x4960 GRAY8 two-page sheet, --layout double."""
+    from unpaper_gpu_b200.lib import Engine
+    w, h = 7016, 4960
+    pages = np.stack([synth.double_sheet(i, w, h) for i in range(2)])
+    cfg = U.default_sheet_config()
+    cfg.layout = U.LAYOUT_DOUBLE
+    eng = Engine(cfg, w, h, U.FMT_GRAY8, group_pages=2, lanes=1)
+    out, res = eng.process_numpy(pages)
+    out2, res2 = eng.process_numpy(pages)
+    eng.close()
+    assert np.array_equal(out, out2)
+    for r in res:
+        assert r.status == 0
+        assert r.deskew_mask_count == 2 and r.center_mask_count == 2 and r.border_count == 2
+        for k in range(2):
+            x0, y0, x1, y1 = U.rect_tuple(r.deskew_masks[k])
+            assert 0 <= x0 < x1 < w and y0 == 0 and y1 == h - 1
+            assert abs(r.rotation[k]) <= np.deg2rad(5.1) + 1e-6
+        # the two page masks do not overlap and sit in their own halves
+        assert U.rect_tuple(r.deskew_masks[0])[2] < w // 2 + 60 < U.rect_tuple(r.deskew_masks[1])[2]
+    # dark scan edges are gone, the sheet is mostly white, ink survives
+    assert (out[:, :, :30] == 255).all()
+    frac_dark = (out < 128).mean()
+    assert 0.01 < frac_dark < 0.2

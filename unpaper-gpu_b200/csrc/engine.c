@@ -376,14 +376,17 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
 
   mark(e, ln, STG_DECODE);
   b200k_page_reset(c.st, c.pages, n);
-  /* decode stage: page(s) -> sheet */
-  for (int p = 0; p < n; p++)
-    for (int j = 0; j < ic; j++)
-      ln->decode_copy_host_tmpl[(size_t)p * ic + j].src.data = (uint8_t *)pages_dev_in + e->page_bytes * ((size_t)p * ic + j);
-  /* job records are tiny; one pageable H2D per group */
-  CUDA_OK(cudaMemcpyAsync(ln->decode_copy, ln->decode_copy_host_tmpl, sizeof(DCopyJob) * n * ic, cudaMemcpyHostToDevice, c.st));
-  b200k_copy_jobs(c.st, ln->decode_copy, n * ic, e->page_row, e->page_h);
-  c.launches += 2;
+  /* decode stage: page(s) -> sheet (pages_dev_in == NULL: the upload already placed them) */
+  if (pages_dev_in) {
+    for (int p = 0; p < n; p++)
+      for (int j = 0; j < ic; j++)
+        ln->decode_copy_host_tmpl[(size_t)p * ic + j].src.data = (uint8_t *)pages_dev_in + e->page_bytes * ((size_t)p * ic + j);
+    /* job records are tiny; one pageable H2D per group */
+    CUDA_OK(cudaMemcpyAsync(ln->decode_copy, ln->decode_copy_host_tmpl, sizeof(DCopyJob) * n * ic, cudaMemcpyHostToDevice, c.st));
+    b200k_copy_jobs(c.st, ln->decode_copy, n * ic, e->page_row, e->page_h);
+    c.launches += 1;
+  }
+  c.launches += 1;
   run_static(e, ln, &c, 0, n);
 
   mark(e, ln, STG_BLACK);
@@ -510,9 +513,17 @@ static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_shee
     ln->fl[ln->slot].first = first; ln->fl[ln->slot].n = n; ln->host_mode = host_mode;
     const uint8_t *src = pages + e->page_bytes * ic * (size_t)first;
     if (host_mode) {
-      CUDA_OK(cudaMemcpyAsync(ln->page_stage, src, e->page_bytes * ic * (size_t)n, cudaMemcpyHostToDevice, ln->st));
       ln->out_host = out + out_sheet * first;
-      issue_group(e, ln, ln->page_stage, n);
+      if (ic == 1 && e->sheet_pitch == e->page_row) {
+        /* page == sheet geometry: the upload IS the decode stage's centre copy
+         * (one 2-D copy, one "row" per sheet slot) */
+        CUDA_OK(cudaMemcpy2DAsync(ln->sheets, e->sheet_stride, src, e->page_bytes, e->page_bytes, (size_t)n,
+                                  cudaMemcpyHostToDevice, ln->st));
+        issue_group(e, ln, NULL, n);
+      } else {
+        CUDA_OK(cudaMemcpyAsync(ln->page_stage, src, e->page_bytes * ic * (size_t)n, cudaMemcpyHostToDevice, ln->st));
+        issue_group(e, ln, ln->page_stage, n);
+      }
     } else {
       ln->out_dev = out + out_sheet * first;
       issue_group(e, ln, src, n);

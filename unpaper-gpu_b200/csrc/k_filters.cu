@@ -398,13 +398,14 @@ __global__ void k_nf_classify(DPage *pages, int intensity, int white, int all_mu
 // fixed at 8 so that every tile word is 4-byte aligned, 4 classes per store.
 #define NF_G8_HX 8
 #define NF_G8_TWB (NF_TW + 2 * NF_G8_HX)
+#define NF_G8_TH 32   /* interior rows per block: two 16-row halves per thread */
 __global__ void k_nf_classify_g8(DPage *pages, int intensity, int white) {
   extern __shared__ uint8_t tile[];
   DPage &pg = pages[blockIdx.z];
   const DImg &im = pg.img;
   int halo = intensity + 1;
-  int th = NF_TH + 2 * halo;
-  int bx = blockIdx.x * NF_TW, by = blockIdx.y * NF_TH;
+  int th = NF_G8_TH + 2 * halo;
+  int bx = blockIdx.x * NF_TW, by = blockIdx.y * NF_G8_TH;
   if (bx >= im.w || by >= im.h) return;
   int band = 2 * intensity;
   bool aligned = ((im.pitch & 3) == 0) && (((uintptr_t)im.data & 3) == 0);
@@ -439,7 +440,8 @@ __global__ void k_nf_classify_g8(DPage *pages, int intensity, int white) {
   __syncthreads();
   int need = intensity + 1;
   int t = threadIdx.x;
-  int ly = t / (NF_TW / 4), lx0 = 4 * (t % (NF_TW / 4));
+  for (int half = 0; half < NF_G8_TH / 16; half++) {
+  int ly = t / (NF_TW / 4) + 16 * half, lx0 = 4 * (t % (NF_TW / 4));
   int y = by + ly;
   if (y >= im.h) return;
   unsigned out = 0;
@@ -469,6 +471,7 @@ __global__ void k_nf_classify_g8(DPage *pages, int intensity, int white) {
   size_t o = (size_t)y * im.w + bx + lx0;
   if ((im.w & 3) == 0 && bx + lx0 + 3 < im.w && ((uintptr_t)pg.cls & 3) == 0) *(unsigned *)(pg.cls + o) = out;
   else for (int q = 0; q < 4 && bx + lx0 + q < im.w; q++) pg.cls[o + q] = (uint8_t)(out >> (8 * q));
+  }
 }
 
 __device__ __forceinline__ bool nf_live(const uint8_t *cls, int w, int h, int x, int y) {
@@ -765,8 +768,9 @@ int b200k_noisefilter(cudaStream_t st, DPage *pages, int npages, int maxw, int m
   size_t sm = (size_t)(NF_TW + 2 * halo) * (NF_TH + 2 * halo);
   dim3 g(cdiv(maxw, NF_TW), cdiv(maxh, NF_TH), npages);
   if (fmt == DF_GRAY8 && I <= 7) {
-    size_t smg = (size_t)NF_G8_TWB * (NF_TH + 2 * (I + 1));
-    k_nf_classify_g8<<<g, 256, smg, st>>>(pages, I, white);
+    size_t smg = (size_t)NF_G8_TWB * (NF_G8_TH + 2 * (I + 1));
+    dim3 g8(cdiv(maxw, NF_TW), cdiv(maxh, NF_G8_TH), npages);
+    k_nf_classify_g8<<<g8, 256, smg, st>>>(pages, I, white);
   } else
     k_nf_classify<<<g, 256, sm, st>>>(pages, I, white, all_mut);
   k_nf_resolve<<<npages, 256, 0, st>>>(pages, I);
