@@ -285,14 +285,17 @@ def main():
 
         per_stage, dom_conc = table(prof, args.group)
         iso_stage, dom = table(iso[0], iso[1])
-        traffic = None
+        traffic, traffic_src = None, None
         tj = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tj):
             with open(tj) as f:
-                traffic = json.load(f).get(dom)
+                tr = json.load(f).get(dom)
+            if tr:   # dram__bytes_read.sum + dram__bytes_write.sum per sheet, from the committed ncu capture
+                traffic, traffic_src = tr["bytes_per_sheet"] * iso[1], tr["source"]
         a = iso_stage[dom]["alg_gbs"]
         roof = {"bound": "hbm", "kernel": dom, "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": round(a / peaks["hbm_gbs"], 4), "traffic": traffic, "peak_source": peak_src,
+                "frac": round(a / peaks["hbm_gbs"], 4), "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sb.get(dom, 0) * iso[1],
                 "launch": f"one stage launch sequence over a group of {iso[1]} sheets, timed alone with CUDA events "
                           "on the launching stream",

@@ -104,6 +104,84 @@ __device__ __noinline__ int ff_fill_line(const DImg &im, int px, int py, int dx,
   }
 }
 
+
+// The four fill_line calls of flood_fill (fill.c:88-95) walk four disjoint pixel
+// sets (row left / column up / row right / column down of the centre), so they
+// cannot see each other's paint: they are advanced together, sharing the rounds.
+__device__ __noinline__ void ff_fill_cross(const DImg &im, int px, int py, int lo, int hi,
+                                           unsigned long long intensity, BfShared &sh, int len[4]) {
+  const int DX[4] = {-1, 0, 1, 0}, DY[4] = {0, -1, 0, 1};   // left, up, right, down
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int dist[4] = {0, 0, 0, 0};
+  unsigned long long cnt[4] = {1, 1, 1, 1};
+  bool done[4] = {false, false, false, false};
+  for (;;) {
+    int act[4], na = 0;
+    for (int d = 0; d < 4; d++) if (!done[d]) act[na++] = d;
+    if (na == 0) break;
+    int per = BF_CH / na;   // chunks of 32 pixels per active line in this round
+    bool full = true;
+#pragma unroll
+    for (int u = 0; u < FF_U; u++) {
+      int c = warp * FF_U + u, li = c / per;
+      unsigned M = 0, I = 0;
+      if (li < na) {
+        int d = act[li];
+        int s = dist[d] + (c - li * per) * 32 + lane + 1;
+        int qx = px + s * DX[d], qy = py + s * DY[d];
+        bool inb = in_img(im, qx, qy);
+        bool m = ff_match(im, qx, qy, lo, hi);
+        M = __ballot_sync(0xffffffffu, m);
+        I = __ballot_sync(0xffffffffu, inb);
+      }
+      if (lane == 0) { sh.M[c] = M; sh.I[c] = I; }
+      if (li < na && (M & I) != 0xffffffffu) full = false;
+    }
+    // barrier + "did every evaluated chunk match in full?" in one step
+    bool all_full = __syncthreads_and(full) != 0;
+    int tot[4] = {0, 0, 0, 0};
+    if (all_full && intensity != 0) {
+      // nothing stops in this round: every active line advances by all its chunks
+      for (int li = 0; li < na; li++) { tot[li] = per * 32; cnt[act[li]] = intensity; }
+    } else
+    for (int li = 0; li < na; li++) {
+      int d = act[li];
+      bool stop = false;
+      for (int k = 0; k < per && !stop; k++) {
+        unsigned M = sh.M[li * per + k], I = sh.I[li * per + k];
+        int painted = 32;
+        if ((M & I) == 0xffffffffu) {
+          cnt[d] = intensity;
+          if (cnt[d] == 0) painted = 0;
+        } else {
+          for (int i = 0; i < 32; i++) {
+            if ((M >> i) & 1u) cnt[d] = intensity; else cnt[d]--;
+            if (cnt[d] == 0 || !((I >> i) & 1u)) { painted = i; break; }
+          }
+        }
+        tot[li] += painted;
+        if (painted < 32) stop = true;
+      }
+      if (stop) done[d] = true;
+    }
+#pragma unroll
+    for (int u = 0; u < FF_U; u++) {
+      int c = warp * FF_U + u, li = c / per;
+      if (li < na) {
+        int d = act[li];
+        int idx = (c - li * per) * 32 + lane;
+        if (idx < tot[li]) {
+          int s = dist[d] + idx + 1;
+          ff_paint(im, px + s * DX[d], py + s * DY[d]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int li = 0; li < na; li++) dist[act[li]] += tot[li];
+  }
+  for (int d = 0; d < 4; d++) len[d] = dist[d];
+}
+
 struct FFFrame { int cx, cy; int L, T, R, B; unsigned cursor; };
 
 __device__ __forceinline__ void ff_cand(const FFFrame &f, unsigned idx, int &x, int &y) {
@@ -132,10 +210,9 @@ __device__ __noinline__ bool ff_open(DPage &pg, const DImg &im, int x, int y, in
   if (threadIdx.x == 0) ff_paint(im, x, y);
   __syncthreads();
   top.cx = x; top.cy = y;
-  top.L = ff_fill_line(im, x, y, -1, 0, lo, hi, intensity, sh);
-  top.T = ff_fill_line(im, x, y, 0, -1, lo, hi, intensity, sh);
-  top.R = ff_fill_line(im, x, y, 1, 0, lo, hi, intensity, sh);
-  top.B = ff_fill_line(im, x, y, 0, 1, lo, hi, intensity, sh);
+  int len[4];
+  ff_fill_cross(im, x, y, lo, hi, intensity, sh, len);
+  top.L = len[0]; top.T = len[1]; top.R = len[2]; top.B = len[3];
   top.cursor = 0;
   sp++;
   return true;
@@ -149,6 +226,7 @@ __device__ __noinline__ void ff_run(DPage &pg, const DImg &im, int lo, int hi, u
     unsigned total = 2u * ((unsigned)top.L + top.T + top.R + top.B);
     bool opened = false;
     while (top.cursor < total) {
+      unsigned anym = 0;
 #pragma unroll
       for (int u = 0; u < FF_U; u++) {
         int c = warp * FF_U + u;
@@ -158,12 +236,14 @@ __device__ __noinline__ void ff_run(DPage &pg, const DImg &im, int lo, int hi, u
         if (idx < total) { ff_cand(top, idx, x, y); m = in_img(im, x, y) && ff_match(im, x, y, lo, hi); }
         unsigned M = __ballot_sync(0xffffffffu, m);
         if (lane == 0) sh.M[c] = M;
+        anym |= M;
       }
-      __syncthreads();
       int hit = -1;
       unsigned Mh = 0;
-      for (int c = 0; c < BF_CH; c++) { unsigned M = sh.M[c]; if (M) { hit = c; Mh = M; break; } }
-      __syncthreads();   // sh.M is rewritten by the next round / by ff_open
+      if (__syncthreads_or(anym != 0)) {   // barrier; the common round has no match at all
+        for (int c = 0; c < BF_CH; c++) { unsigned M = sh.M[c]; if (M) { hit = c; Mh = M; break; } }
+        __syncthreads();   // sh.M is rewritten by the next round / by ff_open
+      }
       if (hit >= 0) {
         unsigned idx = top.cursor + hit * 32 + (__ffs(Mh) - 1);
         int fx, fy;
@@ -246,6 +326,7 @@ __global__ void __launch_bounds__(BF_THREADS) k_bf_scan(DPage *pages, const DBfP
     int sp = 0;
     FFFrame top;
     for (int rb = 0; rb < n;) {
+      unsigned anym = 0;
 #pragma unroll
       for (int u = 0; u < FF_U; u++) {
         int c = warp * FF_U + u;
@@ -253,12 +334,14 @@ __global__ void __launch_bounds__(BF_THREADS) k_bf_scan(DPage *pages, const DBfP
         bool m = i < n && ff_match(im, x0 + i % w, y0 + i / w, mask_lo, mask_hi);
         unsigned M = __ballot_sync(0xffffffffu, m);
         if (lane == 0) sh.M[c] = M;
+        anym |= M;
       }
-      __syncthreads();
       int hit = -1;
       unsigned Mh = 0;
-      for (int c = 0; c < BF_CH; c++) { unsigned M = sh.M[c]; if (M) { hit = c; Mh = M; break; } }
-      __syncthreads();
+      if (__syncthreads_or(anym != 0)) {
+        for (int c = 0; c < BF_CH; c++) { unsigned M = sh.M[c]; if (M) { hit = c; Mh = M; break; } }
+        __syncthreads();
+      }
       if (hit < 0) { rb += BF_ROUND; continue; }
       int i = rb + hit * 32 + (__ffs(Mh) - 1);
       rb = i + 1;
