@@ -55,57 +55,7 @@ struct BfShared {
   unsigned long long red[BF_WARPS];
 };
 
-// fill_line (fill.c:16-43): returns the painted distance
-__device__ __noinline__ int ff_fill_line(const DImg &im, int px, int py, int dx, int dy, int lo, int hi,
-                                         unsigned long long intensity, BfShared &sh) {
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int distance = 0;
-  unsigned long long cnt = 1;
-  for (;;) {
-#pragma unroll
-    for (int u = 0; u < FF_U; u++) {
-      int c = warp * FF_U + u;
-      int s = distance + c * 32 + lane + 1;
-      int qx = px + s * dx, qy = py + s * dy;
-      bool inb = in_img(im, qx, qy);
-      bool m = ff_match(im, qx, qy, lo, hi);
-      unsigned M = __ballot_sync(0xffffffffu, m), I = __ballot_sync(0xffffffffu, inb);
-      if (lane == 0) { sh.M[c] = M; sh.I[c] = I; }
-    }
-    __syncthreads();
-    int total = 0;
-    bool stop = false;
-    for (int c = 0; c < BF_CH && !stop; c++) {
-      unsigned M = sh.M[c], I = sh.I[c];
-      int painted = 32;
-      if ((M & I) == 0xffffffffu) {
-        cnt = intensity;
-        if (cnt == 0) painted = 0;   // degenerate intensity 0: stops on the first pixel
-      } else {
-        for (int i = 0; i < 32; i++) {
-          if ((M >> i) & 1u) cnt = intensity; else cnt--;
-          if (cnt == 0 || !((I >> i) & 1u)) { painted = i; break; }
-        }
-      }
-      total += painted;
-      if (painted < 32) stop = true;
-    }
-#pragma unroll
-    for (int u = 0; u < FF_U; u++) {
-      int idx = (warp * FF_U + u) * 32 + lane;
-      if (idx < total) {
-        int s = distance + idx + 1;
-        ff_paint(im, px + s * dx, py + s * dy);
-      }
-    }
-    __syncthreads();
-    distance += total;
-    if (stop) return distance;
-  }
-}
-
-
-// The four fill_line calls of flood_fill (fill.c:88-95) walk four disjoint pixel
+// fill_line (fill.c:16-43) x 4.  The four calls of flood_fill (fill.c:88-95) walk four disjoint pixel
 // sets (row left / column up / row right / column down of the centre), so they
 // cannot see each other's paint: they are advanced together, sharing the rounds.
 __device__ __noinline__ void ff_fill_cross(const DImg &im, int px, int py, int lo, int hi,
