@@ -64,6 +64,7 @@ static void op_begin(Op *o, Image *image, int need_aux, int need_nf, int u32_nee
   o->sc.npages = 1;
   o->sc.pages = o->dp;
   o->sc.w = v.w; o->sc.h = v.h; o->sc.fmt = v.fmt;
+  o->sc.rows_aligned16 = ((v.pitch & 15) == 0) && (((uintptr_t)v.data & 15) == 0);
   o->hp.rot_cos[0] = 1.0f;
 }
 

@@ -370,6 +370,7 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
   StageCtx c;
   memset(&c, 0, sizeof(c));
   c.st = ln->st; c.npages = n; c.pages = ln->pages_dev; c.w = e->sheet_w; c.h = e->sheet_h; c.fmt = e->dfmt;
+  c.rows_aligned16 = (e->sheet_pitch & 15) == 0;   /* slabs are 256-byte aligned, strides multiples of 256 */
   c.fillA = ln->fillA; c.fillB = ln->fillB; c.fillC = ln->fillC; c.copyA = ln->copyA; c.copyB = ln->copyB; c.maskJ = ln->maskJ;
   ln->fl[ln->slot].ev_mask = 0;
   int ic = cfg->input_count;

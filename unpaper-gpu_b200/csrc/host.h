@@ -89,6 +89,7 @@ typedef struct {
   int npages;
   DPage *pages;               /* device array */
   int w, h, fmt;              /* geometry shared by the group (device fmt code) */
+  int rows_aligned16;         /* every page: data and pitch are multiples of 16 bytes */
   DFillJob *fillA, *fillB, *fillC; /* device job arrays, npages each */
   DCopyJob *copyA, *copyB;
   DMaskJob *maskJ;

@@ -507,6 +507,158 @@ __global__ void k_nf_classify_g8(DPage *pages, int intensity, int white) {
   }
 }
 
+/* GRAY8 bit-plane specialisation (intensity <= 7, 16-byte aligned rows).
+ *
+ * The tile (64x32 interior, 32 columns / intensity+1 rows of halo) is held as
+ * one bit per pixel, four 32-bit words per row:
+ *   dark  = value < white and inside the image        (ring-dark == trigger-dark for gray)
+ *   nb    = dark outside the left/top band            (pixels that may form permanent components)
+ * "Has >= need nb-pixels in its 3x3 block" is then a bit-sliced population count
+ * over 9 shifted planes (core), and every nb pixel that is a core pixel or
+ * touches one belongs to a component of >= need pixels (all members of a core
+ * pixel's block touch it) — settled for 32 pixels per instruction.  Only the
+ * few dark pixels that this test leaves open run the exact bounded walk. */
+#define NFB_TW 64
+#define NFB_TH 32
+#define NFB_ROWS (NFB_TH + 2 * 8)
+
+__device__ __forceinline__ bool nfb_bit(const unsigned (*nb)[4], int x, int y) { return (nb[y][x >> 5] >> (x & 31)) & 1u; }
+
+__device__ __noinline__ bool nfb_small_component(const unsigned (*nb)[4], int rows, int tx, int ty, int need) {
+  short vx[8], vy[8];
+  int n = 1, head = 0;
+  vx[0] = (short)tx; vy[0] = (short)ty;
+  while (head < n && n < need) {
+    int cx = vx[head], cy = vy[head]; head++;
+#pragma unroll 1
+    for (int k = 0; k < 9 && n < need; k++) {
+      if (k == 4) continue;
+      int nx = cx + k % 3 - 1, ny = cy + k / 3 - 1;
+      if (nx < 0 || ny < 0 || nx >= 128 || ny >= rows) continue;
+      if (!nfb_bit(nb, nx, ny)) continue;
+      bool seen = false;
+#pragma unroll 1
+      for (int q = 0; q < n; q++) seen |= (vx[q] == nx && vy[q] == ny);
+      if (!seen) { vx[n] = (short)nx; vy[n] = (short)ny; n++; }
+    }
+  }
+  return n < need;
+}
+
+__global__ void __launch_bounds__(256) k_nf_classify_bits(DPage *pages, int intensity, int white) {
+  __shared__ unsigned s_dark[NFB_ROWS][4], s_nb[NFB_ROWS][4], s_h0[NFB_ROWS][4], s_h1[NFB_ROWS][4],
+      s_core[NFB_ROWS][4], s_big[NFB_ROWS][4];
+  DPage &pg = pages[blockIdx.z];
+  const DImg &im = pg.img;
+  int halo = intensity + 1, rows = NFB_TH + 2 * halo, need = intensity + 1, band = 2 * intensity;
+  int bx = blockIdx.x * NFB_TW, by = blockIdx.y * NFB_TH;
+  if (bx >= im.w || by >= im.h) return;
+  int x_org = bx - 32, y_org = by - halo;
+  unsigned white4 = white > 255 ? 0xFFFFFFFFu : (unsigned)max(white, 0) * 0x01010101u;
+  // phase 1: bit planes
+  for (int item = threadIdx.x; item < rows * 4; item += blockDim.x) {
+    int r = item >> 2, k = item & 3;
+    int y = y_org + r, x0 = x_org + 32 * k;
+    unsigned dark = 0;
+    if (y >= 0 && y < im.h && x0 + 31 >= 0 && x0 < im.w) {
+      const uint8_t *rp = im.data + (size_t)y * im.pitch;
+      if (x0 >= 0 && x0 + 31 < im.w) {
+        const uint4 *q = (const uint4 *)(rp + x0);
+        uint4 a = q[0], b = q[1];
+        unsigned wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          unsigned m = __vcmpltu4(wv[j], white4);
+          dark |= ((((m & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * j);
+        }
+      } else {
+        for (int i = 0; i < 32; i++) { int x = x0 + i; if (x >= 0 && x < im.w && (int)rp[x] < white) dark |= 1u << i; }
+      }
+    }
+    unsigned inb;
+    if (y < band || x0 + 31 < band) inb = 0xFFFFFFFFu;
+    else if (x0 >= band) inb = 0u;
+    else inb = (band - x0 >= 32) ? 0xFFFFFFFFu : ((1u << (band - x0)) - 1u);
+    s_dark[r][k] = dark;
+    s_nb[r][k] = dark & ~inb;
+  }
+  __syncthreads();
+  // phase 2a: per row, how many of (left, self, right) are set: h1:h0
+  for (int item = threadIdx.x; item < rows * 4; item += blockDim.x) {
+    int r = item >> 2, k = item & 3;
+    unsigned C = s_nb[r][k], P = k > 0 ? s_nb[r][k - 1] : 0u, N = k < 3 ? s_nb[r][k + 1] : 0u;
+    unsigned L = (C << 1) | (P >> 31), R = (C >> 1) | (N << 31);
+    s_h0[r][k] = L ^ C ^ R;
+    s_h1[r][k] = (L & C) | (C & R) | (L & R);
+  }
+  __syncthreads();
+  // phase 2b: 3x3 population (bit-sliced) >= need, centred on an nb pixel
+  for (int item = threadIdx.x; item < rows * 4; item += blockDim.x) {
+    int r = item >> 2, k = item & 3;
+    unsigned core = 0;
+    if (r >= 1 && r + 1 < rows) {
+      unsigned a0 = s_h0[r - 1][k], a1 = s_h1[r - 1][k], b0 = s_h0[r][k], b1 = s_h1[r][k], c0 = s_h0[r + 1][k], c1 = s_h1[r + 1][k];
+      unsigned s0 = a0 ^ b0 ^ c0, k0 = (a0 & b0) | (b0 & c0) | (a0 & c0);      // weight 1, carry (weight 2)
+      unsigned t1 = a1 ^ b1 ^ c1, k1 = (a1 & b1) | (b1 & c1) | (a1 & c1);      // weight 2, carry (weight 4)
+      unsigned u1 = t1 ^ k0, c2 = t1 & k0;                                      // weight 2, carry (weight 4)
+      unsigned v2 = k1 ^ c2, v3 = k1 & c2;                                      // weight 4, weight 8
+      unsigned bits[4] = {s0, u1, v2, v3};
+      unsigned gt = 0, eq = 0xFFFFFFFFu;
+#pragma unroll
+      for (int b = 3; b >= 0; b--) {
+        unsigned kb = ((need >> b) & 1) ? 0xFFFFFFFFu : 0u;
+        gt |= eq & bits[b] & ~kb;
+        eq &= ~(bits[b] ^ kb);
+      }
+      core = (gt | eq) & s_nb[r][k];
+      if (need > 9) core = 0;
+    }
+    s_core[r][k] = core;
+  }
+  __syncthreads();
+  // phase 2c: nb pixels that are a core pixel or touch one
+  for (int item = threadIdx.x; item < rows * 4; item += blockDim.x) {
+    int r = item >> 2, k = item & 3;
+    unsigned D = 0;
+    if (r >= 1 && r + 1 < rows) {
+#pragma unroll
+      for (int rr = -1; rr <= 1; rr++) {
+        unsigned C = s_core[r + rr][k], P = k > 0 ? s_core[r + rr][k - 1] : 0u, N = k < 3 ? s_core[r + rr][k + 1] : 0u;
+        D |= C | (C << 1) | (P >> 31) | (C >> 1) | (N << 31);
+      }
+    }
+    s_big[r][k] = s_nb[r][k] & D;
+  }
+  __syncthreads();
+  // phase 3: eight pixels per thread
+  int ly = threadIdx.x >> 3, lx0 = (threadIdx.x & 7) * 8;
+  int y = by + ly, r = ly + halo;
+  if (y >= im.h || bx + lx0 >= im.w) return;
+  int k = 1 + (lx0 >> 5), sh = lx0 & 31;
+  unsigned dark8 = (s_dark[r][k] >> sh) & 0xFFu, nb8 = (s_nb[r][k] >> sh) & 0xFFu, big8 = (s_big[r][k] >> sh) & 0xFFu;
+  unsigned lo = 0, hi = 0;   // eight class bytes
+  unsigned todo = dark8;
+  while (todo) {
+    int i = __ffs(todo) - 1;
+    todo &= todo - 1;
+    bool mut;
+    if (!((nb8 >> i) & 1u)) mut = true;                               // in the left/top band
+    else if ((big8 >> i) & 1u) mut = false;
+    else mut = nfb_small_component(s_nb, rows, 32 + lx0 + i, r, need);
+    unsigned c = NF_LIVE | NF_TRIG;
+    if (mut) {
+      c |= NF_MUT | NF_UNDEC;
+      unsigned idx = atomicAdd(&pg.list_n, 1u);
+      if (idx < (unsigned)pg.list_cap) pg.list[idx] = ((unsigned)y << 16) | (unsigned)(bx + lx0 + i);
+      else atomicOr(&pg.error, DERR_LIST_OVERFLOW);
+    }
+    if (i < 4) lo |= c << (8 * i); else hi |= c << (8 * (i - 4));
+  }
+  size_t o = (size_t)y * im.w + bx + lx0;
+  if ((im.w & 7) == 0 && ((uintptr_t)pg.cls & 7) == 0) *(uint2 *)(pg.cls + o) = make_uint2(lo, hi);
+  else for (int i = 0; i < 8 && bx + lx0 + i < im.w; i++) pg.cls[o + i] = (uint8_t)((i < 4 ? lo >> (8 * i) : hi >> (8 * (i - 4))) & 0xFFu);
+}
+
 __device__ __forceinline__ bool nf_live(const uint8_t *cls, int w, int h, int x, int y) {
   return (unsigned)x < (unsigned)w && (unsigned)y < (unsigned)h && (cls[(size_t)y * w + x] & NF_LIVE);
 }
@@ -792,7 +944,7 @@ void b200k_bf_scan(cudaStream_t st, DPage *pages, int npages, const DBfPos *pos_
 }
 
 int b200k_noisefilter(cudaStream_t st, DPage *pages, int npages, int maxw, int maxh, int fmt,
-                      unsigned long long intensity, int white) {
+                      unsigned long long intensity, int white, int flags) {
   if (npages <= 0 || intensity == 0) return 0;
   if (intensity > 4000) return -1;
   int I = (int)intensity;
@@ -800,7 +952,11 @@ int b200k_noisefilter(cudaStream_t st, DPage *pages, int npages, int maxw, int m
   int halo = all_mut ? 0 : I + 1;
   size_t sm = (size_t)(NF_TW + 2 * halo) * (NF_TH + 2 * halo);
   dim3 g(cdiv(maxw, NF_TW), cdiv(maxh, NF_TH), npages);
-  if (fmt == DF_GRAY8 && I <= 7) {
+  if (fmt == DF_GRAY8 && I <= 7 && (flags & 1)) {
+    // rows 16-byte aligned (checked by the caller): one bit per pixel
+    dim3 gb(cdiv(maxw, NFB_TW), cdiv(maxh, NFB_TH), npages);
+    k_nf_classify_bits<<<gb, 256, 0, st>>>(pages, I, white);
+  } else if (fmt == DF_GRAY8 && I <= 7) {
     size_t smg = (size_t)NF_G8_TWB * (NF_G8_TH + 2 * (I + 1));
     dim3 g8(cdiv(maxw, NF_TW), cdiv(maxh, NF_G8_TH), npages);
     k_nf_classify_g8<<<g8, 256, smg, st>>>(pages, I, white);

@@ -46,7 +46,7 @@ void b200k_prep_border_maskjob(cudaStream_t st, DPage *pages, int npages, DMaskJ
 void b200k_bf_scan(cudaStream_t st, DPage *pages, int npages, const DBfPos *pos_dev, int npos,
                    int abs_threshold, long long intensity, int mask_lo, int mask_hi, int flag_off);
 int b200k_noisefilter(cudaStream_t st, DPage *pages, int npages, int maxw, int maxh, int fmt,
-                      unsigned long long intensity, int white);
+                      unsigned long long intensity, int white, int flags /* bit0: rows 16-byte aligned */);
 void b200k_blur_decide(cudaStream_t st, DPage *pages, int npages, int n, int nrows,
                        unsigned long long T, float intensity, int cnt_off, int state_off, int flag_off);
 void b200k_blur_wipe(cudaStream_t st, DPage *pages, int npages, int n, int nrows, int bw, int bh, int flag_off);

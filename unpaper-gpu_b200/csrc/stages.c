@@ -365,7 +365,7 @@ void stage_blackfilter(StageCtx *c, const BfPlan *pl) {
 
 int stage_noisefilter(StageCtx *c, uint64_t intensity, int white) {
   if (c->h >= 32768 || c->w >= 65536) { b200_set_error("noisefilter: image too large"); return -1; }
-  int rc = b200k_noisefilter(c->st, c->pages, c->npages, c->w, c->h, c->fmt, intensity, white);
+  int rc = b200k_noisefilter(c->st, c->pages, c->npages, c->w, c->h, c->fmt, intensity, white, c->rows_aligned16 ? 1 : 0);
   if (rc) b200_set_error("noisefilter: unsupported intensity");
   c->launches += 2;
   return rc;
