@@ -206,8 +206,24 @@ def main():
             t_h2d = min(t_h2d, a.elapsed_time(b))
             a.record(); host_out[:n].copy_(dev_out[:n], non_blocking=True); b.record(); b.synchronize()
             t_d2h = min(t_d2h, a.elapsed_time(b))
+        # both directions at once (what the e2e arm asks of the link): two streams, one clock
+        t_bi = 1e9
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        scratch = torch.empty_like(dev_out[:n])
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            s1.wait_event(a); s2.wait_event(a)
+            with torch.cuda.stream(s1):
+                scratch.copy_(host_in[:n], non_blocking=True)
+            with torch.cuda.stream(s2):
+                host_out[:n].copy_(dev_out[:n], non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s1); torch.cuda.current_stream().wait_stream(s2)
+            b.record(); b.synchronize()
+            t_bi = min(t_bi, a.elapsed_time(b))
         gb = n * W * H / 1e9
-        return round(gb / (t_h2d / 1e3), 1), round(gb / (t_d2h / 1e3), 1)
+        return round(gb / (t_h2d / 1e3), 1), round(gb / (t_d2h / 1e3), 1), round(gb / (t_bi / 1e3), 1)
 
     def step_device():
         eng.process_ptr(dev_in.data_ptr(), dev_out.data_ptr(), args.pages, False, res)
@@ -240,7 +256,7 @@ def main():
     eng.set_profiling(False)
     e2e_ms, e2e_wall_ms, _ = timed(step_host, args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
-    h2d_gbs, d2h_gbs = pcie_gbs()
+    h2d_gbs, d2h_gbs, bidir_gbs = pcie_gbs()
 
     # correctness guard: every sheet deskewed and flagged ok
     bad = sum(1 for r in res if r.status != 0)
@@ -317,7 +333,8 @@ def main():
                         "d2h_bytes_per_step": e2e_pages * S * world, "ms_per_step": e2e_ms / args.steps,
                         "wall_ms_per_step": e2e_wall_ms / args.steps, "pages_per_step_per_gpu": e2e_pages,
                         "pcie_h2d_gbs": h2d_gbs, "pcie_d2h_gbs": d2h_gbs,
-                        "pcie_bound_pages_per_sec_per_gpu": round(min(h2d_gbs, d2h_gbs) * 1e9 / S, 1)},
+                        "pcie_bidir_gbs_each_way": bidir_gbs,
+                        "pcie_bound_pages_per_sec_per_gpu": round(min(h2d_gbs, d2h_gbs, bidir_gbs) * 1e9 / S, 1)},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "stages": per_stage,
                 "stages_isolated": iso_stage,
                 "failed_sheets": bad}

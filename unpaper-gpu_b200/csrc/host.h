@@ -64,6 +64,7 @@ typedef struct {
   int edges[4];
   int peak_off, u32_need, scan_cap;
   long long pre_need;              /* u32 elements of column-prefix scratch per page */
+  int run_cap;                     /* max vertical runs of a scan line (0: too many for the warp kernel) */
   DeskewParameters p;
 } RotPlan;
 

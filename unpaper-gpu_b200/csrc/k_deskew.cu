@@ -278,6 +278,99 @@ __global__ void k_rot_peaks_h(DPage *pages, const float *tan_tab, RotParams rp, 
   }
 }
 
+// Warp form of the same scan: a CTA of RW_ANG warps takes RW_ANG angles of one
+// (page, mask, edge).  Phase A: the first RW_ANG lanes of warp 0 run the
+// sequential float chains of those angles side by side and record the runs.
+// Phase B: one warp per angle with lane = depth; the early exit of deskew.c:119
+// and the max-difference tracking become a warp prefix sum and a ballot, so
+// there is no block barrier and no single-thread scan inside the depth loop.
+#define RW_ANG 8
+__global__ void __launch_bounds__(32 * RW_ANG) k_rot_peaks_w(DPage *pages, const float *tan_tab, RotParams rp, int mi, int rstride) {
+  extern __shared__ int rsm[];          // [RW_ANG][rstride] run x | [RW_ANG][rstride] run start k
+  __shared__ int rn[RW_ANG];
+  int *rx = rsm, *rk = rsm + RW_ANG * rstride;
+  DPage &pg = pages[blockIdx.z];
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int e = blockIdx.y ? 2 : 0;
+  if (mi >= pg.mask_count || !rp.edges[e]) return;
+  const DImg &im = pg.img;
+  DRect mask = pg.masks[mi];
+  int sw = abs(mask.x0 - mask.x1) + 1;
+  int shx = e == 0 ? 1 : -1;
+  int scan, Y0;
+  rot_line_geometry(mask, rp.scan_size, scan, Y0);
+  int maxDepth = sw / 2;
+  int maxAbs = (int)(255 * rp.scan_size * rp.scan_depth);
+  if (threadIdx.x < RW_ANG) {
+    int t = threadIdx.x, a = blockIdx.x * RW_ANG + t;
+    int n = 0;
+    bool overflow = false;
+    if (a < rp.nangles) {
+      float m = tan_tab[a];
+      int half = scan / 2;
+      int outer = (int)(fabsf(m) * half);
+      int side = shx > 0 ? mask.x0 - outer : mask.x1 + outer;
+      float X = side + half * m;          // deskew.c:88
+      float stepX = -m;
+      int prev = 0;
+      for (int k = 0; k < scan; k++) {    // deskew.c:108-113, sequential float accumulation
+        int xi = (int)X;
+        if (k == 0 || xi != prev) {
+          if (n < rstride) { rx[t * rstride + n] = xi; rk[t * rstride + n] = k; }
+          else overflow = true;
+          n++; prev = xi;
+        }
+        X += stepX;
+      }
+    }
+    rn[t] = overflow ? -1 : n;
+  }
+  __syncthreads();
+  int a = blockIdx.x * RW_ANG + warp;
+  if (a >= rp.nangles) return;
+  int nruns = rn[warp];
+  if (nruns < 0) { if (lane == 0) atomicOr(&pg.error, DERR_UNSUPPORTED); nruns = 0; }
+  const int *jx = rx + warp * rstride, *jk = rk + warp * rstride;
+  int mx0 = min(mask.x0, mask.x1), mx1 = max(mask.x0, mask.x1);
+  int vx0 = max(mx0, 0), vx1 = min(mx1, im.w - 1);
+  const unsigned *C = pg.pre;
+  bool have = (long long)(scan + 1) * im.w <= pg.pre_cap && scan > 0;
+  int last = 0, maxDiff = 0, acc = 0, dep = 0;
+  for (int base = 0; base < maxDepth; base += 32) {
+    int ox = (base + lane) * shx;
+    int b = 0;
+    if (have)
+      for (int r = 0; r < nruns; r++) {
+        int x = jx[r] + ox;
+        int kend = (r + 1 < nruns) ? jk[r + 1] : scan;
+        if (x >= vx0 && x <= vx1) b += (int)(C[(size_t)kend * im.w + x] - C[(size_t)jk[r] * im.w + x]);
+      }
+    // running total before each depth step (deskew.c:119 tests it before the step)
+    int incl = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    bool proc = (acc + incl - b < maxAbs) && (base + lane < maxDepth);
+    unsigned pm = __ballot_sync(0xffffffffu, proc);
+    int nproc = __popc(pm);            // the processed steps are a prefix: blackness >= 0
+    int prevb = __shfl_up_sync(0xffffffffu, b, 1);
+    if (lane == 0) prevb = last;
+    int diff = proc ? b - prevb : -2147483647 - 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) diff = max(diff, __shfl_xor_sync(0xffffffffu, diff, o));
+    if (nproc > 0) {
+      maxDiff = max(maxDiff, diff);    // `if (diff >= maxDiff) maxDiff = diff` from 0
+      acc += __shfl_sync(0xffffffffu, incl, nproc - 1);
+      last = __shfl_sync(0xffffffffu, b, nproc - 1);
+      dep += nproc;
+    }
+    if (nproc < 32) break;
+  }
+  if (lane == 0) {
+    int peak = (dep < maxDepth) ? maxDiff : 0;   // deskew.c:137-141
+    pg.u32[rp.peak_off + ((size_t)mi * 4 + e) * rp.nangles + a] = (unsigned)peak;
+  }
+}
+
 struct RotFinalParams {
   int nangles;
   int edges[4];
@@ -548,12 +641,15 @@ __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) 
 #pragma unroll
           for (int i = 0; i < 4; i++) {
             unsigned b0 = rw[i] & 0xFFu;
-            // a row of four equal taps interpolates to that value exactly
-            r4[i] = (rw[i] == b0 * 0x01010101u)
-                        ? u8f(b0)
-                        : u8f(cubic_scale_f(fx, u8f(b0), u8f((rw[i] >> 8) & 0xFFu), u8f((rw[i] >> 16) & 0xFFu), u8f(rw[i] >> 24)));
+            // a row of four equal taps interpolates to that value exactly; a row equal
+            // to the one above (vertical strokes) has the same result as that row
+            if (rw[i] == b0 * 0x01010101u) r4[i] = u8f(b0);
+            else if (i > 0 && rw[i] == rw[i - 1]) r4[i] = r4[i - 1];
+            else r4[i] = u8f(cubic_scale_f(fx, u8f(b0), u8f((rw[i] >> 8) & 0xFFu), u8f((rw[i] >> 16) & 0xFFu), u8f(rw[i] >> 24)));
           }
-          o = cubic_scale_f(fy, r4[0], r4[1], r4[2], r4[3]);
+          // four equal row results: the vertical pass returns that value exactly
+          if (r4[1] == r4[0] && r4[2] == r4[0] && r4[3] == r4[0]) o = (unsigned)__float2int_rz(r4[0]);
+          else o = cubic_scale_f(fy, r4[0], r4[1], r4[2], r4[3]);
         }
         orow[x] = (uint8_t)o;
         continue;
@@ -581,7 +677,7 @@ __global__ void k_stretch(DImg src, DImg dst, float hr, float vr, int interp) {
 extern "C" {
 int b200k_rot_peaks(cudaStream_t st, DPage *pages, int npages, int max_masks, const float *tan_tab_dev,
                     int nangles, int scan_size_param, float scan_depth, const int edges[4],
-                    int peak_off, int scan_cap, int maxw, int use_prefix) {
+                    int peak_off, int scan_cap, int maxw, int use_prefix, int run_cap) {
   if (npages <= 0 || max_masks <= 0 || nangles <= 0) return 0;
   RotParams rp;
   rp.scan_size = scan_size_param; rp.scan_depth = scan_depth; rp.nangles = nangles; rp.peak_off = peak_off;
@@ -596,7 +692,13 @@ int b200k_rot_peaks(cudaStream_t st, DPage *pages, int npages, int max_masks, co
   if (use_prefix && horiz) {
     for (int mi = 0; mi < max_masks; mi++) {
       k_rot_colprefix<<<dim3(cdiv(maxw, 128), npages), 32 * RP_SEG, 0, st>>>(pages, mi, scan_size_param);
-      k_rot_peaks_h<<<dim3(nangles, 2, npages), 64, sm, st>>>(pages, tan_tab_dev, rp, mi);
+      if (run_cap > 0) {
+        int rstride = run_cap | 1;   // odd stride: the lanes of phase A hit different banks
+        size_t smw = (size_t)(2 * RW_ANG * rstride) * sizeof(int);
+        k_rot_peaks_w<<<dim3(cdiv(nangles, RW_ANG), 2, npages), 32 * RW_ANG, smw, st>>>(pages, tan_tab_dev, rp, mi, rstride);
+      } else {
+        k_rot_peaks_h<<<dim3(nangles, 2, npages), 64, sm, st>>>(pages, tan_tab_dev, rp, mi);
+      }
     }
     rp.edges[0] = 0; rp.edges[2] = 0;   // the sampling kernel below only does what is left
   }

@@ -55,7 +55,7 @@ void b200k_gray_cascade(cudaStream_t st, DPage *pages, int npages, const int *gp
 /* k_deskew.cu */
 int b200k_rot_peaks(cudaStream_t st, DPage *pages, int npages, int max_masks, const float *tan_tab_dev,
                     int nangles, int scan_size_param, float scan_depth, const int edges[4],
-                    int peak_off, int scan_cap, int maxw, int use_prefix);
+                    int peak_off, int scan_cap, int maxw, int use_prefix, int run_cap /* 0: one CTA per angle */);
 void b200k_rot_finalize(cudaStream_t st, DPage *pages, int npages, const float *rot_tab_dev,
                         const float *pair_tab_dev, int nangles, const int edges[4], int peak_off,
                         float deviation);

@@ -304,6 +304,11 @@ int rot_plan_build(RotPlan *pl, int w, int h, const DeskewParameters *p, int max
   pl->scan_cap = imax(1, imin(sc, 10000));
   /* rows of the column-prefix table: the scan length is at most the mask height (<= h + 1) */
   pl->pre_need = (long long)(imin(pl->scan_cap, h + 1) + 2) * w;
+  /* a scan line changes column at most every 1/|tan| rows */
+  float maxtan = 0.0f;
+  for (int i = 0; i < n; i++) if (fabsf(pl->tan_host[i]) > maxtan) maxtan = fabsf(pl->tan_host[i]);
+  long long runs = (long long)(maxtan * imin(pl->scan_cap, imax(w, h) + 1)) + 4;
+  pl->run_cap = (runs <= 700) ? (int)runs : 0;   /* 2 x 8 x run_cap ints of shared memory */
   if (with_pair && n <= 512) {
     int m = 2 * n;
     float *t = (float *)malloc(sizeof(float) * 4 * (size_t)m * m);
@@ -409,7 +414,7 @@ void stage_detect_masks(StageCtx *c, const MaskPlan *pl) {
 int stage_detect_rotation(StageCtx *c, const RotPlan *pl, int max_masks) {
   int rc = b200k_rot_peaks(c->st, c->pages, c->npages, max_masks, pl->tan_dev, pl->nangles,
                            pl->p.deskewScanSize, pl->p.deskewScanDepth, pl->edges, pl->peak_off, pl->scan_cap,
-                           c->w, 1);
+                           c->w, 1, pl->run_cap);
   if (rc) { b200_set_error("deskew: scan size too large"); return rc; }
   b200k_rot_finalize(c->st, c->pages, c->npages, pl->rot_dev, pl->pair_dev, pl->nangles, pl->edges,
                      pl->peak_off, pl->p.deskewScanDeviationRad);
