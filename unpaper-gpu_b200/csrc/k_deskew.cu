@@ -450,6 +450,26 @@ __device__ __forceinline__ unsigned cubic_scale_f(float f, float a, float b, flo
   int result = __float2int_rz(b + 0.5f * f * ((c - a) + f * (2.0f * a - 5.0f * b + 4.0f * c - d + f * (3.0f * (b - c) + d - a))));
   return (unsigned)clip_u8(result);
 }
+// cubic_scale on four taps packed in one word (a = byte 0 ... d = byte 3).  The three
+// integer combinations of interpolate.c:24-32 — c - a, 2a - 5b + 4c - d and
+// 3(b - c) + d - a — are exact in float (|v| < 2^24), so any way of forming them gives
+// the reference's operands: one byte dot product each, accumulated onto the bit
+// pattern of 1.5 * 2^23 so that a single float subtraction finishes the int -> float
+// conversion.  The float steps that round (the f-multiplications and the sums with
+// them) keep the reference's order.  `hf` is 0.5f * f.
+__device__ __forceinline__ float dot_to_float(unsigned taps, int weights) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(taps), "r"(weights), "r"(0x4B400000));
+  return __int_as_float(d) - 12582912.0f;
+}
+__device__ __forceinline__ unsigned cubic_scale_w(float f, float hf, unsigned taps) {
+  float R = dot_to_float(taps, 0x000100FF);          // c - a
+  float P = dot_to_float(taps, (int)0xFF04FB02u);    // 2a - 5b + 4c - d
+  float Q = dot_to_float(taps, 0x01FD03FF);          // -a + 3b - 3c + d
+  float B = dot_to_float(taps, 0x00000100);          // b
+  float v = B + hf * (R + f * (P + f * Q));
+  return min(__float2uint_rz(v), 255u);               // (int) then av_clip_uint8; negatives saturate to 0
+}
 __device__ __forceinline__ int linear_scale(float x, int a, int b) {   // interpolate.c:62-64
   return (int)(uint8_t)(int)((1.0f - x) * a + x * b);
 }
@@ -637,19 +657,23 @@ __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) 
         // all 16 taps equal: every cubic term cancels exactly and the result is that value
         if (!(rw[0] == o * 0x01010101u && rw[1] == rw[0] && rw[2] == rw[0] && rw[3] == rw[0])) {
           float fx = srcX - px, fy = srcY - py;
-          float r4[4];
+          float hfx = 0.5f * fx;
+          unsigned r4[4];
 #pragma unroll
           for (int i = 0; i < 4; i++) {
             unsigned b0 = rw[i] & 0xFFu;
             // a row of four equal taps interpolates to that value exactly; a row equal
             // to the one above (vertical strokes) has the same result as that row
-            if (rw[i] == b0 * 0x01010101u) r4[i] = u8f(b0);
+            if (rw[i] == b0 * 0x01010101u) r4[i] = b0;
             else if (i > 0 && rw[i] == rw[i - 1]) r4[i] = r4[i - 1];
-            else r4[i] = u8f(cubic_scale_f(fx, u8f(b0), u8f((rw[i] >> 8) & 0xFFu), u8f((rw[i] >> 16) & 0xFFu), u8f(rw[i] >> 24)));
+            else r4[i] = cubic_scale_w(fx, hfx, rw[i]);
           }
           // four equal row results: the vertical pass returns that value exactly
-          if (r4[1] == r4[0] && r4[2] == r4[0] && r4[3] == r4[0]) o = (unsigned)__float2int_rz(r4[0]);
-          else o = cubic_scale_f(fy, r4[0], r4[1], r4[2], r4[3]);
+          if (r4[1] == r4[0] && r4[2] == r4[0] && r4[3] == r4[0]) o = r4[0];
+          else {
+            unsigned lo = __byte_perm(r4[0], r4[1], 0x0040), hi = __byte_perm(r4[2], r4[3], 0x0040);
+            o = cubic_scale_w(fy, 0.5f * fy, __byte_perm(lo, hi, 0x5410));
+          }
         }
         orow[x] = (uint8_t)o;
         continue;

@@ -762,15 +762,10 @@ __global__ void k_nf_resolve(DPage *pages, int intensity) {
  * (filters.c:160-167) — and wipe the flagged blocks.
  * layout in u32: [c0: n][h: nrows*(n+1)][state: 3*(n+2)][flags: nrows*n]
  * ====================================================================== */
-__global__ void k_blur_decide(DPage *pages, int npages, int n, int nrows, unsigned long long T,
-                              float intensity, int cnt_off, int state_off, int flag_off) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= npages) return;
-  DPage &pg = pages[p];
-  const unsigned *c0 = pg.u32 + cnt_off;
-  const unsigned *h = c0 + n;
-  unsigned *flat = pg.u32 + state_off;
-  unsigned *flag = pg.u32 + flag_off;
+// the scalar state machine of filters.c:170-230 on arrays `c0`, `h`, `flat`, `flag`
+// (shared or global memory)
+__device__ __forceinline__ void blur_state_machine(const unsigned *c0, const unsigned *h, unsigned *flat, unsigned *flag,
+                                                   int n, int nrows, unsigned long long T, float intensity) {
   unsigned Tu = (unsigned)T;
   for (int i = 0; i < 3 * (n + 2); i++) flat[i] = 0;
   int prev = 0, cur = 1, next = 2;
@@ -788,6 +783,33 @@ __global__ void k_blur_decide(DPage *pages, int npages, int n, int nrows, unsign
     }
     int tmp = prev; prev = cur; cur = next; next = tmp;
   }
+}
+
+// one warp per page: the counts are staged in shared memory so the serial walk
+// pays shared-memory latency per step, not an L2 round trip
+__global__ void __launch_bounds__(32) k_blur_decide_sm(DPage *pages, int n, int nrows, unsigned long long T,
+                                                      float intensity, int cnt_off, int state_off, int flag_off) {
+  extern __shared__ unsigned bsm[];   // [c0: n][h: nrows*(n+1)][flat: 3*(n+2)][flag: nrows*n]
+  DPage &pg = pages[blockIdx.x];
+  int ncnt = n + nrows * (n + 1);
+  unsigned *flat = bsm + ncnt, *flag = flat + 3 * (n + 2);
+  const unsigned *src = pg.u32 + cnt_off;
+  for (int i = threadIdx.x; i < ncnt; i += 32) bsm[i] = src[i];
+  __syncwarp();
+  if (threadIdx.x == 0) blur_state_machine(bsm, bsm + n, flat, flag, n, nrows, T, intensity);
+  __syncwarp();
+  unsigned *gflat = pg.u32 + state_off, *gflag = pg.u32 + flag_off;
+  for (int i = threadIdx.x; i < 3 * (n + 2); i += 32) gflat[i] = flat[i];
+  for (int i = threadIdx.x; i < nrows * n; i += 32) gflag[i] = flag[i];
+}
+
+__global__ void k_blur_decide(DPage *pages, int npages, int n, int nrows, unsigned long long T,
+                              float intensity, int cnt_off, int state_off, int flag_off) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npages) return;
+  DPage &pg = pages[p];
+  const unsigned *c0 = pg.u32 + cnt_off;
+  blur_state_machine(c0, c0 + n, pg.u32 + state_off, pg.u32 + flag_off, n, nrows, T, intensity);
 }
 
 __global__ void k_blur_wipe(DPage *pages, int n, int bw, int bh, int flag_off) {
@@ -969,7 +991,11 @@ int b200k_noisefilter(cudaStream_t st, DPage *pages, int npages, int maxw, int m
 void b200k_blur_decide(cudaStream_t st, DPage *pages, int npages, int n, int nrows,
                        unsigned long long T, float intensity, int cnt_off, int state_off, int flag_off) {
   if (npages <= 0) return;
-  k_blur_decide<<<cdiv(npages, 32), 32, 0, st>>>(pages, npages, n, nrows, T, intensity, cnt_off, state_off, flag_off);
+  size_t sm = ((size_t)n + (size_t)nrows * (n + 1) + 3 * ((size_t)n + 2) + (size_t)nrows * n) * sizeof(unsigned);
+  if (sm <= 40 * 1024)
+    k_blur_decide_sm<<<npages, 32, sm, st>>>(pages, n, nrows, T, intensity, cnt_off, state_off, flag_off);
+  else
+    k_blur_decide<<<cdiv(npages, 32), 32, 0, st>>>(pages, npages, n, nrows, T, intensity, cnt_off, state_off, flag_off);
 }
 void b200k_blur_wipe(cudaStream_t st, DPage *pages, int npages, int n, int nrows, int bw, int bh, int flag_off) {
   if (npages <= 0 || n <= 0 || nrows <= 0) return;
