@@ -468,7 +468,10 @@ __device__ __forceinline__ unsigned cubic_scale_w(float f, float hf, unsigned ta
   float Q = dot_to_float(taps, 0x01FD03FF);          // -a + 3b - 3c + d
   float B = dot_to_float(taps, 0x00000100);          // b
   float v = B + hf * (R + f * (P + f * Q));
-  return min(__float2uint_rz(v), 255u);               // (int) then av_clip_uint8; negatives saturate to 0
+  // (int) then av_clip_uint8 without the conversion pipe: clamp, then add 2^23 rounding
+  // toward zero, which leaves the truncated value in the low mantissa bits
+  v = fminf(fmaxf(v, 0.0f), 255.0f);
+  return __float_as_uint(__fadd_rz(v, 8388608.0f)) & 0xFFu;
 }
 __device__ __forceinline__ int linear_scale(float x, int a, int b) {   // interpolate.c:62-64
   return (int)(uint8_t)(int)((1.0f - x) * a + x * b);
@@ -631,10 +634,14 @@ __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) 
   for (int y = yt; y < yte; y++) {
   uint8_t *orow = aux.data + (size_t)y * aux.pitch;
   {
-    float srcX = scx + (x - tcx) * cosval + (y - tcy) * sinval;
-    float srcY = scy + (y - tcy) * cosval - (x - tcx) * sinval;
+    float xf = u8f((unsigned)x), yf = u8f((unsigned)y);   // == (float)x, (float)y for 0 <= v < 2^23
+    float srcX = scx + (xf - tcx) * cosval + (yf - tcy) * sinval;
+    float srcY = scy + (yf - tcy) * cosval - (xf - tcx) * sinval;
     if (fast) {
-      int px = (int)srcX, py = (int)srcY;
+      // (int)srcX for 1 <= srcX < 2^23 by the 2^23 trick (anything else fails the
+      // range test below and takes the general path): no conversion instructions
+      float tX = __fadd_rz(srcX, 8388608.0f), tY = __fadd_rz(srcY, 8388608.0f);
+      int px = __float_as_int(tX) - 0x4B000000, py = __float_as_int(tY) - 0x4B000000;
       if ((unsigned)(px - 1) < (unsigned)(im.w - 3) && (unsigned)(py - 1) < (unsigned)(im.h - 3)) {
         // the 4x4 taps as four packed words (two aligned loads + funnel shift per row)
         const uint8_t *p0 = im.data + (size_t)(py - 1) * im.pitch + (px - 1);
@@ -656,7 +663,7 @@ __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) 
         unsigned o = rw[0] & 0xFFu;
         // all 16 taps equal: every cubic term cancels exactly and the result is that value
         if (!(rw[0] == o * 0x01010101u && rw[1] == rw[0] && rw[2] == rw[0] && rw[3] == rw[0])) {
-          float fx = srcX - px, fy = srcY - py;
+          float fx = srcX - (tX - 8388608.0f), fy = srcY - (tY - 8388608.0f);   // srcX - (float)px
           float hfx = 0.5f * fx;
           unsigned r4[4];
 #pragma unroll
