@@ -162,6 +162,8 @@ def main():
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("BENCH_LANES", "8")))
     ap.add_argument("--distinct", type=int, default=int(os.environ.get("BENCH_DISTINCT", "8")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--out-format", default="page", choices=["page", "mono"],
+                    help="sheet_stage_output format: 'page' (GRAY8, the headline config) or 'mono' (pbm, 1 bit/px D2H)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -186,6 +188,9 @@ def main():
 
     cfg = U.default_sheet_config()
     eng = Engine(cfg, W, H, U.FMT_GRAY8, group_pages=args.group, lanes=args.lanes, device=local)
+    if args.out_format == "mono":
+        eng.set_output_format(U.FMT_MONOWHITE)
+    out_bytes = eng.sheet_bytes
     distinct = make_pages(args.distinct, rank)
     reps = (args.pages + args.distinct - 1) // args.distinct
     host_np = np.concatenate([distinct] * reps)[:args.pages]
@@ -323,14 +328,14 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "pages_per_step_per_gpu": args.pages, "group_pages": args.group,
+                "config": {"workload": WORKLOAD, "output_format": args.out_format, "pages_per_step_per_gpu": args.pages, "group_pages": args.group,
                            "lanes": args.lanes, "distinct_pages": args.distinct,
                            "l2": f"inputs larger than L2 ({args.pages * S / 1e6:.0f} MB of pages per step vs 126 MB L2)",
                            "parallelism": f"page-sharded x{world}, no collective",
                            "timing": "CUDA events on the engine's streams (first enqueue -> last lane done), max over ranks",
                            "wall_ms_per_step": dev_wall_ms / args.steps},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_pages * S * world,
-                        "d2h_bytes_per_step": e2e_pages * S * world, "ms_per_step": e2e_ms / args.steps,
+                        "d2h_bytes_per_step": e2e_pages * out_bytes * world, "ms_per_step": e2e_ms / args.steps,
                         "wall_ms_per_step": e2e_wall_ms / args.steps, "pages_per_step_per_gpu": e2e_pages,
                         "pcie_h2d_gbs": h2d_gbs, "pcie_d2h_gbs": d2h_gbs,
                         "pcie_bidir_gbs_each_way": bidir_gbs,

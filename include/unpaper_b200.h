@@ -124,6 +124,20 @@ int unpaper_b200_host_detect_rotation(const B200HostImage *img, const Rectangle 
                                       const DeskewParameters *p, float *radians_out);
 int unpaper_b200_host_deskew(B200HostImage *img, const Rectangle *mask, float radians, int32_t interp);
 
+/* Output side (sheet_stage_output -> saveImage, file.c:134-260).
+ * unpaper_b200_output_format: the format saveImage() really writes for a
+ *   requested one (Y400A -> GRAY8, MONOBLACK -> MONOWHITE; file.c:201-208).
+ * unpaper_b200_host_convert_format: saveImage()'s conversion into `out`
+ *   (same size; out->format must already be an output format): MONOWHITE
+ *   thresholds gray < in->abs_black_threshold (file.c:215-243), MONOBLACK input
+ *   inverts bytes (:244-255), otherwise copy_rectangle semantics (:258).
+ * unpaper_b200_pnm_header / _write_pnm: saveImageDirect (file.c:134-176). */
+int unpaper_b200_output_format(int av_pix_fmt);
+int unpaper_b200_host_convert_format(const B200HostImage *in, B200HostImage *out);
+int unpaper_b200_pnm_header(int av_pix_fmt, int width, int height, char *buf, size_t cap);
+int unpaper_b200_write_pnm(const char *path, const uint8_t *data, int linesize,
+                           int width, int height, int av_pix_fmt);
+
 /* ------------------------------------------------------------------------
  * (3) sheet engine
  * --------------------------------------------------------------------- */
@@ -200,8 +214,15 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device,
 void unpaper_b200_engine_destroy(B200Engine *e);
 int unpaper_b200_engine_sheet_width(const B200Engine *e);
 int unpaper_b200_engine_sheet_height(const B200Engine *e);
-/* bytes of one output sheet (format = page format for GRAY8/RGB24 input) */
+/* bytes of one output sheet (format = page format unless an output format
+ * was set) */
 size_t unpaper_b200_engine_sheet_bytes(const B200Engine *e);
+/* sheet_stage_output's format conversion on the device (so the D2H carries
+ * 1 bit/px for pbm output): sheets leave process_* in `av_pix_fmt` (mapped by
+ * unpaper_b200_output_format), tight rows; -1 restores the page format.
+ * Call between process_* calls. */
+int unpaper_b200_engine_set_output_format(B200Engine *e, int av_pix_fmt);
+int unpaper_b200_engine_output_format(const B200Engine *e);
 
 /* Pages resident in device memory: `pages_dev` holds n_sheets*input_count
  * tightly packed pages (row stride = width*bpp); `out_dev` receives n_sheets

@@ -72,6 +72,41 @@ int orc_host_grayfilter(B200HostImage *img, const GrayfilterParameters *p) { OIm
 int orc_host_detect_rotation(const B200HostImage *img, const Rectangle *m, const DeskewParameters *p, float *out) { OImg im = wrap(img); *out = o_detect_rotation(&im, R(m), p); return 0; }
 int orc_host_deskew(B200HostImage *img, const Rectangle *m, float rad, int32_t interp) { OImg im = wrap(img); o_deskew(&im, R(m), rad, interp); return 0; }
 
+/* saveImage()'s pixel-format conversion (file.c:197-260).  file.c itself needs
+ * libavcodec/libavformat and is not part of oracle/_ref, so for this one function
+ * the restatement is pinned only through the A1 golden record (gray < 170 -> black
+ * against the reference's goldenA1.pbm, tests/golden/make_golden.py) and, for the
+ * generic branch, through copy_rectangle which IS checked against oracle/_ref. */
+int orc_host_convert_format(const B200HostImage *in, B200HostImage *out) {
+  OImg s = wrap(in), d = wrap(out);
+  int w = s.w, h = s.h;
+  if (d.w != w || d.h != h) return -1;
+  if (s.fmt == d.fmt) {                                 /* file.c:210: no conversion */
+    int row = s.fmt == B200_FMT_RGB24 ? 3 * w : s.fmt == B200_FMT_Y400A ? 2 * w : s.fmt == B200_FMT_GRAY8 ? w : (w + 7) / 8;
+    for (int y = 0; y < h; y++) memcpy(d.d + (size_t)y * d.ls, s.d + (size_t)y * s.ls, (size_t)row);
+    return 0;
+  }
+  if ((s.fmt == B200_FMT_RGB24 || s.fmt == B200_FMT_GRAY8) && d.fmt == B200_FMT_MONOWHITE) {   /* :215-243 */
+    for (int y = 0; y < h; y++) {
+      const uint8_t *src = s.d + (size_t)y * s.ls;
+      uint8_t *dst = d.d + (size_t)y * d.ls;
+      for (int x = 0; x < w; x++) {
+        int gray = s.fmt == B200_FMT_RGB24 ? (src[x * 3] + src[x * 3 + 1] + src[x * 3 + 2]) / 3 : src[x];
+        int bit = x % 8;
+        if (bit == 0) dst[x / 8] = 0;
+        if (gray < s.abt) dst[x / 8] |= (0x80 >> bit);
+      }
+    }
+  } else if (s.fmt == B200_FMT_MONOBLACK && d.fmt == B200_FMT_MONOWHITE) {                       /* :244-255 */
+    for (int y = 0; y < h; y++)
+      for (int x = 0; x < (w + 7) / 8; x++) d.d[(size_t)y * d.ls + x] = s.d[(size_t)y * s.ls + x] ^ 0xFF;
+  } else {                                                                                          /* :257-259 */
+    ORect full = {0, 0, w - 1, h - 1};
+    o_copy(&s, &d, full, 0, 0);
+  }
+  return 0;
+}
+
 /* ---- process_sheet(): decode, pre, filters, masks, deskew, post (sheet_stages.c) ---- */
 
 static int one_sheet(const B200SheetConfig *c, const uint8_t *pages, int pw, int ph, int fmt, uint8_t *out, B200SheetResult *res) {

@@ -1,0 +1,111 @@
+"""Output side: sheet_stage_output's pixel-format conversion on the
+device and the direct PNM writer — reference file.c:134-260.
+
+file.c needs libavcodec, so it is not part of oracle/_ref; the checker here is the
+restatement `orc_host_convert_format` (its threshold rule is pinned by the A1 golden
+record, its generic branch is copy_rectangle which is checked against oracle/_ref)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import unpaper_gpu_b200 as U
+from unpaper_gpu_b200 import synth
+from util import himg, linesize, noise_image
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def orc_ops():
+    from oracle import checker
+    lib = checker.load_oracle()
+    if lib is None:
+        pytest.skip("oracle/liboracle.so not built")
+    return U.HostOps(lib, "orc_host_")
+
+
+@pytest.mark.parametrize("sfmt,dfmt", [(U.FMT_GRAY8, U.FMT_MONOWHITE), (U.FMT_RGB24, U.FMT_MONOWHITE),
+                                       (U.FMT_MONOBLACK, U.FMT_MONOWHITE), (U.FMT_Y400A, U.FMT_MONOWHITE),
+                                       (U.FMT_RGB24, U.FMT_GRAY8), (U.FMT_GRAY8, U.FMT_RGB24),
+                                       (U.FMT_MONOWHITE, U.FMT_GRAY8), (U.FMT_MONOBLACK, U.FMT_RGB24),
+                                       (U.FMT_Y400A, U.FMT_GRAY8), (U.FMT_GRAY8, U.FMT_GRAY8),
+                                       (U.FMT_MONOWHITE, U.FMT_MONOWHITE)])
+@pytest.mark.parametrize("w,h", [(37, 29), (203, 77), (640, 64)])
+@pytest.mark.parametrize("abt", [170, 84])
+def test_convert_format(cuda_ops, orc_ops, sfmt, dfmt, w, h, abt):
+    src = noise_image(11, w, h, sfmt, dark=0.4)
+    outs = []
+    for ops in (cuda_ops, orc_ops):
+        d = np.full((h, linesize(dfmt, w)), 0x5A, dtype=np.uint8)
+        ops.call("convert_format", C.byref(himg(src, sfmt, w, abt=abt)), C.byref(himg(d, dfmt, w, abt=abt)))
+        outs.append(d)
+    row = U.bytes_per_row(dfmt, w)
+    a, b = outs[0][:, :row].copy(), outs[1][:, :row].copy()
+    if dfmt == U.FMT_MONOWHITE and sfmt not in (U.FMT_GRAY8, U.FMT_RGB24, U.FMT_MONOBLACK) and w % 8:
+        # generic branch (file.c:257-259): set_pixel only touches the w real pixels of a
+        # create_image(fill=false) buffer, the tail bits of the last byte are unspecified
+        keep = (0xFF << (8 - w % 8)) & 0xFF
+        a[:, -1] &= keep
+        b[:, -1] &= keep
+    assert np.array_equal(a, b)
+    assert (outs[0][:, row:] == 0x5A).all()     # nothing written past the row
+
+
+def test_output_format_mapping_and_header():
+    from unpaper_gpu_b200 import lib as L
+    lib = L.load()
+    assert lib.unpaper_b200_output_format(U.FMT_Y400A) == U.FMT_GRAY8          # file.c:201-208
+    assert lib.unpaper_b200_output_format(U.FMT_MONOBLACK) == U.FMT_MONOWHITE
+    assert lib.unpaper_b200_output_format(U.FMT_RGB24) == U.FMT_RGB24
+    buf = C.create_string_buffer(64)
+    for fmt, want in ((U.FMT_GRAY8, b"P5\n31 7\n255\n"), (U.FMT_RGB24, b"P6\n31 7\n255\n"), (U.FMT_MONOWHITE, b"P4\n31 7\n")):
+        n = lib.unpaper_b200_pnm_header(fmt, 31, 7, buf, 64)
+        assert buf.raw[:n] == want
+    assert lib.unpaper_b200_pnm_header(U.FMT_Y400A, 31, 7, buf, 64) < 0
+
+
+def test_engine_mono_output(orc_ops, tmp_path):
+    """pbm output: the engine converts on the device, D2H carries 1 bit/px; the bytes
+    equal saveImage()'s conversion of the engine's own GRAY8 output (which the other
+    engine tests compare with the reference)."""
+    from unpaper_gpu_b200.lib import Engine
+    from unpaper_gpu_b200 import lib as L
+    w, h = 620, 877
+    pages = np.stack([synth.gray_page(i, w, h, box=(0.60, 0.72)) for i in range(5)])
+    cfg = U.default_sheet_config()
+    eng = Engine(cfg, w, h, U.FMT_GRAY8, group_pages=2, lanes=2)
+    gray, _ = eng.process_numpy(pages)
+    eng.set_output_format(U.FMT_MONOBLACK)      # written as MONOWHITE
+    assert eng.out_fmt == U.FMT_MONOWHITE
+    row = (eng.sheet_w + 7) // 8
+    assert eng.sheet_bytes == row * eng.sheet_h
+    mono, res = eng.process_numpy(pages)
+    assert mono.shape == (5, eng.sheet_h, row)
+    for i in range(5):
+        want = np.zeros((eng.sheet_h, row), dtype=np.uint8)
+        g = np.ascontiguousarray(gray[i])
+        orc_ops.call("convert_format", C.byref(himg(g, U.FMT_GRAY8, eng.sheet_w, abt=cfg.abs_black_threshold)),
+                     C.byref(himg(want, U.FMT_MONOWHITE, eng.sheet_w, abt=cfg.abs_black_threshold)))
+        assert np.array_equal(mono[i], want), f"sheet {i}"
+        assert res[i].status == 0
+    # device-resident path gives the same bytes
+    import torch
+    d_in = torch.from_numpy(pages.reshape(-1)).cuda()
+    d_out = torch.empty(5 * eng.sheet_bytes, dtype=torch.uint8, device="cuda")
+    eng.process_ptr(d_in.data_ptr(), d_out.data_ptr(), 5, False, None)
+    assert np.array_equal(d_out.cpu().numpy().reshape(mono.shape), mono)
+    # back to the page format
+    eng.set_output_format(-1)
+    again, _ = eng.process_numpy(pages)
+    assert np.array_equal(again, gray)
+    eng.close()
+    # direct PNM writer (file.c:134-176)
+    path = os.path.join(str(tmp_path), "sheet.pbm")
+    m0 = np.ascontiguousarray(mono[0])
+    rc = L.load().unpaper_b200_write_pnm(path.encode(), m0.ctypes.data, row, eng.sheet_w, eng.sheet_h, U.FMT_MONOWHITE)
+    assert rc == 0
+    blob = open(path, "rb").read()
+    hdr = b"P4\n%d %d\n" % (eng.sheet_w, eng.sheet_h)
+    assert blob[:len(hdr)] == hdr and blob[len(hdr):] == m0.tobytes()

@@ -116,3 +116,25 @@ def test_orc_sheet_vs_ref(orc_lib, ref_lib):
     b, rb = checker.process_sheets_cpu(ref_lib, "ref_", cfg, pages, w, h, fmt)
     assert [G.result_dict(r) for r in ra] == [G.result_dict(r) for r in rb]
     assert np.array_equal(a, b)
+
+
+def test_orc_output_conversion_vs_numpy(orc_ops):
+    """saveImage()'s conversion (file.c:211-259) restated in oracle_sheet.c against a
+    numpy statement of the same rule: bit = gray < abs_black_threshold, MSB first,
+    tail bits of the last byte clear."""
+    import ctypes as C
+    from util import himg, linesize, noise_image
+    w, h = 203, 9
+    for abt in (170, 84):
+        src = noise_image(11, w, h, U.FMT_GRAY8, dark=0.4)
+        d = np.full((h, linesize(U.FMT_MONOWHITE, w)), 0x5A, dtype=np.uint8)
+        orc_ops.call("convert_format", C.byref(himg(src, U.FMT_GRAY8, w, abt=abt)), C.byref(himg(d, U.FMT_MONOWHITE, w, abt=abt)))
+        want = np.packbits(src[:, :w] < abt, axis=1)
+        assert np.array_equal(d[:, :want.shape[1]], want)
+        rgb = noise_image(12, w, h, U.FMT_RGB24, dark=0.4)
+        orc_ops.call("convert_format", C.byref(himg(rgb, U.FMT_RGB24, w, abt=abt)), C.byref(himg(d, U.FMT_MONOWHITE, w, abt=abt)))
+        g = rgb[:, :3 * w].reshape(h, w, 3).astype(int).sum(2) // 3
+        assert np.array_equal(d[:, :want.shape[1]], np.packbits(g < abt, axis=1))
+        mb = noise_image(13, w, h, U.FMT_MONOBLACK, dark=0.4)
+        orc_ops.call("convert_format", C.byref(himg(mb, U.FMT_MONOBLACK, w, abt=abt)), C.byref(himg(d, U.FMT_MONOWHITE, w, abt=abt)))
+        assert np.array_equal(d[:, :want.shape[1]], mb[:, :want.shape[1]] ^ 0xFF)

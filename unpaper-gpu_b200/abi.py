@@ -170,6 +170,11 @@ _HOST_SIGS = {
 }
 
 
+_OUTPUT_SIGS = {
+    "convert_format": [C.POINTER(HostImage), C.POINTER(HostImage)],
+}
+
+
 class HostOps:
     """The 21 host-buffer ops of one library, numpy in / numpy out.
 
@@ -184,6 +189,13 @@ class HostOps:
             f = getattr(lib, prefix + name)
             f.argtypes, f.restype = sig, C.c_int
             self.fn[name] = f
+        # output side: exists in the product and in the restatement, not in the
+        # reference build (file.c needs libavcodec)
+        for name, sig in _OUTPUT_SIGS.items():
+            if hasattr(lib, prefix + name):
+                f = getattr(lib, prefix + name)
+                f.argtypes, f.restype = sig, C.c_int
+                self.fn[name] = f
 
     @staticmethod
     def himg(a, fmt, width, bg=(255, 255, 255), abt=170):

@@ -51,6 +51,7 @@ typedef struct {
   uint32_t *pre;
   uint8_t *ink;
   uint8_t *page_stage;    /* device staging for host-mode pages */
+  uint8_t *out_stage;     /* device staging for converted output sheets (host mode) */
   DPage *pages_dev, *pages_tmpl /* host */;
   DFillJob *fillA, *fillB, *fillC, *decode_fill;
   DCopyJob *copyA, *copyB, *decode_copy, *decode_copy_host_tmpl;
@@ -82,6 +83,7 @@ struct B200Engine {
   int bad_sheets, bad_first;
   unsigned bad_flags;
   cudaEvent_t ev_begin;
+  int out_fmt, out_dfmt, out_row;   /* output conversion (av format, -1 = none) */
   double last_device_ms;
   double stage_ms[STG_COUNT];
   uint64_t stage_groups[STG_COUNT];
@@ -91,7 +93,32 @@ static int imax(int a, int b) { return a > b ? a : b; }
 
 int unpaper_b200_engine_sheet_width(const B200Engine *e) { return e->sheet_w; }
 int unpaper_b200_engine_sheet_height(const B200Engine *e) { return e->sheet_h; }
-size_t unpaper_b200_engine_sheet_bytes(const B200Engine *e) { return (size_t)e->sheet_row * e->sheet_h; }
+size_t unpaper_b200_engine_sheet_bytes(const B200Engine *e) {
+  return (size_t)(e->out_fmt >= 0 ? e->out_row : e->sheet_row) * e->sheet_h;
+}
+int unpaper_b200_engine_output_format(const B200Engine *e) { return e->out_fmt >= 0 ? e->out_fmt : e->page_fmt; }
+
+/* sheet_stage_output's conversion (sheet_stages.c:536-631 -> file.c:197-260) moved onto
+ * the device, so that the D2H (or the device-side sink) carries the output format */
+int unpaper_b200_engine_set_output_format(B200Engine *e, int av_pix_fmt) {
+  if (!e) return -1;
+  unpaper_b200_set_device(e->device);
+  CUDA_OK(cudaDeviceSynchronize());
+  int fmt = av_pix_fmt < 0 ? -1 : unpaper_b200_output_format(av_pix_fmt);
+  if (fmt == e->page_fmt) fmt = -1;
+  if (fmt >= 0) {
+    int df = b200_fmt_to_dev(fmt), row = b200_fmt_row_bytes(fmt, e->sheet_w);
+    if (df < 0 || row <= 0) { b200_set_error("engine: unsupported output format %d", av_pix_fmt); return -1; }
+    e->out_dfmt = df; e->out_row = row;
+    for (int i = 0; i < e->nlanes; i++) {
+      Lane *ln = &e->lanes[i];
+      if (ln->out_stage) b200_dev_free(ln->out_stage);
+      ln->out_stage = (uint8_t *)b200_dev_alloc((size_t)row * e->sheet_h * e->group + 64);
+    }
+  }
+  e->out_fmt = fmt;
+  return 0;
+}
 uint64_t unpaper_b200_engine_launch_count(const B200Engine *e) { return e->launches; }
 double unpaper_b200_engine_last_device_ms(const B200Engine *e) { return e->last_device_ms; }
 int unpaper_b200_engine_set_profiling(B200Engine *e, int enabled) {
@@ -160,7 +187,7 @@ static int build_static(B200Engine *e, Lane *ln, int slot, const Rectangle *wipe
 }
 
 static void lane_free(Lane *ln) {
-  void *ptrs[] = {ln->sheets, ln->aux, ln->cls, ln->list, ln->u32, ln->stack, ln->pre, ln->ink, ln->page_stage, ln->pages_dev,
+  void *ptrs[] = {ln->sheets, ln->aux, ln->cls, ln->list, ln->u32, ln->stack, ln->pre, ln->ink, ln->page_stage, ln->out_stage, ln->pages_dev,
                   ln->fillA, ln->fillB, ln->fillC, ln->decode_fill, ln->copyA, ln->copyB, ln->decode_copy, ln->maskJ,
                   ln->static_fill[0], ln->static_fill[1], ln->static_fill[2], ln->static_mask[0], ln->static_mask[1],
                   ln->static_mask[2], ln->static_mask_rects[0], ln->static_mask_rects[1], ln->static_mask_rects[2]};
@@ -198,6 +225,7 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
   B200Engine *e = (B200Engine *)calloc(1, sizeof(*e));
   e->cfg = *cfg; e->device = device;
   e->page_w = page_w; e->page_h = page_h; e->page_fmt = page_format; e->dfmt = b200_fmt_to_dev(page_format);
+  e->out_fmt = -1;
   e->bpp = page_format == AV_PIX_FMT_GRAY8 ? 1 : 3;
   e->group = group_pages; e->nlanes = lanes;
   /* sheet size = input pages side by side (sheet_stages.c:140-145) */
@@ -424,7 +452,19 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
   run_static(e, ln, &c, 2, n);
   mark(e, ln, STG_OUTPUT);
   /* output stage: sheet -> caller (tight rows) + the decisions */
-  if (ln->host_mode) {
+  if (e->out_fmt >= 0) {
+    size_t out_bytes = (size_t)e->out_row * e->sheet_h;
+    DImg sv;
+    memset(&sv, 0, sizeof(sv));
+    sv.data = ln->sheets; sv.w = e->sheet_w; sv.h = e->sheet_h; sv.pitch = e->sheet_pitch; sv.fmt = e->dfmt;
+    sv.abt = cfg->abs_black_threshold;
+    DImg dv = sv;
+    dv.data = ln->host_mode ? ln->out_stage : ln->out_dev; dv.pitch = e->out_row; dv.fmt = e->out_dfmt;
+    b200k_convert_out(c.st, sv, dv, n, e->sheet_stride, out_bytes);
+    c.launches++;
+    if (ln->host_mode)
+      CUDA_OK(cudaMemcpyAsync(ln->out_host, ln->out_stage, out_bytes * n, cudaMemcpyDeviceToHost, c.st));
+  } else if (ln->host_mode) {
     size_t sheet_bytes = (size_t)e->sheet_row * e->sheet_h;
     if (e->sheet_pitch == e->sheet_row) {
       /* rows are tight, sheets are `sheet_stride` apart: one 2-D copy with one "row" per sheet */
@@ -500,7 +540,7 @@ static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_shee
   if (!e || !pages || !out || n_sheets < 0) { b200_set_error("engine: bad arguments"); return -1; }
   unpaper_b200_set_device(e->device);
   int P = e->group, ic = e->cfg.input_count;
-  size_t out_sheet = (size_t)e->sheet_row * e->sheet_h;
+  size_t out_sheet = unpaper_b200_engine_sheet_bytes(e);
   int g = 0;
   for (int i = 0; i < e->nlanes; i++) e->lanes[i].ran = 0;
   /* every lane is idle here, so an event on lane 0 marks the start of device work */

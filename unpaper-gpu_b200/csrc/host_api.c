@@ -4,6 +4,7 @@
 #define _GNU_SOURCE
 #include <libavutil/frame.h>
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 
 #include "host.h"
@@ -190,3 +191,73 @@ void unpaper_b200_sheet_config_defaults(B200SheetConfig *c) {
   c->border_scan = (BorderScanParameters){
       .scan_size = {5, 5}, .scan_step = {5, 5}, .scan_threshold = {5, 5}, .scan_direction = {false, true}};
 }
+
+/* ---- output side (sheet_stage_output, sheet_stages.c:536-631 -> saveImage) ---- */
+
+/* the format saveImage() really writes for a requested one (file.c:201-208) */
+int unpaper_b200_output_format(int av_pix_fmt) {
+  if (av_pix_fmt == AV_PIX_FMT_Y400A) return AV_PIX_FMT_GRAY8;
+  if (av_pix_fmt == AV_PIX_FMT_MONOBLACK) return AV_PIX_FMT_MONOWHITE;
+  return av_pix_fmt;
+}
+
+int unpaper_b200_host_convert_format(const B200HostImage *in, B200HostImage *out) {
+  if (!in || !out || !out->data) { b200_set_error("bad image"); return -1; }
+  if (out->width != in->width || out->height != in->height) { b200_set_error("convert: size mismatch"); return -1; }
+  int ofmt = unpaper_b200_output_format(out->format);
+  if (ofmt != out->format) { b200_set_error("convert: format %d is written as %d", out->format, ofmt); return -1; }
+  int orow = b200_fmt_row_bytes(out->format, out->width);
+  if (orow < 0 || b200_fmt_to_dev(out->format) < 0 || out->linesize < orow) { b200_set_error("bad format/linesize"); return -1; }
+  Borrow b;
+  if (borrow(&b, in)) return -1;
+  if (in->format == out->format) {   /* file.c:210: written as it is */
+    for (int y = 0; y < in->height; y++)
+      memcpy(out->data + (size_t)y * out->linesize, in->data + (size_t)y * in->linesize, (size_t)orow);
+    return 0;
+  }
+  image_ensure_cuda(&b.img);
+  DImg sv, dv;
+  if (!b200_image_view(&b.img, &sv)) { drop(&b); b200_set_error("unsupported pixel format"); return -1; }
+  size_t bytes = (size_t)orow * out->height;
+  uint8_t *d = (uint8_t *)b200_dev_alloc(bytes);
+  dv = sv; dv.data = d; dv.pitch = orow; dv.fmt = b200_fmt_to_dev(out->format);
+  cudaStream_t st = b200_rt_stream();
+  b200k_convert_out(st, sv, dv, 1, 0, 0);
+  CUDA_OK(cudaMemcpy2DAsync(out->data, (size_t)out->linesize, d, (size_t)orow, (size_t)orow, (size_t)out->height,
+                            cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaGetLastError());
+  b200_dev_free(d);
+  drop(&b);
+  return 0;
+}
+
+/* saveImageDirect (file.c:134-176): PNM header + tight rows */
+int unpaper_b200_pnm_header(int av_pix_fmt, int width, int height, char *buf, size_t cap) {
+  int n;
+  switch (av_pix_fmt) {
+  case AV_PIX_FMT_GRAY8: n = snprintf(buf, cap, "P5\n%d %d\n255\n", width, height); break;
+  case AV_PIX_FMT_RGB24: n = snprintf(buf, cap, "P6\n%d %d\n255\n", width, height); break;
+  case AV_PIX_FMT_MONOWHITE: n = snprintf(buf, cap, "P4\n%d %d\n", width, height); break;
+  default: b200_set_error("pnm: unsupported pixel format %d", av_pix_fmt); return -1;
+  }
+  if (n < 0 || (size_t)n >= cap) { b200_set_error("pnm: header buffer too small"); return -1; }
+  return n;
+}
+
+int unpaper_b200_write_pnm(const char *path, const uint8_t *data, int linesize, int width, int height, int av_pix_fmt) {
+  char hdr[64];
+  int n = unpaper_b200_pnm_header(av_pix_fmt, width, height, hdr, sizeof(hdr));
+  int row = b200_fmt_row_bytes(av_pix_fmt, width);
+  if (n < 0 || row < 0 || !data || linesize < row) { if (n >= 0) b200_set_error("pnm: bad arguments"); return -1; }
+  FILE *f = fopen(path, "wb");
+  if (!f) { b200_set_error("pnm: unable to open %s", path); return -1; }
+  bool ok = fwrite(hdr, 1, (size_t)n, f) == (size_t)n;
+  if (linesize == row) ok = ok && fwrite(data, 1, (size_t)row * height, f) == (size_t)row * height;
+  else
+    for (int y = 0; ok && y < height; y++) ok = fwrite(data + (size_t)y * linesize, 1, (size_t)row, f) == (size_t)row;
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) { b200_set_error("pnm: short write to %s", path); return -1; }
+  return 0;
+}
+

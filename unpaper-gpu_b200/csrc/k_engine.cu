@@ -39,7 +39,52 @@ __global__ void k_pack_rows(const uint8_t *src, int src_pitch, uint8_t *dst, int
   }
 }
 
+// saveImage()'s pixel-format conversion (file.c:197-260) for `nimages` images of
+// equal geometry: MONOWHITE output thresholds gray < abs_black_threshold with a
+// cleared tail in the last byte (:211-243), MONOBLACK -> MONOWHITE inverts whole
+// bytes (:244-255), everything else is copy_rectangle()'s get_pixel/set_pixel.
+// One thread per output byte (mono) or pixel.
+__global__ void k_convert_out(DImg src, DImg dst, size_t src_stride, size_t dst_stride) {
+  src.data += (size_t)blockIdx.z * src_stride;
+  dst.data += (size_t)blockIdx.z * dst_stride;
+  int y = blockIdx.y;
+  if (dst.fmt == DF_MONOWHITE) {
+    int row_bytes = (src.w + 7) / 8;
+    for (int bx = blockIdx.x * blockDim.x + threadIdx.x; bx < row_bytes; bx += gridDim.x * blockDim.x) {
+      unsigned v = 0;
+      if (src.fmt == DF_MONOBLACK) v = src.data[(size_t)y * src.pitch + bx] ^ 0xFFu;
+      else if (src.fmt == DF_GRAY8 && bx * 8 + 8 <= src.w && ((src.pitch | (unsigned)(uintptr_t)src.data) & 7) == 0) {
+        uint2 q = *(const uint2 *)(src.data + (size_t)y * src.pitch + (size_t)bx * 8);
+        unsigned t4 = (unsigned)src.abt * 0x01010101u;
+        unsigned m0 = __vcmpltu4(q.x, t4), m1 = __vcmpltu4(q.y, t4);   // 0xFF per dark byte
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          v |= ((m0 >> (8 * k)) & 1u) << (7 - k);
+          v |= ((m1 >> (8 * k)) & 1u) << (3 - k);
+        }
+      } else {
+        for (int k = 0; k < 8; k++) {
+          int x = bx * 8 + k;
+          if (x < src.w && px_gray(px_load(src, x, y)) < src.abt) v |= 0x80u >> k;
+        }
+      }
+      dst.data[(size_t)y * dst.pitch + bx] = (uint8_t)v;
+    }
+  } else {
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < src.w; x += gridDim.x * blockDim.x) {
+      Px p = px_load(src, x, y);
+      px_store(dst, x, y, p.r, p.g, p.b);
+    }
+  }
+}
+
 extern "C" {
+void b200k_convert_out(cudaStream_t st, DImg src, DImg dst, int nimages, size_t src_stride, size_t dst_stride) {
+  if (nimages <= 0 || src.w <= 0 || src.h <= 0) return;
+  unsigned per_row = dst.fmt == DF_MONOWHITE ? (unsigned)(src.w + 7) / 8 : (unsigned)src.w;
+  dim3 g(min(cdiv(per_row, 256), 16u), src.h, nimages);
+  k_convert_out<<<g, 256, 0, st>>>(src, dst, src_stride, dst_stride);
+}
 void b200k_page_reset(cudaStream_t st, DPage *pages, int npages) {
   if (npages <= 0) return;
   k_page_reset<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages);

@@ -68,6 +68,9 @@ void b200k_page_reset(cudaStream_t st, DPage *pages, int npages);
 void b200k_pack_rows(cudaStream_t st, const uint8_t *src, int src_pitch, uint8_t *dst, int dst_pitch,
                      int row_bytes, int rows, int nimages, size_t src_stride, size_t dst_stride);
 
+/* saveImage()'s output pixel-format conversion (file.c:197-260) of nimages images */
+void b200k_convert_out(cudaStream_t st, DImg src, DImg dst, int nimages, size_t src_stride, size_t dst_stride);
+
 #ifdef __cplusplus
 }
 #endif

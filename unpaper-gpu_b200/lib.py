@@ -41,6 +41,11 @@ def load():
         f = getattr(lib, name)
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(SheetResult)]
         f.restype = C.c_int
+    lib.unpaper_b200_engine_set_output_format.argtypes = [C.c_void_p, C.c_int]
+    lib.unpaper_b200_engine_output_format.argtypes = [C.c_void_p]
+    lib.unpaper_b200_output_format.argtypes = [C.c_int]
+    lib.unpaper_b200_pnm_header.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    lib.unpaper_b200_write_pnm.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.unpaper_b200_engine_launch_count.argtypes = [C.c_void_p]
     lib.unpaper_b200_engine_launch_count.restype = C.c_uint64
     lib.unpaper_b200_engine_last_device_ms.argtypes = [C.c_void_p]
@@ -76,6 +81,7 @@ class Engine:
         self.sheet_bytes = self.lib.unpaper_b200_engine_sheet_bytes(self.h)
         self.page_bytes = bytes_per_row(fmt, page_w) * page_h
         self.sheet_in_bytes = self.page_bytes * cfg.input_count
+        self.out_fmt = fmt
 
     def close(self):
         if self.h:
@@ -103,6 +109,13 @@ class Engine:
         res = (SheetResult * n)()
         self.process_ptr(pages.ctypes.data, out.ctypes.data, n, True, res)
         return out, list(res)
+
+    def set_output_format(self, fmt):
+        """Device-side sheet_stage_output conversion (e.g. FMT_MONOWHITE for .pbm); -1 = page format."""
+        if self.lib.unpaper_b200_engine_set_output_format(self.h, fmt) != 0:
+            raise RuntimeError("set_output_format failed: " + last_error())
+        self.sheet_bytes = self.lib.unpaper_b200_engine_sheet_bytes(self.h)
+        self.out_fmt = self.lib.unpaper_b200_engine_output_format(self.h)
 
     def launch_count(self):
         return int(self.lib.unpaper_b200_engine_launch_count(self.h))
