@@ -228,7 +228,7 @@ static void *worker(void *a) {
 }
 int orc_process_sheets(const B200SheetConfig *cfg, const uint8_t *pages, int pw, int ph, int fmt, int n, uint8_t *out,
                        B200SheetResult *results, int threads, int *sw, int *sh) {
-  if (fmt != B200_FMT_GRAY8 && fmt != B200_FMT_RGB24) return -1;
+  if (fmt != B200_FMT_GRAY8 && fmt != B200_FMT_RGB24 && fmt != B200_FMT_MONOWHITE && fmt != B200_FMT_MONOBLACK) return -1;
   int W = pw * cfg->input_count;
   if (sw) *sw = W;
   if (sh) *sh = ph;

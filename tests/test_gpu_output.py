@@ -109,3 +109,57 @@ def test_engine_mono_output(orc_ops, tmp_path):
     blob = open(path, "rb").read()
     hdr = b"P4\n%d %d\n" % (eng.sheet_w, eng.sheet_h)
     assert blob[:len(hdr)] == hdr and blob[len(hdr):] == m0.tobytes()
+
+
+def _mono_pages(fmt, w, h, n, seed=200, box=(0.60, 0.72)):
+    out = []
+    for i in range(n):
+        g = synth.gray_page(seed + i, w, h, box=box)
+        bits = np.packbits(g < 128, axis=1)
+        out.append(bits if fmt == U.FMT_MONOWHITE else bits ^ 0xFF)
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("fmt", [U.FMT_MONOWHITE, U.FMT_MONOBLACK])
+def test_engine_mono_pages(ref_lib, fmt):
+    """1-bit pages (pbm scans / the PDF path): expanded by the decode stage, processed
+    in the 1 B/px working sheet, written as MONOWHITE — against the reference's
+    process_sheet() on the same 1-bit pages."""
+    from oracle import checker
+    from unpaper_gpu_b200.lib import Engine
+    w, h = 624, 880
+    pages = _mono_pages(fmt, w, h, 5)
+    cfg = U.default_sheet_config()
+    eng = Engine(cfg, w, h, fmt, group_pages=2, lanes=2)
+    assert eng.out_fmt == U.FMT_MONOWHITE and eng.sheet_bytes == (w // 8) * h
+    out, res = eng.process_numpy(pages)
+    eng.close()
+    rout, rres = checker.process_sheets_cpu(ref_lib, "ref_", cfg, pages, w, h, fmt, threads=8)
+    if fmt == U.FMT_MONOBLACK:
+        rout = rout ^ 0xFF      # the harness hands back MONOBLACK; saveImage() writes MONOWHITE (file.c:205-207)
+    for i, (a, b) in enumerate(zip(res, rres)):
+        assert a.status == 0 and b.status == 0
+        assert a.deskew_mask_count == b.deskew_mask_count
+        for k in range(a.deskew_mask_count):
+            assert U.rect_tuple(a.deskew_masks[k]) == U.rect_tuple(b.deskew_masks[k])
+            assert a.rotation[k] == b.rotation[k]
+        for k in range(a.border_count):
+            assert U.border_tuple(a.borders[k]) == U.border_tuple(b.borders[k])
+    assert np.array_equal(out, rout), f"{int((out != rout).sum())} differing bytes"
+
+
+def test_engine_mono_a4_properties():
+    """Full-size 1-bit A4: deterministic, dark scan edges removed, ink kept."""
+    from unpaper_gpu_b200.lib import Engine
+    w, h = synth.A4_W, synth.A4_H
+    pages = _mono_pages(U.FMT_MONOWHITE, w, h, 3, seed=0, box=(0.76, 0.80))
+    eng = Engine(U.default_sheet_config(), w, h, U.FMT_MONOWHITE, group_pages=2, lanes=2)
+    out1, res = eng.process_numpy(pages)
+    out2, _ = eng.process_numpy(pages)
+    eng.close()
+    assert np.array_equal(out1, out2)
+    for r in res:
+        assert r.status == 0 and r.deskew_mask_count == 1
+    bits = np.unpackbits(out1, axis=2)
+    assert (bits[:, :, :24] == 0).all()               # left scan edge gone
+    assert 0.005 < bits.mean() < 0.2

@@ -66,7 +66,8 @@ typedef struct {
 
 struct B200Engine {
   B200SheetConfig cfg;
-  int device, page_w, page_h, page_fmt, dfmt, bpp;
+  int device, page_w, page_h, page_fmt, dfmt, bpp;   /* dfmt/bpp: the working sheet */
+  int page_dfmt;                                      /* the pages as they arrive */
   int sheet_w, sheet_h, sheet_pitch, page_row, sheet_row;
   size_t sheet_stride, page_bytes;
   int group, nlanes;
@@ -96,7 +97,9 @@ int unpaper_b200_engine_sheet_height(const B200Engine *e) { return e->sheet_h; }
 size_t unpaper_b200_engine_sheet_bytes(const B200Engine *e) {
   return (size_t)(e->out_fmt >= 0 ? e->out_row : e->sheet_row) * e->sheet_h;
 }
-int unpaper_b200_engine_output_format(const B200Engine *e) { return e->out_fmt >= 0 ? e->out_fmt : e->page_fmt; }
+int unpaper_b200_engine_output_format(const B200Engine *e) {
+  return e->out_fmt >= 0 ? e->out_fmt : (e->dfmt == DF_GRAY8 ? AV_PIX_FMT_GRAY8 : AV_PIX_FMT_RGB24);
+}
 
 /* sheet_stage_output's conversion (sheet_stages.c:536-631 -> file.c:197-260) moved onto
  * the device, so that the D2H (or the device-side sink) carries the output format */
@@ -104,8 +107,10 @@ int unpaper_b200_engine_set_output_format(B200Engine *e, int av_pix_fmt) {
   if (!e) return -1;
   unpaper_b200_set_device(e->device);
   CUDA_OK(cudaDeviceSynchronize());
-  int fmt = av_pix_fmt < 0 ? -1 : unpaper_b200_output_format(av_pix_fmt);
-  if (fmt == e->page_fmt) fmt = -1;
+  /* -1: what sheet_stage_output picks without an explicit type, the page format
+   * (sheet_stages.c:130-131), as saveImage() writes it (file.c:201-208) */
+  int fmt = unpaper_b200_output_format(av_pix_fmt < 0 ? e->page_fmt : av_pix_fmt);
+  if (fmt == (e->dfmt == DF_GRAY8 ? AV_PIX_FMT_GRAY8 : AV_PIX_FMT_RGB24)) fmt = -1;   /* the working sheet as it is */
   if (fmt >= 0) {
     int df = b200_fmt_to_dev(fmt), row = b200_fmt_row_bytes(fmt, e->sheet_w);
     if (df < 0 || row <= 0) { b200_set_error("engine: unsupported output format %d", av_pix_fmt); return -1; }
@@ -217,20 +222,26 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
                                        int page_format, int group_pages, int lanes) {
   if (!cfg || page_w <= 0 || page_h <= 0 || group_pages <= 0 || lanes <= 0) { b200_set_error("engine: bad arguments"); return NULL; }
   if (unpaper_b200_set_device(device)) return NULL;
-  if (page_format != AV_PIX_FMT_GRAY8 && page_format != AV_PIX_FMT_RGB24) { b200_set_error("engine: page format must be GRAY8 or RGB24"); return NULL; }
+  /* 1-bit pages (pbm scans, the PDF path's expand_1bit_to_8bit) are expanded into the
+   * 1 B/px working sheet by the decode stage's copy and leave as MONOWHITE again */
+  bool mono_pages = page_format == AV_PIX_FMT_MONOWHITE || page_format == AV_PIX_FMT_MONOBLACK;
+  if (page_format != AV_PIX_FMT_GRAY8 && page_format != AV_PIX_FMT_RGB24 && !mono_pages) {
+    b200_set_error("engine: page format must be GRAY8, RGB24, MONOWHITE or MONOBLACK"); return NULL;
+  }
   if (cfg->input_count < 1 || cfg->input_count > 2) { b200_set_error("engine: input_count must be 1 or 2"); return NULL; }
   bool gray_colors = cfg->sheet_background.r == cfg->sheet_background.g && cfg->sheet_background.g == cfg->sheet_background.b &&
                      cfg->mask_color.r == cfg->mask_color.g && cfg->mask_color.g == cfg->mask_color.b;
-  if (page_format == AV_PIX_FMT_GRAY8 && !gray_colors) { b200_set_error("engine: GRAY8 pages need gray background and mask colours"); return NULL; }
+  if (page_format != AV_PIX_FMT_RGB24 && !gray_colors) { b200_set_error("engine: gray and 1-bit pages need gray background and mask colours"); return NULL; }
   B200Engine *e = (B200Engine *)calloc(1, sizeof(*e));
   e->cfg = *cfg; e->device = device;
-  e->page_w = page_w; e->page_h = page_h; e->page_fmt = page_format; e->dfmt = b200_fmt_to_dev(page_format);
+  e->page_w = page_w; e->page_h = page_h; e->page_fmt = page_format; e->page_dfmt = b200_fmt_to_dev(page_format);
+  e->dfmt = page_format == AV_PIX_FMT_RGB24 ? DF_RGB24 : DF_GRAY8;
   e->out_fmt = -1;
-  e->bpp = page_format == AV_PIX_FMT_GRAY8 ? 1 : 3;
+  e->bpp = e->dfmt == DF_GRAY8 ? 1 : 3;
   e->group = group_pages; e->nlanes = lanes;
   /* sheet size = input pages side by side (sheet_stages.c:140-145) */
   e->sheet_w = page_w * cfg->input_count; e->sheet_h = page_h;
-  e->page_row = page_w * e->bpp; e->sheet_row = e->sheet_w * e->bpp;
+  e->page_row = b200_fmt_row_bytes(page_format, page_w); e->sheet_row = e->sheet_w * e->bpp;
   e->sheet_pitch = (e->sheet_row + 15) & ~15;
   e->sheet_stride = (((size_t)e->sheet_pitch * e->sheet_h + 64) + 255) & ~(size_t)255;
   e->page_bytes = (size_t)e->page_row * page_h;
@@ -352,7 +363,7 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
       dfill[p].enabled = 0;
       for (int j = 0; j < cfg->input_count; j++) {
         DCopyJob *cj = &ln->decode_copy_host_tmpl[(size_t)p * cfg->input_count + j];
-        cj->src = (DImg){NULL, page_w, page_h, e->page_row, e->dfmt, cfg->abs_black_threshold, {255, 255, 255}};
+        cj->src = (DImg){NULL, page_w, page_h, e->page_row, e->page_dfmt, cfg->abs_black_threshold, {255, 255, 255}};
         cj->dst = pg->img;
         cj->area = (DRect){0, 0, page_w - 1, page_h - 1};
         cj->tx = W * j / cfg->input_count; cj->ty = 0;
@@ -373,6 +384,8 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
     e->n_static_mask_jobs[2] = build_static(e, ln, 2, cfg->post_wipes, cfg->no_wipe ? 0 : cfg->post_wipe_count,
                                          cfg->no_border ? none : cfg->post_border, NULL, 0, NULL);
   }
+  /* 1-bit pages leave in their own format unless the caller asks otherwise */
+  if (mono_pages && unpaper_b200_engine_set_output_format(e, -1) != 0) { unpaper_b200_engine_destroy(e); return NULL; }
   return e;
 }
 
@@ -555,7 +568,7 @@ static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_shee
     const uint8_t *src = pages + e->page_bytes * ic * (size_t)first;
     if (host_mode) {
       ln->out_host = out + out_sheet * first;
-      if (ic == 1 && e->sheet_pitch == e->page_row) {
+      if (ic == 1 && e->sheet_pitch == e->page_row && e->page_dfmt == e->dfmt) {
         /* page == sheet geometry: the upload IS the decode stage's centre copy
          * (one 2-D copy, one "row" per sheet slot) */
         CUDA_OK(cudaMemcpy2DAsync(ln->sheets, e->sheet_stride, src, e->page_bytes, e->page_bytes, (size_t)n,

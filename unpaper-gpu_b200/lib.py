@@ -81,7 +81,7 @@ class Engine:
         self.sheet_bytes = self.lib.unpaper_b200_engine_sheet_bytes(self.h)
         self.page_bytes = bytes_per_row(fmt, page_w) * page_h
         self.sheet_in_bytes = self.page_bytes * cfg.input_count
-        self.out_fmt = fmt
+        self.out_fmt = self.lib.unpaper_b200_engine_output_format(self.h)
 
     def close(self):
         if self.h:
