@@ -30,14 +30,16 @@ def test_wipe_rectangle(cuda_ops, ref_ops, fmt, w, h):
                                        (U.FMT_RGB24, U.FMT_RGB24), (U.FMT_RGB24, U.FMT_GRAY8),
                                        (U.FMT_Y400A, U.FMT_Y400A), (U.FMT_MONOWHITE, U.FMT_RGB24),
                                        (U.FMT_RGB24, U.FMT_MONOBLACK), (U.FMT_MONOWHITE, U.FMT_MONOWHITE),
-                                       (U.FMT_Y400A, U.FMT_GRAY8)])
+                                       (U.FMT_Y400A, U.FMT_GRAY8), (U.FMT_MONOWHITE, U.FMT_GRAY8),
+                                       (U.FMT_MONOBLACK, U.FMT_GRAY8)])
 def test_copy_rectangle(cuda_ops, ref_ops, sfmt, dfmt):
     sw, sh, dw, dh = 90, 70, 120, 81
     src = noise_image(2, sw, sh, sfmt, dark=0.4)
     dst = noise_image(3, dw, dh, dfmt, dark=0.2)
     cases = [(U.rect(0, 0, sw - 1, sh - 1), U.Point(5, 6)), (U.rect(10, 10, 50, 40), U.Point(100, 60)),
              (U.rect(-5, -5, 30, 30), U.Point(-3, -2)), (U.rect(60, 50, 200, 200), U.Point(0, 0)),
-             (U.rect(40, 30, 10, 5), U.Point(7, 7))]
+             (U.rect(40, 30, 10, 5), U.Point(7, 7)), (U.rect(16, 3, 77, 60), U.Point(8, 1)),
+             (U.rect(8, 0, 89, 69), U.Point(3, 0))]
     for i, (area, tgt) in enumerate(cases):
         outs = []
         for ops in (cuda_ops, ref_ops):

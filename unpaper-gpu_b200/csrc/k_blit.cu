@@ -95,6 +95,8 @@ __global__ void k_copy_jobs(const DCopyJob *jobs) {
   int bpp = bytes_pp(s.fmt);
   bool raw = s.fmt == d.fmt && bpp > 0 && j.tx >= 0 && j.ty >= 0 &&
              j.tx + width <= d.w && j.ty + height <= d.h;
+  bool expand = (s.fmt == DF_MONOWHITE || s.fmt == DF_MONOBLACK) && d.fmt == DF_GRAY8 && (ax0 & 7) == 0 &&
+                j.tx >= 0 && j.ty >= 0 && j.tx + width <= d.w && j.ty + height <= d.h;
   // one block per COPY_ROWS rows; all its threads stride across each row
   for (int r = blockIdx.y * COPY_ROWS; r < min(height, (int)(blockIdx.y + 1) * COPY_ROWS); r++) {
     int sy = ay0 + r, ty = j.ty + r;
@@ -102,6 +104,29 @@ __global__ void k_copy_jobs(const DCopyJob *jobs) {
       const uint8_t *sp = s.data + (size_t)sy * s.pitch + (size_t)ax0 * bpp;
       uint8_t *dp = d.data + (size_t)ty * d.pitch + (size_t)j.tx * bpp;
       copy_run(dp, sp, width * bpp, threadIdx.x, blockDim.x);
+    } else if (expand) {
+      // 1-bit page -> gray sheet (get_pixel's 0/255, pixel.c:45-62): a source byte becomes 8 bytes
+      const uint8_t *sp = s.data + (size_t)sy * s.pitch + (ax0 >> 3);
+      uint8_t *dp = d.data + (size_t)ty * d.pitch + j.tx;
+      bool al = ((uintptr_t)dp & 7) == 0;
+      unsigned inv = s.fmt == DF_MONOWHITE ? 0xFFu : 0u;
+      int nb = width >> 3;
+      for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        unsigned v = sp[i] ^ inv;   // bit set = white
+        unsigned lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          lo |= (0u - ((v >> (7 - k)) & 1u)) & (0xFFu << (8 * k));
+          hi |= (0u - ((v >> (3 - k)) & 1u)) & (0xFFu << (8 * k));
+        }
+        if (al) *(uint2 *)(dp + 8 * (size_t)i) = make_uint2(lo, hi);
+        else
+          for (int k = 0; k < 8; k++) dp[8 * (size_t)i + k] = (uint8_t)((k < 4 ? lo >> (8 * k) : hi >> (8 * (k - 4))) & 0xFFu);
+      }
+      for (int i = (nb << 3) + threadIdx.x; i < width; i += blockDim.x) {
+        Px p = px_load(s, ax0 + i, sy);
+        px_store(d, j.tx + i, ty, p.r, p.g, p.b);
+      }
     } else {
       for (int i = threadIdx.x; i < width; i += blockDim.x) {
         Px p = px_load(s, ax0 + i, sy);
