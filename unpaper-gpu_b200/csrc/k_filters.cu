@@ -518,13 +518,14 @@ __global__ void k_nf_classify_g8(DPage *pages, int intensity, int white) {
  * touches one belongs to a component of >= need pixels (all members of a core
  * pixel's block touch it) — settled for 32 pixels per instruction.  Only the
  * few dark pixels that this test leaves open run the exact bounded walk. */
-#define NFB_TW 64
+#define NFB_NW 8                      /* words per plane row: one halo word each side */
+#define NFB_TW (32 * (NFB_NW - 2))
 #define NFB_TH 32
 #define NFB_ROWS (NFB_TH + 2 * 8)
 
-__device__ __forceinline__ bool nfb_bit(const unsigned (*nb)[4], int x, int y) { return (nb[y][x >> 5] >> (x & 31)) & 1u; }
+__device__ __forceinline__ bool nfb_bit(const unsigned (*nb)[NFB_NW], int x, int y) { return (nb[y][x >> 5] >> (x & 31)) & 1u; }
 
-__device__ __noinline__ bool nfb_small_component(const unsigned (*nb)[4], int rows, int tx, int ty, int need) {
+__device__ __noinline__ bool nfb_small_component(const unsigned (*nb)[NFB_NW], int rows, int tx, int ty, int need) {
   short vx[8], vy[8];
   int n = 1, head = 0;
   vx[0] = (short)tx; vy[0] = (short)ty;
@@ -534,7 +535,7 @@ __device__ __noinline__ bool nfb_small_component(const unsigned (*nb)[4], int ro
     for (int k = 0; k < 9 && n < need; k++) {
       if (k == 4) continue;
       int nx = cx + k % 3 - 1, ny = cy + k / 3 - 1;
-      if (nx < 0 || ny < 0 || nx >= 128 || ny >= rows) continue;
+      if (nx < 0 || ny < 0 || nx >= 32 * NFB_NW || ny >= rows) continue;
       if (!nfb_bit(nb, nx, ny)) continue;
       bool seen = false;
 #pragma unroll 1
@@ -546,8 +547,8 @@ __device__ __noinline__ bool nfb_small_component(const unsigned (*nb)[4], int ro
 }
 
 __global__ void __launch_bounds__(256) k_nf_classify_bits(DPage *pages, int intensity, int white) {
-  __shared__ unsigned s_dark[NFB_ROWS][4], s_nb[NFB_ROWS][4], s_h0[NFB_ROWS][4], s_h1[NFB_ROWS][4],
-      s_core[NFB_ROWS][4], s_big[NFB_ROWS][4];
+  __shared__ unsigned s_dark[NFB_ROWS][NFB_NW], s_nb[NFB_ROWS][NFB_NW], s_h0[NFB_ROWS][NFB_NW], s_h1[NFB_ROWS][NFB_NW],
+      s_core[NFB_ROWS][NFB_NW], s_big[NFB_ROWS][NFB_NW];
   DPage &pg = pages[blockIdx.z];
   const DImg &im = pg.img;
   int halo = intensity + 1, rows = NFB_TH + 2 * halo, need = intensity + 1, band = 2 * intensity;
@@ -556,13 +557,20 @@ __global__ void __launch_bounds__(256) k_nf_classify_bits(DPage *pages, int inte
   int x_org = bx - 32, y_org = by - halo;
   unsigned white4 = white > 255 ? 0xFFFFFFFFu : (unsigned)max(white, 0) * 0x01010101u;
   // phase 1: bit planes
-  for (int item = threadIdx.x; item < rows * 4; item += blockDim.x) {
-    int r = item >> 2, k = item & 3;
+  for (int item = threadIdx.x; item < rows * NFB_NW; item += blockDim.x) {
+    int r = item / NFB_NW, k = item % NFB_NW;
     int y = y_org + r, x0 = x_org + 32 * k;
     unsigned dark = 0;
     if (y >= 0 && y < im.h && x0 + 31 >= 0 && x0 < im.w) {
       const uint8_t *rp = im.data + (size_t)y * im.pitch;
-      if (x0 >= 0 && x0 + 31 < im.w) {
+      if (x0 >= 0 && x0 + 31 < im.w && (k == 0 || k == NFB_NW - 1)) {
+        // halo word: only the 8 pixels next to the interior are ever looked at (halo <= 8)
+        int off = k == 0 ? 24 : 0;
+        uint2 a = *(const uint2 *)(rp + x0 + off);
+        unsigned m0 = __vcmpltu4(a.x, white4), m1 = __vcmpltu4(a.y, white4);
+        unsigned d8 = ((((m0 & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) | (((((m1 & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << 4);
+        dark = d8 << off;
+      } else if (x0 >= 0 && x0 + 31 < im.w) {
         const uint4 *q = (const uint4 *)(rp + x0);
         uint4 a = q[0], b = q[1];
         unsigned wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -584,17 +592,17 @@ __global__ void __launch_bounds__(256) k_nf_classify_bits(DPage *pages, int inte
   }
   __syncthreads();
   // phase 2a: per row, how many of (left, self, right) are set: h1:h0
-  for (int item = threadIdx.x; item < rows * 4; item += blockDim.x) {
-    int r = item >> 2, k = item & 3;
-    unsigned C = s_nb[r][k], P = k > 0 ? s_nb[r][k - 1] : 0u, N = k < 3 ? s_nb[r][k + 1] : 0u;
+  for (int item = threadIdx.x; item < rows * NFB_NW; item += blockDim.x) {
+    int r = item / NFB_NW, k = item % NFB_NW;
+    unsigned C = s_nb[r][k], P = k > 0 ? s_nb[r][k - 1] : 0u, N = k < NFB_NW - 1 ? s_nb[r][k + 1] : 0u;
     unsigned L = (C << 1) | (P >> 31), R = (C >> 1) | (N << 31);
     s_h0[r][k] = L ^ C ^ R;
     s_h1[r][k] = (L & C) | (C & R) | (L & R);
   }
   __syncthreads();
   // phase 2b: 3x3 population (bit-sliced) >= need, centred on an nb pixel
-  for (int item = threadIdx.x; item < rows * 4; item += blockDim.x) {
-    int r = item >> 2, k = item & 3;
+  for (int item = threadIdx.x; item < rows * NFB_NW; item += blockDim.x) {
+    int r = item / NFB_NW, k = item % NFB_NW;
     unsigned core = 0;
     if (r >= 1 && r + 1 < rows) {
       unsigned a0 = s_h0[r - 1][k], a1 = s_h1[r - 1][k], b0 = s_h0[r][k], b1 = s_h1[r][k], c0 = s_h0[r + 1][k], c1 = s_h1[r + 1][k];
@@ -617,23 +625,24 @@ __global__ void __launch_bounds__(256) k_nf_classify_bits(DPage *pages, int inte
   }
   __syncthreads();
   // phase 2c: nb pixels that are a core pixel or touch one
-  for (int item = threadIdx.x; item < rows * 4; item += blockDim.x) {
-    int r = item >> 2, k = item & 3;
+  for (int item = threadIdx.x; item < rows * NFB_NW; item += blockDim.x) {
+    int r = item / NFB_NW, k = item % NFB_NW;
     unsigned D = 0;
     if (r >= 1 && r + 1 < rows) {
 #pragma unroll
       for (int rr = -1; rr <= 1; rr++) {
-        unsigned C = s_core[r + rr][k], P = k > 0 ? s_core[r + rr][k - 1] : 0u, N = k < 3 ? s_core[r + rr][k + 1] : 0u;
+        unsigned C = s_core[r + rr][k], P = k > 0 ? s_core[r + rr][k - 1] : 0u, N = k < NFB_NW - 1 ? s_core[r + rr][k + 1] : 0u;
         D |= C | (C << 1) | (P >> 31) | (C >> 1) | (N << 31);
       }
     }
     s_big[r][k] = s_nb[r][k] & D;
   }
   __syncthreads();
-  // phase 3: eight pixels per thread
-  int ly = threadIdx.x >> 3, lx0 = (threadIdx.x & 7) * 8;
+  // phase 3: eight pixels per item
+  for (int it = threadIdx.x; it < (NFB_TW / 8) * NFB_TH; it += blockDim.x) {
+  int ly = it / (NFB_TW / 8), lx0 = (it % (NFB_TW / 8)) * 8;
   int y = by + ly, r = ly + halo;
-  if (y >= im.h || bx + lx0 >= im.w) return;
+  if (y >= im.h || bx + lx0 >= im.w) continue;
   int k = 1 + (lx0 >> 5), sh = lx0 & 31;
   unsigned dark8 = (s_dark[r][k] >> sh) & 0xFFu, nb8 = (s_nb[r][k] >> sh) & 0xFFu, big8 = (s_big[r][k] >> sh) & 0xFFu;
   unsigned lo = 0, hi = 0;   // eight class bytes
@@ -657,6 +666,7 @@ __global__ void __launch_bounds__(256) k_nf_classify_bits(DPage *pages, int inte
   size_t o = (size_t)y * im.w + bx + lx0;
   if ((im.w & 7) == 0 && ((uintptr_t)pg.cls & 7) == 0) *(uint2 *)(pg.cls + o) = make_uint2(lo, hi);
   else for (int i = 0; i < 8 && bx + lx0 + i < im.w; i++) pg.cls[o + i] = (uint8_t)((i < 4 ? lo >> (8 * i) : hi >> (8 * (i - 4))) & 0xFFu);
+  }
 }
 
 __device__ __forceinline__ bool nf_live(const uint8_t *cls, int w, int h, int x, int y) {
