@@ -44,7 +44,7 @@ __device__ __forceinline__ bool ff_match(const DImg &im, int x, int y, int lo, i
 // the per-chunk ballots meet in shared memory and every thread replays the same
 // scalar decision, so the recursion state stays uniform across the block.
 #define FF_U 4
-#define BF_WARPS 8
+#define BF_WARPS 16
 #define BF_THREADS (BF_WARPS * 32)
 #define BF_CH (BF_WARPS * FF_U)
 #define BF_ROUND (BF_CH * 32)
@@ -53,6 +53,7 @@ struct BfShared {
   unsigned M[BF_CH];
   unsigned I[BF_CH];
   unsigned long long red[BF_WARPS];
+  unsigned wcnt[BF_WARPS];
 };
 
 // fill_line (fill.c:16-43) x 4.  The four calls of flood_fill (fill.c:88-95) walk four disjoint pixel
@@ -255,19 +256,63 @@ __global__ void __launch_bounds__(BF_THREADS) k_bf_scan(DPage *pages, const DBfP
     cand[k] = darkness >= abs_threshold ? 1 : 0;
   }
   __syncthreads();
-  // phase 2: candidates in scan order (every thread walks the same list)
+  // ordered list of the candidates: every warp compacts its own segment of positions
+  unsigned *clist = pg.u32 + flag_off + (npos + 3) / 4 + 1;
+  int nc;
+  {
+    int seg = (npos + BF_WARPS - 1) / BF_WARPS, b0 = warp * seg, b1 = min(b0 + seg, npos);
+    unsigned cntw = 0;
+    for (int base = b0; base < b1; base += 32) {
+      int k = base + lane;
+      cntw += __popc(__ballot_sync(0xffffffffu, k < b1 && cand[k]));
+    }
+    if (lane == 0) sh.wcnt[warp] = cntw;
+    __syncthreads();
+    unsigned off = 0, total = 0;
+    for (int w = 0; w < BF_WARPS; w++) { if (w < warp) off += sh.wcnt[w]; total += sh.wcnt[w]; }
+    for (int base = b0; base < b1; base += 32) {
+      int k = base + lane;
+      bool c = k < b1 && cand[k];
+      unsigned m = __ballot_sync(0xffffffffu, c);
+      if (c) clist[off + __popc(m & ((1u << lane) - 1u))] = (unsigned)k;
+      off += __popc(m);
+    }
+    nc = (int)total;
+    __syncthreads();
+  }
+  // phase 2: candidates in scan order.  Before the first fill a candidate is a true hit;
+  // afterwards a candidate has to be measured again, and as long as no further fill
+  // happens those measurements are independent: one warp each, BF_WARPS per round
   bool dirty = false;
   unsigned fills = 0;
-  for (int k = 0; k < npos; k++) {
-    if (!cand[k]) continue;
-    DBfPos q = pos[k];
-    int x0 = max(q.r.x0, 0), x1 = min(q.r.x1, im.w - 1), y0 = max(q.r.y0, 0), y1 = min(q.r.y1, im.h - 1);
+  for (int ci = 0; ci < nc;) {
     if (dirty) {
-      unsigned long long cnt = (unsigned long long)(abs(x0 - x1) + 1) * (unsigned long long)(abs(y0 - y1) + 1);
-      unsigned long long s = block_rect_maxch_sum(im, x0, y0, x1, y1, sh);
-      int darkness = (int)(uint8_t)(0xFF - (s / cnt));
-      if (darkness < abs_threshold) continue;
+      int mine = ci + warp;
+      bool dark = false;
+      if (mine < nc) {
+        DBfPos q = pos[clist[mine]];
+        int x0 = max(q.r.x0, 0), x1 = min(q.r.x1, im.w - 1), y0 = max(q.r.y0, 0), y1 = min(q.r.y1, im.h - 1);
+        unsigned long long cnt = (unsigned long long)(abs(x0 - x1) + 1) * (unsigned long long)(abs(y0 - y1) + 1);
+        unsigned long long s = 0;
+        if (x0 <= x1 && y0 <= y1) {
+          int w = x1 - x0 + 1, n = w * (y1 - y0 + 1);
+          for (int i = lane; i < n; i += 32) s += (unsigned)px_darkinv(px_load(im, x0 + i % w, y0 + i / w));
+        }
+        s = warp_sum_u64(s);
+        int darkness = (int)(uint8_t)(0xFF - (s / cnt));
+        dark = darkness >= abs_threshold;
+      }
+      if (lane == 0) sh.M[warp] = dark ? 1u : 0u;
+      __syncthreads();
+      int first = -1;
+      for (int w = 0; w < BF_WARPS; w++) if (sh.M[w]) { first = w; break; }
+      __syncthreads();
+      if (first < 0) { ci += BF_WARPS; continue; }
+      ci += first;
     }
+    DBfPos q = pos[clist[ci]];
+    ci++;
+    int x0 = max(q.r.x0, 0), x1 = min(q.r.x1, im.w - 1), y0 = max(q.r.y0, 0), y1 = min(q.r.y1, im.h - 1);
     dirty = true;
     fills++;
     // flood_fill from every pixel of the area in raster order (filters.c:86-89);

@@ -174,7 +174,31 @@ __global__ void k_cellstats(DPage *pages, int gx, int gy, int ncx, int ncy, int 
   __syncthreads();
   int y0 = cy * gy, y1 = min(y0 + gy - 1, im.h - 1);
   int xlim = min(ncx * gx, im.w);
-  if (im.fmt == DF_GRAY8 && (gx & 1) == 0 && (im.pitch & 1) == 0 && ((uintptr_t)im.data & 1) == 0) {
+  if (im.fmt == DF_GRAY8 && gx >= 4 && (im.pitch & 3) == 0 && ((uintptr_t)im.data & 3) == 0) {
+    // four pixels per 32-bit load; a word touches at most two cells (gx >= 4): the first
+    // `nb` bytes belong to cell c, the rest to cell c + 1.  Packed-byte compare / SAD do
+    // the counting and the sum.
+    unsigned dm4 = (unsigned)min(max(dark_max, -1) + 1, 256);   // v <= dark_max  <=>  v < dark_max + 1
+    bool all_dark = dm4 > 255u;
+    unsigned t4 = (dm4 & 0xFFu) * 0x01010101u;
+    for (int x = 4 * threadIdx.x; x < xlim; x += 4 * blockDim.x) {
+      int c = x / gx;
+      int nb = min((c + 1) * gx - x, 4);               // bytes of this word in cell c
+      int nv = min(xlim - x, 4);                       // bytes of this word inside the grid
+      unsigned mv = nv >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nv)) - 1u);
+      unsigned m0 = (nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u)) & mv, m1 = mv & ~m0;
+      unsigned d0 = 0, d1 = 0, l0 = 0, l1 = 0;
+      for (int y = y0; y <= y1; y++) {
+        unsigned v = *(const unsigned *)(im.data + (size_t)y * im.pitch + x);
+        unsigned dk = all_dark ? 0xFFFFFFFFu : (dm4 == 0u ? 0u : __vcmpltu4(v, t4));
+        d0 += __popc(dk & m0); d1 += __popc(dk & m1);
+        l0 += __vsadu4(v & m0, 0u); l1 += __vsadu4(v & m1, 0u);
+      }
+      if (d0) atomicAdd(&sd[c], d0 >> 3);
+      atomicAdd(&sl[c], l0);
+      if (m1) { if (d1) atomicAdd(&sd[c + 1], d1 >> 3); atomicAdd(&sl[c + 1], l1); }
+    }
+  } else if (im.fmt == DF_GRAY8 && (gx & 1) == 0 && (im.pitch & 1) == 0 && ((uintptr_t)im.data & 1) == 0) {
     // two pixels per 16-bit load: a pixel pair never straddles a cell when gx is even
     unsigned dm = (unsigned)dark_max;
     for (int x = 2 * threadIdx.x; x < xlim; x += 2 * blockDim.x) {

@@ -135,7 +135,8 @@ int bf_plan_build(BfPlan *pl, int w, int h, const BlackfilterParameters *p, int 
   pl->npos = pv.n;
   pl->sums_len = nb * stride;
   pl->flag_off = pl->sums_len;
-  pl->u32_need = pl->flag_off + (pv.n + 3) / 4 + 1;
+  /* [flags: n bytes][ordered candidate list: n u32] */
+  pl->u32_need = pl->flag_off + (pv.n + 3) / 4 + 1 + pv.n + 1;
   pl->pos_dev = (DBfPos *)blob_upload(pv.v, (size_t)pv.n * sizeof(DBfPos));
   pl->jobs_dev = (DLineJob *)blob_upload(pl->jobs_host, (size_t)nb * sizeof(DLineJob));
   free(pv.v);
