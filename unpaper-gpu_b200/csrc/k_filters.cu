@@ -3,6 +3,7 @@
 // (reference imageprocess/filters.c:49-402, imageprocess/fill.c:16-107).
 // Replaces backend_cuda_filters.c + cuda_kernels_filters.cu + the OpenCV CCL /
 // NPP-integral paths of opencv_bridge.cpp (which are NOT CPU-exact).
+#include <stdio.h>
 #include "common.cuh"
 #include "launch.h"
 
@@ -14,233 +15,294 @@ static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
  * The scan positions (filters.c:60-103) depend only on geometry, so the host
  * enumerates them once, in order, dropping excluded ones.  Flood fills only
  * ever whiten pixels, so an area's darkness can only fall while the filter
- * runs: "hit on the untouched image" is a superset of the true hits.  One
- * warp per page walks that candidate list in order, re-measures a candidate
- * exactly if any fill ran before it, and emulates flood_fill()'s recursion
- * (fill.c:81-107) with an explicit frame stack so that the painted set —
- * including fill_line's overruns — matches the CPU order-dependent result.
+ * runs: "hit on the untouched image" is a superset of the true hits.  One CTA
+ * per page walks that candidate list in order, re-measures candidates after a
+ * fill, and emulates flood_fill()'s recursion (fill.c:81-107) with an explicit
+ * frame stack so that the painted set — including fill_line's overruns —
+ * matches the CPU's order-dependent result.
+ *
+ * The emulation is a chain of dependent steps, so it is written for latency:
+ *  - every step is BF_ROUND pixels wide (64 chunks of 32; the per-chunk ballots
+ *    meet in shared memory and every thread replays the same scalar decision);
+ *  - all per-fill state (the four line lengths and counters, the top frame, the
+ *    page description) lives in registers: no dynamically indexed local arrays,
+ *    no structs behind references that byte stores could alias;
+ *  - vertical lines touch one 32-byte sector per pixel and consecutive frames
+ *    walk adjacent columns, so the CTA keeps a 32-column strip of the whole
+ *    page height in shared memory (A4: 3508 x 32 B = 110 KB), write-back; it
+ *    moves when a frame opens outside it and is flushed at the end.
  * ====================================================================== */
-
-// The flood fill is one warp of serial work: code size matters more than
-// inlining (the fully inlined kernel was ~22 k SASS instructions and ran out of
-// the instruction caches), so pixel access goes through two small calls.
-__device__ __forceinline__ int ff_gray_at(const DImg &im, int x, int y) {
-  if (im.fmt == DF_GRAY8) return in_img(im, x, y) ? (int)im.data[(size_t)y * im.pitch + x] : 255;
-  return px_gray(px_get(im, x, y));
-}
-__device__ __forceinline__ void ff_paint(const DImg &im, int x, int y) {
-  if (im.fmt == DF_GRAY8) { im.data[(size_t)y * im.pitch + x] = 255; return; }
-  px_store(im, x, y, 255, 255, 255);
-}
-__device__ __forceinline__ bool ff_match(const DImg &im, int x, int y, int lo, int hi) {
-  int g = ff_gray_at(im, x, y);
-  return g >= lo && g <= hi;
-}
-
-// ---- block-cooperative emulation --------------------------------------------------
-// One CTA of BF_WARPS warps per page.  Every step of the (inherently serial)
-// recursion is made as wide as possible: a round looks at BF_ROUND consecutive
-// pixels of a line / candidates of a frame at once (each warp FF_U chunks of 32),
-// the per-chunk ballots meet in shared memory and every thread replays the same
-// scalar decision, so the recursion state stays uniform across the block.
 #define FF_U 4
 #define BF_WARPS 16
 #define BF_THREADS (BF_WARPS * 32)
 #define BF_CH (BF_WARPS * FF_U)
+#define BF_CH_LOG2 6
 #define BF_ROUND (BF_CH * 32)
+static_assert(BF_CH == 64 && (1 << BF_CH_LOG2) == BF_CH, "two chunks per lane in the replay");
+
+#ifdef BF_STATS
+__device__ unsigned long long g_bfs[16];
+#define BFS_ADD(i, v) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_bfs[i] += (v); } while (0)
+#else
+#define BFS_ADD(i, v) do {} while (0)
+#endif
 
 struct BfShared {
   unsigned M[BF_CH];
   unsigned I[BF_CH];
-  unsigned long long red[BF_WARPS];
   unsigned wcnt[BF_WARPS];
 };
 
-// fill_line (fill.c:16-43) x 4.  The four calls of flood_fill (fill.c:88-95) walk four disjoint pixel
-// sets (row left / column up / row right / column down of the centre), so they
-// cannot see each other's paint: they are advanced together, sharing the rounds.
-__device__ __noinline__ void ff_fill_cross(const DImg &im, int px, int py, int lo, int hi,
-                                           unsigned long long intensity, BfShared &sh, int len[4]) {
-  const int DX[4] = {-1, 0, 1, 0}, DY[4] = {0, -1, 0, 1};   // left, up, right, down
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int dist[4] = {0, 0, 0, 0};
-  unsigned long long cnt[4] = {1, 1, 1, 1};
-  bool done[4] = {false, false, false, false};
+// The page as the flood fill sees it; passed by value so that it stays in registers.
+struct BfCtx {
+  uint8_t *data;       // GRAY8 pixels (gen == NULL)
+  uint8_t *sbuf;       // column strip, 32 bytes per row
+  const DImg *gen;     // other formats: generic accessors on the device record
+  int pitch, w, h;
+  int sx0;             // first column of the strip (multiple of 32), -64: nothing loaded
+  int son;             // strip usable for this page
+};
+
+__device__ __noinline__ int ff_gray_generic(const DImg *im, int x, int y) { return px_gray(px_get(*im, x, y)); }
+__device__ __noinline__ void ff_paint_generic(const DImg *im, int x, int y) { px_store(*im, x, y, 255, 255, 255); }
+
+__device__ __forceinline__ bool cx_in(const BfCtx &c, int x, int y) { return (unsigned)x < (unsigned)c.w && (unsigned)y < (unsigned)c.h; }
+__device__ __forceinline__ int ff_gray_at(const BfCtx &c, int x, int y) {   // outside the image reads as white
+  if (c.gen) return ff_gray_generic(c.gen, x, y);
+  if (!cx_in(c, x, y)) return 255;
+  unsigned dx = (unsigned)(x - c.sx0);
+  if (dx < 32u) return (int)c.sbuf[y * 32 + (int)dx];
+  return (int)c.data[(size_t)y * c.pitch + x];
+}
+__device__ __forceinline__ void ff_paint(const BfCtx &c, int x, int y) {    // (x, y) inside the image
+  if (c.gen) { ff_paint_generic(c.gen, x, y); return; }
+  unsigned dx = (unsigned)(x - c.sx0);
+  if (dx < 32u) c.sbuf[y * 32 + (int)dx] = 255;
+  else c.data[(size_t)y * c.pitch + x] = 255;
+}
+// block-cooperative; callers put barriers around it
+__device__ __forceinline__ void strip_copy(const BfCtx &c, bool to_global) {
+  int nv = min(32, c.pitch - c.sx0) >> 4;   // 16-byte pieces per row inside the row's pitch
+  for (int i = threadIdx.x; i < c.h * nv; i += blockDim.x) {
+    int row = i / nv, part = i - row * nv;
+    uint4 *g = (uint4 *)(c.data + (size_t)row * c.pitch + c.sx0 + part * 16);
+    uint4 *l = (uint4 *)(c.sbuf + row * 32 + part * 16);
+    if (to_global) *g = *l; else *l = *g;
+  }
+}
+
+// candidate `idx` of a frame (fill.c:45-79: the two neighbours of every painted
+// pixel of the left, top, right, bottom line, nearest first)
+__device__ __forceinline__ void ff_cand(int cx, int cy, int L, int T, int R, unsigned idx, int &x, int &y) {
+  unsigned d = (idx >> 1) + 1u, sub = idx & 1u;
+  unsigned nL = 2u * L, nT = 2u * T, nR = 2u * R;
+  if (idx < nL) { x = cx - (int)d; y = cy + (sub ? -1 : 1); return; }
+  idx -= nL; d = (idx >> 1) + 1u;
+  if (idx < nT) { x = cx + (sub ? -1 : 1); y = cy - (int)d; return; }
+  idx -= nT; d = (idx >> 1) + 1u;
+  if (idx < nR) { x = cx + (int)d; y = cy + (sub ? -1 : 1); return; }
+  idx -= nR; d = (idx >> 1) + 1u;
+  x = cx + (sub ? -1 : 1); y = cy + (int)d;
+}
+
+#define SEL4(i, a, b, c, d) ((i) == 0 ? (a) : (i) == 1 ? (b) : (i) == 2 ? (c) : (d))
+
+// flood_fill(x, y) (fill.c:81-107) for a pixel that is known to match, run to
+// completion.  Returns the strip position (it may have moved).
+__device__ __noinline__ int ff_flood(BfCtx c, unsigned long long *stack, int stack_cap, unsigned *err, BfShared &sh,
+                                     int x, int y, int lo, int hi, unsigned long long intensity) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int sp = 0;
+  int t_cx = 0, t_cy = 0, t_L = 0, t_T = 0, t_R = 0, t_B = 0;   // the top frame
+  unsigned t_cur = 0;
+  int fx = x, fy = y;
+  bool pending = true;
   for (;;) {
-    int act[4], na = 0;
-    for (int d = 0; d < 4; d++) if (!done[d]) act[na++] = d;
-    if (na == 0) break;
-    int per = BF_CH / na;   // chunks of 32 pixels per active line in this round
-    bool full = true;
-#pragma unroll
-    for (int u = 0; u < FF_U; u++) {
-      int c = warp * FF_U + u, li = c / per;
-      unsigned M = 0, I = 0;
-      if (li < na) {
-        int d = act[li];
-        int s = dist[d] + (c - li * per) * 32 + lane + 1;
-        int qx = px + s * DX[d], qy = py + s * DY[d];
-        bool inb = in_img(im, qx, qy);
-        bool m = ff_match(im, qx, qy, lo, hi);
-        M = __ballot_sync(0xffffffffu, m);
-        I = __ballot_sync(0xffffffffu, inb);
+    if (pending) {
+      // ---- open a frame: paint the centre and its cross (fill.c:85-95) ----
+      if (sp >= stack_cap) { if (threadIdx.x == 0) atomicOr(err, DERR_STACK_OVERFLOW); break; }
+      if (sp > 0 && threadIdx.x == 0) {   // spill the caller's frame
+        unsigned long long *s = stack + (size_t)(sp - 1) * 4;
+        s[0] = (unsigned)t_cx | ((unsigned long long)(unsigned)t_cy << 32);
+        s[1] = (unsigned long long)(unsigned)t_L | ((unsigned long long)(unsigned)t_T << 32);
+        s[2] = (unsigned long long)(unsigned)t_R | ((unsigned long long)(unsigned)t_B << 32);
+        s[3] = t_cur;
       }
-      if (lane == 0) { sh.M[c] = M; sh.I[c] = I; }
-      if (li < na && (M & I) != 0xffffffffu) full = false;
-    }
-    // barrier + "did every evaluated chunk match in full?" in one step
-    bool all_full = __syncthreads_and(full) != 0;
-    int tot[4] = {0, 0, 0, 0};
-    if (all_full && intensity != 0) {
-      // nothing stops in this round: every active line advances by all its chunks
-      for (int li = 0; li < na; li++) { tot[li] = per * 32; cnt[act[li]] = intensity; }
-    } else
-    for (int li = 0; li < na; li++) {
-      int d = act[li];
-      bool stop = false;
-      for (int k = 0; k < per && !stop; k++) {
-        unsigned M = sh.M[li * per + k], I = sh.I[li * per + k];
-        int painted = 32;
-        if ((M & I) == 0xffffffffu) {
-          cnt[d] = intensity;
-          if (cnt[d] == 0) painted = 0;
+      if (c.son && (unsigned)(fx - c.sx0) >= 32u) {   // bring the strip to the column this frame walks
+        BFS_ADD(14, 1);
+        __syncthreads();
+        if (c.sx0 >= 0) strip_copy(c, true);
+        __syncthreads();
+        c.sx0 = fx & ~31;
+        strip_copy(c, false);
+      }
+      if (threadIdx.x == 0) ff_paint(c, fx, fy);
+      __syncthreads();
+      BFS_ADD(1, 1);
+      // fill_line (fill.c:16-43) x 4: the four lines of the cross touch disjoint pixels,
+      // so they advance together and share the rounds.  d: 0 left, 1 up, 2 right, 3 down
+      int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+      unsigned long long c0 = 1, c1 = 1, c2 = 1, c3 = 1;
+      unsigned active = intensity == 0 ? 0u : 0xFu;   // intensity 0: every line stops on its first pixel
+      while (active) {
+        BFS_ADD(0, 1);
+        const int na = __popc(active);
+        const int shift = BF_CH_LOG2 - (na == 1 ? 0 : na == 2 ? 1 : 2);   // log2(chunks per line)
+        const int per = 1 << shift;
+        unsigned packed = 0;   // direction of the li-th active line, 2 bits each
+        {
+          int q = 0;
+#pragma unroll
+          for (int d = 0; d < 4; d++) if ((active >> d) & 1u) { packed |= (unsigned)d << (2 * q); q++; }
+        }
+        bool full = true;
+#pragma unroll
+        for (int u = 0; u < FF_U; u++) {
+          int ch = warp * FF_U + u, li = ch >> shift;
+          unsigned M = 0, I = 0;
+          if (li < na) {
+            int d = (packed >> (2 * li)) & 3;
+            int dist = SEL4(d, d0, d1, d2, d3);
+            int s = dist + ((ch & (per - 1)) << 5) + lane + 1;
+            int dx = (d & 1) ? 0 : d - 1, dy = (d & 1) ? d - 2 : 0;
+            int qx = fx + s * dx, qy = fy + s * dy;
+            int g = ff_gray_at(c, qx, qy);
+            M = __ballot_sync(0xffffffffu, g >= lo && g <= hi);
+            I = __ballot_sync(0xffffffffu, cx_in(c, qx, qy));
+            if ((M & I) != 0xffffffffu) full = false;
+          }
+          if (lane == 0) { sh.M[ch] = M; sh.I[ch] = I; }
+        }
+        // barrier + "did every evaluated chunk match in full?" in one step
+        bool all_full = __syncthreads_and(full) != 0;
+        int t0 = 0, t1 = 0, t2 = 0, t3 = 0;   // pixels painted in this round, per active line
+        unsigned still = active;
+        if (all_full) {
+          // nothing stops: every active line advances by all its chunks
+          t0 = t1 = t2 = t3 = per * 32;
+          c0 = c1 = c2 = c3 = intensity;
         } else {
-          for (int i = 0; i < 32; i++) {
-            if ((M >> i) & 1u) cnt[d] = intensity; else cnt[d]--;
-            if (cnt[d] == 0 || !((I >> i) & 1u)) { painted = i; break; }
+          // which chunks did not match in full (two chunks per lane)
+          unsigned Ma = sh.M[lane], Ia = sh.I[lane], Mb = sh.M[32 + lane], Ib = sh.I[32 + lane];
+          unsigned long long nf = (unsigned long long)__ballot_sync(0xffffffffu, (Ma & Ia) != 0xffffffffu) |
+                                  ((unsigned long long)__ballot_sync(0xffffffffu, (Mb & Ib) != 0xffffffffu) << 32);
+#pragma unroll
+          for (int li = 0; li < 4; li++) {
+            if (li >= na) break;
+            int d = (packed >> (2 * li)) & 3;
+            unsigned long long cnt = SEL4(d, c0, c1, c2, c3);
+            int base = li << shift;
+            unsigned long long lm = nf >> base;
+            if (per < 64) lm &= (1ull << per) - 1ull;
+            int k = 0, tot = 0;
+            bool stop = false;
+            while (k < per && !stop) {
+              unsigned long long rest = lm >> k;
+              if (rest == 0) { tot += (per - k) * 32; cnt = intensity; break; }
+              int skip = __ffsll((long long)rest) - 1;     // full chunks: every pixel matches
+              if (skip > 0) { tot += skip * 32; cnt = intensity; k += skip; }
+              unsigned M = sh.M[base + k], I = sh.I[base + k];
+              int painted = 32;
+              for (int i = 0; i < 32; i++) {               // fill.c:27-39, pixel by pixel
+                if ((M >> i) & 1u) cnt = intensity; else cnt--;
+                if (cnt == 0 || !((I >> i) & 1u)) { painted = i; break; }
+              }
+              tot += painted;
+              if (painted < 32) stop = true;
+              k++;
+            }
+            if (stop) still &= ~(1u << d);
+            if (d == 0) c0 = cnt; else if (d == 1) c1 = cnt; else if (d == 2) c2 = cnt; else c3 = cnt;
+            if (li == 0) t0 = tot; else if (li == 1) t1 = tot; else if (li == 2) t2 = tot; else t3 = tot;
           }
         }
-        tot[li] += painted;
-        if (painted < 32) stop = true;
-      }
-      if (stop) done[d] = true;
-    }
 #pragma unroll
-    for (int u = 0; u < FF_U; u++) {
-      int c = warp * FF_U + u, li = c / per;
-      if (li < na) {
-        int d = act[li];
-        int idx = (c - li * per) * 32 + lane;
-        if (idx < tot[li]) {
-          int s = dist[d] + idx + 1;
-          ff_paint(im, px + s * DX[d], py + s * DY[d]);
+        for (int u = 0; u < FF_U; u++) {
+          int ch = warp * FF_U + u, li = ch >> shift;
+          if (li < na) {
+            int d = (packed >> (2 * li)) & 3;
+            int idx = ((ch & (per - 1)) << 5) + lane;
+            if (idx < SEL4(li, t0, t1, t2, t3)) {
+              int s = SEL4(d, d0, d1, d2, d3) + idx + 1;
+              int dx = (d & 1) ? 0 : d - 1, dy = (d & 1) ? d - 2 : 0;
+              ff_paint(c, fx + s * dx, fy + s * dy);
+            }
+          }
         }
+        __syncthreads();
+#pragma unroll
+        for (int li = 0; li < 4; li++) {
+          if (li >= na) break;
+          int d = (packed >> (2 * li)) & 3, tot = SEL4(li, t0, t1, t2, t3);
+          if (d == 0) d0 += tot; else if (d == 1) d1 += tot; else if (d == 2) d2 += tot; else d3 += tot;
+        }
+        active = still;
       }
+      t_cx = fx; t_cy = fy; t_L = d0; t_T = d1; t_R = d2; t_B = d3; t_cur = 0;
+      sp++;
+      pending = false;
     }
-    __syncthreads();
-    for (int li = 0; li < na; li++) dist[act[li]] += tot[li];
-  }
-  for (int d = 0; d < 4; d++) len[d] = dist[d];
-}
-
-struct FFFrame { int cx, cy; int L, T, R, B; unsigned cursor; };
-
-__device__ __forceinline__ void ff_cand(const FFFrame &f, unsigned idx, int &x, int &y) {
-  unsigned d = (idx >> 1) + 1u, sub = idx & 1u;
-  unsigned nL = 2u * f.L, nT = 2u * f.T, nR = 2u * f.R;
-  if (idx < nL) { x = f.cx - (int)d; y = f.cy + (sub ? -1 : 1); return; }
-  idx -= nL; d = (idx >> 1) + 1u;
-  if (idx < nT) { x = f.cx + (sub ? -1 : 1); y = f.cy - (int)d; return; }
-  idx -= nT; d = (idx >> 1) + 1u;
-  if (idx < nR) { x = f.cx + (int)d; y = f.cy + (sub ? -1 : 1); return; }
-  idx -= nR; d = (idx >> 1) + 1u;
-  x = f.cx + (sub ? -1 : 1); y = f.cy + (int)d;
-}
-
-// flood_fill(p) for a p that is known to match: paint the cross and push.
-__device__ __noinline__ bool ff_open(DPage &pg, const DImg &im, int x, int y, int lo, int hi,
-                                     unsigned long long intensity, BfShared &sh, int &sp, FFFrame &top) {
-  if (sp >= pg.stack_cap) { if (threadIdx.x == 0) atomicOr(&pg.error, DERR_STACK_OVERFLOW); return false; }
-  if (sp > 0 && threadIdx.x == 0) {   // spill the current top
-    unsigned long long *s = (unsigned long long *)pg.stack + (size_t)(sp - 1) * 4;
-    s[0] = (unsigned)top.cx | ((unsigned long long)(unsigned)top.cy << 32);
-    s[1] = (unsigned long long)(unsigned)top.L | ((unsigned long long)(unsigned)top.T << 32);
-    s[2] = (unsigned long long)(unsigned)top.R | ((unsigned long long)(unsigned)top.B << 32);
-    s[3] = top.cursor;
-  }
-  if (threadIdx.x == 0) ff_paint(im, x, y);
-  __syncthreads();
-  top.cx = x; top.cy = y;
-  int len[4];
-  ff_fill_cross(im, x, y, lo, hi, intensity, sh, len);
-  top.L = len[0]; top.T = len[1]; top.R = len[2]; top.B = len[3];
-  top.cursor = 0;
-  sp++;
-  return true;
-}
-
-// Runs the recursion to completion starting from an already-open frame.
-__device__ __noinline__ void ff_run(DPage &pg, const DImg &im, int lo, int hi, unsigned long long intensity,
-                                    BfShared &sh, int &sp, FFFrame &top) {
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  while (sp > 0) {
-    unsigned total = 2u * ((unsigned)top.L + top.T + top.R + top.B);
-    bool opened = false;
-    while (top.cursor < total) {
+    // ---- flood_fill_around_line x 4 (fill.c:45-79, :97-104): next still-matching neighbour ----
+    unsigned total = 2u * ((unsigned)t_L + t_T + t_R + t_B);
+    while (t_cur < total) {
+      BFS_ADD(2, 1);
       unsigned anym = 0;
 #pragma unroll
       for (int u = 0; u < FF_U; u++) {
-        int c = warp * FF_U + u;
-        unsigned idx = top.cursor + c * 32 + lane;
-        int x = 0, y = 0;
+        int ch = warp * FF_U + u;
+        unsigned idx = t_cur + ch * 32 + lane;
         bool m = false;
-        if (idx < total) { ff_cand(top, idx, x, y); m = in_img(im, x, y) && ff_match(im, x, y, lo, hi); }
+        if (idx < total) {
+          int qx, qy;
+          ff_cand(t_cx, t_cy, t_L, t_T, t_R, idx, qx, qy);
+          if (cx_in(c, qx, qy)) { int g = ff_gray_at(c, qx, qy); m = g >= lo && g <= hi; }
+        }
         unsigned M = __ballot_sync(0xffffffffu, m);
-        if (lane == 0) sh.M[c] = M;
+        if (lane == 0) sh.M[ch] = M;
         anym |= M;
       }
-      int hit = -1;
-      unsigned Mh = 0;
       if (__syncthreads_or(anym != 0)) {   // barrier; the common round has no match at all
-        for (int c = 0; c < BF_CH; c++) { unsigned M = sh.M[c]; if (M) { hit = c; Mh = M; break; } }
-        __syncthreads();   // sh.M is rewritten by the next round / by ff_open
-      }
-      if (hit >= 0) {
-        unsigned idx = top.cursor + hit * 32 + (__ffs(Mh) - 1);
-        int fx, fy;
-        ff_cand(top, idx, fx, fy);
-        top.cursor = idx + 1;
-        if (!ff_open(pg, im, fx, fy, lo, hi, intensity, sh, sp, top)) { sp = 0; return; }
-        opened = true;
+        unsigned Ma = sh.M[lane], Mb = sh.M[32 + lane];
+        unsigned b_lo = __ballot_sync(0xffffffffu, Ma != 0), b_hi = __ballot_sync(0xffffffffu, Mb != 0);
+        int hit = b_lo ? __ffs(b_lo) - 1 : 32 + __ffs(b_hi) - 1;
+        unsigned Mh = sh.M[hit];
+        __syncthreads();   // sh.M is rewritten by the next round
+        unsigned idx = t_cur + hit * 32 + (__ffs(Mh) - 1);
+        ff_cand(t_cx, t_cy, t_L, t_T, t_R, idx, fx, fy);
+        t_cur = idx + 1;
+        pending = true;
         break;
       }
-      top.cursor += BF_ROUND;
+      t_cur += BF_ROUND;
     }
-    if (opened) continue;
+    if (pending) continue;
     sp--;   // frame exhausted: return to the caller's frame
-    if (sp > 0) {
-      const unsigned long long *s = (const unsigned long long *)pg.stack + (size_t)(sp - 1) * 4;
-      unsigned long long a = s[0], b = s[1], c = s[2], d = s[3];
-      top.cx = (int)(unsigned)a; top.cy = (int)(unsigned)(a >> 32);
-      top.L = (int)(unsigned)b; top.T = (int)(unsigned)(b >> 32);
-      top.R = (int)(unsigned)c; top.B = (int)(unsigned)(c >> 32);
-      top.cursor = (unsigned)d;
-    }
+    if (sp == 0) break;
+    const unsigned long long *s = stack + (size_t)(sp - 1) * 4;
+    unsigned long long a = s[0], b = s[1], e = s[2], f = s[3];
+    t_cx = (int)(unsigned)a; t_cy = (int)(unsigned)(a >> 32);
+    t_L = (int)(unsigned)b; t_T = (int)(unsigned)(b >> 32);
+    t_R = (int)(unsigned)e; t_B = (int)(unsigned)(e >> 32);
+    t_cur = (unsigned)f;
   }
-}
-
-__device__ __noinline__ unsigned long long block_rect_maxch_sum(const DImg &im, int x0, int y0, int x1, int y1, BfShared &sh) {
-  unsigned long long s = 0;
-  if (x0 <= x1 && y0 <= y1) {
-    int w = x1 - x0 + 1, n = w * (y1 - y0 + 1);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s += (unsigned)px_darkinv(px_load(im, x0 + i % w, y0 + i / w));
-  }
-  s = warp_sum_u64(s);
-  if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  unsigned long long t = 0;
-  for (int w = 0; w < BF_WARPS; w++) t += sh.red[w];
-  __syncthreads();
-  return t;
+  return c.sx0;
 }
 
 __global__ void __launch_bounds__(BF_THREADS) k_bf_scan(DPage *pages, const DBfPos *pos, int npos, int abs_threshold,
-                          unsigned long long intensity, int mask_lo, int mask_hi, int flag_off) {
+                          unsigned long long intensity, int mask_lo, int mask_hi, int flag_off, int strip_rows) {
   __shared__ BfShared sh;
+  extern __shared__ uint4 bf_strip[];
   DPage &pg = pages[blockIdx.x];
   const DImg im = pg.img;
+  BfCtx c;
+  c.data = im.data; c.sbuf = (uint8_t *)bf_strip; c.gen = im.fmt == DF_GRAY8 ? (const DImg *)0 : &pg.img;
+  c.pitch = im.pitch; c.w = im.w; c.h = im.h; c.sx0 = -64;
+  c.son = im.fmt == DF_GRAY8 && im.h <= strip_rows && (im.pitch & 15) == 0 && ((uintptr_t)im.data & 15) == 0;
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t *cand = (uint8_t *)(pg.u32 + flag_off);
+#ifdef BF_STATS
+  long long T0 = clock64();
+#endif
   // phase 1: darkness of every position on the untouched image (blit.c:131-146)
   for (int k = threadIdx.x; k < npos; k += blockDim.x) {
     DBfPos q = pos[k];
@@ -272,9 +334,9 @@ __global__ void __launch_bounds__(BF_THREADS) k_bf_scan(DPage *pages, const DBfP
     for (int w = 0; w < BF_WARPS; w++) { if (w < warp) off += sh.wcnt[w]; total += sh.wcnt[w]; }
     for (int base = b0; base < b1; base += 32) {
       int k = base + lane;
-      bool c = k < b1 && cand[k];
-      unsigned m = __ballot_sync(0xffffffffu, c);
-      if (c) clist[off + __popc(m & ((1u << lane) - 1u))] = (unsigned)k;
+      bool cf = k < b1 && cand[k];
+      unsigned m = __ballot_sync(0xffffffffu, cf);
+      if (cf) clist[off + __popc(m & ((1u << lane) - 1u))] = (unsigned)k;
       off += __popc(m);
     }
     nc = (int)total;
@@ -287,6 +349,7 @@ __global__ void __launch_bounds__(BF_THREADS) k_bf_scan(DPage *pages, const DBfP
   unsigned fills = 0;
   for (int ci = 0; ci < nc;) {
     if (dirty) {
+      BFS_ADD(3, 1);
       int mine = ci + warp;
       bool dark = false;
       if (mine < nc) {
@@ -296,7 +359,9 @@ __global__ void __launch_bounds__(BF_THREADS) k_bf_scan(DPage *pages, const DBfP
         unsigned long long s = 0;
         if (x0 <= x1 && y0 <= y1) {
           int w = x1 - x0 + 1, n = w * (y1 - y0 + 1);
-          for (int i = lane; i < n; i += 32) s += (unsigned)px_darkinv(px_load(im, x0 + i % w, y0 + i / w));
+          for (int i = lane; i < n; i += 32)
+            s += c.gen ? (unsigned)px_darkinv(px_load(*c.gen, x0 + i % w, y0 + i / w))
+                       : (unsigned)ff_gray_at(c, x0 + i % w, y0 + i / w);
         }
         s = warp_sum_u64(s);
         int darkness = (int)(uint8_t)(0xFF - (s / cnt));
@@ -318,34 +383,41 @@ __global__ void __launch_bounds__(BF_THREADS) k_bf_scan(DPage *pages, const DBfP
     // flood_fill from every pixel of the area in raster order (filters.c:86-89);
     // pixels outside the image never match
     int w = x1 - x0 + 1, n = (x0 <= x1 && y0 <= y1) ? w * (y1 - y0 + 1) : 0;
-    int sp = 0;
-    FFFrame top;
     for (int rb = 0; rb < n;) {
       unsigned anym = 0;
 #pragma unroll
       for (int u = 0; u < FF_U; u++) {
-        int c = warp * FF_U + u;
-        int i = rb + c * 32 + lane;
-        bool m = i < n && ff_match(im, x0 + i % w, y0 + i / w, mask_lo, mask_hi);
+        int ch = warp * FF_U + u;
+        int i = rb + ch * 32 + lane;
+        bool m = false;
+        if (i < n) { int g = ff_gray_at(c, x0 + i % w, y0 + i / w); m = g >= mask_lo && g <= mask_hi; }
         unsigned M = __ballot_sync(0xffffffffu, m);
-        if (lane == 0) sh.M[c] = M;
+        if (lane == 0) sh.M[ch] = M;
         anym |= M;
       }
       int hit = -1;
       unsigned Mh = 0;
       if (__syncthreads_or(anym != 0)) {
-        for (int c = 0; c < BF_CH; c++) { unsigned M = sh.M[c]; if (M) { hit = c; Mh = M; break; } }
+        for (int ch = 0; ch < BF_CH; ch++) { unsigned M = sh.M[ch]; if (M) { hit = ch; Mh = M; break; } }
         __syncthreads();
       }
       if (hit < 0) { rb += BF_ROUND; continue; }
       int i = rb + hit * 32 + (__ffs(Mh) - 1);
       rb = i + 1;
-      if (ff_open(pg, im, x0 + i % w, y0 + i / w, mask_lo, mask_hi, intensity, sh, sp, top))
-        ff_run(pg, im, mask_lo, mask_hi, intensity, sh, sp, top);
-      sp = 0;
+      c.sx0 = ff_flood(c, (unsigned long long *)pg.stack, pg.stack_cap, (unsigned *)&pg.error, sh,
+                       x0 + i % w, y0 + i / w, mask_lo, mask_hi, intensity);
     }
   }
+  if (c.sx0 >= 0) { __syncthreads(); strip_copy(c, true); }
   if (threadIdx.x == 0) pg.bf_fills = fills;
+#ifdef BF_STATS
+  BFS_ADD(7, (unsigned long long)(clock64() - T0));
+  BFS_ADD(8, (unsigned long long)nc);
+  BFS_ADD(9, fills);
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("BFSTATS cross_steps %llu frames %llu cand_rounds %llu remeasure_rounds %llu total_cycles %llu ncand %llu fills %llu strip_moves %llu\n",
+           g_bfs[0], g_bfs[1], g_bfs[2], g_bfs[3], g_bfs[7], g_bfs[8], g_bfs[9], g_bfs[14]);
+#endif
 }
 
 /* =========================================================================
@@ -1014,10 +1086,15 @@ __global__ void k_gray_wipe(DPage *pages, GrayParams gp, int white_off) {
 extern "C" {
 
 void b200k_bf_scan(cudaStream_t st, DPage *pages, int npages, const DBfPos *pos_dev, int npos,
-                   int abs_threshold, long long intensity, int mask_lo, int mask_hi, int flag_off) {
+                   int abs_threshold, long long intensity, int mask_lo, int mask_hi, int flag_off, int maxh) {
   if (npages <= 0 || npos <= 0) return;
-  k_bf_scan<<<npages, BF_THREADS, 0, st>>>(pages, pos_dev, npos, abs_threshold, (unsigned long long)intensity,
-                                  mask_lo, mask_hi, flag_off);
+  // the shared-memory column strip: 32 bytes per image row, if the page height allows
+  int strip_rows = (maxh > 0 && (size_t)maxh * 32 <= 200 * 1024) ? maxh : 0;
+  size_t sm = (size_t)strip_rows * 32;
+  static int sm_set = 0;
+  if ((int)sm > sm_set) { cudaFuncSetAttribute(k_bf_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); sm_set = (int)sm; }
+  k_bf_scan<<<npages, BF_THREADS, sm, st>>>(pages, pos_dev, npos, abs_threshold, (unsigned long long)intensity,
+                                  mask_lo, mask_hi, flag_off, strip_rows);
 }
 
 int b200k_noisefilter(cudaStream_t st, DPage *pages, int npages, int maxw, int maxh, int fmt,

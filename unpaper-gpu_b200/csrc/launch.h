@@ -44,7 +44,8 @@ void b200k_prep_border_maskjob(cudaStream_t st, DPage *pages, int npages, DMaskJ
 
 /* k_filters.cu */
 void b200k_bf_scan(cudaStream_t st, DPage *pages, int npages, const DBfPos *pos_dev, int npos,
-                   int abs_threshold, long long intensity, int mask_lo, int mask_hi, int flag_off);
+                   int abs_threshold, long long intensity, int mask_lo, int mask_hi, int flag_off,
+                   int maxh /* tallest page of the group: sizes the shared-memory column strip */);
 int b200k_noisefilter(cudaStream_t st, DPage *pages, int npages, int maxw, int maxh, int fmt,
                       unsigned long long intensity, int white, int flags /* bit0: rows 16-byte aligned */);
 void b200k_blur_decide(cudaStream_t st, DPage *pages, int npages, int n, int nrows,

@@ -365,7 +365,7 @@ void stage_blackfilter(StageCtx *c, const BfPlan *pl) {
   b200k_zero_u32(c->st, c->pages, c->npages, 0, pl->sums_len);
   b200k_linesums(c->st, c->pages, c->npages, pl->jobs_dev, pl->jobs_host, pl->njobs, ST_MAXCH, 0, 0);
   b200k_bf_scan(c->st, c->pages, c->npages, pl->pos_dev, pl->npos, pl->abs_threshold, pl->intensity, 0,
-                pl->mask_hi, pl->flag_off);
+                pl->mask_hi, pl->flag_off, c->h);
   c->launches += 4;
 }
 
