@@ -818,7 +818,7 @@ __device__ unsigned nf_ring(DPage &pg, uint8_t *cls, int px, int py, int level, 
   return count;
 }
 
-__global__ void k_nf_resolve(DPage *pages, int intensity) {
+__global__ void __launch_bounds__(1024) k_nf_resolve(DPage *pages, int intensity) {
   DPage &pg = pages[blockIdx.x];
   const DImg &im = pg.img;
   uint8_t *cls = pg.cls;
@@ -844,8 +844,20 @@ __global__ void k_nf_resolve(DPage *pages, int intensity) {
       for (int yy = ya; yy <= y && ready; yy++) {
         const uint8_t *row = cls + (size_t)yy * im.w;
         int xe = (yy == y) ? x - 1 : xb;
-        for (int xx = xa; xx <= xe; xx++)
-          if (row[xx] & NF_UNDEC) { ready = false; break; }
+        if (xe < xa) continue;
+        // the window row as aligned words (independent loads; the class map has 64 bytes
+        // of slack behind its last row), bytes outside [xa, xe] masked off
+        uintptr_t p0 = (uintptr_t)(row + xa), p1 = (uintptr_t)(row + xe);
+        const unsigned *wp = (const unsigned *)(p0 & ~(uintptr_t)3);
+        int nw = (int)(((p1 & ~(uintptr_t)3) - (p0 & ~(uintptr_t)3)) >> 2) + 1;
+        unsigned acc = 0;
+        for (int k = 0; k < nw; k++) {
+          unsigned v = wp[k];
+          if (k == 0) v &= 0xFFFFFFFFu << (8 * (unsigned)(p0 & 3));
+          if (k == nw - 1) v &= 0xFFFFFFFFu >> (8 * (3 - (unsigned)(p1 & 3)));
+          acc |= v;
+        }
+        if (acc & (NF_UNDEC * 0x01010101u)) ready = false;
       }
       if (ready) pg.list[e] = v | 0x80000000u;
     }
@@ -1116,7 +1128,7 @@ int b200k_noisefilter(cudaStream_t st, DPage *pages, int npages, int maxw, int m
     k_nf_classify_g8<<<g8, 256, smg, st>>>(pages, I, white);
   } else
     k_nf_classify<<<g, 256, sm, st>>>(pages, I, white, all_mut);
-  k_nf_resolve<<<npages, 256, 0, st>>>(pages, I);
+  k_nf_resolve<<<npages, 1024, 0, st>>>(pages, I);   // one CTA per page: latency-bound rounds, so as wide as a CTA gets
   return 0;
 }
 
