@@ -323,8 +323,15 @@ def main():
                 "concurrent": {"kernel": dom_conc, "achieved": per_stage[dom_conc]["alg_gbs"],
                                "frac": round(per_stage[dom_conc]["alg_gbs"] / peaks["hbm_gbs"], 4),
                                "note": "same stage timed inside the timed region with all lanes competing"},
+                "whole_sheet": {"algorithmic_bytes_per_sheet": sum(sb.values()),
+                                "achieved": round(sum(sb.values()) * value / world / 1e9, 1), "unit": "GB/s",
+                                "frac": round(sum(sb.values()) * value / world / 1e9 / peaks["hbm_gbs"], 4),
+                                "note": "all stages: sum of the per-stage algorithmic bytes x measured sheets/s per GPU "
+                                        "(the throughput arm, all lanes overlapping)"},
                 "note": "algorithmic bytes per SURVEY 8(d) with the 1 B/px working sheet; the dominant stage is "
-                        "the one with the largest share of the isolated per-sheet time"}
+                        "the one with the largest share of the isolated per-sheet time. The stages are not HBM-bound "
+                        "in this implementation: the limits are instruction issue (rotate, noise classification) "
+                        "and chains of dependent steps (flood fill, cascades) - see DESIGN.md section 5"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
