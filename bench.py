@@ -173,6 +173,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    affinity = shard.bind_near_gpu(local) if world > 1 else None   # before CUDA/pinned allocations
     import torch
     import torch.distributed as dist
     from unpaper_gpu_b200.lib import Engine
@@ -338,7 +339,7 @@ def main():
                 "config": {"workload": WORKLOAD, "output_format": args.out_format, "pages_per_step_per_gpu": args.pages, "group_pages": args.group,
                            "lanes": args.lanes, "distinct_pages": args.distinct,
                            "l2": f"inputs larger than L2 ({args.pages * S / 1e6:.0f} MB of pages per step vs 126 MB L2)",
-                           "parallelism": f"page-sharded x{world}, no collective",
+                           "parallelism": f"page-sharded x{world}, no collective", "cpu_affinity": affinity,
                            "timing": "CUDA events on the engine's streams (first enqueue -> last lane done), max over ranks",
                            "wall_ms_per_step": dev_wall_ms / args.steps},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_pages * S * world,

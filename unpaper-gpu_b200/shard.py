@@ -36,3 +36,25 @@ def sum_over_ranks(values, device=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return [float(x) for x in t]
+
+
+def bind_near_gpu(local_rank):
+    """Pin this process to the CPUs NVML names as closest to GPU `local_rank`, so that the
+    pinned staging buffers it allocates land on that GPU's NUMA node (with 8 ranks feeding
+    8 GPUs the host side, not the device, bounds the host-buffer arm).  Returns a short
+    description, or None if NVML is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        cpus = [c for c in cpus if c < ncpu]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} cpus near gpu {local_rank} ({cpus[0]}..{cpus[-1]})"
+    except Exception:
+        return None
+
