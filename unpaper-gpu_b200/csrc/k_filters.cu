@@ -1103,8 +1103,8 @@ void b200k_bf_scan(cudaStream_t st, DPage *pages, int npages, const DBfPos *pos_
   // the shared-memory column strip: 32 bytes per image row, if the page height allows
   int strip_rows = (maxh > 0 && (size_t)maxh * 32 <= 200 * 1024) ? maxh : 0;
   size_t sm = (size_t)strip_rows * 32;
-  static int sm_set = 0;
-  if ((int)sm > sm_set) { cudaFuncSetAttribute(k_bf_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); sm_set = (int)sm; }
+  // per device and cheap, so set on every launch (an engine per GPU may live in one process)
+  if (sm > 40 * 1024) cudaFuncSetAttribute(k_bf_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   k_bf_scan<<<npages, BF_THREADS, sm, st>>>(pages, pos_dev, npos, abs_threshold, (unsigned long long)intensity,
                                   mask_lo, mask_hi, flag_off, strip_rows);
 }
