@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 : > gpurun_out/summary.txt
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-for f in ${FILES:-test_gpu_blit test_gpu_output test_gpu_filters test_gpu_engine}; do
+for f in ${FILES:-test_gpu_blit test_gpu_output test_gpu_filters test_gpu_fuzz test_gpu_engine}; do
   timeout 900 python -m pytest tests/$f.py -m gpu -q --timeout=240 --timeout-method=thread -p no:cacheprovider ${1:+-k "$1"} > gpurun_out/$f.log 2>&1
   echo "$f exit $?" >> gpurun_out/summary.txt
   tail -n 3 gpurun_out/$f.log
