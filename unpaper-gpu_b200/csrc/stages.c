@@ -32,7 +32,7 @@ int b200_fmt_row_bytes(int f, int width) {
 }
 
 void *blob_upload(const void *host, size_t bytes) {
-  if (bytes == 0) bytes = 4;
+  if (bytes == 0 || !host) return b200_dev_alloc(4);   /* an empty table: a valid pointer nobody reads */
   void *d = b200_dev_alloc(bytes);
   cudaStream_t s = b200_rt_stream();
   CUDA_OK(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, s));
