@@ -174,6 +174,11 @@ typedef struct {
   Rectangle pre_masks[8];
   int32_t pre_wipe_count, wipe_count, post_wipe_count;
   Rectangle pre_wipes[8], wipes[8], post_wipes[8];
+  /* size-preserving geometry options: options->pre_mirror / pre_shift before the
+   * pre-masks (sheet_stages.c:200-208), post_mirror / post_shift after the post
+   * border (:499-508) */
+  Direction pre_mirror, post_mirror;
+  Delta pre_shift, post_shift;
 } B200SheetConfig;
 
 #define B200_TRACE_MAX_MASKS 8

@@ -128,6 +128,10 @@ static int one_sheet(const B200SheetConfig *c, const uint8_t *pages, int pw, int
   Point pts[8]; int npts = c->point_count; memcpy(pts, c->points, sizeof(Point) * 8);
   ORect outside[2]; int nout = 0;
   MaskDetectionParameters mp = c->mask_detection;
+  if (c->pre_mirror.horizontal || c->pre_mirror.vertical) o_mirror(&sheet, c->pre_mirror.horizontal, c->pre_mirror.vertical);   /* :200-203 */
+  if (c->pre_shift.horizontal != 0 || c->pre_shift.vertical != 0) {                                                              /* :205-208 */
+    OImg n = o_shift(&sheet, c->pre_shift.horizontal, c->pre_shift.vertical); o_free(&sheet); sheet = n;
+  }
   if (c->pre_mask_count > 0) { ORect r[8]; for (int i = 0; i < c->pre_mask_count; i++) r[i] = R(&c->pre_masks[i]); o_apply_masks(&sheet, r, (size_t)c->pre_mask_count, mc); }
   if (c->layout == LAYOUT_SINGLE) {
     if (npts == 0) pts[npts++] = (Point){W / 2, H / 2};
@@ -206,6 +210,10 @@ static int one_sheet(const B200SheetConfig *c, const uint8_t *pages, int pw, int
   }
   if (!c->no_wipe) { ORect r[8]; for (int i = 0; i < c->post_wipe_count; i++) r[i] = R(&c->post_wipes[i]); o_apply_wipes(&sheet, r, (size_t)c->post_wipe_count, mc); }
   if (!c->no_border) o_apply_border(&sheet, c->post_border, mc);
+  if (c->post_mirror.horizontal || c->post_mirror.vertical) o_mirror(&sheet, c->post_mirror.horizontal, c->post_mirror.vertical); /* :499-502 */
+  if (c->post_shift.horizontal != 0 || c->post_shift.vertical != 0) {                                                             /* :504-508 */
+    OImg n = o_shift(&sheet, c->post_shift.horizontal, c->post_shift.vertical); o_free(&sheet); sheet = n;
+  }
   /* output in the page's format (saveImage(), file.c:211-262) */
   if (out) {
     OImg o = {out, W, H, row_bytes(fmt, W), fmt, {255, 255, 255}, c->abs_black_threshold};

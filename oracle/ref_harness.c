@@ -360,6 +360,8 @@ static void options_from_cfg(Options *o, Rectangle *bf_excl, const B200SheetConf
   o->pre_wipes.count = (size_t)c->pre_wipe_count;
   o->wipes.count = (size_t)c->wipe_count;
   o->post_wipes.count = (size_t)c->post_wipe_count;
+  o->pre_mirror = c->pre_mirror; o->post_mirror = c->post_mirror;
+  o->pre_shift = c->pre_shift; o->post_shift = c->post_shift;
   for (int i = 0; i < 8; i++) {
     o->pre_wipes.areas[i] = c->pre_wipes[i];
     o->wipes.areas[i] = c->wipes[i];

@@ -144,3 +144,22 @@ def test_engine_double_600dpi_properties():
     assert (out[:, :, :30] == 255).all()
     frac_dark = (out < 128).mean()
     assert 0.01 < frac_dark < 0.2
+
+
+def test_engine_pre_post_mirror_shift(ref_lib):
+    """Size-preserving geometry options of the pre and post stages
+    (sheet_stages.c:200-208, :499-508): mirror, then shift_image."""
+    w, h = 620, 877
+    pages = np.stack([synth.gray_page(90 + i, w, h, box=SMALL_BOX) for i in range(3)])
+    for pm, ps, qm, qs in (((True, False), (7, -5), (False, True), (-3, 11)),
+                           ((True, True), (0, 0), (False, False), (12, 0)),
+                           ((False, False), (-9, 4), (True, True), (0, 0))):
+        cfg = U.default_sheet_config()
+        cfg.pre_mirror, cfg.pre_shift = U.Direction(*pm), U.Delta(*ps)
+        cfg.post_mirror, cfg.post_shift = U.Direction(*qm), U.Delta(*qs)
+        _compare(cfg, pages, w, h, U.FMT_GRAY8, ref_lib, group=2, lanes=2)
+    cfg = U.default_sheet_config()
+    cfg.no_blackfilter = cfg.no_noisefilter = 1
+    cfg.pre_mirror, cfg.post_shift = U.Direction(False, True), U.Delta(5, -7)
+    rgb = np.stack([synth.color_page(i, w, h) for i in range(2)])
+    _compare(cfg, rgb, w, h, U.FMT_RGB24, ref_lib, group=2, lanes=1)

@@ -81,7 +81,8 @@ SheetConfig = _S("B200SheetConfig", [
     ("point_count", C.c_int32), ("points", Point * 8),
     ("pre_mask_count", C.c_int32), ("pre_masks", Rectangle * 8),
     ("pre_wipe_count", C.c_int32), ("wipe_count", C.c_int32), ("post_wipe_count", C.c_int32),
-    ("pre_wipes", Rectangle * 8), ("wipes", Rectangle * 8), ("post_wipes", Rectangle * 8)])
+    ("pre_wipes", Rectangle * 8), ("wipes", Rectangle * 8), ("post_wipes", Rectangle * 8),
+    ("pre_mirror", Direction), ("post_mirror", Direction), ("pre_shift", Delta), ("post_shift", Delta)])
 
 SheetResult = _S("B200SheetResult", [
     ("status", C.c_int32), ("sheet_width", C.c_int32), ("sheet_height", C.c_int32),

@@ -56,6 +56,9 @@ typedef struct {
   DFillJob *fillA, *fillB, *fillC, *decode_fill;
   DCopyJob *copyA, *copyB, *decode_copy, *decode_copy_host_tmpl;
   DMaskJob *maskJ;
+  /* shift_image (blit.c:360-368) before / after the pipeline: sheet -> aux, wipe, aux -> sheet at the delta */
+  DCopyJob *shift_out[2], *shift_in[2];
+  DFillJob *shift_fill[2];
   DFillJob *static_fill[3];   /* pre / mid / post wipe+border rectangles, per page */
   int static_fill_n[3];
   DMaskJob *static_mask[3];
@@ -193,6 +196,7 @@ static int build_static(B200Engine *e, Lane *ln, int slot, const Rectangle *wipe
 
 static void lane_free(Lane *ln) {
   void *ptrs[] = {ln->sheets, ln->aux, ln->cls, ln->list, ln->u32, ln->stack, ln->pre, ln->ink, ln->page_stage, ln->out_stage, ln->pages_dev,
+                  ln->shift_out[0], ln->shift_out[1], ln->shift_in[0], ln->shift_in[1], ln->shift_fill[0], ln->shift_fill[1],
                   ln->fillA, ln->fillB, ln->fillC, ln->decode_fill, ln->copyA, ln->copyB, ln->decode_copy, ln->maskJ,
                   ln->static_fill[0], ln->static_fill[1], ln->static_fill[2], ln->static_mask[0], ln->static_mask[1],
                   ln->static_mask[2], ln->static_mask_rects[0], ln->static_mask_rects[1], ln->static_mask_rects[2]};
@@ -370,6 +374,26 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
         cj->enabled = 1;
       }
     }
+    for (int k = 0; k < 2; k++) {
+      Delta d = k == 0 ? cfg->pre_shift : cfg->post_shift;
+      if (d.horizontal == 0 && d.vertical == 0) continue;
+      DCopyJob *so = (DCopyJob *)calloc((size_t)P, sizeof(DCopyJob)), *si = (DCopyJob *)calloc((size_t)P, sizeof(DCopyJob));
+      DFillJob *sf = (DFillJob *)calloc((size_t)P, sizeof(DFillJob));
+      for (int p = 0; p < P; p++) {
+        const DPage *pg = &ln->pages_tmpl[p];
+        DImg tmp = pg->aux;
+        tmp.w = W; tmp.h = H;
+        so[p].src = pg->img; so[p].dst = tmp; so[p].area = (DRect){0, 0, W - 1, H - 1}; so[p].tx = 0; so[p].ty = 0; so[p].enabled = 1;
+        sf[p].img = pg->img; sf[p].r = (DRect){0, 0, W - 1, H - 1}; sf[p].enabled = 1;
+        sf[p].c[0] = cfg->sheet_background.r; sf[p].c[1] = cfg->sheet_background.g; sf[p].c[2] = cfg->sheet_background.b;
+        si[p].src = tmp; si[p].dst = pg->img; si[p].area = (DRect){0, 0, W - 1, H - 1};
+        si[p].tx = d.horizontal; si[p].ty = d.vertical; si[p].enabled = 1;
+      }
+      ln->shift_out[k] = (DCopyJob *)blob_upload(so, sizeof(DCopyJob) * P);
+      ln->shift_in[k] = (DCopyJob *)blob_upload(si, sizeof(DCopyJob) * P);
+      ln->shift_fill[k] = (DFillJob *)blob_upload(sf, sizeof(DFillJob) * P);
+      free(so); free(si); free(sf);
+    }
     CUDA_OK(cudaMemcpy(ln->pages_dev, ln->pages_tmpl, sizeof(DPage) * P, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(ln->decode_fill, dfill, sizeof(DFillJob) * P, cudaMemcpyHostToDevice));
     free(dfill);
@@ -406,6 +430,18 @@ static void run_static(B200Engine *e, Lane *ln, StageCtx *c, int slot, int n) {
   if (q < e->n_static_mask_jobs[slot]) { b200k_apply_masks(c->st, ln->static_mask[slot] + (size_t)q * P, n, e->sheet_w, e->sheet_h); c->launches++; }
 }
 
+/* mirror() then shift_image() on every sheet of the group (sheet_stages.c:200-208, :499-508) */
+static void run_geometry(B200Engine *e, Lane *ln, StageCtx *c, int k, int n) {
+  Direction m = k == 0 ? e->cfg.pre_mirror : e->cfg.post_mirror;
+  if (m.horizontal || m.vertical) { b200k_mirror_pages(c->st, c->pages, n, e->sheet_w, e->sheet_h, m.horizontal, m.vertical); c->launches++; }
+  if (ln->shift_out[k]) {
+    b200k_copy_jobs(c->st, ln->shift_out[k], n, e->sheet_row, e->sheet_h);
+    b200k_fill_jobs(c->st, ln->shift_fill[k], n, e->sheet_w, e->sheet_h);
+    b200k_copy_jobs(c->st, ln->shift_in[k], n, e->sheet_row, e->sheet_h);
+    c->launches += 3;
+  }
+}
+
 static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, int n) {
   const B200SheetConfig *cfg = &e->cfg;
   StageCtx c;
@@ -429,6 +465,7 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
     c.launches += 1;
   }
   c.launches += 1;
+  run_geometry(e, ln, &c, 0, n);
   run_static(e, ln, &c, 0, n);
 
   mark(e, ln, STG_BLACK);
@@ -463,6 +500,7 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
     if (!cfg->no_border_align) stage_align_masks(&c, &cfg->mask_alignment, e->noutside);
   }
   run_static(e, ln, &c, 2, n);
+  run_geometry(e, ln, &c, 1, n);
   mark(e, ln, STG_OUTPUT);
   /* output stage: sheet -> caller (tight rows) + the decisions */
   if (e->out_fmt >= 0) {

@@ -202,6 +202,23 @@ __global__ void k_mirror(DImg im, int dir_h, int dir_v) {
   }
 }
 
+// the same for every sheet of a group (grid z = sheet)
+__global__ void k_mirror_pages(DPage *pages, int dir_h, int dir_v) {
+  const DImg &im = pages[blockIdx.z].img;
+  int ymax = dir_v ? (im.h - 1) / 2 : im.h - 1;
+  for (int y = blockIdx.y; y <= ymax; y += gridDim.y) {
+    int yy = dir_v ? im.h - y - 1 : y;
+    int xmax = im.w - 1;
+    if (dir_h && (!dir_v || y == yy)) xmax = (im.w - 1) / 2;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x <= xmax; x += gridDim.x * blockDim.x) {
+      int xx = dir_h ? im.w - x - 1 : x;
+      Px p1 = px_load(im, x, y), p2 = px_load(im, xx, yy);
+      px_store(im, x, y, p2.r, p2.g, p2.b);
+      px_store(im, xx, yy, p1.r, p1.g, p1.b);
+    }
+  }
+}
+
 // ---- flip_rotate_90 (blit.c:291-314) -------------------------------------
 __global__ void k_rotate90(DImg src, DImg dst, int dir) {
   int y = blockIdx.y;
@@ -233,6 +250,11 @@ void b200k_apply_masks(cudaStream_t st, const DMaskJob *jobs, int njobs, int max
   if (njobs <= 0 || maxw <= 0 || maxh <= 0) return;
   dim3 g(1, min(cdiv((unsigned)maxh, 4u), 1024u), njobs);
   k_apply_masks<<<g, 64, 0, st>>>(jobs);
+}
+void b200k_mirror_pages(cudaStream_t st, DPage *pages, int npages, int maxw, int maxh, int dir_h, int dir_v) {
+  if (npages <= 0 || maxw <= 0 || maxh <= 0 || (!dir_h && !dir_v)) return;
+  dim3 g(min(cdiv((unsigned)maxw, 256u), 8u), min((unsigned)maxh, 2048u), npages);
+  k_mirror_pages<<<g, 256, 0, st>>>(pages, dir_h, dir_v);
 }
 void b200k_mirror(cudaStream_t st, DImg im, int dir_h, int dir_v) {
   if (im.w <= 0 || im.h <= 0) return;

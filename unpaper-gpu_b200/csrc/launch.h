@@ -16,6 +16,7 @@ void b200k_fill_jobs(cudaStream_t st, const DFillJob *jobs, int njobs, int maxw,
 void b200k_copy_jobs(cudaStream_t st, const DCopyJob *jobs, int njobs, int maxw_bytes, int maxh);
 void b200k_apply_masks(cudaStream_t st, const DMaskJob *jobs, int njobs, int maxw, int maxh);
 void b200k_mirror(cudaStream_t st, DImg im, int dir_h, int dir_v);
+void b200k_mirror_pages(cudaStream_t st, DPage *pages, int npages, int maxw, int maxh, int dir_h, int dir_v);
 void b200k_rotate90(cudaStream_t st, DImg src, DImg dst, int dir);
 
 /* k_stats.cu */
