@@ -65,3 +65,27 @@ def test_product_does_not_touch_oracle():
                 if "oracle" in open(os.path.join(dp, f), errors="ignore").read().lower().replace("oracle/makefile", ""):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_output_side_host_functions(tmp_path):
+    """The parts of the output side that are plain host code: saveImage()'s format
+    mapping (file.c:201-208) and saveImageDirect's PNM layout (file.c:134-176)."""
+    import numpy as np
+    from unpaper_gpu_b200 import lib as L
+    lib = L.load()
+    assert lib.unpaper_b200_output_format(U.FMT_Y400A) == U.FMT_GRAY8
+    assert lib.unpaper_b200_output_format(U.FMT_MONOBLACK) == U.FMT_MONOWHITE
+    assert lib.unpaper_b200_output_format(U.FMT_GRAY8) == U.FMT_GRAY8
+    buf = C.create_string_buffer(64)
+    for fmt, want in ((U.FMT_GRAY8, b"P5\n31 7\n255\n"), (U.FMT_RGB24, b"P6\n31 7\n255\n"), (U.FMT_MONOWHITE, b"P4\n31 7\n")):
+        n = lib.unpaper_b200_pnm_header(fmt, 31, 7, buf, 64)
+        assert buf.raw[:n] == want
+    assert lib.unpaper_b200_pnm_header(U.FMT_Y400A, 31, 7, buf, 64) < 0
+    assert lib.unpaper_b200_pnm_header(U.FMT_GRAY8, 31, 7, buf, 4) < 0          # buffer too small
+    # rows with padding are written tight
+    img = np.arange(5 * 16, dtype=np.uint8).reshape(5, 16)
+    path = os.path.join(str(tmp_path), "t.pgm")
+    assert lib.unpaper_b200_write_pnm(path.encode(), img.ctypes.data, 16, 13, 5, U.FMT_GRAY8) == 0
+    blob = open(path, "rb").read()
+    assert blob == b"P5\n13 5\n255\n" + img[:, :13].tobytes()
+    assert lib.unpaper_b200_write_pnm(b"/nonexistent-dir/x.pgm", img.ctypes.data, 16, 13, 5, U.FMT_GRAY8) < 0
