@@ -241,6 +241,17 @@ int unpaper_b200_engine_process_device(B200Engine *e, const uint8_t *pages_dev,
 int unpaper_b200_engine_process_host(B200Engine *e, const uint8_t *pages_host,
                                      uint8_t *out_host, int n_sheets,
                                      B200SheetResult *results);
+/* Per-sheet completion hook (reference: BatchWorkerPostProcessFn,
+ * lib/batch_worker.h:22-25, called at batch_worker.c:153-158 after a successful
+ * process_sheet()).  Called on the thread that runs process_*, in sheet order,
+ * as soon as the sheet's group has finished — in host mode its bytes are
+ * already in `sheet` (caller memory), while later groups are still running, so
+ * encoding/writing overlaps with the GPU.  In device mode `sheet` is the device
+ * pointer.  A non-zero return marks the call as failed (process_* returns -3
+ * after draining).  NULL removes the hook. */
+typedef int (*B200SheetDoneFn)(void *user, int sheet_index, const uint8_t *sheet,
+                               const B200SheetResult *result);
+void unpaper_b200_engine_set_sheet_callback(B200Engine *e, B200SheetDoneFn fn, void *user);
 /* Kernel launches issued by the engine since creation (for bench.py). */
 uint64_t unpaper_b200_engine_launch_count(const B200Engine *e);
 /* Device time of the last process_* call: CUDA events from the first enqueue on

@@ -187,3 +187,22 @@ def test_fuzz_moves(cuda_ops, ref_ops, seed):
     a = run_inplace(cuda_ops, "align_mask", img, fmt, w, C.byref(area), C.byref(outside), C.byref(p))
     b = run_inplace(ref_ops, "align_mask", img, fmt, w, C.byref(area), C.byref(outside), C.byref(p))
     assert_same(a, b, fmt, w, f"fuzz align_mask seed={seed}")
+
+
+def test_detect_rotation_steep_range(cuda_ops, ref_ops):
+    """A scan range steep enough (30 degrees over 1500 rows: > 700 column changes per
+    line) that the warp-per-angle kernel's shared-memory run table does not apply and
+    the one-CTA-per-angle form runs instead."""
+    from util import himg
+    w, h = 1240, 1754
+    fmt = U.FMT_GRAY8
+    img = _page(700, w, h, fmt)
+    p = U.default_sheet_config().deskew
+    p.deskewScanRangeRad = float(np.float32(np.deg2rad(30.0)))
+    p.deskewScanStepRad = float(np.float32(np.deg2rad(0.5)))
+    p.deskewScanDeviationRad = float(np.float32(np.deg2rad(5.0)))
+    mask = U.rect(int(w * 0.06), 0, int(w * 0.94), h - 1)
+    ra, rb = C.c_float(), C.c_float()
+    cuda_ops.call("detect_rotation", C.byref(himg(img, fmt, w)), C.byref(mask), C.byref(p), C.byref(ra))
+    ref_ops.call("detect_rotation", C.byref(himg(img, fmt, w)), C.byref(mask), C.byref(p), C.byref(rb))
+    assert ra.value == rb.value, f"cuda {ra.value} ref {rb.value}"

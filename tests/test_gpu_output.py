@@ -163,3 +163,41 @@ def test_engine_mono_a4_properties():
     bits = np.unpackbits(out1, axis=2)
     assert (bits[:, :, :24] == 0).all()               # left scan edge gone
     assert 0.005 < bits.mean() < 0.2
+
+
+def test_engine_sheet_callback_streams_pnm(tmp_path):
+    """The per-sheet completion hook (reference post_process_fn, batch_worker.c:153-158):
+    called in sheet order with the finished bytes while later groups are in flight;
+    here it writes every sheet with the direct PNM writer."""
+    from unpaper_gpu_b200.lib import Engine
+    from unpaper_gpu_b200 import lib as L
+    w, h = 620, 877
+    pages = np.stack([synth.gray_page(i, w, h, box=(0.60, 0.72)) for i in range(7)])
+    eng = Engine(U.default_sheet_config(), w, h, U.FMT_GRAY8, group_pages=2, lanes=2)
+    plain, _ = eng.process_numpy(pages)
+    eng.set_output_format(U.FMT_MONOWHITE)
+    row = (w + 7) // 8
+    seen = []
+
+    def done(idx, ptr, res):
+        seen.append((idx, res.status, res.deskew_mask_count))
+        path = os.path.join(str(tmp_path), f"sheet{idx:03d}.pbm").encode()
+        return L.load().unpaper_b200_write_pnm(path, ptr, row, w, h, U.FMT_MONOWHITE)
+
+    eng.set_sheet_callback(done)
+    mono, res = eng.process_numpy(pages)
+    assert [s[0] for s in seen] == list(range(7))
+    assert all(s[1] == 0 and s[2] == 1 for s in seen)
+    hdr = b"P4\n%d %d\n" % (w, h)
+    for i in range(7):
+        blob = open(os.path.join(str(tmp_path), f"sheet{i:03d}.pbm"), "rb").read()
+        assert blob == hdr + mono[i].tobytes()
+    # a failing hook fails the call (after draining), and the engine stays usable
+    eng.set_sheet_callback(lambda idx, ptr, res: 1 if idx == 3 else 0)
+    with pytest.raises(RuntimeError, match="-3"):
+        eng.process_numpy(pages)
+    eng.set_sheet_callback(None)
+    eng.set_output_format(-1)
+    again, _ = eng.process_numpy(pages)
+    assert np.array_equal(again, plain)
+    eng.close()

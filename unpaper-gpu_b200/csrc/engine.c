@@ -40,6 +40,7 @@ typedef struct {
     cudaEvent_t ev[STG_COUNT + 1];
     int ev_mask;          /* which stage boundaries were recorded */
     DPage *pages_res;     /* pinned */
+    const uint8_t *out;   /* where this flight's sheets land (caller memory) */
     int busy, first, n;
   } fl[2];
   int slot;               /* flight being issued / collected */
@@ -88,6 +89,7 @@ struct B200Engine {
   unsigned bad_flags;
   cudaEvent_t ev_begin;
   int out_fmt, out_dfmt, out_row;   /* output conversion (av format, -1 = none) */
+  B200SheetDoneFn done_fn; void *done_user; int done_failed;
   double last_device_ms;
   double stage_ms[STG_COUNT];
   uint64_t stage_groups[STG_COUNT];
@@ -99,6 +101,10 @@ int unpaper_b200_engine_sheet_width(const B200Engine *e) { return e->sheet_w; }
 int unpaper_b200_engine_sheet_height(const B200Engine *e) { return e->sheet_h; }
 size_t unpaper_b200_engine_sheet_bytes(const B200Engine *e) {
   return (size_t)(e->out_fmt >= 0 ? e->out_row : e->sheet_row) * e->sheet_h;
+}
+void unpaper_b200_engine_set_sheet_callback(B200Engine *e, B200SheetDoneFn fn, void *user) {
+  if (!e) return;
+  e->done_fn = fn; e->done_user = user;
 }
 int unpaper_b200_engine_output_format(const B200Engine *e) {
   return e->out_fmt >= 0 ? e->out_fmt : (e->dfmt == DF_GRAY8 ? AV_PIX_FMT_GRAY8 : AV_PIX_FMT_RGB24);
@@ -555,10 +561,11 @@ static void collect(B200Engine *e, Lane *ln, B200SheetResult *results) {
   }
   for (int p = 0; p < ln->fl[ln->slot].n; p++)
     if (ln->fl[ln->slot].pages_res[p].error) { e->bad_sheets++; e->bad_flags |= ln->fl[ln->slot].pages_res[p].error; e->bad_first = ln->fl[ln->slot].first + p; }
-  if (results) {
+  if (results || e->done_fn) {
     for (int p = 0; p < ln->fl[ln->slot].n; p++) {
       const DPage *pg = &ln->fl[ln->slot].pages_res[p];
-      B200SheetResult *r = &results[ln->fl[ln->slot].first + p];
+      B200SheetResult local;
+      B200SheetResult *r = results ? &results[ln->fl[ln->slot].first + p] : &local;
       memset(r, 0, sizeof(*r));
       r->status = pg->error ? -(int)pg->error : 0;
       r->sheet_width = e->sheet_w; r->sheet_height = e->sheet_h;
@@ -582,6 +589,12 @@ static void collect(B200Engine *e, Lane *ln, B200SheetResult *results) {
       }
       r->blackfilter_fills = (int32_t)pg->bf_fills;
       r->noise_clusters = (int32_t)pg->nf_clusters;
+      /* the sheet is complete (in host mode: downloaded): hand it to the caller while
+       * later groups are still in flight (reference: post_process_fn, batch_worker.c:153-158) */
+      if (e->done_fn) {
+        const uint8_t *sheet = ln->fl[ln->slot].out + unpaper_b200_engine_sheet_bytes(e) * (size_t)p;
+        if (e->done_fn(e->done_user, ln->fl[ln->slot].first + p, sheet, r) != 0) e->done_failed++;
+      }
     }
   }
   ln->fl[ln->slot].busy = 0;
@@ -604,6 +617,7 @@ static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_shee
     int n = n_sheets - first < P ? n_sheets - first : P;
     ln->fl[ln->slot].first = first; ln->fl[ln->slot].n = n; ln->host_mode = host_mode;
     const uint8_t *src = pages + e->page_bytes * ic * (size_t)first;
+    ln->fl[ln->slot].out = out + out_sheet * first;
     if (host_mode) {
       ln->out_host = out + out_sheet * first;
       if (ic == 1 && e->sheet_pitch == e->page_row && e->page_dfmt == e->dfmt) {
@@ -635,6 +649,12 @@ static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_shee
     float ms = 0;
     if (e->lanes[i].ran && cudaEventElapsedTime(&ms, e->ev_begin, e->lanes[i].last_done_t) == cudaSuccess && ms > e->last_device_ms)
       e->last_device_ms = ms;
+  }
+  if (e->done_failed) {
+    int nf = e->done_failed;
+    e->done_failed = 0; e->bad_sheets = 0; e->bad_flags = 0;
+    b200_set_error("engine: the sheet callback failed for %d sheet(s)", nf);
+    return -3;
   }
   int bad = e->bad_sheets;
   e->bad_sheets = 0;

@@ -11,6 +11,9 @@ import numpy as np
 from . import abi
 from .abi import (HostOps, SheetConfig, SheetResult, bytes_per_row)
 
+# B200SheetDoneFn (include/unpaper_b200.h): user, sheet index, sheet bytes, result
+SHEET_DONE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(SheetResult))
+
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libunpaper_b200.so")
 _lib = None
 
@@ -46,6 +49,8 @@ def load():
     lib.unpaper_b200_output_format.argtypes = [C.c_int]
     lib.unpaper_b200_pnm_header.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
     lib.unpaper_b200_write_pnm.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.unpaper_b200_engine_set_sheet_callback.argtypes = [C.c_void_p, SHEET_DONE_FN, C.c_void_p]
+    lib.unpaper_b200_engine_set_sheet_callback.restype = None
     lib.unpaper_b200_engine_launch_count.argtypes = [C.c_void_p]
     lib.unpaper_b200_engine_launch_count.restype = C.c_uint64
     lib.unpaper_b200_engine_last_device_ms.argtypes = [C.c_void_p]
@@ -116,6 +121,15 @@ class Engine:
             raise RuntimeError("set_output_format failed: " + last_error())
         self.sheet_bytes = self.lib.unpaper_b200_engine_sheet_bytes(self.h)
         self.out_fmt = self.lib.unpaper_b200_engine_output_format(self.h)
+
+    def set_sheet_callback(self, fn):
+        """fn(sheet_index, sheet_ptr, result) -> int, called as each sheet completes
+        (the reference's post_process_fn); None removes it."""
+        if fn is None:
+            self._cb = SHEET_DONE_FN(0)
+        else:
+            self._cb = SHEET_DONE_FN(lambda user, idx, ptr, res: int(fn(idx, ptr, res.contents) or 0))
+        self.lib.unpaper_b200_engine_set_sheet_callback(self.h, self._cb, None)
 
     def launch_count(self):
         return int(self.lib.unpaper_b200_engine_launch_count(self.h))
