@@ -455,7 +455,7 @@ static float detect_rotation_b200(Image image, Rectangle mask, const DeskewParam
 static void deskew_b200(Image source, Rectangle mask, float radians, Interpolation interp) {
   if (!source.frame) return;
   Op o; op_begin(&o, &source, 1, 0, 0, 0);
-  int ink_cells = ((o.hp.img.w + 15) / 16) * ((o.hp.img.h + 15) / 16);
+  int ink_cells = ((o.hp.img.w + D_INK_CELL - 1) / D_INK_CELL) * ((o.hp.img.h + D_INK_CELL - 1) / D_INK_CELL);
   o.pre = b200_dev_alloc((size_t)ink_cells + 64);   /* freed with the other scratch */
   o.hp.ink = (uint8_t *)o.pre; o.hp.ink_cap = ink_cells;
   o.hp.mask_count = 1;

@@ -15,6 +15,7 @@ extern "C" {
 #endif
 
 /* internal pixel-format codes */
+#define D_INK_CELL 8   /* cell size of the ink map used by rotate() to skip white tiles */
 enum { DF_GRAY8 = 0, DF_Y400A = 1, DF_RGB24 = 2, DF_MONOWHITE = 3, DF_MONOBLACK = 4 };
 
 typedef struct { int32_t x0, y0, x1, y1; } DRect;      /* inclusive, like Rectangle */
@@ -54,7 +55,7 @@ typedef struct DPage {
   uint32_t *list;        /* noisefilter mutable list */
   uint32_t *u32;         /* general u32 scratch */
   uint64_t *stack;       /* flood-fill frame stack (4 x u64 per frame) */
-  uint8_t *ink;          /* 16x16-pixel cells: 1 = every pixel of the cell is pure white */
+  uint8_t *ink;          /* D_INK_CELL x D_INK_CELL pixel cells: 1 = every pixel of the cell is pure white */
   int32_t ink_ncx, ink_ncy, ink_ok, ink_cap;
   uint32_t *pre;         /* column prefix sums for the rotation scan: [rows+1][img.w] */
   int64_t pre_cap;       /* capacity of `pre` in u32 elements */

@@ -331,7 +331,7 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
     ln->u32 = (uint32_t *)b200_dev_alloc((size_t)e->need.u32_cap * 4 * P);
     ln->stack = (uint64_t *)b200_dev_alloc((size_t)e->need.stack_cap * 32 * P);
     if (e->need.pre_cap > 0) ln->pre = (uint32_t *)b200_dev_alloc((size_t)e->need.pre_cap * 4 * P);
-    int ink_cells = ((W + 15) / 16) * ((H + 15) / 16);
+    int ink_cells = ((W + D_INK_CELL - 1) / D_INK_CELL) * ((H + D_INK_CELL - 1) / D_INK_CELL);
     size_t ink_stride = ((size_t)ink_cells + 255) & ~(size_t)255;
     ln->ink = (uint8_t *)b200_dev_alloc(ink_stride * P);
     ln->page_stage = (uint8_t *)b200_dev_alloc(e->page_bytes * cfg->input_count * P + 64);

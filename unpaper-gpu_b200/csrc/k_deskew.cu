@@ -521,18 +521,20 @@ __device__ __forceinline__ Px interp_any(const DImg &im, float fx, float fy, int
 }
 
 
-/* Ink map: which 16x16 cells of the image are pure white.  A target tile whose
+/* Ink map: which INK_CELL x INK_CELL cells of the image are pure white.  A target tile whose
  * source footprint (plus the interpolation taps) only touches white cells — or
  * lies outside the image, which reads as white — is white after bicubic
  * interpolation (all 16 taps equal => every term of interpolate.c:24-32 cancels
- * exactly), so rotate() can write it without touching a pixel. */
-#define INK_CELL 16
+ * exactly), so rotate() can write it without touching a pixel.  Cells of 8 pixels
+ * are fine enough to catch the gaps between text lines. */
+#define INK_CELL D_INK_CELL
+static_assert(INK_CELL == 8, "k_inkmap reads a cell row as one 8-byte (GRAY8) / 24-byte (RGB24) piece");
 __global__ void k_inkmap(DPage *pages) {
   DPage &pg = pages[blockIdx.y];
   const DImg &im = pg.img;
   int ncx = (im.w + INK_CELL - 1) / INK_CELL, ncy = (im.h + INK_CELL - 1) / INK_CELL;
   int bpp = im.fmt == DF_GRAY8 ? 1 : im.fmt == DF_RGB24 ? 3 : 0;
-  bool ok = bpp && (im.pitch & 15) == 0 && ((uintptr_t)im.data & 15) == 0 && ncx * ncy <= pg.ink_cap && pg.ink;
+  bool ok = bpp && (im.pitch & 7) == 0 && ((uintptr_t)im.data & 7) == 0 && ncx * ncy <= pg.ink_cap && pg.ink;
   if (blockIdx.x == 0 && threadIdx.x == 0) { pg.ink_ncx = ncx; pg.ink_ncy = ncy; pg.ink_ok = ok; }
   if (!ok) return;
   for (int cy = blockIdx.x; cy < ncy; cy += gridDim.x) {
@@ -542,8 +544,8 @@ __global__ void k_inkmap(DPage *pages) {
       int x0 = c * INK_CELL;
       if (x0 + INK_CELL <= im.w) {
         for (int y = y0; y < y1 && white; y++) {
-          const uint4 *q = (const uint4 *)(im.data + (size_t)y * im.pitch + (size_t)x0 * bpp);
-          for (int v = 0; v < bpp; v++) { uint4 t = q[v]; white = white && ((t.x & t.y & t.z & t.w) == 0xFFFFFFFFu); }
+          const uint2 *q = (const uint2 *)(im.data + (size_t)y * im.pitch + (size_t)x0 * bpp);
+          for (int v = 0; v < bpp; v++) { uint2 t = q[v]; white = white && ((t.x & t.y) == 0xFFFFFFFFu); }
         }
       } else {
         for (int y = y0; y < y1 && white; y++)
