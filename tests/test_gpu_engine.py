@@ -163,3 +163,22 @@ def test_engine_pre_post_mirror_shift(ref_lib):
     cfg.pre_mirror, cfg.post_shift = U.Direction(False, True), U.Delta(5, -7)
     rgb = np.stack([synth.color_page(i, w, h) for i in range(2)])
     _compare(cfg, rgb, w, h, U.FMT_RGB24, ref_lib, group=2, lanes=1)
+
+
+def test_engine_two_pages_per_sheet(ref_lib):
+    """input_count = 2: two decoded pages are placed side by side on one sheet
+    (sheet_stages.c:140-165), double layout — through host buffers and device-resident."""
+    import torch
+    from unpaper_gpu_b200.lib import Engine
+    w, h = 620, 877
+    pages = np.stack([synth.gray_page(120 + i, w, h, box=SMALL_BOX) for i in range(6)])   # 3 sheets x 2 pages
+    cfg = U.default_sheet_config()
+    cfg.input_count, cfg.layout = 2, U.LAYOUT_DOUBLE
+    out, res = _compare(cfg, pages, w, h, U.FMT_GRAY8, ref_lib, group=2, lanes=2)
+    assert out.shape == (3, h, 2 * w)
+    eng = Engine(cfg, w, h, U.FMT_GRAY8, group_pages=2, lanes=1)
+    d_in = torch.from_numpy(pages.reshape(-1)).cuda()
+    d_out = torch.empty(out.size, dtype=torch.uint8, device="cuda")
+    eng.process_ptr(d_in.data_ptr(), d_out.data_ptr(), 3, False, None)
+    eng.close()
+    assert np.array_equal(d_out.cpu().numpy().reshape(out.shape), out)
