@@ -182,3 +182,27 @@ def test_engine_two_pages_per_sheet(ref_lib):
     eng.process_ptr(d_in.data_ptr(), d_out.data_ptr(), 3, False, None)
     eng.close()
     assert np.array_equal(d_out.cpu().numpy().reshape(out.shape), out)
+
+
+def _wipes_borders_cfg():
+    cfg = U.default_sheet_config()
+    cfg.pre_wipe_count = 1; cfg.pre_wipes[0] = U.rect(100, 120, 160, 170)
+    cfg.wipe_count = 2; cfg.wipes[0] = U.rect(300, 400, 340, 460); cfg.wipes[1] = U.rect(-5, 800, 50, 900)
+    cfg.post_wipe_count = 1; cfg.post_wipes[0] = U.rect(500, 50, 619, 90)
+    cfg.pre_border = U.Border(3, 4, 5, 6); cfg.border = U.Border(10, 0, 0, 12); cfg.post_border = U.Border(0, 7, 8, 0)
+    cfg.pre_mask_count = 1; cfg.pre_masks[0] = U.rect(20, 20, 600, 860)
+    cfg.noisefilter_intensity = 6
+    return cfg
+
+
+def test_engine_wipes_borders_premasks_points(ref_lib):
+    """The static rectangles of the pre/mid/post stages (pre-masks, wipes — one of them
+    partly outside the sheet —, borders), a non-default noise intensity, then a user
+    point, a gray mask colour and an off-white sheet background."""
+    w, h = 620, 877
+    pages = np.stack([synth.gray_page(140 + i, w, h, box=SMALL_BOX) for i in range(3)])
+    _compare(_wipes_borders_cfg(), pages, w, h, U.FMT_GRAY8, ref_lib, group=2, lanes=2)
+    cfg = _wipes_borders_cfg()
+    cfg.point_count = 1; cfg.points[0] = U.Point(300, 430)
+    cfg.mask_color = U.Pixel(200, 200, 200); cfg.sheet_background = U.Pixel(250, 250, 250)
+    _compare(cfg, pages, w, h, U.FMT_GRAY8, ref_lib, group=3, lanes=1)
