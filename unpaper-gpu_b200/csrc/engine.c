@@ -610,11 +610,26 @@ static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_shee
   /* every lane is idle here, so an event on lane 0 marks the start of device work */
   if (!e->ev_begin) CUDA_OK(cudaEventCreate(&e->ev_begin));
   CUDA_OK(cudaEventRecord(e->ev_begin, e->lanes[0].st));
-  for (int first = 0; first < n_sheets; first += P, g++) {
+  /* Through host buffers the first groups only start computing once their upload is
+   * done and the last download runs after everything else: ramp the group size up at
+   * the start and down at the end (quarter, half, full) so that both are short. */
+  int q = P / 4 > 0 ? P / 4 : 1, hf = P / 2 > 0 ? P / 2 : 1;
+  int ramp = host_mode && n_sheets >= 4 * e->nlanes * (q + hf) ? e->nlanes * (q + hf) : 0;   /* sheets in each ramp */
+  for (int first = 0, n = 0; first < n_sheets; first += n, g++) {
     Lane *ln = &e->lanes[g % e->nlanes];
     ln->slot = (g / e->nlanes) & 1;
     collect(e, ln, results);          /* the flight issued two rounds ago on this lane */
-    int n = n_sheets - first < P ? n_sheets - first : P;
+    int left = n_sheets - first;
+    n = P;
+    if (ramp) {
+      if (first < e->nlanes * q) n = q;
+      else if (first < ramp) n = hf;
+      else if (left <= e->nlanes * q) n = q;
+      else if (left <= ramp) n = hf;
+      else if (left - P < ramp) n = left - ramp;   /* the last full-size group ends where the down-ramp begins */
+    }
+    if (n > left) n = left;
+    if (n > P) n = P;
     ln->fl[ln->slot].first = first; ln->fl[ln->slot].n = n; ln->host_mode = host_mode;
     const uint8_t *src = pages + e->page_bytes * ic * (size_t)first;
     ln->fl[ln->slot].out = out + out_sheet * first;
