@@ -144,7 +144,7 @@ __device__ __forceinline__ void rot_line_geometry(const DRect &mask, int scan_pa
   Y0 = mask.y0 + mid - half;
 }
 
-__global__ void k_rot_colprefix(DPage *pages, int mi, int scan_param) {
+__global__ void __launch_bounds__(32 * RP_SEG, 2) k_rot_colprefix(DPage *pages, int mi, int scan_param) {
   // block = 32 lanes x RP_SEG row segments; a lane owns 4 adjacent columns (one
   // 32-bit load per row, one 16-byte store of four running sums)
   __shared__ uint4 tot[RP_SEG][32];
@@ -165,6 +165,10 @@ __global__ void k_rot_colprefix(DPage *pages, int mi, int scan_param) {
   bool fast = im.fmt == DF_GRAY8 && (im.pitch & 3) == 0 && ((uintptr_t)im.data & 3) == 0 && (im.w & 3) == 0 &&
               ((uintptr_t)pg.pre & 15) == 0;
   int ncol = min(4, im.w - x);          // columns this lane really owns (<= 0: none)
+  {   // only the mask's columns are ever read back (k_rot_peaks_*: vx0..vx1)
+    int mx0 = min(mask.x0, mask.x1), mx1 = max(mask.x0, mask.x1);
+    if (x + 3 < max(mx0, 0) || x > min(mx1, im.w - 1)) ncol = 0;
+  }
   uint4 t = make_uint4(0, 0, 0, 0);
   if (ncol > 0)
     for (int r = r0; r < r1; r++) {
