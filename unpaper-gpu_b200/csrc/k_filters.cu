@@ -663,7 +663,7 @@ __device__ __noinline__ bool nfb_small_component(const unsigned (*nb)[NFB_NW], i
   return n < need;
 }
 
-__global__ void __launch_bounds__(256) k_nf_classify_bits(DPage *pages, int intensity, int white) {
+__global__ void __launch_bounds__(256, 8) k_nf_classify_bits(DPage *pages, int intensity, int white) {
   __shared__ unsigned s_dark[NFB_ROWS][NFB_NW], s_nb[NFB_ROWS][NFB_NW], s_h0[NFB_ROWS][NFB_NW], s_h1[NFB_ROWS][NFB_NW],
       s_core[NFB_ROWS][NFB_NW], s_big[NFB_ROWS][NFB_NW];
   DPage &pg = pages[blockIdx.z];
