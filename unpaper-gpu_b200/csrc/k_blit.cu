@@ -60,7 +60,7 @@ __device__ __forceinline__ void copy_run(uint8_t *dst, const uint8_t *src, int n
   for (int i = head + (nvec << 4) + tid; i < n; i += nthreads) dst[i] = src[i];
 }
 
-__global__ void k_fill_jobs(const DFillJob *jobs) {
+__global__ void __launch_bounds__(256, 8) k_fill_jobs(const DFillJob *jobs) {
   const DFillJob &j = jobs[blockIdx.z];
   if (!j.enabled) return;
   const DImg &im = j.img;
@@ -83,7 +83,7 @@ __global__ void k_fill_jobs(const DFillJob *jobs) {
 }
 
 // ---- copy (imageprocess/blit.c:30-80) -------------------------------------
-__global__ void k_copy_jobs(const DCopyJob *jobs) {
+__global__ void __launch_bounds__(256, 8) k_copy_jobs(const DCopyJob *jobs) {
   const DCopyJob &j = jobs[blockIdx.z];
   if (!j.enabled) return;
   const DImg &s = j.src, &d = j.dst;

@@ -104,7 +104,7 @@ __global__ void k_linesum_rows(DPage *pages, const DLineJob *jobs, int njobs, in
 // Count of pixels with gray in [lo,hi] inside rect k of a static list; pixels
 // outside the image read as white (blit.c:148-167 does not clip).  One warp per
 // rectangle.  out = pages[p].u32 + out_off + k.
-__global__ void k_rect_count(DPage *pages, const DRect *rects, int nrects, int lo, int hi, int out_off) {
+__global__ void __launch_bounds__(256, 8) k_rect_count(DPage *pages, const DRect *rects, int nrects, int lo, int hi, int out_off) {
   int page = blockIdx.y;
   int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
@@ -165,7 +165,7 @@ __global__ void k_rect_count(DPage *pages, const DRect *rects, int nrects, int l
 //   light[c] = sum of min-channel over the in-image pixels
 // One block per cell row; columns accumulate in registers over the g rows and
 // merge into shared per-cell counters.  Layout in u32: [dark ncx*ncy][light ncx*ncy].
-__global__ void k_cellstats(DPage *pages, int gx, int gy, int ncx, int ncy, int dark_max, int out_off) {
+__global__ void __launch_bounds__(256, 8) k_cellstats(DPage *pages, int gx, int gy, int ncx, int ncy, int dark_max, int out_off) {
   extern __shared__ unsigned sm[];
   unsigned *sd = sm, *sl = sm + ncx;
   int page = blockIdx.y, cy = blockIdx.x;
