@@ -9,6 +9,9 @@ Vectors:
     reference CPU backend decided, a digest of its output, and the differing-
     pixel ratio against tests/golden_images/goldenA1.pbm (pins oracle/_ref to
     the reference's golden image);
+  * "C1", "F3", "E1": the reference's other golden images on this path
+    (tests/unpaper_tests.py:568-599, :763-810): C1 and F3 are reproduced EXACTLY by
+    oracle/_ref; C1 ships as a fixture (c1_fixture.npz: input + golden image);
   * "sheets": seeded synthetic pages (generator in unpaper-gpu_b200/synth.py)
     through the reference process_sheet(): decisions + output digests;
   * "ops": digests of single reference ops on seeded images.
@@ -37,7 +40,7 @@ def main():
     lib = checker.load_ref()
     assert lib is not None, "build oracle/_ref first (make -C oracle ref)"
     ops = U.HostOps(lib, "ref_host_")
-    out = {"A1": None, "sheets": {}, "ops": {}}
+    out = {"A1": None, "C1": None, "F3": None, "E1": None, "sheets": {}, "ops": {}}
     ref_root = os.environ.get("UNPAPER_REFERENCE", "/root/reference")
     src = os.path.join(ref_root, "tests/source_images/imgsrc001.png")
     if os.path.exists(src):
@@ -51,6 +54,48 @@ def main():
                      "result": G.result_dict(res[0]), "output_sha256": hashlib.sha256(o[0].tobytes()).hexdigest(),
                      "golden_diff_ratio_thr170": ratio}
         assert ratio < 1e-4, ratio
+    # C1 (tests/unpaper_tests.py:568-599): mask/border scan + pre-wipe/pre-border, filters and deskew
+    # off; the reference test demands EXACT equality with goldenC1.ppm.  Small enough to ship as a
+    # fixture (input and golden image): the CUDA engine and the restatement are checked against it.
+    src = os.path.join(ref_root, "tests/source_images/imgsrc006.png")
+    if os.path.exists(src):
+        from PIL import Image
+        a = np.array(Image.open(src).convert("RGB"), dtype=np.uint8)
+        gold = np.array(Image.open(os.path.join(ref_root, "tests/golden_images/goldenC1.ppm")).convert("RGB"), dtype=np.uint8)
+        h, w, _ = a.shape
+        o, res = checker.process_sheets_cpu(lib, "ref_", G.c1_config(), a.reshape(1, h, 3 * w), w, h, U.FMT_RGB24)
+        assert np.array_equal(o[0].reshape(h, w, 3), gold), "oracle/_ref does not reproduce goldenC1.ppm"
+        np.savez_compressed(os.path.join(HERE, "c1_fixture.npz"), page=a, golden=gold)
+        out["C1"] = {"size": [w, h], "equals_reference_golden": True, "result": G.result_dict(res[0])}
+    # F3 (:787-810): two 1-bit pages merged on one double-layout sheet -> goldenF.pbm (the reference
+    # test allows 5 %; the build here reproduces it exactly).  E1 (:763-783): double-layout scans, the
+    # two halves of the sheet against goldenE1-0N.pbm.  Too large to ship: digests and ratios only.
+    srcs = [os.path.join(ref_root, f"tests/source_images/imgsrcE00{i}.png") for i in (1, 2, 3)]
+    if all(os.path.exists(x) for x in srcs):
+        from PIL import Image
+        bits = [np.packbits(np.array(Image.open(x).convert("L")) > 127, axis=1) for x in srcs]   # MONOBLACK: set = white
+        w, h = Image.open(srcs[0]).size
+        cfg = U.default_sheet_config()
+        cfg.layout, cfg.input_count = U.LAYOUT_DOUBLE, 2
+        o, res = checker.process_sheets_cpu(lib, "ref_", cfg, np.stack(bits[:2]).reshape(1, -1), w, h, U.FMT_MONOBLACK)
+        gold = np.array(Image.open(os.path.join(ref_root, "tests/golden_images/goldenF.pbm")).convert("L")) < 128
+        black = np.unpackbits(o[0], axis=1)[:, :2 * w] == 0
+        out["F3"] = {"size": [2 * w, h], "differing_pixels_vs_goldenF": int((black != gold).sum()),
+                     "input_sha256": [hashlib.sha256(b.tobytes()).hexdigest() for b in bits[:2]],
+                     "output_sha256": hashlib.sha256(o[0].tobytes()).hexdigest(), "result": G.result_dict(res[0])}
+        assert out["F3"]["differing_pixels_vs_goldenF"] == 0
+        cfg = U.default_sheet_config()
+        cfg.layout = U.LAYOUT_DOUBLE
+        e1 = []
+        for k, b in enumerate(bits):
+            o, res = checker.process_sheets_cpu(lib, "ref_", cfg, b.reshape(1, -1), w, h, U.FMT_MONOBLACK)
+            black = np.unpackbits(o[0], axis=1)[:, :w] == 0
+            for half in range(2):
+                gold = np.array(Image.open(os.path.join(ref_root, f"tests/golden_images/goldenE1-0{2 * k + half + 1}.pbm")).convert("L")) < 128
+                part = black[:, half * (w // 2):half * (w // 2) + gold.shape[1]]
+                e1.append(float(np.mean(part != gold)))
+        out["E1"] = {"golden_diff_ratio": e1}
+        assert max(e1) < 1e-4, e1
     for name, (cfg, pages, w, h, fmt) in G.sheet_cases().items():
         o, res = checker.process_sheets_cpu(lib, "ref_", cfg, pages, w, h, fmt, threads=8)
         out["sheets"][name] = {"results": [G.result_dict(r) for r in res],

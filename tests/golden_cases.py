@@ -91,3 +91,20 @@ def op_cases():
                 "deskew": _digest(d, U.FMT_GRAY8, w)}
 
     return {"noisefilter": noise, "blackfilter": black, "blur_gray": blur_gray, "detect": detect}
+
+
+def c1_config():
+    """The options of the reference's test_c1_mask_border_scan_fixture
+    (tests/unpaper_tests.py:575-595)."""
+    cfg = U.default_sheet_config()
+    cfg.no_deskew = cfg.no_blackfilter = cfg.no_noisefilter = cfg.no_blurfilter = cfg.no_grayfilter = 1
+    cfg.no_mask_center = 1
+    cfg.mask_detection.scan_direction = U.Direction(True, True)
+    cfg.mask_detection.scan_threshold.horizontal = cfg.mask_detection.scan_threshold.vertical = 0.8
+    cfg.mask_detection.minimum_width = cfg.mask_detection.minimum_height = 1
+    cfg.border_scan.scan_direction = U.Direction(True, True)
+    cfg.pre_wipe_count = 1
+    cfg.pre_wipes[0] = U.rect(0, 0, 9, 9)
+    cfg.pre_border = U.Border(2, 2, 2, 2)
+    return cfg
+

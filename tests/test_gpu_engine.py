@@ -206,3 +206,23 @@ def test_engine_wipes_borders_premasks_points(ref_lib):
     cfg.point_count = 1; cfg.points[0] = U.Point(300, 430)
     cfg.mask_color = U.Pixel(200, 200, 200); cfg.sheet_background = U.Pixel(250, 250, 250)
     _compare(cfg, pages, w, h, U.FMT_GRAY8, ref_lib, group=3, lanes=1)
+
+
+def test_engine_reference_golden_c1():
+    """The reference's own exact golden on this path (tests/unpaper_tests.py:568-599:
+    mask + border scan in both directions, pre-wipe, pre-border, RGB24) through the CUDA
+    engine: every byte equals goldenC1.ppm (fixture tests/golden/c1_fixture.npz)."""
+    import os
+    import golden_cases as G
+    from unpaper_gpu_b200.lib import Engine
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", "c1_fixture.npz"))
+    page, golden = f["page"], f["golden"]
+    h, w, _ = page.shape
+    pages = np.stack([page.reshape(h, 3 * w)] * 3)
+    eng = Engine(G.c1_config(), w, h, U.FMT_RGB24, group_pages=2, lanes=2)
+    out, res = eng.process_numpy(pages)
+    eng.close()
+    for i in range(3):
+        assert res[i].status == 0
+        assert np.array_equal(out[i].reshape(h, w, 3), golden), f"sheet {i}"
+        assert U.border_tuple(res[i].borders[0]) == (35, 20, 16, 21)

@@ -138,3 +138,34 @@ def test_orc_output_conversion_vs_numpy(orc_ops):
         mb = noise_image(13, w, h, U.FMT_MONOBLACK, dark=0.4)
         orc_ops.call("convert_format", C.byref(himg(mb, U.FMT_MONOBLACK, w, abt=abt)), C.byref(himg(d, U.FMT_MONOWHITE, w, abt=abt)))
         assert np.array_equal(d[:, :want.shape[1]], mb[:, :want.shape[1]] ^ 0xFF)
+
+
+def _c1_fixture():
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", "c1_fixture.npz"))
+    return f["page"], f["golden"]
+
+
+def test_reference_goldens_c1_f3_e1_records():
+    """When the vectors were made, oracle/_ref reproduced the reference's goldenC1.ppm and
+    goldenF.pbm exactly and the six goldenE1 pages to < 1e-4 (tests/unpaper_tests.py:568-599, :763-810)."""
+    assert GOLD["C1"]["equals_reference_golden"] is True
+    assert GOLD["F3"]["differing_pixels_vs_goldenF"] == 0
+    assert len(GOLD["E1"]["golden_diff_ratio"]) == 6 and max(GOLD["E1"]["golden_diff_ratio"]) < 1e-4
+
+
+@pytest.mark.parametrize("which", ["orc", "ref"])
+def test_golden_c1_fixture_exact(orc_lib, which):
+    """The reference's own exact golden for this path (mask/border scan + pre-wipe/border,
+    unpaper_tests.py:568-599) against the restatement and, when built, the reference."""
+    import golden_cases as G
+    page, golden = _c1_fixture()
+    h, w, _ = page.shape
+    if which == "ref":
+        lib, prefix = checker.load_ref(), "ref_"
+        if lib is None:
+            pytest.skip("oracle/_ref not built")
+    else:
+        lib, prefix = orc_lib, "orc_"
+    out, res = checker.process_sheets_cpu(lib, prefix, G.c1_config(), page.reshape(1, h, 3 * w), w, h, U.FMT_RGB24)
+    assert np.array_equal(out[0].reshape(h, w, 3), golden)
+    assert G.result_dict(res[0]) == GOLD["C1"]["result"]
