@@ -89,3 +89,19 @@ def test_output_side_host_functions(tmp_path):
     blob = open(path, "rb").read()
     assert blob == b"P5\n13 5\n255\n" + img[:, :13].tobytes()
     assert lib.unpaper_b200_write_pnm(b"/nonexistent-dir/x.pgm", img.ctypes.data, 16, 13, 5, U.FMT_GRAY8) < 0
+
+
+def test_library_carries_sm_100a_code_with_line_info():
+    """The in-tree library is built for sm_100a (SASS + compute_100a PTX) with -lineinfo and
+    without FMA contraction, as csrc/Makefile says."""
+    import shutil
+    mk = open(os.path.join(ROOT, "unpaper-gpu_b200", "csrc", "Makefile")).read()
+    assert "arch=compute_100a,code=[sm_100a,compute_100a]" in mk and "-lineinfo" in mk and "--fmad=false" in mk
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    so = os.path.join(ROOT, "unpaper-gpu_b200", "libunpaper_b200.so")
+    elfs = subprocess.run([cuobjdump, "-lelf", so], capture_output=True, text=True).stdout
+    kernels = [l for l in elfs.splitlines() if "sm_100a" in l]
+    assert len(kernels) >= 6, elfs          # one cubin per k_*.cu
