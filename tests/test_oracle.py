@@ -169,3 +169,41 @@ def test_golden_c1_fixture_exact(orc_lib, which):
     out, res = checker.process_sheets_cpu(lib, prefix, G.c1_config(), page.reshape(1, h, 3 * w), w, h, U.FMT_RGB24)
     assert np.array_equal(out[0].reshape(h, w, 3), golden)
     assert G.result_dict(res[0]) == GOLD["C1"]["result"]
+
+
+def _small_pages(seed0, n, w=620, h=877):
+    return np.stack([synth.gray_page(seed0 + i, w, h, box=(0.60, 0.72)) for i in range(n)])
+
+
+@pytest.mark.parametrize("case", ["mirror_shift", "two_pages", "wipes_borders", "mono_pages", "stage_switches"])
+def test_orc_sheet_vs_ref_configurations(orc_lib, ref_lib, case):
+    """The restatement against the unmodified reference over the configuration space the
+    engine tests use: geometry options, two pages per sheet, static rectangles, 1-bit pages,
+    stage switches — decisions and every output byte."""
+    w, h, fmt = 620, 877, U.FMT_GRAY8
+    cfg = U.default_sheet_config()
+    pages = _small_pages(300, 2)
+    if case == "mirror_shift":
+        cfg.pre_mirror, cfg.pre_shift = U.Direction(True, False), U.Delta(7, -5)
+        cfg.post_mirror, cfg.post_shift = U.Direction(False, True), U.Delta(-3, 11)
+    elif case == "two_pages":
+        cfg.input_count, cfg.layout = 2, U.LAYOUT_DOUBLE
+        pages = _small_pages(310, 4)
+    elif case == "wipes_borders":
+        cfg.pre_wipe_count = 1; cfg.pre_wipes[0] = U.rect(100, 120, 160, 170)
+        cfg.wipe_count = 2; cfg.wipes[0] = U.rect(300, 400, 340, 460); cfg.wipes[1] = U.rect(-5, 800, 50, 900)
+        cfg.post_wipe_count = 1; cfg.post_wipes[0] = U.rect(500, 50, 619, 90)
+        cfg.pre_border = U.Border(3, 4, 5, 6); cfg.border = U.Border(10, 0, 0, 12); cfg.post_border = U.Border(0, 7, 8, 0)
+        cfg.pre_mask_count = 1; cfg.pre_masks[0] = U.rect(20, 20, 600, 860)
+        cfg.noisefilter_intensity = 6
+        cfg.point_count = 1; cfg.points[0] = U.Point(300, 430)
+        cfg.mask_color = U.Pixel(200, 200, 200); cfg.sheet_background = U.Pixel(250, 250, 250)
+    elif case == "mono_pages":
+        w, h, fmt = 624, 880, U.FMT_MONOWHITE
+        pages = np.stack([np.packbits(synth.gray_page(320 + i, w, h, box=(0.60, 0.72)) < 128, axis=1) for i in range(2)])
+    elif case == "stage_switches":
+        cfg.no_mask_center = cfg.no_border_align = cfg.no_grayfilter = 1
+    a, ra = checker.process_sheets_cpu(orc_lib, "orc_", cfg, pages, w, h, fmt, threads=2)
+    b, rb = checker.process_sheets_cpu(ref_lib, "ref_", cfg, pages, w, h, fmt, threads=2)
+    assert [G.result_dict(r) for r in ra] == [G.result_dict(r) for r in rb]
+    assert np.array_equal(a, b)
