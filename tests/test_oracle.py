@@ -207,3 +207,18 @@ def test_orc_sheet_vs_ref_configurations(orc_lib, ref_lib, case):
     b, rb = checker.process_sheets_cpu(ref_lib, "ref_", cfg, pages, w, h, fmt, threads=2)
     assert [G.result_dict(r) for r in ra] == [G.result_dict(r) for r in rb]
     assert np.array_equal(a, b)
+
+
+def test_orc_ops_fuzz_vs_ref(orc_ops, ref_ops):
+    """The seeded parameter fuzz of test_gpu_fuzz.py, restatement against the live reference."""
+    import test_gpu_fuzz as Z
+    for seed in range(16):
+        Z.test_fuzz_blackfilter(orc_ops, ref_ops, seed)
+        Z.test_fuzz_noisefilter(orc_ops, ref_ops, seed)
+    for seed in range(10):
+        Z.test_fuzz_gray_blur(orc_ops, ref_ops, seed)
+        Z.test_fuzz_deskew(orc_ops, ref_ops, seed)
+        Z.test_fuzz_detect_border_and_masks(orc_ops, ref_ops, seed)
+        Z.test_fuzz_moves(orc_ops, ref_ops, seed)
+    for seed in range(12):
+        Z.test_fuzz_detect_rotation(orc_ops, ref_ops, seed)
