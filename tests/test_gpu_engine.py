@@ -226,3 +226,47 @@ def test_engine_reference_golden_c1():
         assert res[i].status == 0
         assert np.array_equal(out[i].reshape(h, w, 3), golden), f"sheet {i}"
         assert U.border_tuple(res[i].borders[0]) == (35, 20, 16, 21)
+
+
+def _overlap_cfg(edges=(False, False, True, False)):
+    """Two user points whose masks hit the maximum-width fallback (masks.c:149-169) and
+    therefore overlap: detect_rotation(mask 1) must see mask 0 already deskewed
+    (sheet_stages.c:406-413).  One scan edge, because the other edge of each mask cuts
+    through the text."""
+    cfg = U.default_sheet_config()
+    cfg.point_count = 2
+    cfg.points[0] = U.Point(250, 430); cfg.points[1] = U.Point(370, 430)
+    cfg.mask_detection.maximum_width = 300
+    cfg.deskew.scan_edges = U.Edges(*edges)
+    return cfg
+
+
+def test_engine_overlapping_masks(ref_lib):
+    w, h = 620, 877
+    pages = np.stack([synth.gray_page(200 + i, w, h, box=SMALL_BOX) for i in range(4)])
+    for edges in ((False, False, True, False), (True, False, False, False)):
+        out, res = _compare(_overlap_cfg(edges), pages, w, h, U.FMT_GRAY8, ref_lib, group=2, lanes=2)
+        overl = 0
+        for r in res:
+            assert r.deskew_mask_count == 2
+            a, b = U.rect_tuple(r.deskew_masks[0]), U.rect_tuple(r.deskew_masks[1])
+            overl += a != b and a[2] >= b[0] and r.rotation[0] != 0.0
+        assert overl >= 3, "the fixture no longer produces overlapping, rotated masks"
+    # double layout on a width divisible by 4: the fallback masks share column W/2
+    w2 = 1240
+    pages2 = np.stack([synth.double_sheet(210 + i, w2, h) for i in range(2)])
+    cfg = U.default_sheet_config()
+    cfg.layout = U.LAYOUT_DOUBLE
+    cfg.mask_detection.maximum_width = 400
+    _compare(cfg, pages2, w2, h, U.FMT_GRAY8, ref_lib, group=2, lanes=1)
+
+
+@pytest.mark.parametrize("edges", [(True, True, True, True), (True, True, True, False), (False, True, False, True)])
+def test_engine_deskew_scan_edges(ref_lib, edges):
+    """3-4 scan edges: average / deviation / sinf / cosf of deskew.c:218-261 come from the
+    host's libm through a stream-ordered host function; top/bottom edges use the sampling kernel."""
+    w, h = 620, 877
+    pages = np.stack([synth.gray_page(220 + i, w, h, box=SMALL_BOX) for i in range(3)])
+    cfg = U.default_sheet_config()
+    cfg.deskew.scan_edges = U.Edges(*edges)
+    out, res = _compare(cfg, pages, w, h, U.FMT_GRAY8, ref_lib, group=2, lanes=2)

@@ -66,6 +66,9 @@ typedef struct {
   DRect *static_mask_rects[3];
   uint8_t *out_host; uint8_t *out_dev;
   int host_mode;
+  /* detect_rotation's host tail (3-4 scan edges): see stages.c:rot_host_tail */
+  RotHostJob rot_jobs[2][D_MAX_MASKS];
+  DPage *rot_pull; float *rot_tab_host, *rot_tab_dev;
 } Lane;
 
 struct B200Engine {
@@ -214,6 +217,9 @@ static void lane_free(Lane *ln) {
     if (ln->fl[ln->slot].done_t) cudaEventDestroy(ln->fl[ln->slot].done_t);
     for (int i = 0; i <= STG_COUNT; i++) if (ln->fl[ln->slot].ev[i]) cudaEventDestroy(ln->fl[ln->slot].ev[i]);
   }
+  if (ln->rot_pull) b200_pinned_free(ln->rot_pull);
+  if (ln->rot_tab_host) b200_pinned_free(ln->rot_tab_host);
+  if (ln->rot_tab_dev) b200_dev_free(ln->rot_tab_dev);
   if (ln->st) b200_stream_release(ln->st);
   memset(ln, 0, sizeof(*ln));
 }
@@ -336,6 +342,11 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
     ln->ink = (uint8_t *)b200_dev_alloc(ink_stride * P);
     ln->page_stage = (uint8_t *)b200_dev_alloc(e->page_bytes * cfg->input_count * P + 64);
     ln->pages_dev = (DPage *)b200_dev_alloc(sizeof(DPage) * P);
+    if (!cfg->no_deskew && e->rot.host_tail) {
+      ln->rot_pull = (DPage *)b200_pinned_alloc(sizeof(DPage) * P);
+      ln->rot_tab_host = (float *)b200_pinned_alloc(sizeof(float) * 4 * P);
+      ln->rot_tab_dev = (float *)b200_dev_alloc(sizeof(float) * 4 * P);
+    }
     ln->pages_tmpl = (DPage *)calloc((size_t)P, sizeof(DPage));
     ln->fillA = (DFillJob *)b200_dev_alloc(sizeof(DFillJob) * P);
     ln->fillB = (DFillJob *)b200_dev_alloc(sizeof(DFillJob) * P);
@@ -455,6 +466,7 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
   c.st = ln->st; c.npages = n; c.pages = ln->pages_dev; c.w = e->sheet_w; c.h = e->sheet_h; c.fmt = e->dfmt;
   c.rows_aligned16 = (e->sheet_pitch & 15) == 0;   /* slabs are 256-byte aligned, strides multiples of 256 */
   c.fillA = ln->fillA; c.fillB = ln->fillB; c.fillC = ln->fillC; c.copyA = ln->copyA; c.copyB = ln->copyB; c.maskJ = ln->maskJ;
+  if (ln->rot_pull) { c.rot_jobs = ln->rot_jobs[ln->slot]; c.rot_pull = ln->rot_pull; c.rot_tab_host = ln->rot_tab_host; c.rot_tab_dev = ln->rot_tab_dev; }
   ln->fl[ln->slot].ev_mask = 0;
   int ic = cfg->input_count;
 
@@ -489,9 +501,14 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
   if (!cfg->no_deskew) {
     if (!cfg->no_mask_scan) stage_detect_masks(&c, &e->mask);
     mark(e, ln, STG_ROTDET);
-    stage_detect_rotation(&c, &e->rot, nm);
-    mark(e, ln, STG_DESKEW);
-    stage_deskew(&c, cfg->interpolate_type, nm);
+    /* mask by mask like sheet_stages.c:406-413: detect_rotation(mask i+1) sees the
+     * sheet with mask i already deskewed (the masks may share pixels) */
+    for (int mi = 0; mi < nm; mi++) {
+      stage_detect_rotation_mask(&c, &e->rot, mi);
+      if (mi == nm - 1) mark(e, ln, STG_DESKEW);   /* profile split: exact for one mask */
+      stage_deskew_mask(&c, cfg->interpolate_type, mi);
+    }
+    if (nm == 0) mark(e, ln, STG_DESKEW);
   } else { mark(e, ln, STG_ROTDET); mark(e, ln, STG_DESKEW); }
   mark(e, ln, STG_CENTER);
   if (!cfg->no_mask_center) {

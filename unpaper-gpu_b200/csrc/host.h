@@ -65,8 +65,12 @@ typedef struct {
   int peak_off, u32_need, scan_cap;
   long long pre_need;              /* u32 elements of column-prefix scratch per page */
   int run_cap;                     /* max vertical runs of a scan line (0: too many for the warp kernel) */
+  int host_tail;                   /* no pair table for this case: average/deviation/sin/cos come from the host's libm */
   DeskewParameters p;
 } RotPlan;
+
+/* stream-ordered host evaluation of detect_rotation's float tail (stages.c:rot_host_tail) */
+typedef struct { const RotPlan *pl; const DPage *pulled; float *tab; int n, mi; } RotHostJob;
 
 int bf_plan_build(BfPlan *pl, int w, int h, const BlackfilterParameters *p, int abs_black_threshold);
 void bf_plan_free(BfPlan *pl);
@@ -94,6 +98,10 @@ typedef struct {
   DFillJob *fillA, *fillB, *fillC; /* device job arrays, npages each */
   DCopyJob *copyA, *copyB;
   DMaskJob *maskJ;
+  /* engine only (NULL in the vtable, which finishes detect_rotation on the host itself) */
+  RotHostJob *rot_jobs;       /* host memory, D_MAX_MASKS entries that stay valid until the group is done */
+  DPage *rot_pull;            /* pinned, npages records */
+  float *rot_tab_host, *rot_tab_dev;   /* pinned / device, 4 floats per page */
   uint64_t launches;
 } StageCtx;
 
@@ -103,7 +111,9 @@ void stage_blurfilter(StageCtx *c, const BlurPlan *pl);
 int stage_grayfilter(StageCtx *c, const GrayPlan *pl);
 void stage_detect_masks(StageCtx *c, const MaskPlan *pl);
 int stage_detect_rotation(StageCtx *c, const RotPlan *pl, int max_masks);
+int stage_detect_rotation_mask(StageCtx *c, const RotPlan *pl, int mi);
 void stage_deskew(StageCtx *c, int interp, int max_masks);
+void stage_deskew_mask(StageCtx *c, int interp, int mi);
 void stage_center_masks(StageCtx *c, int max_masks);
 void stage_detect_border(StageCtx *c, const BorderPlan *pl);
 void stage_apply_border_masks(StageCtx *c, Pixel color);

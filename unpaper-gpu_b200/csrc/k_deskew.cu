@@ -24,12 +24,12 @@ struct RotParams {
 };
 
 // detect_edge_rotation_peak (deskew.c:48-142) for one (page, mask, edge, angle)
-__global__ void k_rot_peaks(DPage *pages, const float *tan_tab, RotParams rp) {
+__global__ void k_rot_peaks(DPage *pages, const float *tan_tab, RotParams rp, int mi0) {
   extern __shared__ int2 pts[];
   __shared__ int s_red[8][ROT_CHUNK];
   __shared__ int s_done, s_max, s_dep;
   DPage &pg = pages[blockIdx.z];
-  int a = blockIdx.x, mi = blockIdx.y >> 2, e = blockIdx.y & 3;
+  int a = blockIdx.x, mi = mi0 + (blockIdx.y >> 2), e = blockIdx.y & 3;
   if (mi >= pg.mask_count || !rp.edges[e]) return;
   const DImg &im = pg.img;
   DRect mask = pg.masks[mi];
@@ -381,6 +381,7 @@ struct RotFinalParams {
   int peak_off;
   float deviation;
   int use_table;         // 1: pair table indexed [vi][vj], v = sign*nangles + angle
+  int mi_first, mi_count; // masks to finalize (the engine goes mask by mask, sheet_stages.c:406-413)
 };
 
 // detect_edge_rotation's argmax (deskew.c:156-168) + detect_rotation_cpu's
@@ -390,6 +391,7 @@ __global__ void k_rot_finalize(DPage *pages, int npages, const float *rot_tab, c
   int p = t / D_MAX_MASKS, mi = t % D_MAX_MASKS;
   if (p >= npages) return;
   DPage &pg = pages[p];
+  if (mi < fp.mi_first || mi >= fp.mi_first + fp.mi_count) return;
   if (mi == 0) pg.mask_count_deskew = pg.mask_count;
   if (mi >= pg.mask_count) return;
   pg.masks_deskew[mi] = pg.masks[mi];
@@ -435,6 +437,18 @@ __global__ void k_rot_finalize(DPage *pages, int npages, const float *rot_tab, c
   pg.rotation[mi] = result;
   pg.rot_sin[mi] = s; pg.rot_cos[mi] = c;
   pg.rot_apply[mi] = result != 0.0f;
+}
+
+// the float tail of detect_rotation_cpu (deskew.c:218-240) evaluated by the host's libm
+// (3-4 scan edges: no pair table): tab[page] = {rotation, sinf(-rotation), cosf(-rotation), -}
+__global__ void k_rot_set(DPage *pages, int npages, int mi, const float *tab) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npages) return;
+  DPage &pg = pages[p];
+  if (mi >= pg.mask_count) return;
+  float r = tab[p * 4 + 0];
+  pg.rotation[mi] = r; pg.rot_sin[mi] = tab[p * 4 + 1]; pg.rot_cos[mi] = tab[p * 4 + 2];
+  pg.rot_apply[mi] = r != 0.0f;
 }
 
 // ---- interpolation (interpolate.c:13-129) ----------------------------------
@@ -712,10 +726,10 @@ __global__ void k_stretch(DImg src, DImg dst, float hr, float vr, int interp) {
 }
 
 extern "C" {
-int b200k_rot_peaks(cudaStream_t st, DPage *pages, int npages, int max_masks, const float *tan_tab_dev,
+int b200k_rot_peaks(cudaStream_t st, DPage *pages, int npages, int mi_first, int mi_count, const float *tan_tab_dev,
                     int nangles, int scan_size_param, float scan_depth, const int edges[4],
                     int peak_off, int scan_cap, int maxw, int use_prefix, int run_cap) {
-  if (npages <= 0 || max_masks <= 0 || nangles <= 0) return 0;
+  if (npages <= 0 || mi_count <= 0 || nangles <= 0) return 0;
   RotParams rp;
   rp.scan_size = scan_size_param; rp.scan_depth = scan_depth; rp.nangles = nangles; rp.peak_off = peak_off;
   for (int i = 0; i < 4; i++) rp.edges[i] = edges[i];
@@ -727,7 +741,7 @@ int b200k_rot_peaks(cudaStream_t st, DPage *pages, int npages, int max_masks, co
   }
   bool horiz = edges[0] || edges[2], vert = edges[1] || edges[3];
   if (use_prefix && horiz) {
-    for (int mi = 0; mi < max_masks; mi++) {
+    for (int mi = mi_first; mi < mi_first + mi_count; mi++) {
       k_rot_colprefix<<<dim3(cdiv(maxw, 128), npages), 32 * RP_SEG, 0, st>>>(pages, mi, scan_size_param);
       if (run_cap > 0) {
         int rstride = run_cap | 1;   // odd stride: the lanes of phase A hit different banks
@@ -740,19 +754,24 @@ int b200k_rot_peaks(cudaStream_t st, DPage *pages, int npages, int max_masks, co
     rp.edges[0] = 0; rp.edges[2] = 0;   // the sampling kernel below only does what is left
   }
   if ((!use_prefix && horiz) || vert) {
-    dim3 g(nangles, max_masks * 4, npages);
-    k_rot_peaks<<<g, 256, sm, st>>>(pages, tan_tab_dev, rp);
+    dim3 g(nangles, mi_count * 4, npages);
+    k_rot_peaks<<<g, 256, sm, st>>>(pages, tan_tab_dev, rp, mi_first);
   }
   return 0;
 }
 void b200k_rot_finalize(cudaStream_t st, DPage *pages, int npages, const float *rot_tab_dev,
                         const float *pair_tab_dev, int nangles, const int edges[4], int peak_off,
-                        float deviation) {
+                        float deviation, int mi_first, int mi_count) {
   if (npages <= 0) return;
   RotFinalParams fp;
   fp.nangles = nangles; fp.peak_off = peak_off; fp.deviation = deviation; fp.use_table = pair_tab_dev != NULL;
+  fp.mi_first = mi_first; fp.mi_count = mi_count;
   for (int i = 0; i < 4; i++) fp.edges[i] = edges[i];
   k_rot_finalize<<<cdiv(npages * D_MAX_MASKS, 64), 64, 0, st>>>(pages, npages, rot_tab_dev, pair_tab_dev, fp);
+}
+void b200k_rot_set_sincos(cudaStream_t st, DPage *pages, int npages, int mi, const float *tab_dev) {
+  if (npages <= 0) return;
+  k_rot_set<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages, mi, tab_dev);
 }
 void b200k_rotate(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int maxw, int maxh,
                   DCopyJob *back_jobs) {

@@ -55,12 +55,15 @@ void b200k_blur_wipe(cudaStream_t st, DPage *pages, int npages, int n, int nrows
 void b200k_gray_cascade(cudaStream_t st, DPage *pages, int npages, const int *gp18, int white_off);
 
 /* k_deskew.cu */
-int b200k_rot_peaks(cudaStream_t st, DPage *pages, int npages, int max_masks, const float *tan_tab_dev,
+int b200k_rot_peaks(cudaStream_t st, DPage *pages, int npages, int mi_first, int mi_count, const float *tan_tab_dev,
                     int nangles, int scan_size_param, float scan_depth, const int edges[4],
                     int peak_off, int scan_cap, int maxw, int use_prefix, int run_cap /* 0: one CTA per angle */);
 void b200k_rot_finalize(cudaStream_t st, DPage *pages, int npages, const float *rot_tab_dev,
                         const float *pair_tab_dev, int nangles, const int edges[4], int peak_off,
-                        float deviation);
+                        float deviation, int mi_first, int mi_count);
+/* sin/cos of -rotation for mask `mi` of every page from a host-computed table
+ * sc[page] = {sin, cos} (only with 3-4 scan edges, where no pair table exists) */
+void b200k_rot_set_sincos(cudaStream_t st, DPage *pages, int npages, int mi, const float *sc_dev);
 void b200k_rotate(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int maxw, int maxh,
                   DCopyJob *back_jobs);
 void b200k_stretch(cudaStream_t st, DImg src, DImg dst, float hr, float vr, int interp);

@@ -299,6 +299,7 @@ int rot_plan_build(RotPlan *pl, int w, int h, const DeskewParameters *p, int max
   pl->tan_dev = (float *)blob_upload(pl->tan_host, sizeof(float) * n);
   pl->edges[0] = p->scan_edges.left; pl->edges[1] = p->scan_edges.top;
   pl->edges[2] = p->scan_edges.right; pl->edges[3] = p->scan_edges.bottom;
+  pl->host_tail = (pl->edges[0] != 0) + (pl->edges[1] != 0) + (pl->edges[2] != 0) + (pl->edges[3] != 0) > 2 || !(with_pair && n <= 512);
   pl->peak_off = 0;
   pl->u32_need = max_masks * 4 * n + 1;
   int sc = p->deskewScanSize == -1 ? imax(w, h) : p->deskewScanSize;
@@ -412,24 +413,57 @@ void stage_detect_masks(StageCtx *c, const MaskPlan *pl) {
   c->launches += 2;
 }
 
-int stage_detect_rotation(StageCtx *c, const RotPlan *pl, int max_masks) {
-  int rc = b200k_rot_peaks(c->st, c->pages, c->npages, max_masks, pl->tan_dev, pl->nangles,
+/* detect_rotation_cpu's float tail (deskew.c:218-240) needs the host's libm when no
+ * pair table covers the case (3-4 scan edges, or more than 512 angles): the angle
+ * indices come back through pinned memory, a stream-ordered host function evaluates
+ * rot_finalize_host + sinf/cosf, the values go back up.  No host thread blocks. */
+static void CUDART_CB rot_host_tail(void *arg) {
+  RotHostJob *j = (RotHostJob *)arg;
+  for (int p = 0; p < j->n; p++) {
+    float r = rot_finalize_host(j->pl, j->pulled[p].rot_angle_idx[j->mi]);
+    float *t = j->tab + 4 * p;
+    t[0] = r; t[1] = sinf(-r); t[2] = cosf(-r); t[3] = 0.0f;   /* deskew.c:260-261 */
+  }
+}
+
+/* detect_rotation() of mask `mi` on every page of the group */
+int stage_detect_rotation_mask(StageCtx *c, const RotPlan *pl, int mi) {
+  int rc = b200k_rot_peaks(c->st, c->pages, c->npages, mi, 1, pl->tan_dev, pl->nangles,
                            pl->p.deskewScanSize, pl->p.deskewScanDepth, pl->edges, pl->peak_off, pl->scan_cap,
                            c->w, 1, pl->run_cap);
   if (rc) { b200_set_error("deskew: scan size too large"); return rc; }
   b200k_rot_finalize(c->st, c->pages, c->npages, pl->rot_dev, pl->pair_dev, pl->nangles, pl->edges,
-                     pl->peak_off, pl->p.deskewScanDeviationRad);
-  c->launches += 2 + 2 * max_masks;
+                     pl->peak_off, pl->p.deskewScanDeviationRad, mi, 1);
+  c->launches += ((pl->edges[0] || pl->edges[2]) ? 2 : 0) + ((pl->edges[1] || pl->edges[3]) ? 1 : 0) + 1;
+  if (pl->host_tail && c->rot_jobs) {
+    RotHostJob *j = &c->rot_jobs[mi];
+    j->pl = pl; j->pulled = c->rot_pull; j->tab = c->rot_tab_host; j->n = c->npages; j->mi = mi;
+    CUDA_OK(cudaMemcpyAsync(c->rot_pull, c->pages, sizeof(DPage) * c->npages, cudaMemcpyDeviceToHost, c->st));
+    CUDA_OK(cudaLaunchHostFunc(c->st, rot_host_tail, j));
+    CUDA_OK(cudaMemcpyAsync(c->rot_tab_dev, c->rot_tab_host, sizeof(float) * 4 * c->npages, cudaMemcpyHostToDevice, c->st));
+    b200k_rot_set_sincos(c->st, c->pages, c->npages, mi, c->rot_tab_dev);
+    c->launches += 1;
+  }
   return 0;
 }
 
-void stage_deskew(StageCtx *c, int interp, int max_masks) {
-  int aw = c->w + 64, ah = c->h + 64;
+int stage_detect_rotation(StageCtx *c, const RotPlan *pl, int max_masks) {
   for (int mi = 0; mi < max_masks; mi++) {
-    b200k_rotate(c->st, c->pages, c->npages, mi, interp, aw, ah, c->copyA);
-    b200k_copy_jobs(c->st, c->copyA, c->npages, aw * bppf(c->fmt), ah);
-    c->launches += 2;
+    int rc = stage_detect_rotation_mask(c, pl, mi);
+    if (rc) return rc;
   }
+  return 0;
+}
+
+void stage_deskew_mask(StageCtx *c, int interp, int mi) {
+  int aw = c->w + 64, ah = c->h + 64;
+  b200k_rotate(c->st, c->pages, c->npages, mi, interp, aw, ah, c->copyA);
+  b200k_copy_jobs(c->st, c->copyA, c->npages, aw * bppf(c->fmt), ah);
+  c->launches += 2 + (interp == 2);
+}
+
+void stage_deskew(StageCtx *c, int interp, int max_masks) {
+  for (int mi = 0; mi < max_masks; mi++) stage_deskew_mask(c, interp, mi);
 }
 
 static void run_move(StageCtx *c) {
