@@ -64,3 +64,70 @@ def process_sheets_cpu(lib, prefix, cfg, pages, page_w, page_h, fmt, threads=1, 
     if rc != 0:
         raise RuntimeError(f"{prefix}process_sheets: {rc}")
     return out, list(res)
+
+
+def read_pnm(path):
+    """(format, width, height, uint8 array [h, row_bytes]) of a P4 / P5 / P6 file as the
+    reference's saveImageDirect() writes it (file.c:134-176)."""
+    from unpaper_gpu_b200.abi import FMT_GRAY8, FMT_MONOWHITE, FMT_RGB24
+    with open(path, "rb") as f:
+        data = f.read()
+    magic = data[:2]
+    fmt = {b"P4": FMT_MONOWHITE, b"P5": FMT_GRAY8, b"P6": FMT_RGB24}[magic]
+    fields, pos = [], 2
+    need = 2 if magic == b"P4" else 3
+    while len(fields) < need:
+        while data[pos:pos + 1].isspace():
+            pos += 1
+        end = pos
+        while not data[end:end + 1].isspace():
+            end += 1
+        fields.append(int(data[pos:end]))
+        pos = end
+    pos += 1   # the single whitespace byte after the header
+    w, h = fields[0], fields[1]
+    row = bytes_per_row(fmt, w)
+    return fmt, w, h, np.frombuffer(data, dtype=np.uint8, count=row * h, offset=pos).reshape(h, row).copy()
+
+
+def process_sheets_files_cpu(lib, cfg, pages, page_w, page_h, fmt, out_fmt=-1, output_count=1, threads=1):
+    """The reference's process_sheet() WITH its output stage (sheet_stages.c:536-631 ->
+    saveImage, file.c:186-262).  Returns ([per sheet: [per output page: (fmt, w, h, array)]], results)."""
+    import shutil
+    import tempfile
+    row = bytes_per_row(fmt, page_w)
+    per_sheet = row * page_h * cfg.input_count
+    pages = np.ascontiguousarray(pages, dtype=np.uint8).reshape(-1)
+    n = pages.size // per_sheet
+    res = (SheetResult * n)()
+    lib.ref_process_sheets_files.argtypes = [
+        C.POINTER(SheetConfig), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+        C.c_char_p, C.POINTER(SheetResult), C.c_int]
+    lib.ref_process_sheets_files.restype = C.c_int
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    d = tempfile.mkdtemp(prefix="unpaper_ref_", dir=base)
+    try:
+        rc = lib.ref_process_sheets_files(C.byref(cfg), pages.ctypes.data, page_w, page_h, fmt, n, out_fmt,
+                                          output_count, d.encode(), res, threads)
+        if rc != 0:
+            raise RuntimeError(f"ref_process_sheets_files: {rc}")
+        out = [[read_pnm(os.path.join(d, f"s{i:06d}_{j}.pnm")) for j in range(output_count)] for i in range(n)]
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    return out, list(res)
+
+
+def save_image_cpu(lib, himg, out_fmt):
+    """The reference's saveImage() (file.c:186-262) on one image; returns (fmt, w, h, array)."""
+    import tempfile
+    from unpaper_gpu_b200.abi import HostImage
+    lib.ref_save_image.argtypes = [C.POINTER(HostImage), C.c_int, C.c_char_p]
+    lib.ref_save_image.restype = C.c_int
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    fd, path = tempfile.mkstemp(prefix="unpaper_ref_", suffix=".pnm", dir=base)
+    os.close(fd)
+    try:
+        lib.ref_save_image(C.byref(himg), out_fmt, path.encode())
+        return read_pnm(path)
+    finally:
+        os.unlink(path)

@@ -41,18 +41,38 @@
 
 /* ---- symbols the reference expects from files we do not compile ---------- */
 
-void loadImage(const char *filename, Image *image, Pixel sheet_background,
-               uint8_t abs_black_threshold) {
-  (void)filename; (void)image; (void)sheet_background; (void)abs_black_threshold;
-  errOutput("ref_harness: loadImage is not available (pages are injected)");
-}
-void saveImage(char *filename, Image image, int fmt) {
-  (void)filename; (void)image; (void)fmt;
-}
-int detectPixelFormatFromExtension(const char *filename) {
-  (void)filename;
-  return AV_PIX_FMT_NONE;
-}
+/* file.c (loadImage / saveImage / detectPixelFormatFromExtension) is compiled from the
+ * reference against oracle/shim_codec; its FFmpeg calls land here.  saveImage() converts
+ * and hands GRAY8 / RGB24 / MONOWHITE to saveImageDirect() (file.c:134-176), which covers
+ * every format saveImage() can produce, so none of these is reached by the tests. */
+#include <libavformat/avformat.h>
+#include <libavutil/opt.h>
+const AVCodec *avcodec_find_decoder(enum AVCodecID id) { (void)id; return NULL; }
+const AVCodec *avcodec_find_encoder(enum AVCodecID id) { (void)id; return NULL; }
+AVCodecContext *avcodec_alloc_context3(const AVCodec *c) { (void)c; return NULL; }
+int avcodec_parameters_to_context(AVCodecContext *c, const AVCodecParameters *p) { (void)c; (void)p; return -1; }
+int avcodec_open2(AVCodecContext *c, const AVCodec *k, void *o) { (void)c; (void)k; (void)o; return -1; }
+int avcodec_send_packet(AVCodecContext *c, const AVPacket *p) { (void)c; (void)p; return -1; }
+int avcodec_receive_frame(AVCodecContext *c, AVFrame *f) { (void)c; (void)f; return -1; }
+int avcodec_send_frame(AVCodecContext *c, const AVFrame *f) { (void)c; (void)f; return -1; }
+int avcodec_receive_packet(AVCodecContext *c, AVPacket *p) { (void)c; (void)p; return -1; }
+void avcodec_free_context(AVCodecContext **c) { (void)c; }
+AVPacket *av_packet_alloc(void) { return NULL; }
+void av_packet_free(AVPacket **p) { (void)p; }
+int avformat_open_input(AVFormatContext **s, const char *u, void *f, void *o) { (void)s; (void)u; (void)f; (void)o; return -1; }
+int avformat_find_stream_info(AVFormatContext *s, void *o) { (void)s; (void)o; return -1; }
+void av_dump_format(AVFormatContext *s, int i, const char *u, int o) { (void)s; (void)i; (void)u; (void)o; }
+int av_read_frame(AVFormatContext *s, AVPacket *p) { (void)s; (void)p; return -1; }
+void avformat_close_input(AVFormatContext **s) { (void)s; }
+int avformat_alloc_output_context2(AVFormatContext **c, void *of, const char *n, const char *f) { (void)of; (void)n; (void)f; if (c) *c = NULL; return -1; }
+AVStream *avformat_new_stream(AVFormatContext *s, const AVCodec *c) { (void)s; (void)c; return NULL; }
+int avio_open(AVIOContext **s, const char *u, int f) { (void)s; (void)u; (void)f; return -1; }
+int avformat_write_header(AVFormatContext *s, void *o) { (void)s; (void)o; return -1; }
+int av_write_frame(AVFormatContext *s, AVPacket *p) { (void)s; (void)p; return -1; }
+int av_write_trailer(AVFormatContext *s) { (void)s; return -1; }
+void avformat_free_context(AVFormatContext *s) { (void)s; }
+int av_opt_set(void *o, const char *n, const char *v, int f) { (void)o; (void)n; (void)v; (void)f; return -1; }
+void saveImage(char *filename, Image image, int fmt);   /* file.c:186 */
 struct EncodeQueue;
 bool encode_queue_gpu_enabled(struct EncodeQueue *q) { (void)q; return false; }
 bool encode_queue_submit_gpu(struct EncodeQueue *q, void *p, size_t pitch, int w,
@@ -372,7 +392,7 @@ static void options_from_cfg(Options *o, Rectangle *bf_excl, const B200SheetConf
 /* One sheet: pages -> reference process_sheet() -> sheet in the page format. */
 static int run_one_sheet(const B200SheetConfig *cfg, const Options *opt,
                          const uint8_t *pages, int page_w, int page_h, int page_fmt,
-                         uint8_t *out, B200SheetResult *res) {
+                         uint8_t *out, B200SheetResult *res, char **out_files, int out_count) {
   int row = av_shim_row_bytes(page_fmt, page_w);
   if (row < 0) return -1;
   size_t page_bytes = (size_t)row * page_h;
@@ -389,7 +409,8 @@ static int run_one_sheet(const B200SheetConfig *cfg, const Options *opt,
   memset(&job, 0, sizeof(job));
   job.sheet_nr = 1;
   job.input_count = cfg->input_count;
-  job.output_count = 1;
+  job.output_count = out_files ? out_count : 1;
+  for (int j = 0; out_files && j < out_count; j++) job.output_files[j] = out_files[j];
   job.layout_override = -1;
 
   SheetProcessState st;
@@ -435,6 +456,7 @@ typedef struct {
   const uint8_t *pages;
   uint8_t *out;
   B200SheetResult *results;
+  const char *out_dir; int out_count;   /* write_output runs: files <dir>/s<sheet>_<page>.pnm */
   int page_w, page_h, page_fmt, n_sheets;
   size_t sheet_in_bytes, sheet_out_bytes;
   atomic_int next;
@@ -446,10 +468,14 @@ static void *worker(void *arg) {
   for (;;) {
     int i = atomic_fetch_add(&jb->next, 1);
     if (i >= jb->n_sheets) break;
+    char names[2][512];
+    char *files[2] = {names[0], names[1]};
+    for (int j = 0; jb->out_dir && j < jb->out_count && j < 2; j++)
+      snprintf(names[j], sizeof(names[j]), "%s/s%06d_%d.pnm", jb->out_dir, i, j);
     int rc = run_one_sheet(jb->cfg, jb->opt, jb->pages + (size_t)i * jb->sheet_in_bytes,
                            jb->page_w, jb->page_h, jb->page_fmt,
                            jb->out ? jb->out + (size_t)i * jb->sheet_out_bytes : NULL,
-                           jb->results ? &jb->results[i] : NULL);
+                           jb->results ? &jb->results[i] : NULL, jb->out_dir ? files : NULL, jb->out_count);
     if (rc != 0) atomic_fetch_add(&jb->failed, 1);
   }
   return NULL;
@@ -487,6 +513,52 @@ int ref_process_sheets(const B200SheetConfig *cfg, const uint8_t *pages, int pag
     free(th);
   }
   return -atomic_load(&jb.failed);
+}
+
+/* The same with the reference's own output stage (sheet_stages.c:536-631): write_output
+ * on, `output_count` files per sheet (1, or 2 = the sheet split of :606-621) written by the
+ * reference's saveImage() (file.c:186-262: format conversion + saveImageDirect) as
+ * <out_dir>/s<sheet>_<page>.pnm.  out_fmt: AVPixelFormat or -1 (= the page format,
+ * sheet_stages.c:130-131). */
+int ref_process_sheets_files(const B200SheetConfig *cfg, const uint8_t *pages, int page_w,
+                             int page_h, int page_fmt, int n_sheets, int out_fmt, int output_count,
+                             const char *out_dir, B200SheetResult *results, int threads) {
+  ensure_init();
+  if (output_count < 1 || output_count > 2 || !out_dir) return -1;
+  Options opt;
+  static __thread Rectangle bf_excl[MAX_MASKS];
+  options_from_cfg(&opt, bf_excl, cfg);
+  opt.write_output = true;
+  opt.output_count = output_count;
+  opt.output_pixel_format = out_fmt < 0 ? AV_PIX_FMT_NONE : out_fmt;
+  int row = av_shim_row_bytes(page_fmt, page_w);
+  if (row < 0) return -1;
+  Job jb = {.cfg = cfg, .opt = &opt, .pages = pages, .out = NULL, .results = results,
+            .out_dir = out_dir, .out_count = output_count,
+            .page_w = page_w, .page_h = page_h, .page_fmt = page_fmt, .n_sheets = n_sheets,
+            .sheet_in_bytes = (size_t)row * page_h * cfg->input_count, .sheet_out_bytes = 0};
+  atomic_init(&jb.next, 0);
+  atomic_init(&jb.failed, 0);
+  if (threads <= 1) {
+    worker(&jb);
+  } else {
+    pthread_t *th = calloc((size_t)threads, sizeof(*th));
+    for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, worker, &jb);
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    free(th);
+  }
+  return -atomic_load(&jb.failed);
+}
+
+/* The reference's saveImage() (file.c:186-262) on an image in caller memory. */
+int ref_save_image(const B200HostImage *in, int out_fmt, const char *path) {
+  ensure_init();
+  Image img = clone_owned(in);
+  char *p = strdup(path);
+  saveImage(p, img, out_fmt);
+  free(p);
+  free_image(&img);
+  return 0;
 }
 
 int ref_online_cpus(void) { return (int)sysconf(_SC_NPROCESSORS_ONLN); }

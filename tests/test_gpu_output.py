@@ -1,9 +1,9 @@
 """Output side: sheet_stage_output's pixel-format conversion on the
 device and the direct PNM writer — reference file.c:134-260.
 
-file.c needs libavcodec, so it is not part of oracle/_ref; the checker here is the
-restatement `orc_host_convert_format` (its threshold rule is pinned by the A1 golden
-record, its generic branch is copy_rectangle which is checked against oracle/_ref)."""
+The checker is the reference's own saveImage() (file.c compiled unmodified into
+oracle/_ref against oracle/shim_codec; saveImageDirect writes the PNM the test reads
+back) — `checker.save_image_cpu`, `checker.process_sheets_files_cpu`."""
 import ctypes as C
 import os
 
@@ -34,15 +34,16 @@ def orc_ops():
                                        (U.FMT_MONOWHITE, U.FMT_MONOWHITE)])
 @pytest.mark.parametrize("w,h", [(37, 29), (203, 77), (640, 64)])
 @pytest.mark.parametrize("abt", [170, 84])
-def test_convert_format(cuda_ops, orc_ops, sfmt, dfmt, w, h, abt):
+def test_convert_format(cuda_ops, ref_lib, sfmt, dfmt, w, h, abt):
+    from oracle import checker
     src = noise_image(11, w, h, sfmt, dark=0.4)
-    outs = []
-    for ops in (cuda_ops, orc_ops):
-        d = np.full((h, linesize(dfmt, w)), 0x5A, dtype=np.uint8)
-        ops.call("convert_format", C.byref(himg(src, sfmt, w, abt=abt)), C.byref(himg(d, dfmt, w, abt=abt)))
-        outs.append(d)
+    d = np.full((h, linesize(dfmt, w)), 0x5A, dtype=np.uint8)
+    cuda_ops.call("convert_format", C.byref(himg(src, sfmt, w, abt=abt)), C.byref(himg(d, dfmt, w, abt=abt)))
+    rfmt, rw, rh, ref = checker.save_image_cpu(ref_lib, himg(src, sfmt, w, abt=abt), dfmt)   # file.c:186-262
+    assert (rfmt, rw, rh) == (dfmt, w, h)
+    outs = [d]
     row = U.bytes_per_row(dfmt, w)
-    a, b = outs[0][:, :row].copy(), outs[1][:, :row].copy()
+    a, b = d[:, :row].copy(), ref.copy()
     if dfmt == U.FMT_MONOWHITE and sfmt not in (U.FMT_GRAY8, U.FMT_RGB24, U.FMT_MONOBLACK) and w % 8:
         # generic branch (file.c:257-259): set_pixel only touches the w real pixels of a
         # create_image(fill=false) buffer, the tail bits of the last byte are unspecified
@@ -66,10 +67,11 @@ def test_output_format_mapping_and_header():
     assert lib.unpaper_b200_pnm_header(U.FMT_Y400A, 31, 7, buf, 64) < 0
 
 
-def test_engine_mono_output(orc_ops, tmp_path):
+def test_engine_mono_output(ref_lib, tmp_path):
     """pbm output: the engine converts on the device, D2H carries 1 bit/px; the bytes
-    equal saveImage()'s conversion of the engine's own GRAY8 output (which the other
-    engine tests compare with the reference)."""
+    equal what the reference's process_sheet() + saveImage() write for the same pages
+    with a MONOBLACK (-> MONOWHITE, file.c:205-207) output format."""
+    from oracle import checker
     from unpaper_gpu_b200.lib import Engine
     from unpaper_gpu_b200 import lib as L
     w, h = 620, 877
@@ -83,11 +85,10 @@ def test_engine_mono_output(orc_ops, tmp_path):
     assert eng.sheet_bytes == row * eng.sheet_h
     mono, res = eng.process_numpy(pages)
     assert mono.shape == (5, eng.sheet_h, row)
+    files, _ = checker.process_sheets_files_cpu(ref_lib, cfg, pages, w, h, U.FMT_GRAY8, out_fmt=U.FMT_MONOBLACK, threads=8)
     for i in range(5):
-        want = np.zeros((eng.sheet_h, row), dtype=np.uint8)
-        g = np.ascontiguousarray(gray[i])
-        orc_ops.call("convert_format", C.byref(himg(g, U.FMT_GRAY8, eng.sheet_w, abt=cfg.abs_black_threshold)),
-                     C.byref(himg(want, U.FMT_MONOWHITE, eng.sheet_w, abt=cfg.abs_black_threshold)))
+        rfmt, rw, rh, want = files[i][0]
+        assert (rfmt, rw, rh) == (U.FMT_MONOWHITE, eng.sheet_w, eng.sheet_h)
         assert np.array_equal(mono[i], want), f"sheet {i}"
         assert res[i].status == 0
     # device-resident path gives the same bytes
