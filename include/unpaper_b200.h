@@ -142,6 +142,12 @@ int unpaper_b200_write_pnm(const char *path, const uint8_t *data, int linesize,
  * (3) sheet engine
  * --------------------------------------------------------------------- */
 
+/* struct MultiIndex (parse.h:15-18) */
+typedef struct {
+  int32_t count;            /* -1: all sheets */
+  const int32_t *indexes;
+} B200MultiIndex;
+
 /* The part of the reference's `Options` + `SheetProcessConfig`
  * (lib/options.h:29-119, sheet_process.h:22-37) that process_sheet() reads on
  * the hot path, flattened to a POD. */
@@ -179,6 +185,26 @@ typedef struct {
    * border (:499-508) */
   Direction pre_mirror, post_mirror;
   Delta pre_shift, post_shift;
+  /* sheet_stage_output (sheet_stages.c:606-621): 0 or 1 = one output image per sheet;
+   * 2 = the sheet is split into two pages of width sheet_width/2 (--output-pages 2),
+   * each converted to the output format on its own like saveImage() does */
+  int32_t output_count;
+  /* job->sheet_nr of the first sheet of a process_* call (1-based; 0 means 1): the
+   * number the per-sheet switches below are tested against */
+  int32_t first_sheet_nr;
+  /* options->no_*_multi_index / ignore_multi_index (parse.h:15-34, tested with
+   * isExcluded() at sheet_stages.c:282-493 and :644-650): sheets for which a stage is
+   * skipped.  count -1 = every sheet (same as the uint8 switch above), 0 = none.
+   * The index arrays are read during engine_create only. */
+  B200MultiIndex no_blackfilter_sheets, no_noisefilter_sheets, no_blurfilter_sheets, no_grayfilter_sheets;
+  B200MultiIndex no_mask_scan_sheets, no_mask_center_sheets, no_deskew_sheets, no_wipe_sheets, no_border_sheets;
+  B200MultiIndex no_border_scan_sheets, no_border_align_sheets, ignore_sheets;
+  /* size-changing options of the decode / pre / post stages (sheet_stages.c:134-145,
+   * :216-230, :511-531).  Rotations in degrees (0, 90, -90); sizes -1,-1 = unset;
+   * zoom factors 0 or 1.0 = none. */
+  int32_t pre_rotate, post_rotate;
+  RectangleSize sheet_size, stretch_size, page_size, post_stretch_size, post_page_size;
+  float pre_zoom_factor, post_zoom_factor;
 } B200SheetConfig;
 
 #define B200_TRACE_MAX_MASKS 8
@@ -219,9 +245,15 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device,
 void unpaper_b200_engine_destroy(B200Engine *e);
 int unpaper_b200_engine_sheet_width(const B200Engine *e);
 int unpaper_b200_engine_sheet_height(const B200Engine *e);
-/* bytes of one output sheet (format = page format unless an output format
- * was set) */
+/* bytes of one sheet's output (format = page format unless an output format was
+ * set): output_count tightly packed images of unpaper_b200_engine_output_width()
+ * x sheet_height, one after the other */
 size_t unpaper_b200_engine_sheet_bytes(const B200Engine *e);
+int unpaper_b200_engine_output_width(const B200Engine *e);
+int unpaper_b200_engine_output_count(const B200Engine *e);
+/* sheet number (job->sheet_nr) of sheet 0 of the next process_* call, for callers that
+ * feed one job list through several calls (the per-sheet switches are tested against it) */
+void unpaper_b200_engine_set_first_sheet_nr(B200Engine *e, int sheet_nr);
 /* sheet_stage_output's format conversion on the device (so the D2H carries
  * 1 bit/px for pbm output): sheets leave process_* in `av_pix_fmt` (mapped by
  * unpaper_b200_output_format), tight rows; -1 restores the page format.

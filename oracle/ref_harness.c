@@ -34,6 +34,7 @@
 #include "imageprocess/pixel.h"
 #include "lib/logging.h"
 #include "lib/options.h"
+#include "parse.h"
 #include "sheet_process.h"
 
 #define UNPAPER_B200_WITH_REFERENCE_HEADERS 1
@@ -349,7 +350,8 @@ static void options_from_cfg(Options *o, Rectangle *bf_excl, const B200SheetConf
   o->mask_color = c->mask_color;
   o->abs_black_threshold = c->abs_black_threshold;
   o->abs_white_threshold = c->abs_white_threshold;
-#define SW(flag, field) o->field = (c->flag) ? MI_ALL : MI_NONE
+#define SW(flag, field) o->field = (c->flag || c->flag##_sheets.count == -1) ? MI_ALL : \
+    (struct MultiIndex){.count = c->flag##_sheets.count, .indexes = (int *)c->flag##_sheets.indexes}
   SW(no_blackfilter, no_blackfilter_multi_index);
   SW(no_noisefilter, no_noisefilter_multi_index);
   SW(no_blurfilter, no_blurfilter_multi_index);
@@ -362,6 +364,7 @@ static void options_from_cfg(Options *o, Rectangle *bf_excl, const B200SheetConf
   SW(no_border_scan, no_border_scan_multi_index);
   SW(no_border_align, no_border_align_multi_index);
 #undef SW
+  o->ignore_multi_index = (struct MultiIndex){.count = c->ignore_sheets.count, .indexes = (int *)c->ignore_sheets.indexes};
   o->noisefilter_intensity = c->noisefilter_intensity;
   o->blackfilter_parameters = c->blackfilter;
   o->blackfilter_parameters.exclusions = bf_excl;
@@ -392,7 +395,7 @@ static void options_from_cfg(Options *o, Rectangle *bf_excl, const B200SheetConf
 /* One sheet: pages -> reference process_sheet() -> sheet in the page format. */
 static int run_one_sheet(const B200SheetConfig *cfg, const Options *opt,
                          const uint8_t *pages, int page_w, int page_h, int page_fmt,
-                         uint8_t *out, B200SheetResult *res, char **out_files, int out_count) {
+                         uint8_t *out, B200SheetResult *res, char **out_files, int out_count, int sheet_nr) {
   int row = av_shim_row_bytes(page_fmt, page_w);
   if (row < 0) return -1;
   size_t page_bytes = (size_t)row * page_h;
@@ -407,7 +410,7 @@ static int run_one_sheet(const B200SheetConfig *cfg, const Options *opt,
 
   BatchJob job;
   memset(&job, 0, sizeof(job));
-  job.sheet_nr = 1;
+  job.sheet_nr = sheet_nr;
   job.input_count = cfg->input_count;
   job.output_count = out_files ? out_count : 1;
   for (int j = 0; out_files && j < out_count; j++) job.output_files[j] = out_files[j];
@@ -428,7 +431,8 @@ static int run_one_sheet(const B200SheetConfig *cfg, const Options *opt,
   B200SheetResult local;
   if (!res) res = &local;
   memset(res, 0, sizeof(*res));
-  Trace tr = {.res = res, .detect_masks_calls = 0, .no_deskew = cfg->no_deskew};
+  Trace tr = {.res = res, .detect_masks_calls = 0,
+              .no_deskew = isExcluded(sheet_nr, opt->no_deskew_multi_index, opt->ignore_multi_index)};
   tls_trace = &tr;
   bool ok = process_sheet(&st, &spc);
   tls_trace = NULL;
@@ -475,7 +479,8 @@ static void *worker(void *arg) {
     int rc = run_one_sheet(jb->cfg, jb->opt, jb->pages + (size_t)i * jb->sheet_in_bytes,
                            jb->page_w, jb->page_h, jb->page_fmt,
                            jb->out ? jb->out + (size_t)i * jb->sheet_out_bytes : NULL,
-                           jb->results ? &jb->results[i] : NULL, jb->out_dir ? files : NULL, jb->out_count);
+                           jb->results ? &jb->results[i] : NULL, jb->out_dir ? files : NULL, jb->out_count,
+                           (jb->cfg->first_sheet_nr > 0 ? jb->cfg->first_sheet_nr : 1) + i);
     if (rc != 0) atomic_fetch_add(&jb->failed, 1);
   }
   return NULL;

@@ -50,6 +50,9 @@ def main():
         o, res = checker.process_sheets_cpu(lib, "ref_", cfg, g, g.shape[1], g.shape[0], U.FMT_GRAY8)
         gold = np.array(Image.open(os.path.join(ref_root, "tests/golden_images/goldenA1.pbm")).convert("L"))
         ratio = float(np.mean((o[0] < cfg.abs_black_threshold) != (gold < 128)))
+        # fixture for the GPU tests: the 1-bit scan (packed, set bit = white) and the reference's golden image
+        np.savez_compressed(os.path.join(HERE, "a1_fixture.npz"), page_bits=np.packbits(g > 127, axis=1),
+                            golden_bits=np.packbits(gold < 128, axis=1), size=np.array(g.shape[::-1]))
         out["A1"] = {"input_sha256": hashlib.sha256(g.tobytes()).hexdigest(), "size": [int(g.shape[1]), int(g.shape[0])],
                      "result": G.result_dict(res[0]), "output_sha256": hashlib.sha256(o[0].tobytes()).hexdigest(),
                      "golden_diff_ratio_thr170": ratio}
@@ -82,7 +85,9 @@ def main():
         black = np.unpackbits(o[0], axis=1)[:, :2 * w] == 0
         out["F3"] = {"size": [2 * w, h], "differing_pixels_vs_goldenF": int((black != gold).sum()),
                      "input_sha256": [hashlib.sha256(b.tobytes()).hexdigest() for b in bits[:2]],
-                     "output_sha256": hashlib.sha256(o[0].tobytes()).hexdigest(), "result": G.result_dict(res[0])}
+                     "output_sha256": hashlib.sha256(o[0].tobytes()).hexdigest(), "result": G.result_dict(res[0]),
+                     # the sheet as MONOWHITE with a cleared tail (what saveImage writes): independent of row padding
+                     "monowhite_sha256": hashlib.sha256(np.packbits(black, axis=1).tobytes()).hexdigest()}
         assert out["F3"]["differing_pixels_vs_goldenF"] == 0
         cfg = U.default_sheet_config()
         cfg.layout = U.LAYOUT_DOUBLE
@@ -96,6 +101,25 @@ def main():
                 e1.append(float(np.mean(part != gold)))
         out["E1"] = {"golden_diff_ratio": e1}
         assert max(e1) < 1e-4, e1
+        # the real E1 run: --layout double --output-pages 2 through the reference's own output stage
+        # (sheet split sheet_stages.c:606-621 + saveImage): the six files the reference test compares
+        files, res = checker.process_sheets_files_cpu(lib, cfg, np.stack(bits).reshape(3, -1), w, h, U.FMT_MONOBLACK,
+                                                      out_fmt=-1, output_count=2, threads=3)
+        e1f, e1sha = [], []
+        for k in range(3):
+            for half in range(2):
+                fmt_, fw, fh, arr = files[k][half]
+                assert fmt_ == U.FMT_MONOWHITE
+                gold = np.array(Image.open(os.path.join(ref_root, f"tests/golden_images/goldenE1-0{2 * k + half + 1}.pbm")).convert("L")) < 128
+                assert gold.shape == (fh, fw), (gold.shape, fw, fh)
+                e1f.append(float(np.mean((np.unpackbits(arr, axis=1)[:, :fw] == 1) != gold)))
+                e1sha.append(hashlib.sha256(arr.tobytes()).hexdigest())
+        out["E1"]["split_files_golden_diff_ratio"] = e1f
+        out["E1"]["split_files_sha256"] = e1sha
+        out["E1"]["split_size"] = [int(fw), int(fh)]
+        out["E1"]["results"] = [G.result_dict(r) for r in res]
+        assert max(e1f) < 1e-4, e1f
+        np.savez_compressed(os.path.join(HERE, "e_fixture.npz"), pages_bits=np.stack(bits), size=np.array([w, h]))
     for name, (cfg, pages, w, h, fmt) in G.sheet_cases().items():
         o, res = checker.process_sheets_cpu(lib, "ref_", cfg, pages, w, h, fmt, threads=8)
         out["sheets"][name] = {"results": [G.result_dict(r) for r in res],

@@ -270,3 +270,158 @@ def test_engine_deskew_scan_edges(ref_lib, edges):
     cfg = U.default_sheet_config()
     cfg.deskew.scan_edges = U.Edges(*edges)
     out, res = _compare(cfg, pages, w, h, U.FMT_GRAY8, ref_lib, group=2, lanes=2)
+
+
+def test_engine_per_sheet_switch_lists(ref_lib):
+    """options->no_*_multi_index with sheet lists + ignore_multi_index (isExcluded(),
+    sheet_stages.c:282-493, :644-650): stages are skipped for the listed sheet numbers only."""
+    w, h = 620, 877
+    pages = np.stack([synth.gray_page(240 + i, w, h, box=SMALL_BOX) for i in range(7)])
+    cfg = U.default_sheet_config()
+    cfg.first_sheet_nr = 3                                   # sheets 3..9
+    cfg.no_deskew_sheets = U.multi_index([4, 8])
+    cfg.no_noisefilter_sheets = U.multi_index([3, 4])
+    cfg.no_mask_center_sheets = U.multi_index([6])
+    cfg.no_border_align_sheets = U.multi_index([6, 7])
+    cfg.no_blackfilter_sheets = U.multi_index([9])
+    cfg.ignore_sheets = U.multi_index([5])
+    cfg.wipe_count = 1; cfg.wipes[0] = U.rect(300, 400, 340, 460)
+    cfg.no_wipe_sheets = U.multi_index([7])
+    cfg.border = U.Border(10, 0, 0, 12)
+    cfg.no_border_sheets = U.multi_index([8])
+    out, res = _compare(cfg, pages, w, h, U.FMT_GRAY8, ref_lib, group=4, lanes=2)
+    assert res[1].deskew_mask_count == 0 and res[0].deskew_mask_count == 1
+    assert res[2].deskew_mask_count == 0 and res[2].border_count == 0      # sheet 5: everything off
+    cfg2 = U.default_sheet_config()
+    cfg2.no_grayfilter_sheets = U.multi_index(None)          # count -1: every sheet
+    cfg3 = U.default_sheet_config()
+    cfg3.no_grayfilter = 1
+    from unpaper_gpu_b200.lib import Engine
+    outs = []
+    for c in (cfg2, cfg3):
+        eng = Engine(c, w, h, U.FMT_GRAY8, group_pages=4, lanes=1)
+        outs.append(eng.process_numpy(pages[:2])[0])
+        eng.close()
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_engine_rejects_bad_counts():
+    """Counts outside the fixed arrays of B200SheetConfig are refused at creation."""
+    from unpaper_gpu_b200.lib import Engine
+    for field, v in (("point_count", 9), ("pre_mask_count", -1), ("wipe_count", 100), ("post_wipe_count", 9),
+                     ("pre_wipe_count", -3), ("output_count", 3), ("input_count", 3)):
+        cfg = U.default_sheet_config()
+        setattr(cfg, field, v)
+        with pytest.raises(RuntimeError, match="engine"):
+            Engine(cfg, 64, 64, U.FMT_GRAY8, group_pages=1, lanes=1)
+
+
+# ---- the reference's own real scans through the CUDA engine --------------------------
+# tests/golden/*.npz hold the reference's 1-bit test scans (packed); golden_vectors.json
+# holds what the UNMODIFIED reference (oracle/_ref) produced for them when the vectors
+# were made (tests/golden/make_golden.py), incl. its distance to the reference's golden images.
+
+def _golden(name):
+    import json
+    import os
+    d = os.path.join(os.path.dirname(__file__), "golden")
+    with open(os.path.join(d, "golden_vectors.json")) as f:
+        vec = json.load(f)
+    return vec, np.load(os.path.join(d, name))
+
+
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_engine_reference_golden_a1():
+    """BASELINE config 1 = the reference's test_a1 (tests/unpaper_tests.py:653-669): default
+    pipeline on imgsrc001.  Every byte of the sheet and every decision equal the reference
+    CPU backend's; the sheet is within 1e-4 of goldenA1.pbm at unpaper's own pbm threshold."""
+    import golden_cases as G
+    from unpaper_gpu_b200.lib import Engine
+    vec, f = _golden("a1_fixture.npz")
+    w, h = (int(v) for v in f["size"])
+    page = (np.unpackbits(f["page_bits"], axis=1)[:, :w] * 255).astype(np.uint8)
+    assert _sha(page) == vec["A1"]["input_sha256"]
+    cfg = U.default_sheet_config()
+    eng = Engine(cfg, w, h, U.FMT_GRAY8, group_pages=1, lanes=1)
+    out, res = eng.process_numpy(page[None])
+    eng.close()
+    assert res[0].status == 0
+    assert G.result_dict(res[0]) == vec["A1"]["result"]
+    assert _sha(out[0]) == vec["A1"]["output_sha256"]
+    gold_black = np.unpackbits(f["golden_bits"], axis=1)[:, :w] == 1
+    ratio = float(np.mean((out[0] < cfg.abs_black_threshold) != gold_black))
+    assert ratio < 1e-4 and abs(ratio - vec["A1"]["golden_diff_ratio_thr170"]) < 1e-12
+    # the same scan as a 1-bit page, written as pbm (the reference test's actual file type)
+    eng = Engine(cfg, w, h, U.FMT_MONOBLACK, group_pages=1, lanes=1)
+    mono, res = eng.process_numpy(f["page_bits"][None])
+    eng.close()
+    assert float(np.mean((np.unpackbits(mono[0], axis=1)[:, :w] == 1) != gold_black)) < 1e-4
+
+
+def test_engine_reference_golden_f3():
+    """The reference's test_f3 (:787-810): two 1-bit scans merged on one double-layout sheet
+    (--input-pages 2); the reference build reproduces goldenF.pbm exactly, and so must this."""
+    import golden_cases as G
+    from unpaper_gpu_b200.lib import Engine
+    vec, f = _golden("e_fixture.npz")
+    w, h = (int(v) for v in f["size"])
+    bits = f["pages_bits"]
+    assert [_sha(b) for b in bits[:2]] == vec["F3"]["input_sha256"]
+    cfg = U.default_sheet_config()
+    cfg.layout, cfg.input_count = U.LAYOUT_DOUBLE, 2
+    eng = Engine(cfg, w, h, U.FMT_MONOBLACK, group_pages=1, lanes=1)
+    out, res = eng.process_numpy(bits[:2].reshape(1, -1))
+    eng.close()
+    assert res[0].status == 0 and G.result_dict(res[0]) == vec["F3"]["result"]
+    assert vec["F3"]["differing_pixels_vs_goldenF"] == 0
+    assert _sha(out[0]) == vec["F3"]["monowhite_sha256"]
+
+
+def test_engine_reference_golden_e1():
+    """The reference's test_e1 (:763-783): --layout double --output-pages 2 on three 1-bit
+    double-page scans; the six pbm files equal the ones the reference's own output stage wrote
+    (sheet split + saveImage), which are within 1e-4 of goldenE1-0N.pbm."""
+    import golden_cases as G
+    from unpaper_gpu_b200.lib import Engine
+    vec, f = _golden("e_fixture.npz")
+    w, h = (int(v) for v in f["size"])
+    cfg = U.default_sheet_config()
+    cfg.layout, cfg.output_count = U.LAYOUT_DOUBLE, 2
+    eng = Engine(cfg, w, h, U.FMT_MONOBLACK, group_pages=2, lanes=2)
+    assert [eng.out_w, eng.sheet_h] == vec["E1"]["split_size"] and eng.out_fmt == U.FMT_MONOWHITE
+    out, res = eng.process_numpy(f["pages_bits"].reshape(3, -1))
+    eng.close()
+    assert max(vec["E1"]["split_files_golden_diff_ratio"]) < 1e-4
+    for k in range(3):
+        assert res[k].status == 0 and G.result_dict(res[k]) == vec["E1"]["results"][k]
+        for half in range(2):
+            assert _sha(out[k, half]) == vec["E1"]["split_files_sha256"][2 * k + half], f"sheet {k} page {half}"
+
+
+@pytest.mark.timeout(900)
+def test_engine_double_600dpi_vs_reference(ref_lib):
+    """BASELINE config 4 at full size (7016x4960, --layout double, sheet split): one sheet bit
+    for bit against the reference's process_sheet() + output stage (about a minute of CPU)."""
+    from oracle import checker
+    from unpaper_gpu_b200.lib import Engine
+    w, h = 7016, 4960
+    pages = synth.double_sheet(1, w, h)[None]
+    cfg = U.default_sheet_config()
+    cfg.layout, cfg.output_count = U.LAYOUT_DOUBLE, 2
+    eng = Engine(cfg, w, h, U.FMT_GRAY8, group_pages=1, lanes=1)
+    out, res = eng.process_numpy(pages)
+    eng.close()
+    files, rres = checker.process_sheets_files_cpu(ref_lib, cfg, pages, w, h, U.FMT_GRAY8, output_count=2)
+    a, b = res[0], rres[0]
+    assert a.status == 0 and b.status == 0 and a.deskew_mask_count == b.deskew_mask_count == 2
+    for k in range(2):
+        assert U.rect_tuple(a.deskew_masks[k]) == U.rect_tuple(b.deskew_masks[k])
+        assert a.rotation[k] == b.rotation[k] and a.rotation[k] != 0.0
+        assert U.rect_tuple(a.center_masks[k]) == U.rect_tuple(b.center_masks[k])
+        assert U.border_tuple(a.borders[k]) == U.border_tuple(b.borders[k])
+        assert files[0][k][:3] == (U.FMT_GRAY8, w // 2, h)
+        assert np.array_equal(out[0, k], files[0][k][3]), f"page {k}: {int((out[0, k] != files[0][k][3]).sum())} differing bytes"

@@ -202,3 +202,42 @@ def test_engine_sheet_callback_streams_pnm(tmp_path):
     again, _ = eng.process_numpy(pages)
     assert np.array_equal(again, plain)
     eng.close()
+
+
+@pytest.mark.parametrize("page_fmt,out_fmt", [(U.FMT_GRAY8, -1), (U.FMT_GRAY8, U.FMT_MONOWHITE), (U.FMT_RGB24, -1),
+                                              (U.FMT_RGB24, U.FMT_GRAY8), (U.FMT_MONOBLACK, -1)])
+def test_engine_output_split(ref_lib, page_fmt, out_fmt):
+    """--output-pages 2 (sheet_stages.c:606-621): the double-layout sheet leaves as two
+    images of width sheet_w/2, each converted like saveImage() does — against the files the
+    reference's own output stage writes.  Odd sheet width: the last column is dropped."""
+    from oracle import checker
+    from unpaper_gpu_b200.lib import Engine
+    w, h = 1241, 620
+    if page_fmt == U.FMT_RGB24:
+        pages = np.stack([np.concatenate([synth.color_page(300 + 2 * i + k, 620 + k, h) .reshape(h, 620 + k, 3) for k in (0, 1)], axis=1).reshape(h, -1)
+                          for i in range(3)])
+    else:
+        g = np.stack([synth.double_sheet(300 + i, w, h) for i in range(3)])
+        pages = g if page_fmt == U.FMT_GRAY8 else np.stack([np.packbits(x >= 128, axis=1) for x in g])
+    cfg = U.default_sheet_config()
+    cfg.layout, cfg.output_count = U.LAYOUT_DOUBLE, 2
+    if page_fmt == U.FMT_RGB24:
+        cfg.no_blackfilter = cfg.no_noisefilter = 1
+    eng = Engine(cfg, w, h, page_fmt, group_pages=2, lanes=2)
+    if out_fmt >= 0:
+        eng.set_output_format(out_fmt)
+    assert eng.out_count == 2 and eng.out_w == w // 2
+    out, res = eng.process_numpy(pages)
+    import torch
+    d_in = torch.from_numpy(np.ascontiguousarray(pages).reshape(-1)).cuda()
+    d_out = torch.empty(out.size, dtype=torch.uint8, device="cuda")
+    eng.process_ptr(d_in.data_ptr(), d_out.data_ptr(), 3, False, None)
+    eng.close()
+    assert np.array_equal(d_out.cpu().numpy().reshape(out.shape), out)
+    files, rres = checker.process_sheets_files_cpu(ref_lib, cfg, pages, w, h, page_fmt, out_fmt=out_fmt, output_count=2, threads=8)
+    for i in range(3):
+        assert res[i].status == 0 and rres[i].status == 0
+        for j in range(2):
+            rfmt, rw, rh, want = files[i][j]
+            assert (rfmt, rw, rh) == (eng.out_fmt, w // 2, h)
+            assert np.array_equal(out[i, j], want), f"sheet {i} page {j}: {int((out[i, j] != want).sum())} differing bytes"

@@ -63,6 +63,8 @@ HostImage = _S("B200HostImage", [
     ("linesize", C.c_int32), ("format", C.c_int32), ("background", Pixel),
     ("abs_black_threshold", C.c_uint8)])
 
+MultiIndex = _S("B200MultiIndex", [("count", C.c_int32), ("indexes", C.POINTER(C.c_int32))])
+
 SheetConfig = _S("B200SheetConfig", [
     ("layout", C.c_int32), ("input_count", C.c_int32), ("interpolate_type", C.c_int32),
     ("sheet_background", Pixel), ("mask_color", Pixel),
@@ -82,7 +84,28 @@ SheetConfig = _S("B200SheetConfig", [
     ("pre_mask_count", C.c_int32), ("pre_masks", Rectangle * 8),
     ("pre_wipe_count", C.c_int32), ("wipe_count", C.c_int32), ("post_wipe_count", C.c_int32),
     ("pre_wipes", Rectangle * 8), ("wipes", Rectangle * 8), ("post_wipes", Rectangle * 8),
-    ("pre_mirror", Direction), ("post_mirror", Direction), ("pre_shift", Delta), ("post_shift", Delta)])
+    ("pre_mirror", Direction), ("post_mirror", Direction), ("pre_shift", Delta), ("post_shift", Delta),
+    ("output_count", C.c_int32), ("first_sheet_nr", C.c_int32),
+    ("no_blackfilter_sheets", MultiIndex), ("no_noisefilter_sheets", MultiIndex), ("no_blurfilter_sheets", MultiIndex),
+    ("no_grayfilter_sheets", MultiIndex), ("no_mask_scan_sheets", MultiIndex), ("no_mask_center_sheets", MultiIndex),
+    ("no_deskew_sheets", MultiIndex), ("no_wipe_sheets", MultiIndex), ("no_border_sheets", MultiIndex),
+    ("no_border_scan_sheets", MultiIndex), ("no_border_align_sheets", MultiIndex), ("ignore_sheets", MultiIndex),
+    ("pre_rotate", C.c_int32), ("post_rotate", C.c_int32),
+    ("sheet_size", RectangleSize), ("stretch_size", RectangleSize), ("page_size", RectangleSize),
+    ("post_stretch_size", RectangleSize), ("post_page_size", RectangleSize),
+    ("pre_zoom_factor", C.c_float), ("post_zoom_factor", C.c_float)])
+
+
+def multi_index(values):
+    """B200MultiIndex over a list of sheet numbers (None = all sheets); keeps the array alive."""
+    m = MultiIndex()
+    if values is None:
+        m.count = -1
+        return m
+    arr = (C.c_int32 * max(len(values), 1))(*values)
+    m.count, m.indexes = len(values), C.cast(arr, C.POINTER(C.c_int32))
+    m._keep = arr
+    return m
 
 SheetResult = _S("B200SheetResult", [
     ("status", C.c_int32), ("sheet_width", C.c_int32), ("sheet_height", C.c_int32),
@@ -139,6 +162,10 @@ def default_sheet_config():
         _F2(0.1, 0.1), 100, -1, 100, -1)
     c.mask_alignment = MaskAlignmentParameters(Edges(False, False, False, False), Delta(0, 0))
     c.border_scan = BorderScanParameters(RectangleSize(5, 5), Delta(5, 5), _I2(5, 5), Direction(False, True))
+    c.output_count, c.first_sheet_nr = 1, 1
+    for f in ("sheet_size", "stretch_size", "page_size", "post_stretch_size", "post_page_size"):
+        setattr(c, f, RectangleSize(-1, -1))
+    c.pre_zoom_factor = c.post_zoom_factor = 1.0
     return c
 
 

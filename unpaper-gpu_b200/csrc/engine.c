@@ -23,6 +23,10 @@
 
 #include "host.h"
 
+/* stage switches: bit k of a sheet's skip mask = isExcluded(sheet_nr, no_<k>_multi_index, ignore_multi_index) */
+enum { SW_BLACK, SW_NOISE, SW_BLUR, SW_GRAY, SW_MASK_SCAN, SW_MASK_CENTER, SW_DESKEW, SW_WIPE, SW_BORDER,
+       SW_BORDER_SCAN, SW_BORDER_ALIGN, SW_COUNT };
+
 enum { STG_DECODE, STG_BLACK, STG_NOISE, STG_BLUR, STG_GRAY, STG_MASKS, STG_ROTDET, STG_DESKEW,
        STG_CENTER, STG_BORDER, STG_OUTPUT, STG_COUNT };
 static const char *STG_NAME[STG_COUNT] = {"decode", "blackfilter", "noisefilter", "blurfilter", "grayfilter",
@@ -42,6 +46,7 @@ typedef struct {
     DPage *pages_res;     /* pinned */
     const uint8_t *out;   /* where this flight's sheets land (caller memory) */
     int busy, first, n;
+    unsigned skip;        /* stage switches of this group's sheets */
   } fl[2];
   int slot;               /* flight being issued / collected */
   int ran;
@@ -91,7 +96,11 @@ struct B200Engine {
   int bad_sheets, bad_first;
   unsigned bad_flags;
   cudaEvent_t ev_begin;
-  int out_fmt, out_dfmt, out_row;   /* output conversion (av format, -1 = none) */
+  int out_fmt, out_dfmt, out_row;   /* output conversion (av format, -1 = none); out_row: tight row of ONE output image */
+  int out_count, out_w;             /* sheet split (sheet_stages.c:606-621): images per sheet, width of each */
+  /* per-sheet stage switches (options->no_*_multi_index + ignore_multi_index) */
+  int first_sheet_nr;
+  int32_t *sw_idx[SW_COUNT + 1]; int sw_n[SW_COUNT + 1];
   B200SheetDoneFn done_fn; void *done_user; int done_failed;
   double last_device_ms;
   double stage_ms[STG_COUNT];
@@ -103,8 +112,10 @@ static int imax(int a, int b) { return a > b ? a : b; }
 int unpaper_b200_engine_sheet_width(const B200Engine *e) { return e->sheet_w; }
 int unpaper_b200_engine_sheet_height(const B200Engine *e) { return e->sheet_h; }
 size_t unpaper_b200_engine_sheet_bytes(const B200Engine *e) {
-  return (size_t)(e->out_fmt >= 0 ? e->out_row : e->sheet_row) * e->sheet_h;
+  return (size_t)e->out_row * e->sheet_h * e->out_count;
 }
+int unpaper_b200_engine_output_width(const B200Engine *e) { return e->out_w; }
+int unpaper_b200_engine_output_count(const B200Engine *e) { return e->out_count; }
 void unpaper_b200_engine_set_sheet_callback(B200Engine *e, B200SheetDoneFn fn, void *user) {
   if (!e) return;
   e->done_fn = fn; e->done_user = user;
@@ -123,17 +134,19 @@ int unpaper_b200_engine_set_output_format(B200Engine *e, int av_pix_fmt) {
    * (sheet_stages.c:130-131), as saveImage() writes it (file.c:201-208) */
   int fmt = unpaper_b200_output_format(av_pix_fmt < 0 ? e->page_fmt : av_pix_fmt);
   if (fmt == (e->dfmt == DF_GRAY8 ? AV_PIX_FMT_GRAY8 : AV_PIX_FMT_RGB24)) fmt = -1;   /* the working sheet as it is */
+  int df = e->dfmt, row = e->out_w * e->bpp;
   if (fmt >= 0) {
-    int df = b200_fmt_to_dev(fmt), row = b200_fmt_row_bytes(fmt, e->sheet_w);
+    df = b200_fmt_to_dev(fmt); row = b200_fmt_row_bytes(fmt, e->out_w);
     if (df < 0 || row <= 0) { b200_set_error("engine: unsupported output format %d", av_pix_fmt); return -1; }
-    e->out_dfmt = df; e->out_row = row;
-    for (int i = 0; i < e->nlanes; i++) {
-      Lane *ln = &e->lanes[i];
-      if (ln->out_stage) b200_dev_free(ln->out_stage);
-      ln->out_stage = (uint8_t *)b200_dev_alloc((size_t)row * e->sheet_h * e->group + 64);
-    }
   }
+  e->out_dfmt = df; e->out_row = row;
   e->out_fmt = fmt;
+  for (int i = 0; i < e->nlanes; i++) {
+    Lane *ln = &e->lanes[i];
+    if (ln->out_stage) { b200_dev_free(ln->out_stage); ln->out_stage = NULL; }
+    if (fmt >= 0 || e->out_count > 1)
+      ln->out_stage = (uint8_t *)b200_dev_alloc((size_t)row * e->sheet_h * e->out_count * e->group + 64);
+  }
   return 0;
 }
 uint64_t unpaper_b200_engine_launch_count(const B200Engine *e) { return e->launches; }
@@ -229,6 +242,7 @@ void unpaper_b200_engine_destroy(B200Engine *e) {
   unpaper_b200_set_device(e->device);
   if (e->lanes) { for (int i = 0; i < e->nlanes; i++) lane_free(&e->lanes[i]); free(e->lanes); }
   if (e->ev_begin) cudaEventDestroy(e->ev_begin);
+  for (int k = 0; k <= SW_COUNT; k++) free(e->sw_idx[k]);
   bf_plan_free(&e->bf); blur_plan_free(&e->blur); mask_plan_free(&e->mask); border_plan_free(&e->border); rot_plan_free(&e->rot);
   free(e);
 }
@@ -245,6 +259,24 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
     b200_set_error("engine: page format must be GRAY8, RGB24, MONOWHITE or MONOBLACK"); return NULL;
   }
   if (cfg->input_count < 1 || cfg->input_count > 2) { b200_set_error("engine: input_count must be 1 or 2"); return NULL; }
+  if (cfg->output_count < 0 || cfg->output_count > 2) { b200_set_error("engine: output_count must be 1 or 2"); return NULL; }
+  /* the fixed arrays of B200SheetConfig and of the device page record */
+  if (cfg->point_count < 0 || cfg->point_count > 8 || cfg->pre_mask_count < 0 || cfg->pre_mask_count > 8 ||
+      cfg->pre_wipe_count < 0 || cfg->pre_wipe_count > 8 || cfg->wipe_count < 0 || cfg->wipe_count > 8 ||
+      cfg->post_wipe_count < 0 || cfg->post_wipe_count > 8) {
+    b200_set_error("engine: point / pre-mask / wipe counts must be within 0..8"); return NULL;
+  }
+  if (cfg->layout == LAYOUT_DOUBLE && cfg->point_count == 0 && D_MAX_MASKS < 2) { b200_set_error("engine: too many points"); return NULL; }
+  if (cfg->blackfilter.exclusions_count > MAX_MASKS || (cfg->blackfilter.exclusions_count > 0 && !cfg->blackfilter.exclusions)) {
+    b200_set_error("engine: bad blackfilter exclusion list"); return NULL;
+  }
+  {
+    const B200MultiIndex *mi[SW_COUNT + 1] = {&cfg->no_blackfilter_sheets, &cfg->no_noisefilter_sheets, &cfg->no_blurfilter_sheets,
+      &cfg->no_grayfilter_sheets, &cfg->no_mask_scan_sheets, &cfg->no_mask_center_sheets, &cfg->no_deskew_sheets, &cfg->no_wipe_sheets,
+      &cfg->no_border_sheets, &cfg->no_border_scan_sheets, &cfg->no_border_align_sheets, &cfg->ignore_sheets};
+    for (int k = 0; k <= SW_COUNT; k++)
+      if (mi[k]->count < -1 || (mi[k]->count > 0 && !mi[k]->indexes)) { b200_set_error("engine: bad per-sheet switch list %d", k); return NULL; }
+  }
   bool gray_colors = cfg->sheet_background.r == cfg->sheet_background.g && cfg->sheet_background.g == cfg->sheet_background.b &&
                      cfg->mask_color.r == cfg->mask_color.g && cfg->mask_color.g == cfg->mask_color.b;
   if (page_format != AV_PIX_FMT_RGB24 && !gray_colors) { b200_set_error("engine: gray and 1-bit pages need gray background and mask colours"); return NULL; }
@@ -254,10 +286,34 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
   e->dfmt = page_format == AV_PIX_FMT_RGB24 ? DF_RGB24 : DF_GRAY8;
   e->out_fmt = -1;
   e->bpp = e->dfmt == DF_GRAY8 ? 1 : 3;
+  e->first_sheet_nr = cfg->first_sheet_nr > 0 ? cfg->first_sheet_nr : 1;
+  {
+    /* the lists are copied; a switch that is off for every sheet (uint8 flag, or count -1) stays in cfg->no_* */
+    const B200MultiIndex *mi[SW_COUNT + 1] = {&cfg->no_blackfilter_sheets, &cfg->no_noisefilter_sheets, &cfg->no_blurfilter_sheets,
+      &cfg->no_grayfilter_sheets, &cfg->no_mask_scan_sheets, &cfg->no_mask_center_sheets, &cfg->no_deskew_sheets, &cfg->no_wipe_sheets,
+      &cfg->no_border_sheets, &cfg->no_border_scan_sheets, &cfg->no_border_align_sheets, &cfg->ignore_sheets};
+    uint8_t *flag[SW_COUNT] = {&e->cfg.no_blackfilter, &e->cfg.no_noisefilter, &e->cfg.no_blurfilter, &e->cfg.no_grayfilter,
+      &e->cfg.no_mask_scan, &e->cfg.no_mask_center, &e->cfg.no_deskew, &e->cfg.no_wipe, &e->cfg.no_border,
+      &e->cfg.no_border_scan, &e->cfg.no_border_align};
+    for (int k = 0; k <= SW_COUNT; k++) {
+      if (mi[k]->count == -1) {
+        if (k < SW_COUNT) *flag[k] = 1; else for (int q = 0; q < SW_COUNT; q++) *flag[q] = 1;
+      } else if (mi[k]->count > 0) {
+        e->sw_n[k] = mi[k]->count;
+        e->sw_idx[k] = (int32_t *)malloc(sizeof(int32_t) * (size_t)mi[k]->count);
+        memcpy(e->sw_idx[k], mi[k]->indexes, sizeof(int32_t) * (size_t)mi[k]->count);
+      }
+    }
+    memset(&e->cfg.no_blackfilter_sheets, 0, sizeof(B200MultiIndex) * (SW_COUNT + 1));   /* no dangling caller pointers */
+    cfg = &e->cfg;
+  }
   e->group = group_pages; e->nlanes = lanes;
   /* sheet size = input pages side by side (sheet_stages.c:140-145) */
   e->sheet_w = page_w * cfg->input_count; e->sheet_h = page_h;
   e->page_row = b200_fmt_row_bytes(page_format, page_w); e->sheet_row = e->sheet_w * e->bpp;
+  e->out_count = cfg->output_count == 2 ? 2 : 1;
+  e->out_w = e->sheet_w / e->out_count;          /* sheet_stages.c:612 */
+  e->out_dfmt = e->dfmt; e->out_row = e->out_w * e->bpp;
   e->sheet_pitch = (e->sheet_row + 15) & ~15;
   e->sheet_stride = (((size_t)e->sheet_pitch * e->sheet_h + 64) + 255) & ~(size_t)255;
   e->page_bytes = (size_t)e->page_row * page_h;
@@ -425,8 +481,11 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
     e->n_static_mask_jobs[2] = build_static(e, ln, 2, cfg->post_wipes, cfg->no_wipe ? 0 : cfg->post_wipe_count,
                                          cfg->no_border ? none : cfg->post_border, NULL, 0, NULL);
   }
-  /* 1-bit pages leave in their own format unless the caller asks otherwise */
-  if (mono_pages && unpaper_b200_engine_set_output_format(e, -1) != 0) { unpaper_b200_engine_destroy(e); return NULL; }
+  /* 1-bit pages leave in their own format unless the caller asks otherwise (this also
+   * allocates the output staging a split sheet needs) */
+  if ((mono_pages || e->out_count > 1) && unpaper_b200_engine_set_output_format(e, mono_pages ? -1 : e->page_fmt) != 0) {
+    unpaper_b200_engine_destroy(e); return NULL;
+  }
   return e;
 }
 
@@ -438,14 +497,26 @@ static void mark(B200Engine *e, Lane *ln, int stage_boundary) {
 
 /* apply pre-masks first (sheet_stages.c:211-214), then wipes (:282-285), then
  * border (:288-291) — same order for the mid and post slots */
-static void run_static(B200Engine *e, Lane *ln, StageCtx *c, int slot, int n) {
+static void run_static(B200Engine *e, Lane *ln, StageCtx *c, int slot, int n, unsigned skip) {
   int P = e->group;
   int q = 0;
   bool has_masks = slot == 0 && e->cfg.pre_mask_count > 0;
   if (has_masks) { b200k_apply_masks(c->st, ln->static_mask[slot] + (size_t)q * P, n, e->sheet_w, e->sheet_h); q++; c->launches++; }
-  for (int k = 0; k < ln->static_fill_n[slot]; k++) { b200k_fill_jobs(c->st, ln->static_fill[slot] + (size_t)k * P, n, e->sheet_w, e->sheet_h); c->launches++; }
-  if (q < e->n_static_mask_jobs[slot]) { b200k_apply_masks(c->st, ln->static_mask[slot] + (size_t)q * P, n, e->sheet_w, e->sheet_h); c->launches++; }
+  if (!(skip >> SW_WIPE & 1))
+    for (int k = 0; k < ln->static_fill_n[slot]; k++) { b200k_fill_jobs(c->st, ln->static_fill[slot] + (size_t)k * P, n, e->sheet_w, e->sheet_h); c->launches++; }
+  if (q < e->n_static_mask_jobs[slot] && !(skip >> SW_BORDER & 1)) { b200k_apply_masks(c->st, ln->static_mask[slot] + (size_t)q * P, n, e->sheet_w, e->sheet_h); c->launches++; }
 }
+
+/* isExcluded(sheet_nr, no_<stage>_multi_index, ignore_multi_index) (parse.h:30-34) for every stage switch */
+static unsigned sheet_skip(const B200Engine *e, int sheet_index) {
+  int nr = e->first_sheet_nr + sheet_index;
+  unsigned m = 0;
+  for (int i = 0; i < e->sw_n[SW_COUNT]; i++) if (e->sw_idx[SW_COUNT][i] == nr) return (1u << SW_COUNT) - 1;
+  for (int k = 0; k < SW_COUNT; k++)
+    for (int i = 0; i < e->sw_n[k]; i++) if (e->sw_idx[k][i] == nr) { m |= 1u << k; break; }
+  return m;
+}
+void unpaper_b200_engine_set_first_sheet_nr(B200Engine *e, int sheet_nr) { if (e) e->first_sheet_nr = sheet_nr; }
 
 /* mirror() then shift_image() on every sheet of the group (sheet_stages.c:200-208, :499-508) */
 static void run_geometry(B200Engine *e, Lane *ln, StageCtx *c, int k, int n) {
@@ -459,8 +530,15 @@ static void run_geometry(B200Engine *e, Lane *ln, StageCtx *c, int k, int n) {
   }
 }
 
-static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, int n) {
+static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, int n, unsigned skip) {
   const B200SheetConfig *cfg = &e->cfg;
+#define OFF(k, flag) (cfg->flag || (skip >> (k) & 1))
+  const bool no_blackfilter = OFF(SW_BLACK, no_blackfilter), no_noisefilter = OFF(SW_NOISE, no_noisefilter);
+  const bool no_blurfilter = OFF(SW_BLUR, no_blurfilter), no_grayfilter = OFF(SW_GRAY, no_grayfilter);
+  const bool no_mask_scan = OFF(SW_MASK_SCAN, no_mask_scan), no_mask_center = OFF(SW_MASK_CENTER, no_mask_center);
+  const bool no_deskew = OFF(SW_DESKEW, no_deskew), no_border_scan = OFF(SW_BORDER_SCAN, no_border_scan);
+  const bool no_border_align = OFF(SW_BORDER_ALIGN, no_border_align);
+#undef OFF
   StageCtx c;
   memset(&c, 0, sizeof(c));
   c.st = ln->st; c.npages = n; c.pages = ln->pages_dev; c.w = e->sheet_w; c.h = e->sheet_h; c.fmt = e->dfmt;
@@ -484,22 +562,22 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
   }
   c.launches += 1;
   run_geometry(e, ln, &c, 0, n);
-  run_static(e, ln, &c, 0, n);
+  run_static(e, ln, &c, 0, n, skip);
 
   mark(e, ln, STG_BLACK);
-  if (!cfg->no_blackfilter) stage_blackfilter(&c, &e->bf);
+  if (!no_blackfilter) stage_blackfilter(&c, &e->bf);
   mark(e, ln, STG_NOISE);
-  if (!cfg->no_noisefilter) stage_noisefilter(&c, cfg->noisefilter_intensity, cfg->abs_white_threshold);
+  if (!no_noisefilter) stage_noisefilter(&c, cfg->noisefilter_intensity, cfg->abs_white_threshold);
   mark(e, ln, STG_BLUR);
-  if (!cfg->no_blurfilter) stage_blurfilter(&c, &e->blur);
+  if (!no_blurfilter) stage_blurfilter(&c, &e->blur);
   mark(e, ln, STG_GRAY);
   /* masks stage: the reference's first detect_masks() result is discarded
    * (sheet_stages.c:368-372) and has no side effect -> not run */
-  if (!cfg->no_grayfilter) stage_grayfilter(&c, &e->gray);
+  if (!no_grayfilter) stage_grayfilter(&c, &e->gray);
   mark(e, ln, STG_MASKS);
   int nm = e->npoints;
-  if (!cfg->no_deskew) {
-    if (!cfg->no_mask_scan) stage_detect_masks(&c, &e->mask);
+  if (!no_deskew) {
+    if (!no_mask_scan) stage_detect_masks(&c, &e->mask);
     mark(e, ln, STG_ROTDET);
     /* mask by mask like sheet_stages.c:406-413: detect_rotation(mask i+1) sees the
      * sheet with mask i already deskewed (the masks may share pixels) */
@@ -511,33 +589,43 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
     if (nm == 0) mark(e, ln, STG_DESKEW);
   } else { mark(e, ln, STG_ROTDET); mark(e, ln, STG_DESKEW); }
   mark(e, ln, STG_CENTER);
-  if (!cfg->no_mask_center) {
-    if (!cfg->no_mask_scan) stage_detect_masks(&c, &e->mask);
+  if (!no_mask_center) {
+    if (!no_mask_scan) stage_detect_masks(&c, &e->mask);
     stage_center_masks(&c, nm);
   }
-  run_static(e, ln, &c, 1, n);
+  run_static(e, ln, &c, 1, n, skip);
   mark(e, ln, STG_BORDER);
-  if (!cfg->no_border_scan) {
+  if (!no_border_scan) {
     stage_detect_border(&c, &e->border);
     stage_apply_border_masks(&c, cfg->mask_color);
-    if (!cfg->no_border_align) stage_align_masks(&c, &cfg->mask_alignment, e->noutside);
+    if (!no_border_align) stage_align_masks(&c, &cfg->mask_alignment, e->noutside);
   }
-  run_static(e, ln, &c, 2, n);
+  run_static(e, ln, &c, 2, n, skip);
   run_geometry(e, ln, &c, 1, n);
   mark(e, ln, STG_OUTPUT);
-  /* output stage: sheet -> caller (tight rows) + the decisions */
-  if (e->out_fmt >= 0) {
-    size_t out_bytes = (size_t)e->out_row * e->sheet_h;
-    DImg sv;
-    memset(&sv, 0, sizeof(sv));
-    sv.data = ln->sheets; sv.w = e->sheet_w; sv.h = e->sheet_h; sv.pitch = e->sheet_pitch; sv.fmt = e->dfmt;
-    sv.abt = cfg->abs_black_threshold;
-    DImg dv = sv;
-    dv.data = ln->host_mode ? ln->out_stage : ln->out_dev; dv.pitch = e->out_row; dv.fmt = e->out_dfmt;
-    b200k_convert_out(c.st, sv, dv, n, e->sheet_stride, out_bytes);
-    c.launches++;
+  /* output stage (sheet_stages.c:536-631): sheet -> caller, tight rows, + the decisions */
+  size_t img_bytes = (size_t)e->out_row * e->sheet_h, out_sheet = img_bytes * e->out_count;
+  if (e->out_fmt >= 0 || e->out_count > 1) {
+    /* per output image: the sheet split of :606-621 (copy_rectangle of the j-th
+     * sheet_w/output_count columns) and saveImage()'s conversion, straight into tight rows */
+    uint8_t *dst = ln->host_mode ? ln->out_stage : ln->out_dev;
+    for (int j = 0; j < e->out_count; j++) {
+      DImg sv;
+      memset(&sv, 0, sizeof(sv));
+      sv.data = ln->sheets + (size_t)j * e->out_w * e->bpp; sv.w = e->out_w; sv.h = e->sheet_h; sv.pitch = e->sheet_pitch;
+      sv.fmt = e->dfmt; sv.abt = cfg->abs_black_threshold;
+      if (e->out_fmt >= 0) {
+        DImg dv = sv;
+        dv.data = dst + img_bytes * j; dv.pitch = e->out_row; dv.fmt = e->out_dfmt;
+        b200k_convert_out(c.st, sv, dv, n, e->sheet_stride, out_sheet);
+      } else {
+        b200k_pack_rows(c.st, sv.data, e->sheet_pitch, dst + img_bytes * j, e->out_row, e->out_row, e->sheet_h, n,
+                        e->sheet_stride, out_sheet);
+      }
+      c.launches++;
+    }
     if (ln->host_mode)
-      CUDA_OK(cudaMemcpyAsync(ln->out_host, ln->out_stage, out_bytes * n, cudaMemcpyDeviceToHost, c.st));
+      CUDA_OK(cudaMemcpyAsync(ln->out_host, ln->out_stage, out_sheet * n, cudaMemcpyDeviceToHost, c.st));
   } else if (ln->host_mode) {
     size_t sheet_bytes = (size_t)e->sheet_row * e->sheet_h;
     if (e->sheet_pitch == e->sheet_row) {
@@ -589,8 +677,10 @@ static void collect(B200Engine *e, Lane *ln, B200SheetResult *results) {
       int nm = pg->mask_count < B200_TRACE_MAX_MASKS ? pg->mask_count : B200_TRACE_MAX_MASKS;
       /* the deskew-stage masks are overwritten by the post-stage detection in
        * the device record; rotation[] belongs to the former, masks[] to the latter */
-      r->center_mask_count = e->cfg.no_mask_center || e->cfg.no_mask_scan ? 0 : pg->mask_count;
-      r->deskew_mask_count = e->cfg.no_deskew || e->cfg.no_mask_scan ? 0 : pg->mask_count_deskew;
+      unsigned sk = ln->fl[ln->slot].skip;
+      bool no_scan = e->cfg.no_mask_scan || (sk >> SW_MASK_SCAN & 1);
+      r->center_mask_count = e->cfg.no_mask_center || (sk >> SW_MASK_CENTER & 1) || no_scan ? 0 : pg->mask_count;
+      r->deskew_mask_count = e->cfg.no_deskew || (sk >> SW_DESKEW & 1) || no_scan ? 0 : pg->mask_count_deskew;
       for (int i = 0; i < nm; i++) {
         r->center_masks[i] = (Rectangle){{{pg->masks[i].x0, pg->masks[i].y0}, {pg->masks[i].x1, pg->masks[i].y1}}};
         r->centered[i] = pg->centered[i];
@@ -599,7 +689,7 @@ static void collect(B200Engine *e, Lane *ln, B200SheetResult *results) {
         r->deskew_masks[i] = (Rectangle){{{pg->masks_deskew[i].x0, pg->masks_deskew[i].y0}, {pg->masks_deskew[i].x1, pg->masks_deskew[i].y1}}};
         r->rotation[i] = pg->rotation[i];
       }
-      r->border_count = e->cfg.no_border_scan ? 0 : pg->outside_count;
+      r->border_count = e->cfg.no_border_scan || (sk >> SW_BORDER_SCAN & 1) ? 0 : pg->outside_count;
       for (int i = 0; i < r->border_count && i < MAX_PAGES; i++) {
         r->borders[i] = (Border){pg->border[i].left, pg->border[i].top, pg->border[i].right, pg->border[i].bottom};
         r->border_masks[i] = (Rectangle){{{pg->border_mask[i].x0, pg->border_mask[i].y0}, {pg->border_mask[i].x1, pg->border_mask[i].y1}}};
@@ -647,7 +737,10 @@ static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_shee
     }
     if (n > left) n = left;
     if (n > P) n = P;
-    ln->fl[ln->slot].first = first; ln->fl[ln->slot].n = n; ln->host_mode = host_mode;
+    /* a group shares its kernel sequence: cut it where the per-sheet stage switches change */
+    unsigned skip = sheet_skip(e, first);
+    for (int m = 1; m < n; m++) if (sheet_skip(e, first + m) != skip) { n = m; break; }
+    ln->fl[ln->slot].first = first; ln->fl[ln->slot].n = n; ln->fl[ln->slot].skip = skip; ln->host_mode = host_mode;
     const uint8_t *src = pages + e->page_bytes * ic * (size_t)first;
     ln->fl[ln->slot].out = out + out_sheet * first;
     if (host_mode) {
@@ -657,14 +750,14 @@ static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_shee
          * (one 2-D copy, one "row" per sheet slot) */
         CUDA_OK(cudaMemcpy2DAsync(ln->sheets, e->sheet_stride, src, e->page_bytes, e->page_bytes, (size_t)n,
                                   cudaMemcpyHostToDevice, ln->st));
-        issue_group(e, ln, NULL, n);
+        issue_group(e, ln, NULL, n, skip);
       } else {
         CUDA_OK(cudaMemcpyAsync(ln->page_stage, src, e->page_bytes * ic * (size_t)n, cudaMemcpyHostToDevice, ln->st));
-        issue_group(e, ln, ln->page_stage, n);
+        issue_group(e, ln, ln->page_stage, n, skip);
       }
     } else {
       ln->out_dev = out + out_sheet * first;
-      issue_group(e, ln, src, n);
+      issue_group(e, ln, src, n, skip);
     }
     ln->fl[ln->slot].busy = 1;
   }

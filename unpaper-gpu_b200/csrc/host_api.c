@@ -190,6 +190,10 @@ void unpaper_b200_sheet_config_defaults(B200SheetConfig *c) {
   c->mask_alignment = (MaskAlignmentParameters){.alignment = {false, false, false, false}, .margin = {0, 0}};
   c->border_scan = (BorderScanParameters){
       .scan_size = {5, 5}, .scan_step = {5, 5}, .scan_threshold = {5, 5}, .scan_direction = {false, true}};
+  c->output_count = 1;
+  c->first_sheet_nr = 1;
+  c->sheet_size = c->stretch_size = c->page_size = c->post_stretch_size = c->post_page_size = (RectangleSize){-1, -1};
+  c->pre_zoom_factor = c->post_zoom_factor = 1.0f;
 }
 
 /* ---- output side (sheet_stage_output, sheet_stages.c:536-631 -> saveImage) ---- */

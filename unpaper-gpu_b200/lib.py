@@ -40,6 +40,10 @@ def load():
     lib.unpaper_b200_engine_sheet_height.argtypes = [C.c_void_p]
     lib.unpaper_b200_engine_sheet_bytes.argtypes = [C.c_void_p]
     lib.unpaper_b200_engine_sheet_bytes.restype = C.c_size_t
+    lib.unpaper_b200_engine_output_width.argtypes = [C.c_void_p]
+    lib.unpaper_b200_engine_output_count.argtypes = [C.c_void_p]
+    lib.unpaper_b200_engine_set_first_sheet_nr.argtypes = [C.c_void_p, C.c_int]
+    lib.unpaper_b200_engine_set_first_sheet_nr.restype = None
     for name in ("unpaper_b200_engine_process_device", "unpaper_b200_engine_process_host"):
         f = getattr(lib, name)
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(SheetResult)]
@@ -84,6 +88,8 @@ class Engine:
         self.sheet_w = self.lib.unpaper_b200_engine_sheet_width(self.h)
         self.sheet_h = self.lib.unpaper_b200_engine_sheet_height(self.h)
         self.sheet_bytes = self.lib.unpaper_b200_engine_sheet_bytes(self.h)
+        self.out_count = self.lib.unpaper_b200_engine_output_count(self.h)
+        self.out_w = self.lib.unpaper_b200_engine_output_width(self.h)
         self.page_bytes = bytes_per_row(fmt, page_w) * page_h
         self.sheet_in_bytes = self.page_bytes * cfg.input_count
         self.out_fmt = self.lib.unpaper_b200_engine_output_format(self.h)
@@ -107,10 +113,12 @@ class Engine:
 
     def process_numpy(self, pages):
         """pages: uint8 array with n*input_count tightly packed pages (host).
-        Returns (out [n, sheet_h, row_bytes], [SheetResult])."""
+        Returns (out [n, sheet_h, row_bytes] — [n, output_count, sheet_h, row_bytes] for a
+        split sheet —, [SheetResult])."""
         pages = np.ascontiguousarray(pages, dtype=np.uint8).reshape(-1)
         n = pages.size // self.sheet_in_bytes
-        out = np.empty((n, self.sheet_h, self.sheet_bytes // self.sheet_h), dtype=np.uint8)
+        row = self.sheet_bytes // self.sheet_h // self.out_count
+        out = np.empty((n, self.sheet_h, row) if self.out_count == 1 else (n, self.out_count, self.sheet_h, row), dtype=np.uint8)
         res = (SheetResult * n)()
         self.process_ptr(pages.ctypes.data, out.ctypes.data, n, True, res)
         return out, list(res)
