@@ -51,15 +51,95 @@ void *image_get_gpu_ptr(Image *image);
 size_t image_get_gpu_pitch(Image *image);
 void image_cuda_release(Image *image);      /* image.c:13,52 */
 
-/* replaces reference imageprocess/cuda_runtime.h (subset used by L3/L4) */
+/* replaces reference imageprocess/cuda_runtime.h, cuda_stream_pool.h, cuda_mempool.h: the
+ * subset the reference's L3/L4 code links against when built with UNPAPER_WITH_CUDA
+ * (lib/perf.c:39,63,86; lib/batch_worker.c:198-255; src/pipeline/image_pipeline.c:303-627).
+ * Defined in csrc/compat.c over the per-device caches and stream pool of csrc/rt.c. */
+#ifdef UNPAPER_B200_WITH_REFERENCE_HEADERS
+#include "imageprocess/cuda_mempool.h"
+#include "imageprocess/cuda_runtime.h"
+#include "imageprocess/cuda_stream_pool.h"
+#else
 typedef enum {
   UNPAPER_CUDA_INIT_OK = 0,
   UNPAPER_CUDA_INIT_NO_RUNTIME = 1,
   UNPAPER_CUDA_INIT_NO_DEVICE = 2,
   UNPAPER_CUDA_INIT_ERROR = 3,
 } UnpaperCudaInitStatus;
+typedef struct UnpaperCudaStream UnpaperCudaStream;   /* cuda_runtime.h:15 */
 UnpaperCudaInitStatus unpaper_cuda_try_init(void); /* cuda_runtime.c:137-215 */
 const char *unpaper_cuda_init_status_string(UnpaperCudaInitStatus st);
+/* cuda_runtime.h:62-67,93: streams; the current stream is per thread */
+UnpaperCudaStream *unpaper_cuda_stream_create(void);
+UnpaperCudaStream *unpaper_cuda_stream_get_default(void);
+void unpaper_cuda_stream_destroy(UnpaperCudaStream *stream);
+void unpaper_cuda_set_current_stream(UnpaperCudaStream *stream);
+UnpaperCudaStream *unpaper_cuda_get_current_stream(void);
+void unpaper_cuda_stream_synchronize_on(UnpaperCudaStream *stream);
+void unpaper_cuda_stream_synchronize(void);
+void *unpaper_cuda_stream_get_raw_handle(UnpaperCudaStream *stream);
+/* cuda_runtime.h:27-47,69-71: raw device memory (e.g. a GPU decoder's output buffer, then
+ * create_image_from_gpu) */
+uint64_t unpaper_cuda_malloc(size_t bytes);
+void unpaper_cuda_free(uint64_t dptr);
+void unpaper_cuda_memcpy_h2d(uint64_t dst, const void *src, size_t bytes);
+void unpaper_cuda_memcpy_d2h(void *dst, uint64_t src, size_t bytes);
+void unpaper_cuda_memcpy_d2d(uint64_t dst, uint64_t src, size_t bytes);
+void unpaper_cuda_memcpy_h2d_async(UnpaperCudaStream *stream, uint64_t dst, const void *src, size_t bytes);
+void unpaper_cuda_memcpy_d2h_async(UnpaperCudaStream *stream, void *dst, uint64_t src, size_t bytes);
+void unpaper_cuda_memcpy_d2d_async(UnpaperCudaStream *stream, uint64_t dst, uint64_t src, size_t bytes);
+void unpaper_cuda_memset_d8(uint64_t dst, uint8_t value, size_t bytes);
+void unpaper_cuda_memset_async(UnpaperCudaStream *stream, uint64_t dst, uint8_t value, size_t bytes);
+/* cuda_runtime.h:86-92: event pairs (perf recorder) */
+bool unpaper_cuda_events_supported(void);
+bool unpaper_cuda_event_pair_start(void **start, void **stop);
+double unpaper_cuda_event_pair_stop_ms(void **start, void **stop);
+bool unpaper_cuda_events_supported_on(UnpaperCudaStream *stream);
+bool unpaper_cuda_event_pair_start_on(UnpaperCudaStream *stream, void **start, void **stop);
+double unpaper_cuda_event_pair_stop_ms_on(UnpaperCudaStream *stream, void **start, void **stop);
+/* cuda_stream_pool.h:22-89 */
+typedef struct CudaStreamPool CudaStreamPool;
+typedef struct {
+  size_t stream_count, total_acquisitions, waits, peak_in_use, current_in_use;
+} CudaStreamPoolStats;
+CudaStreamPool *cuda_stream_pool_create(size_t stream_count);
+void cuda_stream_pool_destroy(CudaStreamPool *pool);
+UnpaperCudaStream *cuda_stream_pool_acquire(CudaStreamPool *pool);
+void cuda_stream_pool_release(CudaStreamPool *pool, UnpaperCudaStream *stream);
+CudaStreamPoolStats cuda_stream_pool_get_stats(const CudaStreamPool *pool);
+void cuda_stream_pool_print_stats(const CudaStreamPool *pool);
+bool cuda_stream_pool_global_init(size_t stream_count);
+void cuda_stream_pool_global_cleanup(void);
+bool cuda_stream_pool_global_active(void);
+UnpaperCudaStream *cuda_stream_pool_global_acquire(void);
+void cuda_stream_pool_global_release(UnpaperCudaStream *stream);
+CudaStreamPoolStats cuda_stream_pool_global_get_stats(void);
+void cuda_stream_pool_global_print_stats(void);
+/* cuda_mempool.h:19-141 (three global pools: image, integral, scratch) */
+typedef struct CudaMemPool CudaMemPool;
+typedef struct {
+  size_t total_allocations, pool_hits, pool_misses, size_mismatches, pool_exhaustion;
+  size_t current_in_use, peak_in_use, total_bytes_pooled, buffer_count, buffer_size;
+} CudaMemPoolStats;
+CudaMemPool *cuda_mempool_create(size_t buffer_count, size_t buffer_size);
+void cuda_mempool_destroy(CudaMemPool *pool);
+uint64_t cuda_mempool_acquire(CudaMemPool *pool, size_t bytes);
+void cuda_mempool_release(CudaMemPool *pool, uint64_t dptr);
+CudaMemPoolStats cuda_mempool_get_stats(const CudaMemPool *pool);
+void cuda_mempool_print_stats(const CudaMemPool *pool);
+#define B200_DECL_GLOBAL_POOL(NAME)                                        \
+  bool cuda_mempool_##NAME##global_init(size_t buffer_count, size_t buffer_size); \
+  void cuda_mempool_##NAME##global_cleanup(void);                          \
+  bool cuda_mempool_##NAME##global_active(void);                           \
+  uint64_t cuda_mempool_##NAME##global_acquire(size_t bytes);              \
+  void cuda_mempool_##NAME##global_release(uint64_t dptr);                 \
+  CudaMemPoolStats cuda_mempool_##NAME##global_get_stats(void);            \
+  void cuda_mempool_##NAME##global_print_stats(void);
+B200_DECL_GLOBAL_POOL()
+B200_DECL_GLOBAL_POOL(integral_)
+B200_DECL_GLOBAL_POOL(scratch_)
+#undef B200_DECL_GLOBAL_POOL
+#endif
 /* Per-thread current device + stream (reference: thread-local current stream,
  * cuda_runtime.c:70,616-626; extended here to {device, stream}). */
 int unpaper_b200_set_device(int device);

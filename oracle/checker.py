@@ -131,3 +131,19 @@ def save_image_cpu(lib, himg, out_fmt):
         return read_pnm(path)
     finally:
         os.unlink(path)
+
+
+def load_dropin():
+    """oracle/_ref/libunpaper_dropin.so: the reference's own L1-L3 built with
+    -DUNPAPER_WITH_CUDA=1 and LINKED AGAINST libunpaper_b200.so (oracle/Makefile target
+    `dropin`).  Same `ref_*` entry points as load_ref() plus ref_select_device()."""
+    p = os.path.join(ROOT, "oracle", "_ref", "libunpaper_dropin.so")
+    if not os.path.exists(p):
+        return None
+    lib = C.CDLL(p)
+    lib.ref_process_sheets.argtypes = [
+        C.POINTER(SheetConfig), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+        C.POINTER(SheetResult), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.ref_process_sheets.restype = C.c_int
+    lib.ref_backend_name.restype = C.c_char_p
+    return lib

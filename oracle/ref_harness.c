@@ -166,6 +166,7 @@ static Border tr_detect_border(Image image, BorderScanParameters p, const Rectan
   return b;
 }
 
+#ifndef REF_DROPIN
 const ImageBackend backend_cuda = {
     .name = "cpu-traced",
     .wipe_rectangle = wipe_rectangle_cpu,
@@ -189,13 +190,85 @@ const ImageBackend backend_cuda = {
     .detect_rotation = tr_detect_rotation,
     .deskew = deskew_cpu,
 };
+#endif
 
+#ifdef REF_DROPIN
+/* DROP-IN BUILD (oracle/Makefile target `dropin`): every reference source file is compiled
+ * with -DUNPAPER_WITH_CUDA=1 and the shared object is linked against libunpaper_b200.so,
+ * which supplies `backend_cuda`, the image residency calls and the cuda_runtime /
+ * stream-pool symbols.  ref_select_device() is the reference's own --device switch
+ * (image_backend_select, backend.c:79-97); process_sheet() then runs the reference's
+ * stage code over whichever backend is selected. */
+static int g_device = UNPAPER_DEVICE_CPU;
+int ref_select_device(int cuda) {
+  verbose = VERBOSE_QUIET;
+  g_device = cuda ? UNPAPER_DEVICE_CUDA : UNPAPER_DEVICE_CPU;
+  image_backend_select((UnpaperDevice)g_device);
+  return 0;
+}
+const char *ref_backend_name(void) { return image_backend_get()->name; }
+static int g_perf = 0;
+/* options->perf: the reference's perf recorder then times every stage with
+ * unpaper_cuda_event_pair_start/stop_ms (lib/perf.c:39,63,86) */
+int ref_set_perf(int on) { g_perf = on; return 0; }
+/* what src/pipeline/image_pipeline.c does around a batch: a global stream pool that
+ * lib/batch_worker.c:198-255 hands out per job */
+#include "imageprocess/cuda_runtime.h"
+#include "imageprocess/cuda_stream_pool.h"
+int ref_stream_pool(int n) {
+  if (n > 0) return cuda_stream_pool_global_init((size_t)n) ? 0 : -1;
+  cuda_stream_pool_global_cleanup();
+  return 0;
+}
+int ref_stream_pool_acquisitions(void) { return (int)cuda_stream_pool_global_get_stats().total_acquisitions; }
+
+/* The residency API the reference's GPU decode / encode paths use (image.h:32-61):
+ * a device buffer that did not come from image_ensure_cuda() becomes an Image
+ * (create_image_from_gpu), is processed in place through the selected backend and read
+ * back.  `mode` 0: the buffer is a view (owns_memory=false, freed by the caller);
+ * 1: unpaper_cuda_malloc'ed and handed over (owns_memory=true, freed with the image).
+ * `pitch` may be any value >= the row bytes.  Ops: detect_masks at the centre, wipe of
+ * `wipe`, copy of `wipe`'s area shifted by (100,60).  Returns the mask count, -1 on a protocol error. */
+int ref_gpu_image_roundtrip(const B200HostImage *in, int pitch, int mode, const Rectangle *wipe,
+                            const MaskDetectionParameters *mp, Rectangle *mask_out, uint8_t *out) {
+  int row = av_shim_row_bytes(in->format, in->width);
+  size_t bytes = (size_t)pitch * in->height;
+  uint8_t *staged = calloc(1, bytes);
+  for (int y = 0; y < in->height; y++) memcpy(staged + (size_t)y * pitch, in->data + (size_t)y * in->linesize, (size_t)row);
+  uint64_t d = unpaper_cuda_malloc(bytes);
+  unpaper_cuda_memcpy_h2d(d, staged, bytes);
+  free(staged);
+  Image img = create_image_from_gpu((void *)(uintptr_t)d, (size_t)pitch, in->width, in->height, in->format,
+                                    in->background, in->abs_black_threshold, mode == 1);
+  if (!img.frame) { unpaper_cuda_free(d); return -1; }
+  int rc = 0;
+  if (!image_is_gpu_resident(&img) || image_get_gpu_ptr(&img) != (void *)(uintptr_t)d ||
+      image_get_gpu_pitch(&img) != (size_t)pitch) rc = -1;
+  Point c = {in->width / 2, in->height / 2};
+  int n = (int)detect_masks(img, *mp, &c, 1, mask_out);
+  wipe_rectangle(img, *wipe, (Pixel){10, 20, 30});
+  copy_rectangle(img, img, *wipe, (Point){wipe->vertex[0].x + 100, wipe->vertex[0].y + 60});   /* disjoint from the source */
+  /* still the caller's buffer: nothing was reallocated or uploaded over it */
+  if (image_get_gpu_ptr(&img) != (void *)(uintptr_t)d) rc = -1;
+  image_ensure_cpu(&img);
+  for (int y = 0; y < in->height; y++) memcpy(out + (size_t)y * row, img.frame->data[0] + (size_t)y * img.frame->linesize[0], (size_t)row);
+  image_set_gpu_resident(&img, false);
+  if (image_is_gpu_resident(&img) || image_get_gpu_ptr(&img) != NULL) rc = -1;
+  image_set_gpu_resident(&img, true);
+  if (!image_is_gpu_resident(&img)) rc = -1;
+  free_image(&img);
+  if (mode == 0) unpaper_cuda_free(d);
+  return rc < 0 ? rc : n;
+}
+static void ensure_init(void) { verbose = VERBOSE_QUIET; }
+#else
 static pthread_once_t init_once = PTHREAD_ONCE_INIT;
 static void do_init(void) {
   verbose = VERBOSE_QUIET;
   image_backend_select(UNPAPER_DEVICE_CUDA); /* = the pass-through above */
 }
 static void ensure_init(void) { pthread_once(&init_once, do_init); }
+#endif
 
 /* ---- host image <-> reference Image ------------------------------------- */
 
@@ -341,8 +414,15 @@ static const struct MultiIndex MI_ALL = {.count = -1, .indexes = NULL};
 static void options_from_cfg(Options *o, Rectangle *bf_excl, const B200SheetConfig *c) {
   options_init(o);
   options_init_filter_defaults(o, bf_excl);
+#ifdef REF_DROPIN
+  o->device = (UnpaperDevice)g_device;
+#else
   o->device = UNPAPER_DEVICE_CPU;
+#endif
   o->write_output = false;
+#ifdef REF_DROPIN
+  o->perf = g_perf != 0;
+#endif
   o->layout = (Layout)c->layout;
   o->input_count = c->input_count;
   o->interpolate_type = (Interpolation)c->interpolate_type;
@@ -447,6 +527,9 @@ static int run_one_sheet(const B200SheetConfig *cfg, const Options *opt,
                          .format = page_fmt, .background = st.sheet.background,
                          .abs_black_threshold = st.sheet.abs_black_threshold};
       AVFrame f;
+#ifdef REF_DROPIN
+      image_ensure_cpu(&st.sheet);   /* what sheet_stage_output does before saving (sheet_stages.c:586) */
+#endif
       copy_rectangle_cpu(st.sheet, wrap(&o, &f), full_image(st.sheet), POINT_ORIGIN);
     }
   }
@@ -472,6 +555,14 @@ static void *worker(void *arg) {
   for (;;) {
     int i = atomic_fetch_add(&jb->next, 1);
     if (i >= jb->n_sheets) break;
+#ifdef REF_DROPIN
+    /* lib/batch_worker.c:198-203: one pooled stream per job, made the thread's current stream */
+    UnpaperCudaStream *stream = NULL;
+    if (g_device == UNPAPER_DEVICE_CUDA && cuda_stream_pool_global_active()) {
+      stream = cuda_stream_pool_global_acquire();
+      if (stream) unpaper_cuda_set_current_stream(stream);
+    }
+#endif
     char names[2][512];
     char *files[2] = {names[0], names[1]};
     for (int j = 0; jb->out_dir && j < jb->out_count && j < 2; j++)
@@ -482,6 +573,13 @@ static void *worker(void *arg) {
                            jb->results ? &jb->results[i] : NULL, jb->out_dir ? files : NULL, jb->out_count,
                            (jb->cfg->first_sheet_nr > 0 ? jb->cfg->first_sheet_nr : 1) + i);
     if (rc != 0) atomic_fetch_add(&jb->failed, 1);
+#ifdef REF_DROPIN
+    if (stream) {   /* lib/batch_worker.c:253-255 */
+      unpaper_cuda_stream_synchronize_on(stream);
+      cuda_stream_pool_global_release(stream);
+      unpaper_cuda_set_current_stream(NULL);
+    }
+#endif
   }
   return NULL;
 }

@@ -13,9 +13,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "unpaper_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = set(re.findall(r"\b((?:unpaper_b200_|unpaper_cuda_|image_|create_image_from_gpu)\w*)\s*\(", text))
+    names = set(re.findall(r"\b((?:unpaper_b200_|unpaper_cuda_|cuda_stream_pool_|image_|create_image_from_gpu)\w*)\s*\(", text))
     names.add("backend_cuda")
-    return sorted(names)
+    for pool in ("", "integral_", "scratch_"):      # B200_DECL_GLOBAL_POOL(...)
+        for fn in ("init", "cleanup", "active", "acquire", "release", "get_stats", "print_stats"):
+            names.add(f"cuda_mempool_{pool}global_{fn}")
+    names |= {"cuda_mempool_create", "cuda_mempool_destroy", "cuda_mempool_acquire", "cuda_mempool_release"}
+    return sorted(n for n in names if not n.endswith("##"))
 
 
 def test_library_exports_every_declared_symbol():
@@ -24,6 +28,19 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in _declared_symbols() if not hasattr(handle, n)]
     assert not missing, missing
     assert len(_declared_symbols()) > 50
+
+
+def test_library_exports_nothing_else():
+    """-fvisibility via the linker map (csrc/exports.map): only the declared API and the
+    reference's boundary names are dynamic symbols — no stage_*, no kernel launchers, no cudart."""
+    from unpaper_gpu_b200 import lib as L
+    out = subprocess.check_output(["nm", "-D", "--defined-only", L.LIB_PATH], text=True)
+    syms = [ln.split()[-1] for ln in out.splitlines() if ln.strip()]
+    allowed = re.compile(r"^(backend_cuda|image_\w+|create_image_from_gpu|unpaper_cuda_\w+|unpaper_b200_\w+|"
+                         r"cuda_stream_pool_\w+|cuda_mempool_\w+)$")
+    extra = [s for s in syms if not allowed.match(s)]
+    assert not extra, extra[:20]
+    assert len(syms) < 160
 
 
 def test_backend_vtable_shape():

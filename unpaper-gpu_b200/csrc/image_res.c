@@ -22,6 +22,8 @@ typedef struct {
   bool cpu_dirty;   /* host copy is newer */
   bool cuda_dirty;  /* device copy is newer */
   bool owns;        /* dptr came from b200_dev_alloc */
+  bool foreign;     /* dptr was handed in by create_image_from_gpu() */
+  bool owns_foreign; /* ... with owns_memory: cudaFree it on release */
   bool host_valid;  /* host buffer holds defined data */
   int device;
 } ImageRes;
@@ -31,6 +33,13 @@ static void res_free(void *opaque, uint8_t *data) {
   ImageRes *st = (ImageRes *)data;
   if (!st) return;
   if (st->dptr && st->owns) b200_dev_free(st->dptr);
+  if (st->dptr && st->owns_foreign) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != st->device) cudaSetDevice(st->device);
+    cudaFree(st->dptr);
+    if (cur != st->device) cudaSetDevice(cur);
+  }
   free(st);
 }
 
@@ -52,10 +61,16 @@ static size_t frame_bytes(const AVFrame *f) { return (size_t)f->linesize[0] * (s
 
 static void res_ensure_buffer(ImageRes *st, const AVFrame *f) {
   size_t need = frame_bytes(f) + 16;   /* +16: mono word atomics may touch the tail word */
+  /* a buffer handed in by create_image_from_gpu() (GRAY8 / RGB24 only: byte stores, no
+   * tail word) is exactly pitch*height bytes and is never replaced while the frame keeps
+   * its geometry */
+  size_t have_need = st->foreign ? frame_bytes(f) : need;
   bool same = st->dptr && st->width == f->width && st->height == f->height &&
-              st->format == f->format && st->pitch == f->linesize[0] && st->bytes >= need;
+              st->format == f->format && st->pitch == f->linesize[0] && st->bytes >= have_need;
   if (same) return;
   if (st->dptr && st->owns) b200_dev_free(st->dptr);
+  if (st->dptr && st->owns_foreign) cudaFree(st->dptr);
+  st->foreign = false; st->owns_foreign = false;
   st->dptr = b200_dev_alloc(need);
   st->owns = true;
   st->bytes = need;
@@ -146,15 +161,13 @@ Image create_image_from_gpu(void *gpu_ptr, size_t pitch, int width, int height, 
   f->linesize[0] = (int)pitch;
   img.frame = f;
   ImageRes *st = res_get(&img, true);
-  st->dptr = gpu_ptr; st->owns = false; st->bytes = bytes;
+  st->dptr = gpu_ptr; st->owns = false; st->foreign = true; st->bytes = bytes;
   st->width = width; st->height = height; st->format = pixel_format; st->pitch = (int)pitch;
   st->device = b200_rt_device();
   st->cpu_dirty = false; st->cuda_dirty = true; st->host_valid = false;
-  if (owns_memory) {
-    /* ownership of a foreign cudaMalloc'ed block: adopt by copying into the
-     * cache-owned buffer would cost a pass; instead free it with cudaFree on release. */
-    st->owns = false;
-  }
+  /* owns_memory (image_cuda.c:307-362): the block was cudaMalloc'ed by the decoder and
+   * now belongs to the image; it is cudaFree'd when the image is released */
+  st->owns_foreign = owns_memory;
   return img;
 }
 
