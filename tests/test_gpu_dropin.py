@@ -106,9 +106,9 @@ def test_create_image_from_gpu(dropin, ref_ops, fmt, mode):
     in place through the vtable (never reallocated, never overwritten by an upload), read back
     with image_ensure_cpu, and released (owns_memory=true frees it)."""
     w, h = 203, 131
-    src = noise_image(21, w, h, fmt, dark=0.25)
-    src[20:110, 30:170] = 255
-    src[40:90, (60 if fmt == U.FMT_GRAY8 else 180):(140 if fmt == U.FMT_GRAY8 else 420)] = 0
+    bpp = 1 if fmt == U.FMT_GRAY8 else 3
+    src = np.full((h, linesize(fmt, w)), 255, dtype=np.uint8)
+    src[30:100, 50 * bpp:150 * bpp] = noise_image(21, 100, 70, fmt, dark=0.5)[:, :100 * bpp]   # ink inside white margins
     row = U.bytes_per_row(fmt, w)
     pitch = row + 13
     wipe = U.rect(10, 12, 60, 40)
