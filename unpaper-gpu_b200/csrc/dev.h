@@ -38,7 +38,7 @@ enum { ST_GRAY = 0, ST_MAXCH = 1, ST_COUNT_GRAY_RANGE = 2 };
 /* a rectangle move: copy src_area of img -> aux(0,0); wipe src_area with bg;
  * copy aux -> img at (tx,ty).  (center_mask masks.c:222-249, align_mask
  * masks.c:265-305) */
-typedef struct { DRect area; int32_t tx, ty; int32_t enabled; int32_t pad; } DMove;
+typedef struct { DRect area; int32_t tx, ty; int32_t enabled; int32_t use_masks; } DMove;
 
 /* one line-sum job: sums `stat` along a band.  axis 0: out[x-xa] = sum over
  * y in [ya,yb] (column sums); axis 1: out[y-ya] = sum over x in [xa,xb]. */
@@ -50,7 +50,13 @@ typedef struct {
 
 typedef struct DPage {
   DImg img;              /* working image */
-  DImg aux;              /* scratch image, same format, capacity >= img */
+  DImg aux;              /* scratch image, same format, capacity >= img (vtable ops; unused by the sheet engine) */
+  /* sheet engine: every sheet slot has two buffers of equal geometry.  Passes that move
+   * pixels (deskew, centre / align a mask, shift) render img -> other in one sweep and
+   * then swap the two pointers; buf[] are the fixed addresses (img.data = buf[0] at the
+   * start of every sheet). */
+  uint8_t *other;
+  uint8_t *buf[2];
   uint8_t *cls;          /* [h*w] noisefilter classes */
   uint32_t *list;        /* noisefilter mutable list */
   uint32_t *u32;         /* general u32 scratch */

@@ -51,7 +51,7 @@ typedef struct {
   int slot;               /* flight being issued / collected */
   int ran;
   cudaEvent_t last_done_t;
-  uint8_t *sheets, *aux, *cls;
+  uint8_t *sheets, *sheets2, *cls;   /* two sheet buffers per slot: moves render from one into the other */
   uint32_t *list, *u32;
   uint64_t *stack;
   uint32_t *pre;
@@ -62,9 +62,6 @@ typedef struct {
   DFillJob *fillA, *fillB, *fillC, *decode_fill;
   DCopyJob *copyA, *copyB, *decode_copy, *decode_copy_host_tmpl;
   DMaskJob *maskJ;
-  /* shift_image (blit.c:360-368) before / after the pipeline: sheet -> aux, wipe, aux -> sheet at the delta */
-  DCopyJob *shift_out[2], *shift_in[2];
-  DFillJob *shift_fill[2];
   DFillJob *static_fill[3];   /* pre / mid / post wipe+border rectangles, per page */
   int static_fill_n[3];
   DMaskJob *static_mask[3];
@@ -217,8 +214,7 @@ static int build_static(B200Engine *e, Lane *ln, int slot, const Rectangle *wipe
 }
 
 static void lane_free(Lane *ln) {
-  void *ptrs[] = {ln->sheets, ln->aux, ln->cls, ln->list, ln->u32, ln->stack, ln->pre, ln->ink, ln->page_stage, ln->out_stage, ln->pages_dev,
-                  ln->shift_out[0], ln->shift_out[1], ln->shift_in[0], ln->shift_in[1], ln->shift_fill[0], ln->shift_fill[1],
+  void *ptrs[] = {ln->sheets, ln->sheets2, ln->cls, ln->list, ln->u32, ln->stack, ln->pre, ln->ink, ln->page_stage, ln->out_stage, ln->pages_dev,
                   ln->fillA, ln->fillB, ln->fillC, ln->decode_fill, ln->copyA, ln->copyB, ln->decode_copy, ln->maskJ,
                   ln->static_fill[0], ln->static_fill[1], ln->static_fill[2], ln->static_mask[0], ln->static_mask[1],
                   ln->static_mask[2], ln->static_mask_rects[0], ln->static_mask_rects[1], ln->static_mask_rects[2]};
@@ -385,9 +381,8 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
     }
     ln->slot = 0;
     ln->sheets = (uint8_t *)b200_dev_alloc(e->sheet_stride * P);
-    size_t aux_stride = (e->need.aux_bytes + 255) & ~(size_t)255;
+    ln->sheets2 = (uint8_t *)b200_dev_alloc(e->sheet_stride * P);
     size_t cls_stride = (e->need.cls_bytes + 255) & ~(size_t)255;
-    ln->aux = (uint8_t *)b200_dev_alloc(aux_stride * P);
     ln->cls = (uint8_t *)b200_dev_alloc(cls_stride * P);
     ln->list = (uint32_t *)b200_dev_alloc((size_t)e->need.list_cap * 4 * P);
     ln->u32 = (uint32_t *)b200_dev_alloc((size_t)e->need.u32_cap * 4 * P);
@@ -418,8 +413,8 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
       DPage *pg = &ln->pages_tmpl[p];
       pg->img = (DImg){ln->sheets + e->sheet_stride * p, W, H, e->sheet_pitch, e->dfmt, cfg->abs_black_threshold,
                        {cfg->sheet_background.r, cfg->sheet_background.g, cfg->sheet_background.b}};
-      pg->aux = pg->img;
-      pg->aux.data = ln->aux + aux_stride * p; pg->aux.pitch = e->need.aux_pitch; pg->aux.h = e->need.aux_h; pg->aux.w = W + 64;
+      pg->buf[0] = pg->img.data; pg->buf[1] = ln->sheets2 + e->sheet_stride * p;
+      pg->other = pg->buf[1];
       pg->cls = ln->cls + cls_stride * p;
       pg->list = ln->list + (size_t)e->need.list_cap * p; pg->list_cap = e->need.list_cap;
       pg->u32 = ln->u32 + (size_t)e->need.u32_cap * p; pg->u32_cap = e->need.u32_cap;
@@ -446,26 +441,6 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
         cj->tx = W * j / cfg->input_count; cj->ty = 0;
         cj->enabled = 1;
       }
-    }
-    for (int k = 0; k < 2; k++) {
-      Delta d = k == 0 ? cfg->pre_shift : cfg->post_shift;
-      if (d.horizontal == 0 && d.vertical == 0) continue;
-      DCopyJob *so = (DCopyJob *)calloc((size_t)P, sizeof(DCopyJob)), *si = (DCopyJob *)calloc((size_t)P, sizeof(DCopyJob));
-      DFillJob *sf = (DFillJob *)calloc((size_t)P, sizeof(DFillJob));
-      for (int p = 0; p < P; p++) {
-        const DPage *pg = &ln->pages_tmpl[p];
-        DImg tmp = pg->aux;
-        tmp.w = W; tmp.h = H;
-        so[p].src = pg->img; so[p].dst = tmp; so[p].area = (DRect){0, 0, W - 1, H - 1}; so[p].tx = 0; so[p].ty = 0; so[p].enabled = 1;
-        sf[p].img = pg->img; sf[p].r = (DRect){0, 0, W - 1, H - 1}; sf[p].enabled = 1;
-        sf[p].c[0] = cfg->sheet_background.r; sf[p].c[1] = cfg->sheet_background.g; sf[p].c[2] = cfg->sheet_background.b;
-        si[p].src = tmp; si[p].dst = pg->img; si[p].area = (DRect){0, 0, W - 1, H - 1};
-        si[p].tx = d.horizontal; si[p].ty = d.vertical; si[p].enabled = 1;
-      }
-      ln->shift_out[k] = (DCopyJob *)blob_upload(so, sizeof(DCopyJob) * P);
-      ln->shift_in[k] = (DCopyJob *)blob_upload(si, sizeof(DCopyJob) * P);
-      ln->shift_fill[k] = (DFillJob *)blob_upload(sf, sizeof(DFillJob) * P);
-      free(so); free(si); free(sf);
     }
     CUDA_OK(cudaMemcpy(ln->pages_dev, ln->pages_tmpl, sizeof(DPage) * P, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(ln->decode_fill, dfill, sizeof(DFillJob) * P, cudaMemcpyHostToDevice));
@@ -501,6 +476,12 @@ static void run_static(B200Engine *e, Lane *ln, StageCtx *c, int slot, int n, un
   int P = e->group;
   int q = 0;
   bool has_masks = slot == 0 && e->cfg.pre_mask_count > 0;
+  /* the tables were built for buffer 0; aim them at the buffer that holds the sheet now */
+  if (ln->static_fill_n[slot] > 0 || e->n_static_mask_jobs[slot] > 0) {
+    b200k_retarget_jobs(c->st, c->pages, n, ln->static_fill[slot], ln->static_fill_n[slot] * P,
+                        ln->static_mask[slot], e->n_static_mask_jobs[slot] * P, P);
+    c->launches++;
+  }
   if (has_masks) { b200k_apply_masks(c->st, ln->static_mask[slot] + (size_t)q * P, n, e->sheet_w, e->sheet_h); q++; c->launches++; }
   if (!(skip >> SW_WIPE & 1))
     for (int k = 0; k < ln->static_fill_n[slot]; k++) { b200k_fill_jobs(c->st, ln->static_fill[slot] + (size_t)k * P, n, e->sheet_w, e->sheet_h); c->launches++; }
@@ -522,12 +503,9 @@ void unpaper_b200_engine_set_first_sheet_nr(B200Engine *e, int sheet_nr) { if (e
 static void run_geometry(B200Engine *e, Lane *ln, StageCtx *c, int k, int n) {
   Direction m = k == 0 ? e->cfg.pre_mirror : e->cfg.post_mirror;
   if (m.horizontal || m.vertical) { b200k_mirror_pages(c->st, c->pages, n, e->sheet_w, e->sheet_h, m.horizontal, m.vertical); c->launches++; }
-  if (ln->shift_out[k]) {
-    b200k_copy_jobs(c->st, ln->shift_out[k], n, e->sheet_row, e->sheet_h);
-    b200k_fill_jobs(c->st, ln->shift_fill[k], n, e->sheet_w, e->sheet_h);
-    b200k_copy_jobs(c->st, ln->shift_in[k], n, e->sheet_row, e->sheet_h);
-    c->launches += 3;
-  }
+  Delta d = k == 0 ? e->cfg.pre_shift : e->cfg.post_shift;
+  (void)ln;
+  if (d.horizontal != 0 || d.vertical != 0) stage_shift_pass(c, d);   /* shift_image (blit.c:360-368) */
 }
 
 static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, int n, unsigned skip) {
@@ -584,27 +562,29 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
     for (int mi = 0; mi < nm; mi++) {
       stage_detect_rotation_mask(&c, &e->rot, mi);
       if (mi == nm - 1) mark(e, ln, STG_DESKEW);   /* profile split: exact for one mask */
-      stage_deskew_mask(&c, cfg->interpolate_type, mi);
+      stage_deskew_mask_pass(&c, cfg->interpolate_type, mi);
     }
     if (nm == 0) mark(e, ln, STG_DESKEW);
   } else { mark(e, ln, STG_ROTDET); mark(e, ln, STG_DESKEW); }
   mark(e, ln, STG_CENTER);
   if (!no_mask_center) {
     if (!no_mask_scan) stage_detect_masks(&c, &e->mask);
-    stage_center_masks(&c, nm);
+    stage_center_masks_pass(&c, nm);
   }
   run_static(e, ln, &c, 1, n, skip);
   mark(e, ln, STG_BORDER);
   if (!no_border_scan) {
     stage_detect_border(&c, &e->border);
-    stage_apply_border_masks(&c, cfg->mask_color);
-    if (!no_border_align) stage_align_masks(&c, &cfg->mask_alignment, e->noutside);
+    /* apply_masks(border masks) is fused into the first align_mask sweep */
+    if (!no_border_align && e->noutside > 0) stage_align_masks_pass(&c, &cfg->mask_alignment, e->noutside, cfg->mask_color);
+    else stage_apply_border_masks(&c, cfg->mask_color);
   }
   run_static(e, ln, &c, 2, n, skip);
   run_geometry(e, ln, &c, 1, n);
   mark(e, ln, STG_OUTPUT);
   /* output stage (sheet_stages.c:536-631): sheet -> caller, tight rows, + the decisions */
   size_t img_bytes = (size_t)e->out_row * e->sheet_h, out_sheet = img_bytes * e->out_count;
+  const uint8_t *cur = c.parity ? ln->sheets2 : ln->sheets;   /* the buffer that holds the finished sheets */
   if (e->out_fmt >= 0 || e->out_count > 1) {
     /* per output image: the sheet split of :606-621 (copy_rectangle of the j-th
      * sheet_w/output_count columns) and saveImage()'s conversion, straight into tight rows */
@@ -612,7 +592,7 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
     for (int j = 0; j < e->out_count; j++) {
       DImg sv;
       memset(&sv, 0, sizeof(sv));
-      sv.data = ln->sheets + (size_t)j * e->out_w * e->bpp; sv.w = e->out_w; sv.h = e->sheet_h; sv.pitch = e->sheet_pitch;
+      sv.data = (uint8_t *)cur + (size_t)j * e->out_w * e->bpp; sv.w = e->out_w; sv.h = e->sheet_h; sv.pitch = e->sheet_pitch;
       sv.fmt = e->dfmt; sv.abt = cfg->abs_black_threshold;
       if (e->out_fmt >= 0) {
         DImg dv = sv;
@@ -630,16 +610,16 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
     size_t sheet_bytes = (size_t)e->sheet_row * e->sheet_h;
     if (e->sheet_pitch == e->sheet_row) {
       /* rows are tight, sheets are `sheet_stride` apart: one 2-D copy with one "row" per sheet */
-      CUDA_OK(cudaMemcpy2DAsync(ln->out_host, sheet_bytes, ln->sheets, e->sheet_stride, sheet_bytes, (size_t)n,
+      CUDA_OK(cudaMemcpy2DAsync(ln->out_host, sheet_bytes, cur, e->sheet_stride, sheet_bytes, (size_t)n,
                                 cudaMemcpyDeviceToHost, c.st));
     } else {
       for (int p = 0; p < n; p++)
         CUDA_OK(cudaMemcpy2DAsync(ln->out_host + sheet_bytes * p, (size_t)e->sheet_row,
-                                  ln->sheets + e->sheet_stride * p, (size_t)e->sheet_pitch, (size_t)e->sheet_row,
+                                  cur + e->sheet_stride * p, (size_t)e->sheet_pitch, (size_t)e->sheet_row,
                                   (size_t)e->sheet_h, cudaMemcpyDeviceToHost, c.st));
     }
   } else {
-    b200k_pack_rows(c.st, ln->sheets, e->sheet_pitch, ln->out_dev, e->sheet_row, e->sheet_row, e->sheet_h, n,
+    b200k_pack_rows(c.st, cur, e->sheet_pitch, ln->out_dev, e->sheet_row, e->sheet_row, e->sheet_h, n,
                     e->sheet_stride, (size_t)e->sheet_row * e->sheet_h);
     c.launches++;
   }

@@ -102,6 +102,7 @@ typedef struct {
   RotHostJob *rot_jobs;       /* host memory, D_MAX_MASKS entries that stay valid until the group is done */
   DPage *rot_pull;            /* pinned, npages records */
   float *rot_tab_host, *rot_tab_dev;   /* pinned / device, 4 floats per page */
+  int parity;                 /* engine: which of the slot's two sheet buffers is the working image (same for the whole group) */
   uint64_t launches;
 } StageCtx;
 
@@ -118,6 +119,11 @@ void stage_center_masks(StageCtx *c, int max_masks);
 void stage_detect_border(StageCtx *c, const BorderPlan *pl);
 void stage_apply_border_masks(StageCtx *c, Pixel color);
 void stage_align_masks(StageCtx *c, const MaskAlignmentParameters *p, int n_outside);
+/* sheet-engine forms (two sheet buffers per slot, one sweep per move, see dev.h DPage.other) */
+void stage_deskew_mask_pass(StageCtx *c, int interp, int mi);
+void stage_center_masks_pass(StageCtx *c, int max_masks);
+void stage_align_masks_pass(StageCtx *c, const MaskAlignmentParameters *p, int n_outside, Pixel mask_color);
+void stage_shift_pass(StageCtx *c, Delta d);
 
 /* scratch sizing for one page of w x h in device format fmt */
 typedef struct { size_t aux_bytes; int aux_pitch, aux_h; size_t cls_bytes; int list_cap, u32_cap, stack_cap; long long pre_cap; } ScratchNeed;

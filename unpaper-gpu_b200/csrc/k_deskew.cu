@@ -714,6 +714,122 @@ __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) 
   }
 }
 
+// Sheet-engine form of deskew() (deskew.c:276-290) for mask `mi` of every page: ONE sweep
+// over the whole sheet from the working buffer into the slot's other buffer,
+//     dst(X,Y) = (X,Y) inside the pasted rectangle [mask.vertex[0], + size) ? rotate(...) : src(X,Y)
+// so there is no mask-sized temporary and no copy back (4 M bytes -> M + S).  Tiles that do
+// not touch the rectangle (and whole pages whose detected rotation is 0: the reference skips
+// deskew() for them, sheet_stages.c:410) are copied 16 bytes per thread.
+// GRAY8 + cubic fast path: the cubic arithmetic is evaluated unconditionally (the "equal
+// taps" identities are exact, so computing the formula gives the same value) — the only
+// branch is warp-uniform: a warp whose 32 pixels all sit on constant 4x4 neighbourhoods
+// skips the arithmetic.  Divergent per-row shortcuts cost more issue slots than they save.
+__global__ void __launch_bounds__(128) k_rotate_sheet(DPage *pages, int mi, int interp) {
+  DPage &pg = pages[blockIdx.z];
+  const DImg &im = pg.img;
+  DImg out = im;
+  out.data = pg.other;
+  const int W = im.w, H = im.h, bpp = bytes_pp(im.fmt);
+  const bool active = mi < pg.mask_count && pg.rot_apply[mi];
+  const DRect mask = pg.masks[mi];
+  const int w = abs(mask.x0 - mask.x1) + 1, h = abs(mask.y0 - mask.y1) + 1;
+  const int ox = mask.x0, oy = mask.y0;   // copy_rectangle(rotated, source, full, mask.vertex[0]) (deskew.c:283)
+  const int X0 = blockIdx.x * 128, Y0 = blockIdx.y * ROT_ROWS;
+  if (X0 >= W || Y0 >= H) return;
+  const int X1 = min(X0 + 127, W - 1), Y1 = min(Y0 + ROT_ROWS - 1, H - 1);
+  const bool touches = active && X1 >= ox && X0 < ox + w && Y1 >= oy && Y0 < oy + h;
+  if (!touches) {
+    int rows = Y1 - Y0 + 1, rowb = (X1 - X0 + 1) * bpp;
+    if (bpp > 0 && (im.pitch & 15) == 0 && (((uintptr_t)im.data | (uintptr_t)out.data) & 15) == 0) {
+      int nch = (rowb + 15) >> 4;      // a row's pitch padding may be copied along
+      for (int i = threadIdx.x; i < nch * rows; i += blockDim.x) {
+        int r = i / nch, c = i - r * nch;
+        size_t off = (size_t)(Y0 + r) * im.pitch + (size_t)X0 * bpp + ((size_t)c << 4);
+        *(uint4 *)(out.data + off) = *(const uint4 *)(im.data + off);
+      }
+    } else {
+      for (int r = 0; r < rows; r++)
+        for (int x = X0 + threadIdx.x; x <= X1; x += blockDim.x) { Px p = px_load(im, x, Y0 + r); px_store(out, x, Y0 + r, p.r, p.g, p.b); }
+    }
+    return;
+  }
+  // center_of_rectangle (primitives.c:136-145) of the (normalised) mask / of the target
+  const int nx0 = min(mask.x0, mask.x1), ny0 = min(mask.y0, mask.y1);
+  const float scx = nx0 + w / 2.0f, scy = ny0 + h / 2.0f;
+  const float tcx = 0 + w / 2.0f, tcy = 0 + h / 2.0f;
+  const float sinval = pg.rot_sin[mi], cosval = pg.rot_cos[mi];
+  const bool gray = im.fmt != DF_RGB24;
+  const bool fast = im.fmt == DF_GRAY8 && interp == 2 && (im.pitch & 3) == 0 && ((uintptr_t)im.data & 3) == 0;
+  const bool can_skip = pg.ink_ok && interp == 2 && (im.fmt == DF_GRAY8 || im.fmt == DF_RGB24);
+  const int lane = threadIdx.x & 31;
+  const int Xw = X0 + (threadIdx.x & ~31);          // this warp's 32 sheet columns
+  if (Xw >= W) return;                              // whole warp (warp-uniform)
+  const int X = Xw + lane;
+  const int x = X - ox;                             // column in the rotated image
+  const bool colin = X < W && x >= 0 && x < w;
+  const int wpitch = im.pitch >> 2;
+  for (int Yt = Y0; Yt <= Y1; Yt += ROT_TILE) {
+    const int Yte = min(Yt + ROT_TILE - 1, Y1);
+    // the warp's tile entirely inside the pasted rectangle and its source footprint pure white?
+    bool tile_in = Xw >= ox && min(Xw + 31, W - 1) < ox + w && Yt >= oy && Yte < oy + h;
+    if (can_skip && tile_in &&
+        rot_tile_white(pg, im, Xw - ox, min(Xw + 31, W - 1) - ox, Yt - oy, Yte - oy, scx, scy, tcx, tcy, sinval, cosval, lane)) {
+      if (X < W)
+        for (int Y = Yt; Y <= Yte; Y++) {
+          uint8_t *o = out.data + (size_t)Y * out.pitch + (size_t)X * bpp;
+          o[0] = 255; if (bpp == 3) { o[1] = 255; o[2] = 255; }
+        }
+      continue;
+    }
+    for (int Y = Yt; Y <= Yte; Y++) {
+      const int y = Y - oy;
+      const bool inside = colin && y >= 0 && y < h;
+      float srcX = 0.0f, srcY = 0.0f;
+      if (inside) {
+        float xf = u8f((unsigned)x), yf = u8f((unsigned)y);   // == (float)x, (float)y for 0 <= v < 2^23
+        srcX = scx + (xf - tcx) * cosval + (yf - tcy) * sinval;
+        srcY = scy + (yf - tcy) * cosval - (xf - tcx) * sinval;
+      }
+      bool fastok = false;
+      unsigned rw[4] = {0, 0, 0, 0};
+      float tX = 0.0f, tY = 0.0f;
+      if (fast && inside) {
+        // (int)srcX for 1 <= srcX < 2^23 by the 2^23 trick (anything else fails the range test)
+        tX = __fadd_rz(srcX, 8388608.0f); tY = __fadd_rz(srcY, 8388608.0f);
+        int px = __float_as_int(tX) - 0x4B000000, py = __float_as_int(tY) - 0x4B000000;
+        fastok = (unsigned)(px - 1) < (unsigned)(W - 3) && (unsigned)(py - 1) < (unsigned)(H - 3);
+        if (fastok) {
+          const uint8_t *p0 = im.data + (size_t)(py - 1) * im.pitch + (px - 1);
+          const unsigned *wp = (const unsigned *)((uintptr_t)p0 & ~(uintptr_t)3);
+          unsigned sh = ((unsigned)(uintptr_t)p0 & 3u) * 8u;
+#pragma unroll
+          for (int i = 0; i < 4; i++) rw[i] = __funnelshift_r(wp[i * wpitch], wp[i * wpitch + 1], sh);
+        }
+      }
+      unsigned o = rw[0] & 0xFFu;
+      bool uni = rw[0] == o * 0x01010101u && rw[1] == rw[0] && rw[2] == rw[0] && rw[3] == rw[0];
+      if (__any_sync(0xffffffffu, fastok && !uni)) {
+        if (fastok) {
+          float fx = srcX - (tX - 8388608.0f), fy = srcY - (tY - 8388608.0f);   // srcX - (float)px
+          float hfx = 0.5f * fx;
+          unsigned r0 = cubic_scale_w(fx, hfx, rw[0]), r1 = cubic_scale_w(fx, hfx, rw[1]);
+          unsigned r2 = cubic_scale_w(fx, hfx, rw[2]), r3 = cubic_scale_w(fx, hfx, rw[3]);
+          unsigned lo = __byte_perm(r0, r1, 0x0040), hi = __byte_perm(r2, r3, 0x0040);
+          o = cubic_scale_w(fy, 0.5f * fy, __byte_perm(lo, hi, 0x5410));
+        }
+      }
+      if (fastok) { out.data[(size_t)Y * out.pitch + X] = (uint8_t)o; continue; }
+      if (inside) {
+        Px q = interp_any(im, srcX, srcY, interp, gray);
+        px_store(out, X, Y, q.r, q.g, q.b);
+      } else if (X < W) {
+        Px q = px_load(im, X, Y);
+        px_store(out, X, Y, q.r, q.g, q.b);
+      }
+    }
+  }
+}
+
 // stretch_frame (blit.c:209-228)
 __global__ void k_stretch(DImg src, DImg dst, float hr, float vr, int interp) {
   int y = blockIdx.y;
@@ -779,6 +895,12 @@ void b200k_rotate(cudaStream_t st, DPage *pages, int npages, int mi, int interp,
   if (interp == 2) k_inkmap<<<dim3(min(cdiv(maxh, INK_CELL), 256u), npages), 128, 0, st>>>(pages);
   dim3 g(min(cdiv(maxw, 128), 64u), cdiv(maxh, ROT_ROWS), npages);
   k_rotate<<<g, 128, 0, st>>>(pages, mi, interp, back_jobs);
+}
+void b200k_rotate_sheet(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int maxw, int maxh) {
+  if (npages <= 0 || maxw <= 0 || maxh <= 0) return;
+  if (interp == 2) k_inkmap<<<dim3(min(cdiv(maxh, INK_CELL), 256u), npages), 128, 0, st>>>(pages);
+  dim3 g(cdiv(maxw, 128), cdiv(maxh, ROT_ROWS), npages);
+  k_rotate_sheet<<<g, 128, 0, st>>>(pages, mi, interp);
 }
 void b200k_stretch(cudaStream_t st, DImg src, DImg dst, float hr, float vr, int interp) {
   if (dst.w <= 0 || dst.h <= 0) return;

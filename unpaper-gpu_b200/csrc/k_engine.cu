@@ -10,12 +10,30 @@ __global__ void k_page_reset(DPage *pages, int npages) {
   if (p >= npages) return;
   DPage &pg = pages[p];
   pg.list_n = 0; pg.nf_clusters = 0; pg.bf_fills = 0; pg.error = 0;
+  if (pg.buf[0]) { pg.img.data = pg.buf[0]; pg.other = pg.buf[1]; }
+  pg.move.enabled = 0; pg.move.use_masks = 0;
   pg.mask_count = 0; pg.mask_count_deskew = 0; pg.ink_ok = 0;
   for (int i = 0; i < D_MAX_MASKS; i++) {
     pg.rotation[i] = 0.0f; pg.rot_sin[i] = 0.0f; pg.rot_cos[i] = 1.0f; pg.rot_apply[i] = 0; pg.centered[i] = 0;
     pg.mask_valid[i] = 0;
     for (int e = 0; e < 4; e++) { pg.edge_count[i][e] = 0; pg.rot_angle_idx[i][e] = -1; }
   }
+}
+
+// after a pass img -> other: the rendered buffer becomes the working image
+__global__ void k_swap_sheets(DPage *pages, int npages) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npages) return;
+  DPage &pg = pages[p];
+  uint8_t *t = pg.img.data; pg.img.data = pg.other; pg.other = t;
+}
+
+// static job tables (wipes, borders, pre-masks: geometry known at engine creation) carry an
+// image descriptor per page; point them at the page's CURRENT working buffer
+__global__ void k_retarget_jobs(const DPage *pages, int npages, DFillJob *fills, int nfill, DMaskJob *masks, int nmask, int stride) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nfill) { int p = i % stride; if (p < npages) fills[i].img.data = pages[p].img.data; }
+  if (i < nmask) { int p = i % stride; if (p < npages) masks[i].img.data = pages[p].img.data; }
 }
 
 // Strided row copy between packed host-layout images and pitched device
@@ -84,6 +102,16 @@ void b200k_convert_out(cudaStream_t st, DImg src, DImg dst, int nimages, size_t 
   unsigned per_row = dst.fmt == DF_MONOWHITE ? (unsigned)(src.w + 7) / 8 : (unsigned)src.w;
   dim3 g(min(cdiv(per_row, 256), 16u), src.h, nimages);
   k_convert_out<<<g, 256, 0, st>>>(src, dst, src_stride, dst_stride);
+}
+void b200k_swap_sheets(cudaStream_t st, DPage *pages, int npages) {
+  if (npages <= 0) return;
+  k_swap_sheets<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages);
+}
+void b200k_retarget_jobs(cudaStream_t st, const DPage *pages, int npages, DFillJob *fills, int nfill,
+                         DMaskJob *masks, int nmask, int stride) {
+  int n = nfill > nmask ? nfill : nmask;
+  if (npages <= 0 || n <= 0) return;
+  k_retarget_jobs<<<cdiv(n, 128), 128, 0, st>>>(pages, npages, fills, nfill, masks, nmask, stride);
 }
 void b200k_page_reset(cudaStream_t st, DPage *pages, int npages) {
   if (npages <= 0) return;

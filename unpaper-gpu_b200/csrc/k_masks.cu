@@ -279,6 +279,48 @@ __global__ void k_prep_align(DPage *pages, int npages, int i, AlignParams ap, Mo
   emit_move(pg, mj, p, inside, tx, ty, enabled);
 }
 
+// the same decisions as k_prep_center / k_prep_align, for the one-sweep move (k_move_pass)
+__global__ void k_prep_center_move(DPage *pages, int npages, int i) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npages) return;
+  DPage &pg = pages[p];
+  DMove mv = {DRect{0, 0, 0, 0}, 0, 0, 0, 0};
+  if (i < pg.mask_count) {
+    mv.area = pg.masks[i];
+    int w = abs(mv.area.x0 - mv.area.x1) + 1, h = abs(mv.area.y0 - mv.area.y1) + 1;
+    mv.tx = pg.px[i] + (-w / 2); mv.ty = pg.py[i] + (-h / 2);
+    DRect full = DRect{0, 0, pg.img.w - 1, pg.img.h - 1};
+    mv.enabled = pt_in_rect(mv.tx, mv.ty, full) && pt_in_rect(mv.tx + w - 1, mv.ty + h - 1, full);
+    pg.centered[i] = mv.enabled;
+  }
+  pg.move = mv;
+}
+__global__ void k_prep_align_move(DPage *pages, int npages, int i, AlignParams ap, int use_masks) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npages) return;
+  DPage &pg = pages[p];
+  DMove mv = {DRect{0, 0, 0, 0}, 0, 0, 0, use_masks};
+  if (i < pg.outside_count) {
+    DRect inside = pg.border_mask[i], out = pg.outside[i];
+    int w = abs(inside.x0 - inside.x1) + 1, h = abs(inside.y0 - inside.y1) + 1;
+    if (ap.left) mv.tx = out.x0 + ap.margin_h;
+    else if (ap.right) mv.tx = out.x1 - w - ap.margin_h;
+    else mv.tx = (out.x0 + out.x1 - w) / 2;
+    if (ap.top) mv.ty = out.y0 + ap.margin_v;
+    else if (ap.bottom) mv.ty = out.y1 - h - ap.margin_v;
+    else mv.ty = (out.y0 + out.y1 - h) / 2;
+    mv.area = inside; mv.enabled = 1;
+  }
+  pg.move = mv;
+}
+__global__ void k_prep_shift_move(DPage *pages, int npages, int dx, int dy) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npages) return;
+  DPage &pg = pages[p];
+  DMove mv = {DRect{0, 0, pg.img.w - 1, pg.img.h - 1}, dx, dy, 1, 0};
+  pg.move = mv;
+}
+
 // apply_masks job over the detected border masks (sheet_stages.c:474-475)
 __global__ void k_prep_border_maskjob(DPage *pages, int npages, DMaskJob *jobs, uint8_t r, uint8_t g, uint8_t b) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -327,6 +369,17 @@ void b200k_prep_align(cudaStream_t st, DPage *pages, int npages, int i, int left
   MoveJobs mj = {fill_aux, copy_out, wipe, copy_in, wipe2};
   AlignParams ap = {left, top, right, bottom, margin_h, margin_v};
   k_prep_align<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages, i, ap, mj);
+}
+void b200k_prep_center_move(cudaStream_t st, DPage *pages, int npages, int i) {
+  if (npages > 0) k_prep_center_move<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages, i);
+}
+void b200k_prep_align_move(cudaStream_t st, DPage *pages, int npages, int i, int left, int top, int right,
+                           int bottom, int margin_h, int margin_v, int use_masks) {
+  AlignParams ap = {left, top, right, bottom, margin_h, margin_v};
+  if (npages > 0) k_prep_align_move<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages, i, ap, use_masks);
+}
+void b200k_prep_shift_move(cudaStream_t st, DPage *pages, int npages, int dx, int dy) {
+  if (npages > 0) k_prep_shift_move<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages, dx, dy);
 }
 void b200k_prep_border_maskjob(cudaStream_t st, DPage *pages, int npages, DMaskJob *jobs, int r, int g, int b) {
   k_prep_border_maskjob<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages, jobs, (uint8_t)r, (uint8_t)g, (uint8_t)b);

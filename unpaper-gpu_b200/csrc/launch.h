@@ -69,6 +69,18 @@ void b200k_rotate(cudaStream_t st, DPage *pages, int npages, int mi, int interp,
 void b200k_stretch(cudaStream_t st, DImg src, DImg dst, float hr, float vr, int interp);
 
 /* k_engine.cu — sheet-engine helpers */
+void b200k_swap_sheets(cudaStream_t st, DPage *pages, int npages);
+void b200k_retarget_jobs(cudaStream_t st, const DPage *pages, int npages, DFillJob *fills, int nfill,
+                         DMaskJob *masks, int nmask, int stride);
+/* one-sweep rectangle move img -> other of every page's DPage.move (k_blit.cu) */
+void b200k_move_pass(cudaStream_t st, DPage *pages, int npages, int maxw_bytes, int maxh, int mc_r, int mc_g, int mc_b);
+/* k_masks.cu: fill DPage.move for center_mask(i) / align_mask(i) / shift_image */
+void b200k_prep_center_move(cudaStream_t st, DPage *pages, int npages, int i);
+void b200k_prep_align_move(cudaStream_t st, DPage *pages, int npages, int i, int left, int top, int right,
+                           int bottom, int margin_h, int margin_v, int use_masks);
+void b200k_prep_shift_move(cudaStream_t st, DPage *pages, int npages, int dx, int dy);
+/* k_deskew.cu: deskew() of mask `mi` as one full-sheet pass img -> other */
+void b200k_rotate_sheet(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int maxw, int maxh);
 void b200k_page_reset(cudaStream_t st, DPage *pages, int npages);
 void b200k_pack_rows(cudaStream_t st, const uint8_t *src, int src_pitch, uint8_t *dst, int dst_pitch,
                      int row_bytes, int rows, int nimages, size_t src_stride, size_t dst_stride);

@@ -466,6 +466,49 @@ void stage_deskew(StageCtx *c, int interp, int max_masks) {
   for (int mi = 0; mi < max_masks; mi++) stage_deskew_mask(c, interp, mi);
 }
 
+/* ---- sheet-engine forms: one sweep img -> other, then the buffers change roles ---- */
+
+void stage_deskew_mask_pass(StageCtx *c, int interp, int mi) {
+  b200k_rotate_sheet(c->st, c->pages, c->npages, mi, interp, c->w, c->h);
+  b200k_swap_sheets(c->st, c->pages, c->npages);
+  c->parity ^= 1;
+  c->launches += 2 + (interp == 2);
+}
+
+static void move_pass(StageCtx *c, Pixel mask_color) {
+  b200k_move_pass(c->st, c->pages, c->npages, c->w * bppf(c->fmt), c->h, mask_color.r, mask_color.g, mask_color.b);
+  b200k_swap_sheets(c->st, c->pages, c->npages);
+  c->parity ^= 1;
+  c->launches += 2;
+}
+
+void stage_center_masks_pass(StageCtx *c, int max_masks) {
+  Pixel none = {0, 0, 0};
+  for (int i = 0; i < max_masks; i++) {
+    b200k_prep_center_move(c->st, c->pages, c->npages, i);
+    c->launches += 1;
+    move_pass(c, none);
+  }
+}
+
+/* apply_masks(border masks) + align_mask() per outside area (sheet_stages.c:474-483); the
+ * mask painting rides on the first move */
+void stage_align_masks_pass(StageCtx *c, const MaskAlignmentParameters *p, int n_outside, Pixel mask_color) {
+  for (int i = 0; i < n_outside; i++) {
+    b200k_prep_align_move(c->st, c->pages, c->npages, i, p->alignment.left, p->alignment.top, p->alignment.right,
+                          p->alignment.bottom, p->margin.horizontal, p->margin.vertical, i == 0);
+    c->launches += 1;
+    move_pass(c, mask_color);
+  }
+}
+
+void stage_shift_pass(StageCtx *c, Delta d) {
+  Pixel none = {0, 0, 0};
+  b200k_prep_shift_move(c->st, c->pages, c->npages, d.horizontal, d.vertical);
+  c->launches += 1;
+  move_pass(c, none);
+}
+
 static void run_move(StageCtx *c) {
   int aw = c->w + 64, ah = c->h + 64;
   b200k_fill_jobs(c->st, c->fillA, c->npages, aw, ah);
