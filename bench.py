@@ -98,8 +98,20 @@ class ClockSampler:
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _one_page(seed):
+    return synth.gray_page(seed, W, H)
+
+
 def make_pages(n_distinct, rank):
-    return np.stack([synth.gray_page(rank * 100003 + i, W, H) for i in range(n_distinct)])
+    """`n_distinct` pages with per-page seeds (BASELINE config 5), generated on the host
+    cores in parallel.  Must run before CUDA is initialised in this process (fork)."""
+    seeds = [rank * 100003 + i for i in range(n_distinct)]
+    nproc = min(len(seeds), max(1, len(os.sched_getaffinity(0))), 32)
+    if nproc <= 1:
+        return np.stack([_one_page(s) for s in seeds])
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(nproc) as pool:
+        return np.stack(pool.map(_one_page, seeds, chunksize=max(1, len(seeds) // (4 * nproc))))
 
 
 def run_reference(args, rank, world):
@@ -162,8 +174,10 @@ def main():
     ap.add_argument("--e2e-pages", type=int, default=int(os.environ.get("BENCH_E2E_PAGES", "1024")), help="sheets per rank per step (host-buffer arm)")
     ap.add_argument("--group", type=int, default=int(os.environ.get("BENCH_GROUP", "32")))
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("BENCH_LANES", "8")))
-    ap.add_argument("--distinct", type=int, default=int(os.environ.get("BENCH_DISTINCT", "8")))
+    ap.add_argument("--distinct", type=int, default=int(os.environ.get("BENCH_DISTINCT", "256")),
+                    help="distinct synthetic pages per rank (per-page seeds); the step's pages cycle through them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-iso", action="store_true", help="skip the isolated per-stage pass (profiling runs)")
     ap.add_argument("--out-format", default="page", choices=["page", "mono"],
                     help="sheet_stage_output format: 'page' (GRAY8, the headline config) or 'mono' (pbm, 1 bit/px D2H)")
     args = ap.parse_args()
@@ -175,7 +189,9 @@ def main():
         run_reference(args, rank, world)
         return
 
-    affinity = shard.bind_near_gpu(local) if world > 1 else None   # before CUDA/pinned allocations
+    affinity = shard.bind_near_gpu(local, world) if world > 1 else None   # before CUDA/pinned allocations
+    args.distinct = max(1, min(args.distinct, args.pages))
+    distinct = make_pages(args.distinct, rank)                      # before CUDA exists in this process (fork)
     import torch
     import torch.distributed as dist
     from unpaper_gpu_b200.lib import Engine
@@ -194,7 +210,6 @@ def main():
     if args.out_format == "mono":
         eng.set_output_format(U.FMT_MONOWHITE)
     out_bytes = eng.sheet_bytes
-    distinct = make_pages(args.distinct, rank)
     reps = (args.pages + args.distinct - 1) // args.distinct
     host_np = np.concatenate([distinct] * reps)[:args.pages]
     e2e_pages = min(args.e2e_pages, args.pages)
@@ -205,13 +220,17 @@ def main():
     res = (U.SheetResult * args.pages)()
 
     def pcie_gbs():
-        """Raw pinned-memory copy bandwidth of this box: the ceiling of the e2e arm."""
+        """Raw pinned-memory copy bandwidth: the ceiling of the e2e arm.  Every phase starts
+        behind a barrier, so with N ranks all N GPUs copy at the same time and the sum of the
+        per-rank rates is what the node (not one link) can move."""
         n = min(e2e_pages, 64)
         t_h2d = t_d2h = 1e9
         for _ in range(3):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
             a.record(); dev_out[:n].copy_(host_in[:n], non_blocking=True); b.record(); b.synchronize()
             t_h2d = min(t_h2d, a.elapsed_time(b))
+            barrier()
             a.record(); host_out[:n].copy_(dev_out[:n], non_blocking=True); b.record(); b.synchronize()
             t_d2h = min(t_d2h, a.elapsed_time(b))
         # both directions at once (what the e2e arm asks of the link): two streams, one clock
@@ -220,7 +239,7 @@ def main():
         scratch = torch.empty_like(dev_out[:n])
         for _ in range(3):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
+            barrier()
             a.record()
             s1.wait_event(a); s2.wait_event(a)
             with torch.cuda.stream(s1):
@@ -231,7 +250,9 @@ def main():
             b.record(); b.synchronize()
             t_bi = min(t_bi, a.elapsed_time(b))
         gb = n * W * H / 1e9
-        return round(gb / (t_h2d / 1e3), 1), round(gb / (t_d2h / 1e3), 1), round(gb / (t_bi / 1e3), 1)
+        mine = [gb / (t_h2d / 1e3), gb / (t_d2h / 1e3), gb / (t_bi / 1e3)]
+        node = shard.sum_over_ranks(mine, device=f"cuda:{local}")       # all ranks copied at the same time
+        return [round(x, 1) for x in mine], [round(x, 1) for x in node]
 
     def step_device():
         eng.process_ptr(dev_in.data_ptr(), dev_out.data_ptr(), args.pages, False, res)
@@ -256,15 +277,16 @@ def main():
         t = shard.max_over_ranks([dev_ms, wall_ms], device=f"cuda:{local}")
         return t[0], t[1], eng.launch_count() - l0
 
+    (h2d_gbs, d2h_gbs, bidir_gbs), node_gbs = pcie_gbs()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     dev_ms, dev_wall_ms, launches = timed(step_device, args.steps, max(args.warmup, 3), profile=True)
     prof = eng.profile()
+    spread = eng.profile_spread()
     eng.set_profiling(False)
-    e2e_ms, e2e_wall_ms, _ = timed(step_host, args.steps, 1)
+    e2e_ms, e2e_wall_ms, _ = timed(step_host, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
-    h2d_gbs, d2h_gbs, bidir_gbs = pcie_gbs()
 
     # correctness guard: every sheet deskewed and flagged ok
     bad = sum(1 for r in res if r.status != 0)
@@ -277,7 +299,9 @@ def main():
     # engine are idle by now).  This is "the kernel's own launch duration"; the numbers
     # taken inside the timed region (all lanes competing for the SMs) are reported too.
     iso = None
-    if rank == 0:
+    if rank == 0 and args.no_iso:
+        iso = (prof, args.group)
+    elif rank == 0:
         ie = Engine(cfg, W, H, U.FMT_GRAY8, group_pages=min(args.group, 64), lanes=1, device=local)
         n_iso = min(args.group, 64)
         for _ in range(2):
@@ -349,9 +373,17 @@ def main():
                         "wall_ms_per_step": e2e_wall_ms / args.steps, "pages_per_step_per_gpu": e2e_pages,
                         "pcie_h2d_gbs": h2d_gbs, "pcie_d2h_gbs": d2h_gbs,
                         "pcie_bidir_gbs_each_way": bidir_gbs,
-                        "pcie_bound_pages_per_sec_per_gpu": round(min(h2d_gbs, d2h_gbs, bidir_gbs) * 1e9 / S, 1)},
+                        "pcie_bound_pages_per_sec_per_gpu": round(min(h2d_gbs, d2h_gbs, bidir_gbs) * 1e9 / S, 1),
+                        # the node ceiling: every rank copying at once, both directions (sum over ranks, GB/s each way)
+                        "node_copy_gbs": {"h2d": node_gbs[0], "d2h": node_gbs[1], "bidir_each_way": node_gbs[2]},
+                        "node_copy_bound_pages_per_sec": round(node_gbs[2] * 1e9 / S, 1),
+                        "frac_of_node_copy_bound": round(e2e_value / (node_gbs[2] * 1e9 / S), 4)},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "stages": per_stage,
                 "stages_isolated": iso_stage,
+                # fastest / slowest group of the serial-per-page stages inside the timed region (pages differ:
+                # a group finishes with its slowest page)
+                "group_spread_ms": {k: [round(v[0], 4), round(v[1], 4)] for k, v in spread.items()
+                                    if k in ("blackfilter", "noisefilter", "grayfilter", "deskew")},
                 "failed_sheets": bad}
         if world == 1 and not args.no_cpu_baseline:
             lib = checker.load_ref()
@@ -364,10 +396,16 @@ def main():
                 if len(sample) < cores:
                     sample = np.concatenate([sample] * ((cores + len(sample) - 1) // len(sample)))[:cores]
                 t0 = time.time()
-                checker.process_sheets_cpu(lib, prefix, cfg, sample, W, H, U.FMT_GRAY8, threads=cores, want_out=False)
+                ref_out, _ = checker.process_sheets_cpu(lib, prefix, cfg, sample, W, H, U.FMT_GRAY8, threads=cores, want_out=True)
                 dt = time.time() - t0
                 line["cpu_baseline"] = {"value": len(sample) / dt, "unit": UNIT, "cores": cores, "kind": kind,
                                         "sample": f"{len(sample)} pages of the same workload, {cores} threads, one pass ({dt:.1f} s)"}
+                # the checker's sheets are at hand: hold the timed e2e output of the same pages to them
+                nv = min(len(sample), e2e_pages, args.pages)
+                got = host_out[:nv].numpy().reshape(nv, -1)
+                bad_bytes = int((got != ref_out[:nv].reshape(nv, -1)).sum()) if args.out_format == "page" else None
+                line["verified_sheets"] = nv if bad_bytes == 0 else 0
+                line["verify_mismatch_bytes"] = bad_bytes
         print(json.dumps(line))
     eng.close()
     if world > 1:

@@ -353,6 +353,20 @@ int unpaper_b200_engine_process_device(B200Engine *e, const uint8_t *pages_dev,
 int unpaper_b200_engine_process_host(B200Engine *e, const uint8_t *pages_host,
                                      uint8_t *out_host, int n_sheets,
                                      B200SheetResult *results);
+/* The same as a stream: begin, feed any number of batches as they become available
+ * (each call issues its groups and returns; sheets are handed to the callback /
+ * `results` as their groups complete, in order), end drains.  This is what a page
+ * scheduler feeds from a decoded-page queue (reference lib/batch_worker.c:101-149
+ * consuming lib/decode_queue.h).  `pages`/`out` of a feed must stay valid until its
+ * sheets have been reported.  `first_index`: job index of the feed's first sheet
+ * (callback index, per-sheet switches); -1 = position in the stream.
+ * stream_poll collects the oldest group in flight (blocking) and returns 1, or 0 if none. */
+int unpaper_b200_engine_stream_begin(B200Engine *e, int host_mode);
+int unpaper_b200_engine_stream_feed(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_sheets,
+                                    B200SheetResult *results, int first_index);
+int unpaper_b200_engine_stream_poll(B200Engine *e);
+int unpaper_b200_engine_stream_in_flight(const B200Engine *e);
+int unpaper_b200_engine_stream_end(B200Engine *e);
 /* Per-sheet completion hook (reference: BatchWorkerPostProcessFn,
  * lib/batch_worker.h:22-25, called at batch_worker.c:153-158 after a successful
  * process_sheet()).  Called on the thread that runs process_*, in sheet order,
@@ -375,6 +389,41 @@ int unpaper_b200_engine_set_profiling(B200Engine *e, int enabled);
 int unpaper_b200_engine_get_profile(const B200Engine *e, int max_entries,
                                     const char **names, double *ms,
                                     uint64_t *launches, double *alg_bytes);
+/* fastest / slowest group of each stage since profiling was switched on (ms) */
+int unpaper_b200_engine_get_profile_spread(const B200Engine *e, int max_entries, double *min_ms, double *max_ms);
+
+/* ------------------------------------------------------------------------
+ * (4) page scheduler across GPUs (replaces lib/batch_worker.c:174-296 +
+ *     lib/decode_queue.h for this path)
+ * --------------------------------------------------------------------- */
+
+/* Producer hook, shaped like DecodeQueueCustomDecoder (lib/decode_queue.h:54-56): put
+ * the input_count decoded pages of job `sheet_index` (tight rows, the engine's page
+ * format) into `dst_pinned`.  Return 0, 1 = no more input (the job list ends before
+ * this sheet), < 0 = error.  Called concurrently from one producer thread per device. */
+typedef int (*B200PageProducerFn)(void *user, int sheet_index, uint8_t *dst_pinned);
+/* Sink: sheet `sheet_index` is finished on `device`; `sheet` (pinned host memory, the
+ * engine's output layout) is valid during the call only.  Called from that device's
+ * feeder thread, in job order per device.  Non-zero fails the run. */
+typedef int (*B200PoolSheetFn)(void *user, int sheet_index, int device, const uint8_t *sheet,
+                               const B200SheetResult *result);
+typedef struct B200Pool B200Pool;
+
+/* One engine, one bounded ring of pinned slots (the decoded-page queue) and two
+ * threads (producer, feeder) per device; job indices come from one shared counter.
+ * devices == NULL: devices 0..n_devices-1.  slot_sheets <= 0: group_pages;
+ * slots_per_device is raised to what the lanes need to stay full. */
+B200Pool *unpaper_b200_pool_create(const B200SheetConfig *cfg, const int *devices, int n_devices,
+                                   int page_width, int page_height, int page_format,
+                                   int group_pages, int lanes, int slot_sheets, int slots_per_device);
+void unpaper_b200_pool_destroy(B200Pool *p);
+/* Process jobs 0..n_sheets-1; returns when all are done.  `results` may be NULL. */
+int unpaper_b200_pool_run(B200Pool *p, int n_sheets, B200PageProducerFn produce, void *produce_user,
+                          B200PoolSheetFn sink, void *sink_user, B200SheetResult *results);
+int unpaper_b200_pool_device_count(const B200Pool *p);
+size_t unpaper_b200_pool_sheet_bytes(const B200Pool *p);
+uint64_t unpaper_b200_pool_sheets_done(const B200Pool *p, int device_index);   /* of the last run */
+B200Engine *unpaper_b200_pool_engine(B200Pool *p, int device_index);           /* e.g. to set the output format */
 
 const char *unpaper_b200_last_error(void);
 const char *unpaper_b200_version(void);

@@ -38,7 +38,12 @@ enum { ST_GRAY = 0, ST_MAXCH = 1, ST_COUNT_GRAY_RANGE = 2 };
 /* a rectangle move: copy src_area of img -> aux(0,0); wipe src_area with bg;
  * copy aux -> img at (tx,ty).  (center_mask masks.c:222-249, align_mask
  * masks.c:265-305) */
-typedef struct { DRect area; int32_t tx, ty; int32_t enabled; int32_t use_masks; } DMove;
+typedef struct {
+  DRect area; int32_t tx, ty; int32_t enabled; int32_t use_masks;
+  /* sorted byte positions along a row where the source of a pixel can change (k_move_pass) */
+  int32_t nseg, pad;
+  int32_t bnd[16];
+} DMove;
 
 /* one line-sum job: sums `stat` along a band.  axis 0: out[x-xa] = sum over
  * y in [ya,yb] (column sums); axis 1: out[y-ya] = sum over x in [xa,xb]. */

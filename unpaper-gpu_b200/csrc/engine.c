@@ -45,7 +45,8 @@ typedef struct {
     int ev_mask;          /* which stage boundaries were recorded */
     DPage *pages_res;     /* pinned */
     const uint8_t *out;   /* where this flight's sheets land (caller memory) */
-    int busy, first, n;
+    int busy, first, n;   /* first: index of the group's first sheet within its stream */
+    B200SheetResult *res; /* where this group's results go (NULL: not wanted) */
     unsigned skip;        /* stage switches of this group's sheets */
   } fl[2];
   int slot;               /* flight being issued / collected */
@@ -100,8 +101,10 @@ struct B200Engine {
   int32_t *sw_idx[SW_COUNT + 1]; int sw_n[SW_COUNT + 1];
   B200SheetDoneFn done_fn; void *done_user; int done_failed;
   double last_device_ms;
-  double stage_ms[STG_COUNT];
+  double stage_ms[STG_COUNT], stage_ms_min[STG_COUNT], stage_ms_max[STG_COUNT];
   uint64_t stage_groups[STG_COUNT];
+  /* stream state: groups [g_done, g) are in flight, at most two per lane */
+  int streaming, host_mode, g, g_done, fed;
 };
 
 static int imax(int a, int b) { return a > b ? a : b; }
@@ -162,6 +165,12 @@ int unpaper_b200_engine_get_profile(const B200Engine *e, int max_entries, const 
     if (alg_bytes) alg_bytes[n] = 0;
     n++;
   }
+  return n;
+}
+
+int unpaper_b200_engine_get_profile_spread(const B200Engine *e, int max_entries, double *min_ms, double *max_ms) {
+  int n = 0;
+  for (int s = 0; s < STG_COUNT && n < max_entries; s++, n++) { min_ms[n] = e->stage_ms_min[s]; max_ms[n] = e->stage_ms_max[s]; }
   return n;
 }
 
@@ -632,14 +641,17 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
   e->launches += c.launches;
 }
 
-static void collect(B200Engine *e, Lane *ln, B200SheetResult *results) {
+static void collect(B200Engine *e, Lane *ln) {
   if (!ln->fl[ln->slot].busy) return;
+  B200SheetResult *results = ln->fl[ln->slot].res;
   CUDA_OK(cudaEventSynchronize(ln->fl[ln->slot].done));
   if (e->profiling) {
     for (int s = 0; s < STG_COUNT; s++) {
       float ms = 0;
       if ((ln->fl[ln->slot].ev_mask >> s & 1) && (ln->fl[ln->slot].ev_mask >> (s + 1) & 1) &&
           cudaEventElapsedTime(&ms, ln->fl[ln->slot].ev[s], ln->fl[ln->slot].ev[s + 1]) == cudaSuccess) {
+        if (e->stage_groups[s] == 0 || ms < e->stage_ms_min[s]) e->stage_ms_min[s] = ms;
+        if (e->stage_groups[s] == 0 || ms > e->stage_ms_max[s]) e->stage_ms_max[s] = ms;
         e->stage_ms[s] += ms; e->stage_groups[s] += 1;
       }
     }
@@ -650,7 +662,7 @@ static void collect(B200Engine *e, Lane *ln, B200SheetResult *results) {
     for (int p = 0; p < ln->fl[ln->slot].n; p++) {
       const DPage *pg = &ln->fl[ln->slot].pages_res[p];
       B200SheetResult local;
-      B200SheetResult *r = results ? &results[ln->fl[ln->slot].first + p] : &local;
+      B200SheetResult *r = results ? &results[p] : &local;
       memset(r, 0, sizeof(*r));
       r->status = pg->error ? -(int)pg->error : 0;
       r->sheet_width = e->sheet_w; r->sheet_height = e->sheet_h;
@@ -687,42 +699,69 @@ static void collect(B200Engine *e, Lane *ln, B200SheetResult *results) {
   ln->fl[ln->slot].busy = 0;
 }
 
-static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_sheets, B200SheetResult *results, int host_mode) {
-  if (!e || !pages || !out || n_sheets < 0) { b200_set_error("engine: bad arguments"); return -1; }
+/* ---- streams: begin, feed any number of batches, end ------------------------------
+ * Groups are issued round-robin over the lanes, two flights per lane, and collected in
+ * issue order; a process_* call is one stream fed once. */
+
+static void collect_next(B200Engine *e) {
+  int k = e->g_done++;
+  Lane *ln = &e->lanes[k % e->nlanes];
+  ln->slot = (k / e->nlanes) & 1;
+  collect(e, ln);
+}
+
+int unpaper_b200_engine_stream_begin(B200Engine *e, int host_mode) {
+  if (!e) { b200_set_error("engine: bad arguments"); return -1; }
+  if (e->streaming) { b200_set_error("engine: a stream is already open"); return -1; }
   unpaper_b200_set_device(e->device);
-  int P = e->group, ic = e->cfg.input_count;
-  size_t out_sheet = unpaper_b200_engine_sheet_bytes(e);
-  int g = 0;
   for (int i = 0; i < e->nlanes; i++) e->lanes[i].ran = 0;
   /* every lane is idle here, so an event on lane 0 marks the start of device work */
   if (!e->ev_begin) CUDA_OK(cudaEventCreate(&e->ev_begin));
   CUDA_OK(cudaEventRecord(e->ev_begin, e->lanes[0].st));
+  e->streaming = 1; e->host_mode = host_mode; e->g = 0; e->g_done = 0; e->fed = 0;
+  return 0;
+}
+
+/* `total`: sheets of the whole stream if known (a process_* call), else -1 */
+static int stream_feed(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_sheets, B200SheetResult *results, int total, int first_index) {
+  if (!e || !e->streaming || (n_sheets > 0 && (!pages || !out)) || n_sheets < 0) { b200_set_error("engine: bad arguments"); return -1; }
+  unpaper_b200_set_device(e->device);
+  int P = e->group, ic = e->cfg.input_count, host_mode = e->host_mode;
+  size_t out_sheet = unpaper_b200_engine_sheet_bytes(e);
   /* Through host buffers the first groups only start computing once their upload is
    * done and the last download runs after everything else: ramp the group size up at
-   * the start and down at the end (quarter, half, full) so that both are short. */
+   * the start and (when the end is known) down at the end — quarter, half, full. */
   int q = P / 4 > 0 ? P / 4 : 1, hf = P / 2 > 0 ? P / 2 : 1;
-  int ramp = host_mode && n_sheets >= 4 * e->nlanes * (q + hf) ? e->nlanes * (q + hf) : 0;   /* sheets in each ramp */
-  for (int first = 0, n = 0; first < n_sheets; first += n, g++) {
-    Lane *ln = &e->lanes[g % e->nlanes];
-    ln->slot = (g / e->nlanes) & 1;
-    collect(e, ln, results);          /* the flight issued two rounds ago on this lane */
+  int ramp_n = e->nlanes * (q + hf);          /* sheets in each ramp */
+  int ramp_up = host_mode && (total < 0 || total >= 4 * ramp_n);
+  int ramp_down = host_mode && total >= 4 * ramp_n;
+  for (int first = 0, n = 0; first < n_sheets; first += n) {
+    while (e->g - e->g_done >= 2 * e->nlanes) collect_next(e);   /* the flight this group reuses */
+    Lane *ln = &e->lanes[e->g % e->nlanes];
+    ln->slot = (e->g / e->nlanes) & 1;
+    int pos = e->fed + first;                 /* position in the stream */
     int left = n_sheets - first;
     n = P;
-    if (ramp) {
-      if (first < e->nlanes * q) n = q;
-      else if (first < ramp) n = hf;
-      else if (left <= e->nlanes * q) n = q;
-      else if (left <= ramp) n = hf;
-      else if (left - P < ramp) n = left - ramp;   /* the last full-size group ends where the down-ramp begins */
+    if (ramp_up && pos < e->nlanes * q) n = q;
+    else if (ramp_up && pos < ramp_n) n = hf;
+    else if (ramp_down) {
+      int tleft = total - pos;
+      if (tleft <= e->nlanes * q) n = q;
+      else if (tleft <= ramp_n) n = hf;
+      else if (tleft - P < ramp_n) n = tleft - ramp_n;   /* the last full-size group ends where the down-ramp begins */
     }
     if (n > left) n = left;
     if (n > P) n = P;
+    if (n < 1) n = 1;
     /* a group shares its kernel sequence: cut it where the per-sheet stage switches change */
-    unsigned skip = sheet_skip(e, first);
-    for (int m = 1; m < n; m++) if (sheet_skip(e, first + m) != skip) { n = m; break; }
-    ln->fl[ln->slot].first = first; ln->fl[ln->slot].n = n; ln->fl[ln->slot].skip = skip; ln->host_mode = host_mode;
+    int idx = first_index >= 0 ? first_index + first : pos;   /* job index of the group's first sheet */
+    unsigned skip = sheet_skip(e, idx);
+    for (int m = 1; m < n; m++) if (sheet_skip(e, idx + m) != skip) { n = m; break; }
+    struct Flight *fl = &ln->fl[ln->slot];
+    fl->first = idx; fl->n = n; fl->skip = skip; fl->res = results ? results + first : NULL;
+    ln->host_mode = host_mode;
     const uint8_t *src = pages + e->page_bytes * ic * (size_t)first;
-    ln->fl[ln->slot].out = out + out_sheet * first;
+    fl->out = out + out_sheet * first;
     if (host_mode) {
       ln->out_host = out + out_sheet * first;
       if (ic == 1 && e->sheet_pitch == e->page_row && e->page_dfmt == e->dfmt) {
@@ -739,15 +778,33 @@ static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_shee
       ln->out_dev = out + out_sheet * first;
       issue_group(e, ln, src, n, skip);
     }
-    ln->fl[ln->slot].busy = 1;
+    fl->busy = 1;
+    e->g++;
   }
-  /* drain in issue order */
-  int total_groups = g;
-  for (int k = (total_groups > 2 * e->nlanes ? total_groups - 2 * e->nlanes : 0); k < total_groups; k++) {
-    Lane *ln = &e->lanes[k % e->nlanes];
-    ln->slot = (k / e->nlanes) & 1;
-    collect(e, ln, results);
-  }
+  e->fed += n_sheets;
+  return 0;
+}
+
+int unpaper_b200_engine_stream_feed(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_sheets, B200SheetResult *results,
+                                    int first_index) {
+  return stream_feed(e, pages, out, n_sheets, results, -1, first_index);
+}
+
+/* collect the oldest group still in flight (blocks until it is done); 0 when nothing is in flight */
+int unpaper_b200_engine_stream_poll(B200Engine *e) {
+  if (!e || !e->streaming) return 0;
+  unpaper_b200_set_device(e->device);
+  if (e->g_done >= e->g) return 0;
+  collect_next(e);
+  return 1;
+}
+int unpaper_b200_engine_stream_in_flight(const B200Engine *e) { return e && e->streaming ? e->g - e->g_done : 0; }
+
+int unpaper_b200_engine_stream_end(B200Engine *e) {
+  if (!e || !e->streaming) { b200_set_error("engine: no open stream"); return -1; }
+  unpaper_b200_set_device(e->device);
+  while (e->g_done < e->g) collect_next(e);   /* drain in issue order */
+  e->streaming = 0;
   CUDA_OK(cudaGetLastError());
   e->last_device_ms = 0.0;
   for (int i = 0; i < e->nlanes; i++) {
@@ -766,6 +823,13 @@ static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_shee
   if (bad) b200_set_error("engine: %d sheet(s) reported device-side failure flags 0x%x (e.g. sheet %d)", bad, e->bad_flags, e->bad_first);
   e->bad_flags = 0;
   return bad ? -2 : 0;
+}
+
+static int process(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_sheets, B200SheetResult *results, int host_mode) {
+  if (!e || !pages || !out || n_sheets < 0) { b200_set_error("engine: bad arguments"); return -1; }
+  if (unpaper_b200_engine_stream_begin(e, host_mode)) return -1;
+  if (stream_feed(e, pages, out, n_sheets, results, n_sheets, -1)) { e->streaming = 0; return -1; }
+  return unpaper_b200_engine_stream_end(e);
 }
 
 int unpaper_b200_engine_process_device(B200Engine *e, const uint8_t *pages_dev, uint8_t *out_dev, int n_sheets,

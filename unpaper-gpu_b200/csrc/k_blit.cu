@@ -200,35 +200,12 @@ __global__ void k_apply_masks(const DMaskJob *jobs) {
 // T = [tx,tx+w) x [ty,ty+h), area' = area clipped to the image with origin a0', and
 // src'(q) = src(q) or — with use_masks, the apply_masks() of the detected border masks that
 // precedes align_mask (sheet_stages.c:474-475) fused in — the mask colour when q lies in no mask.
+// The x positions where the category of a byte can change (edges of T, of its part that
+// has a source, of area', of the masks — unshifted and shifted by the move) do not depend
+// on the row: the prep kernel sorts them once per page into DMove.bnd.  A warp owns a row;
+// for every segment between two boundaries it classifies the first byte (row-dependent,
+// warp-uniform) and streams the segment with 16-byte stores.
 #define MOVE_ROWS 8
-__device__ __forceinline__ uint4 pat16(const uint8_t pat[3], int phase) {
-  unsigned w[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    int o = phase + 4 * k;
-    w[k] = (unsigned)pat[o % 3] | ((unsigned)pat[(o + 1) % 3] << 8) | ((unsigned)pat[(o + 2) % 3] << 16) | ((unsigned)pat[(o + 3) % 3] << 24);
-  }
-  return make_uint4(w[0], w[1], w[2], w[3]);
-}
-__device__ __forceinline__ uint4 load16_any(const uint8_t *p) {
-  unsigned mis = (unsigned)(uintptr_t)p & 3u;
-  const unsigned *q = (const unsigned *)(p - mis);
-  if (mis == 0) return make_uint4(q[0], q[1], q[2], q[3]);
-  unsigned sh = mis * 8, a = q[0], b = q[1], c = q[2], d = q[3], e = q[4];
-  return make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh), __funnelshift_r(c, d, sh), __funnelshift_r(d, e, sh));
-}
-// pixels [xa..xb] of row y against the page's border masks: 0 = in none, 1 = all in one mask, 2 = mixed
-__device__ __forceinline__ int span_in_masks(const DPage &pg, int xa, int xb, int y) {
-  int cls = 0;
-  for (int k = 0; k < pg.outside_count; k++) {
-    DRect r = pg.border_mask[k];
-    int ax = min(r.x0, r.x1), bx = max(r.x0, r.x1), ay = min(r.y0, r.y1), by = max(r.y0, r.y1);
-    if (y < ay || y > by || xb < ax || xa > bx) continue;
-    if (xa >= ax && xb <= bx) return 1;
-    cls = 2;
-  }
-  return cls;
-}
 __device__ __forceinline__ bool px_in_masks(const DPage &pg, int x, int y) {
   for (int k = 0; k < pg.outside_count; k++) if (pt_in_rect(x, y, pg.border_mask[k])) return true;
   return false;
@@ -238,69 +215,49 @@ __global__ void __launch_bounds__(256) k_move_pass(DPage *pages, uint8_t c0, uin
   const DPage &pg = pages[blockIdx.z];
   const DImg &im = pg.img;
   uint8_t *dstb = pg.other;
-  const DMove mv = pg.move;
   const int W = im.w, H = im.h;
   const bool rgb = im.fmt == DF_RGB24;
   const int bpp = rgb ? 3 : 1;
-  const int nx0 = min(mv.area.x0, mv.area.x1), nx1 = max(mv.area.x0, mv.area.x1);
-  const int ny0 = min(mv.area.y0, mv.area.y1), ny1 = max(mv.area.y0, mv.area.y1);
+  const DRect area = pg.move.area;
+  const int nx0 = min(area.x0, area.x1), nx1 = max(area.x0, area.x1);
+  const int ny0 = min(area.y0, area.y1), ny1 = max(area.y0, area.y1);
   const int w = nx1 - nx0 + 1, h = ny1 - ny0 + 1;
   const int ax0 = max(nx0, 0), ax1 = min(nx1, W - 1), ay0 = max(ny0, 0), ay1 = min(ny1, H - 1);   // clip_rectangle
   const int wc = ax1 - ax0 + 1, hc = ay1 - ay0 + 1;
   const bool have_src = wc > 0 && hc > 0;
-  const bool en = mv.enabled != 0;
-  const bool um = mv.use_masks != 0 && pg.outside_count > 0;   // apply_masks paints nothing without masks (masks.c:313-315)
-  const int tx = mv.tx, ty = mv.ty;
+  const bool en = pg.move.enabled != 0;
+  const bool um = pg.move.use_masks != 0 && pg.outside_count > 0;   // apply_masks paints nothing without masks (masks.c:313-315)
+  const int tx = pg.move.tx, ty = pg.move.ty;
+  const int nseg = pg.move.nseg;
   uint8_t bgp[3], mcp[3];
   {
     uint8_t bgg = (uint8_t)((im.bg[0] + im.bg[1] + im.bg[2]) / 3), mcg = (uint8_t)((c0 + c1 + c2) / 3);
     bgp[0] = rgb ? im.bg[0] : bgg; bgp[1] = rgb ? im.bg[1] : bgg; bgp[2] = rgb ? im.bg[2] : bgg;
     mcp[0] = rgb ? c0 : mcg; mcp[1] = rgb ? c1 : mcg; mcp[2] = rgb ? c2 : mcg;
   }
-  const int rowbytes = W * bpp, nch = (rowbytes + 15) >> 4;
-  const bool vec_ok = ((im.pitch & 15) == 0) && (((uintptr_t)im.data | (uintptr_t)dstb) & 15) == 0;
   const int tb0 = tx * bpp, tb1 = (tx + w) * bpp, tsv = tb0 + (have_src ? wc : 0) * bpp, ab0 = ax0 * bpp, ab1 = (ax1 + 1) * bpp;
-  for (int i = threadIdx.x; i < nch * MOVE_ROWS; i += blockDim.x) {
-    int r = i / nch, c = i - r * nch;
-    int y = blockIdx.y * MOVE_ROWS + r;
-    if (y >= H) break;
-    int b0 = c << 4, b1 = min(b0 + 15, rowbytes - 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int yend = min(H, (int)(blockIdx.y + 1) * MOVE_ROWS);
+  for (int y = blockIdx.y * MOVE_ROWS + warp; y < yend; y += 8) {
     const uint8_t *srow = im.data + (size_t)y * im.pitch;
     uint8_t *drow = dstb + (size_t)y * im.pitch;
-    bool rowT = en && y >= ty && y < ty + h;
-    int v = y - ty;
-    bool srcrow = rowT && have_src && v < hc;
-    int tse = srcrow ? tsv : tb0;                 // [tb0, tse): pasted pixels that have a source, [tse, tb1): background
-    bool rowA = en && have_src && y >= ay0 && y <= ay1;
+    const bool rowT = en && y >= ty && y < ty + h;
+    const int v = y - ty;
+    const bool srcrow = rowT && have_src && v < hc;
+    const int tse = srcrow ? tsv : tb0;             // [tb0, tse): pasted pixels that have a source, [tse, tb1): background
+    const bool rowA = en && have_src && y >= ay0 && y <= ay1;
     const uint8_t *trow = im.data + (size_t)(ay0 + v) * im.pitch + ab0 - tb0;   // source of byte b of T: trow[b]
-    bool uniform = vec_ok && b1 - b0 == 15;
-    if (uniform && rowT) uniform = !(tb0 > b0 && tb0 <= b1) && !(tb1 > b0 && tb1 <= b1) && !(tse > b0 && tse <= b1);
-    if (uniform && rowA) uniform = !(ab0 > b0 && ab0 <= b1) && !(ab1 > b0 && ab1 <= b1);
-    if (uniform) {
-      int cat;   // 0 keep, 1 background, 2 pasted
-      if (rowT && b0 >= tb0 && b0 < tb1) cat = b0 < tse ? 2 : 1;
-      else if (rowA && b0 >= ab0 && b0 < ab1) cat = 1;
-      else cat = 0;
-      if (cat == 1) { *(uint4 *)(drow + b0) = pat16(bgp, b0 % 3); continue; }
-      int sxa, sxb, sy;
-      const uint8_t *sp;
-      if (cat == 0) { sp = srow + b0; sxa = b0 / bpp; sxb = b1 / bpp; sy = y; }
-      else { sp = trow + b0; sxa = (b0 - tb0) / bpp + ax0; sxb = (b1 - tb0) / bpp + ax0; sy = ay0 + v; }
-      int cls = um ? span_in_masks(pg, sxa, sxb, sy) : 1;
-      if (cls == 1) { *(uint4 *)(drow + b0) = cat == 0 ? *(const uint4 *)sp : load16_any(sp); continue; }
-      if (cls == 0) { *(uint4 *)(drow + b0) = pat16(mcp, b0 % 3); continue; }
-    }
-    for (int b = b0; b <= b1; b++) {
-      uint8_t val;
-      int sx, sy;
+    for (int s = 0; s < nseg; s++) {
+      const int p = pg.move.bnd[s], q = pg.move.bnd[s + 1];
+      if (q <= p) continue;
       const uint8_t *sp = NULL;
-      if (rowT && b >= tb0 && b < tb1) {
-        if (b < tse) { sp = trow + b; sx = (b - tb0) / bpp + ax0; sy = ay0 + v; }
-      } else if (!(rowA && b >= ab0 && b < ab1)) { sp = srow + b; sx = b / bpp; sy = y; }
-      if (!sp) val = bgp[b % 3];
-      else if (um && !px_in_masks(pg, sx, sy)) val = mcp[b % 3];
-      else val = *sp;
-      drow[b] = val;
+      int sx = 0, sy = 0;
+      if (rowT && p >= tb0 && p < tb1) {
+        if (p < tse) { sp = trow; sx = (p - tb0) / bpp + ax0; sy = ay0 + v; }
+      } else if (!(rowA && p >= ab0 && p < ab1)) { sp = srow; sx = p / bpp; sy = y; }
+      if (!sp) fill_run(drow + p, q - p, bgp, p % 3, lane, 32);
+      else if (um && !px_in_masks(pg, sx, sy)) fill_run(drow + p, q - p, mcp, p % 3, lane, 32);
+      else copy_run(drow + p, sp + p, q - p, lane, 32);
     }
   }
 }

@@ -11,7 +11,7 @@ __global__ void k_page_reset(DPage *pages, int npages) {
   DPage &pg = pages[p];
   pg.list_n = 0; pg.nf_clusters = 0; pg.bf_fills = 0; pg.error = 0;
   if (pg.buf[0]) { pg.img.data = pg.buf[0]; pg.other = pg.buf[1]; }
-  pg.move.enabled = 0; pg.move.use_masks = 0;
+  pg.move.enabled = 0; pg.move.use_masks = 0; pg.move.nseg = 0;
   pg.mask_count = 0; pg.mask_count_deskew = 0; pg.ink_ok = 0;
   for (int i = 0; i < D_MAX_MASKS; i++) {
     pg.rotation[i] = 0.0f; pg.rot_sin[i] = 0.0f; pg.rot_cos[i] = 1.0f; pg.rot_apply[i] = 0; pg.centered[i] = 0;

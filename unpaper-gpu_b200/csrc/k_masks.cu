@@ -279,12 +279,45 @@ __global__ void k_prep_align(DPage *pages, int npages, int i, AlignParams ap, Mo
   emit_move(pg, mj, p, inside, tx, ty, enabled);
 }
 
+// row-independent segment boundaries of a move (see k_move_pass in k_blit.cu)
+__device__ void move_finish(DPage &pg, DMove mv) {
+  const DImg &im = pg.img;
+  int W = im.w, H = im.h, bpp = im.fmt == DF_RGB24 ? 3 : 1, rowbytes = W * bpp;
+  int nx0 = min(mv.area.x0, mv.area.x1), nx1 = max(mv.area.x0, mv.area.x1);
+  int ny0 = min(mv.area.y0, mv.area.y1), ny1 = max(mv.area.y0, mv.area.y1);
+  int w = nx1 - nx0 + 1;
+  int ax0 = max(nx0, 0), ax1 = min(nx1, W - 1), ay0 = max(ny0, 0), ay1 = min(ny1, H - 1);
+  int wc = ax1 - ax0 + 1, hc = ay1 - ay0 + 1;
+  bool have_src = wc > 0 && hc > 0;
+  int tb0 = mv.tx * bpp, tb1 = (mv.tx + w) * bpp, tsv = tb0 + (have_src ? wc : 0) * bpp, ab0 = ax0 * bpp, ab1 = (ax1 + 1) * bpp;
+  int b[16], n = 0;
+#define PUSH(v) { int t_ = (v); b[n++] = t_ < 0 ? 0 : t_ > rowbytes ? rowbytes : t_; }
+  PUSH(0); PUSH(rowbytes);
+  if (mv.enabled) {
+    PUSH(tb0); PUSH(tsv); PUSH(tb1);
+    if (have_src) { PUSH(ab0); PUSH(ab1); }
+  }
+  if (mv.use_masks)
+    for (int k = 0; k < pg.outside_count && k < D_MAX_BORDERS; k++) {
+      DRect r = pg.border_mask[k];
+      int m0 = min(r.x0, r.x1) * bpp, m1 = (max(r.x0, r.x1) + 1) * bpp;
+      PUSH(m0); PUSH(m1);
+      if (mv.enabled) { PUSH(m0 + tb0 - ab0); PUSH(m1 + tb0 - ab0); }
+    }
+#undef PUSH
+  for (int i = 1; i < n; i++) { int v = b[i], j = i - 1; while (j >= 0 && b[j] > v) { b[j + 1] = b[j]; j--; } b[j + 1] = v; }
+  mv.nseg = n - 1; mv.pad = 0;
+  for (int i = 0; i < 16; i++) mv.bnd[i] = i < n ? b[i] : rowbytes;
+  pg.move = mv;
+}
+
 // the same decisions as k_prep_center / k_prep_align, for the one-sweep move (k_move_pass)
 __global__ void k_prep_center_move(DPage *pages, int npages, int i) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npages) return;
   DPage &pg = pages[p];
-  DMove mv = {DRect{0, 0, 0, 0}, 0, 0, 0, 0};
+  DMove mv;
+  mv.area = DRect{0, 0, 0, 0}; mv.tx = 0; mv.ty = 0; mv.enabled = 0; mv.use_masks = 0;
   if (i < pg.mask_count) {
     mv.area = pg.masks[i];
     int w = abs(mv.area.x0 - mv.area.x1) + 1, h = abs(mv.area.y0 - mv.area.y1) + 1;
@@ -293,13 +326,14 @@ __global__ void k_prep_center_move(DPage *pages, int npages, int i) {
     mv.enabled = pt_in_rect(mv.tx, mv.ty, full) && pt_in_rect(mv.tx + w - 1, mv.ty + h - 1, full);
     pg.centered[i] = mv.enabled;
   }
-  pg.move = mv;
+  move_finish(pg, mv);
 }
 __global__ void k_prep_align_move(DPage *pages, int npages, int i, AlignParams ap, int use_masks) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npages) return;
   DPage &pg = pages[p];
-  DMove mv = {DRect{0, 0, 0, 0}, 0, 0, 0, use_masks};
+  DMove mv;
+  mv.area = DRect{0, 0, 0, 0}; mv.tx = 0; mv.ty = 0; mv.enabled = 0; mv.use_masks = use_masks;
   if (i < pg.outside_count) {
     DRect inside = pg.border_mask[i], out = pg.outside[i];
     int w = abs(inside.x0 - inside.x1) + 1, h = abs(inside.y0 - inside.y1) + 1;
@@ -311,14 +345,15 @@ __global__ void k_prep_align_move(DPage *pages, int npages, int i, AlignParams a
     else mv.ty = (out.y0 + out.y1 - h) / 2;
     mv.area = inside; mv.enabled = 1;
   }
-  pg.move = mv;
+  move_finish(pg, mv);
 }
 __global__ void k_prep_shift_move(DPage *pages, int npages, int dx, int dy) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npages) return;
   DPage &pg = pages[p];
-  DMove mv = {DRect{0, 0, pg.img.w - 1, pg.img.h - 1}, dx, dy, 1, 0};
-  pg.move = mv;
+  DMove mv;
+  mv.area = DRect{0, 0, pg.img.w - 1, pg.img.h - 1}; mv.tx = dx; mv.ty = dy; mv.enabled = 1; mv.use_masks = 0;
+  move_finish(pg, mv);
 }
 
 // apply_masks job over the detected border masks (sheet_stages.c:474-475)

@@ -13,6 +13,9 @@ from .abi import (HostOps, SheetConfig, SheetResult, bytes_per_row)
 
 # B200SheetDoneFn (include/unpaper_b200.h): user, sheet index, sheet bytes, result
 SHEET_DONE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(SheetResult))
+# B200PageProducerFn: user, sheet index, pinned destination; B200PoolSheetFn: user, sheet index, device, sheet, result
+PAGE_PRODUCER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)
+POOL_SHEET_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(SheetResult))
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libunpaper_b200.so")
 _lib = None
@@ -62,6 +65,24 @@ def load():
     lib.unpaper_b200_engine_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.unpaper_b200_engine_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                                     C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+    lib.unpaper_b200_engine_get_profile_spread.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.unpaper_b200_engine_stream_begin.argtypes = [C.c_void_p, C.c_int]
+    lib.unpaper_b200_engine_stream_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(SheetResult), C.c_int]
+    lib.unpaper_b200_engine_stream_poll.argtypes = [C.c_void_p]
+    lib.unpaper_b200_engine_stream_in_flight.argtypes = [C.c_void_p]
+    lib.unpaper_b200_engine_stream_end.argtypes = [C.c_void_p]
+    lib.unpaper_b200_pool_create.argtypes = [C.POINTER(SheetConfig), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.unpaper_b200_pool_create.restype = C.c_void_p
+    lib.unpaper_b200_pool_destroy.argtypes = [C.c_void_p]
+    lib.unpaper_b200_pool_run.argtypes = [C.c_void_p, C.c_int, PAGE_PRODUCER_FN, C.c_void_p, POOL_SHEET_FN, C.c_void_p,
+                                          C.POINTER(SheetResult)]
+    lib.unpaper_b200_pool_sheet_bytes.argtypes = [C.c_void_p]
+    lib.unpaper_b200_pool_sheet_bytes.restype = C.c_size_t
+    lib.unpaper_b200_pool_sheets_done.argtypes = [C.c_void_p, C.c_int]
+    lib.unpaper_b200_pool_sheets_done.restype = C.c_uint64
+    lib.unpaper_b200_pool_engine.argtypes = [C.c_void_p, C.c_int]
+    lib.unpaper_b200_pool_engine.restype = C.c_void_p
     _lib = lib
     return lib
 
@@ -154,3 +175,58 @@ class Engine:
         cnt = (C.c_uint64 * 32)()
         n = self.lib.unpaper_b200_engine_get_profile(self.h, 32, names, ms, cnt, None)
         return {names[i].decode(): (ms[i], int(cnt[i])) for i in range(n)}
+
+    def profile_spread(self):
+        """stage -> (fastest group ms, slowest group ms) since profiling was switched on."""
+        names = (C.c_char_p * 32)()
+        ms = (C.c_double * 32)()
+        cnt = (C.c_uint64 * 32)()
+        lo, hi = (C.c_double * 32)(), (C.c_double * 32)()
+        n = self.lib.unpaper_b200_engine_get_profile(self.h, 32, names, ms, cnt, None)
+        self.lib.unpaper_b200_engine_get_profile_spread(self.h, 32, lo, hi)
+        return {names[i].decode(): (lo[i], hi[i]) for i in range(n) if cnt[i]}
+
+    # streams: begin, feed batches as they arrive, end (include/unpaper_b200.h)
+    def stream_begin(self, host=True):
+        if self.lib.unpaper_b200_engine_stream_begin(self.h, 1 if host else 0) != 0:
+            raise RuntimeError("stream_begin failed: " + last_error())
+
+    def stream_feed(self, in_ptr, out_ptr, n, results=None, first_index=-1):
+        if self.lib.unpaper_b200_engine_stream_feed(self.h, in_ptr, out_ptr, n, results, first_index) != 0:
+            raise RuntimeError("stream_feed failed: " + last_error())
+
+    def stream_end(self):
+        rc = self.lib.unpaper_b200_engine_stream_end(self.h)
+        if rc != 0:
+            raise RuntimeError(f"stream_end failed ({rc}): {last_error()}")
+
+
+class Pool:
+    """Python face of the page scheduler across GPUs (include/unpaper_b200.h layer 4)."""
+
+    def __init__(self, cfg, devices, page_w, page_h, fmt, group_pages=32, lanes=2, slot_sheets=0, slots=0):
+        self.lib = load()
+        devs = (C.c_int * len(devices))(*devices)
+        self.h = self.lib.unpaper_b200_pool_create(C.byref(cfg), devs, len(devices), page_w, page_h, fmt, group_pages, lanes,
+                                                   slot_sheets, slots)
+        if not self.h:
+            raise RuntimeError("pool_create failed: " + last_error())
+        self.devices = list(devices)
+        self.sheet_bytes = self.lib.unpaper_b200_pool_sheet_bytes(self.h)
+        self.sheet_in_bytes = bytes_per_row(fmt, page_w) * page_h * cfg.input_count
+
+    def close(self):
+        if self.h:
+            self.lib.unpaper_b200_pool_destroy(self.h)
+            self.h = None
+
+    def run(self, n_sheets, produce, sink, results=None):
+        """produce(sheet_index, dst_ptr) -> 0 / 1 (end) / <0; sink(sheet_index, device, sheet_ptr, result) -> int."""
+        pcb = PAGE_PRODUCER_FN(lambda user, idx, dst: int(produce(idx, dst) or 0))
+        scb = POOL_SHEET_FN(lambda user, idx, dev, ptr, res: int(sink(idx, dev, ptr, res.contents) or 0))
+        rc = self.lib.unpaper_b200_pool_run(self.h, n_sheets, pcb, None, scb, None, results)
+        if rc != 0:
+            raise RuntimeError(f"pool_run failed ({rc}): {last_error()}")
+
+    def sheets_done(self):
+        return [int(self.lib.unpaper_b200_pool_sheets_done(self.h, i)) for i in range(len(self.devices))]

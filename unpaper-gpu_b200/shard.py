@@ -38,11 +38,13 @@ def sum_over_ranks(values, device=None):
     return [float(x) for x in t]
 
 
-def bind_near_gpu(local_rank):
+def bind_near_gpu(local_rank, world=1):
     """Pin this process to the CPUs NVML names as closest to GPU `local_rank`, so that the
     pinned staging buffers it allocates land on that GPU's NUMA node (with 8 ranks feeding
-    8 GPUs the host side, not the device, bounds the host-buffer arm).  Returns a short
-    description, or None if NVML is unavailable (nothing is changed then)."""
+    8 GPUs the host side, not the device, bounds the host-buffer arm).  When NVML names the
+    same set for every GPU (one NUMA node), the set is cut into `world` disjoint slices so
+    that the ranks' enqueue threads do not share cores.  Returns a short description, or
+    None if NVML is unavailable (nothing is changed then)."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -53,6 +55,15 @@ def bind_near_gpu(local_rank):
         cpus = [c for c in cpus if c < ncpu]
         if not cpus:
             return None
+        if world > 1:
+            try:
+                others = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex((local_rank + 1) % world), (ncpu + 63) // 64)
+                same = list(others) == list(words)
+            except Exception:
+                same = False
+            if same and len(cpus) >= world:
+                per = len(cpus) // world
+                cpus = cpus[local_rank * per:(local_rank + 1) * per]
         os.sched_setaffinity(0, cpus)
         return f"{len(cpus)} cpus near gpu {local_rank} ({cpus[0]}..{cpus[-1]})"
     except Exception:
