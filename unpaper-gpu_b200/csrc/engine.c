@@ -33,6 +33,10 @@ static const char *STG_NAME[STG_COUNT] = {"decode", "blackfilter", "noisefilter"
                                           "detect_masks", "detect_rotation", "deskew", "center_mask",
                                           "border", "output"};
 
+typedef struct { int w, h, pitch; } Geo;
+enum { GS_ROT90, GS_STRETCH, GS_CENTER };
+typedef struct { int op, dir; Geo to; } GeoStep;
+
 typedef struct {
   cudaStream_t st;
   /* up to QD groups are queued on a lane's stream, so the stream never runs dry
@@ -58,6 +62,7 @@ typedef struct {
   uint32_t *pre;
   uint8_t *ink;
   uint8_t *page_stage;    /* device staging for host-mode pages */
+  uint8_t *page_stage2;   /* pre_rotate: the pages after flip_rotate_90 */
   uint8_t *out_stage;     /* device staging for converted output sheets (host mode) */
   DPage *pages_dev, *pages_tmpl /* host */;
   DFillJob *fillA, *fillB, *fillC, *decode_fill;
@@ -78,8 +83,15 @@ struct B200Engine {
   B200SheetConfig cfg;
   int device, page_w, page_h, page_fmt, dfmt, bpp;   /* dfmt/bpp: the working sheet */
   int page_dfmt;                                      /* the pages as they arrive */
-  int sheet_w, sheet_h, sheet_pitch, page_row, sheet_row;
+  int sheet_w, sheet_h, sheet_pitch, page_row, sheet_row;   /* the PIPELINE geometry (after the pre-stage stretch / resize) */
   size_t sheet_stride, page_bytes;
+  /* size-changing options (sheet_stages.c:134-145, :216-230, :511-531): every sheet of an engine goes through the
+   * same chain of geometries, fixed at creation.  in: the decoded sheet; steps: passes img -> other with a new size */
+  Geo g_in, g_out;
+  GeoStep pre_steps[3], post_steps[4];
+  int n_pre, n_post, direct_upload;
+  int pre_rot_dir, rp_w, rp_h, rp_row;      /* pre_rotate: the pages after flip_rotate_90 */
+  size_t rp_bytes;
   int group, nlanes;
   int npoints, noutside;
   Point points[D_MAX_MASKS];
@@ -109,10 +121,10 @@ struct B200Engine {
 
 static int imax(int a, int b) { return a > b ? a : b; }
 
-int unpaper_b200_engine_sheet_width(const B200Engine *e) { return e->sheet_w; }
-int unpaper_b200_engine_sheet_height(const B200Engine *e) { return e->sheet_h; }
+int unpaper_b200_engine_sheet_width(const B200Engine *e) { return e->g_out.w; }
+int unpaper_b200_engine_sheet_height(const B200Engine *e) { return e->g_out.h; }
 size_t unpaper_b200_engine_sheet_bytes(const B200Engine *e) {
-  return (size_t)e->out_row * e->sheet_h * e->out_count;
+  return (size_t)e->out_row * e->g_out.h * e->out_count;
 }
 int unpaper_b200_engine_output_width(const B200Engine *e) { return e->out_w; }
 int unpaper_b200_engine_output_count(const B200Engine *e) { return e->out_count; }
@@ -145,7 +157,7 @@ int unpaper_b200_engine_set_output_format(B200Engine *e, int av_pix_fmt) {
     Lane *ln = &e->lanes[i];
     if (ln->out_stage) { b200_dev_free(ln->out_stage); ln->out_stage = NULL; }
     if (fmt >= 0 || e->out_count > 1)
-      ln->out_stage = (uint8_t *)b200_dev_alloc((size_t)row * e->sheet_h * e->out_count * e->group + 64);
+      ln->out_stage = (uint8_t *)b200_dev_alloc((size_t)row * e->g_out.h * e->out_count * e->group + 64);
   }
   return 0;
 }
@@ -223,7 +235,7 @@ static int build_static(B200Engine *e, Lane *ln, int slot, const Rectangle *wipe
 }
 
 static void lane_free(Lane *ln) {
-  void *ptrs[] = {ln->sheets, ln->sheets2, ln->cls, ln->list, ln->u32, ln->stack, ln->pre, ln->ink, ln->page_stage, ln->out_stage, ln->pages_dev,
+  void *ptrs[] = {ln->sheets, ln->sheets2, ln->cls, ln->list, ln->u32, ln->stack, ln->pre, ln->ink, ln->page_stage, ln->page_stage2, ln->out_stage, ln->pages_dev,
                   ln->fillA, ln->fillB, ln->fillC, ln->decode_fill, ln->copyA, ln->copyB, ln->decode_copy, ln->maskJ,
                   ln->static_fill[0], ln->static_fill[1], ln->static_fill[2], ln->static_mask[0], ln->static_mask[1],
                   ln->static_mask[2], ln->static_mask_rects[0], ln->static_mask_rects[1], ln->static_mask_rects[2]};
@@ -313,15 +325,69 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
     cfg = &e->cfg;
   }
   e->group = group_pages; e->nlanes = lanes;
-  /* sheet size = input pages side by side (sheet_stages.c:140-145) */
-  e->sheet_w = page_w * cfg->input_count; e->sheet_h = page_h;
-  e->page_row = b200_fmt_row_bytes(page_format, page_w); e->sheet_row = e->sheet_w * e->bpp;
+  e->page_row = b200_fmt_row_bytes(page_format, page_w);
+  e->page_bytes = (size_t)e->page_row * page_h;
+  /* pages after options->pre_rotate (sheet_stages.c:134-137) */
+  e->pre_rot_dir = cfg->pre_rotate / 90;
+  e->rp_w = e->pre_rot_dir ? page_h : page_w; e->rp_h = e->pre_rot_dir ? page_w : page_h;
+  e->rp_row = b200_fmt_row_bytes(page_format, e->rp_w); e->rp_bytes = (size_t)e->rp_row * e->rp_h;
+  {
+    /* the chain of sheet geometries: decoded sheet = input pages side by side unless --sheet-size says
+     * otherwise (:139-145); pre stage: stretch (+ zoom), resize (:216-230); post stage: rotate, stretch
+     * (+ zoom), resize (:511-531) */
+    const int bpp = e->bpp;
+#define GEO(W_, H_) ((Geo){(W_), (H_), (((W_) * bpp + 15) & ~15)})
+    RectangleSize cur = {cfg->sheet_size.width == -1 ? e->rp_w * cfg->input_count : cfg->sheet_size.width,
+                         cfg->sheet_size.height == -1 ? e->rp_h : cfg->sheet_size.height};
+    e->g_in = GEO(cur.width, cur.height);
+    for (int stage = 0; stage < 2; stage++) {
+      GeoStep *steps = stage ? e->post_steps : e->pre_steps;
+      int ns = 0;
+      RectangleSize st_size = stage ? cfg->post_stretch_size : cfg->stretch_size;
+      RectangleSize pg_size = stage ? cfg->post_page_size : cfg->page_size;
+      float zoom = stage ? cfg->post_zoom_factor : cfg->pre_zoom_factor;
+      if (zoom == 0.0f) zoom = 1.0f;
+      if (stage && cfg->post_rotate / 90 != 0) {
+        steps[ns++] = (GeoStep){GS_ROT90, cfg->post_rotate / 90, GEO(cur.height, cur.width)};
+        cur = (RectangleSize){cur.height, cur.width};
+      }
+      RectangleSize sz = {st_size.width == -1 ? cur.width : st_size.width, st_size.height == -1 ? cur.height : st_size.height};
+      sz.width *= zoom; sz.height *= zoom;                       /* int *= float, like :219-220 */
+      if (sz.width != cur.width || sz.height != cur.height) { steps[ns++] = (GeoStep){GS_STRETCH, 0, GEO(sz.width, sz.height)}; cur = sz; }
+      if (pg_size.width != -1 || pg_size.height != -1) {
+        RectangleSize size = {pg_size.width == -1 ? cur.width : pg_size.width, pg_size.height == -1 ? cur.height : pg_size.height};
+        if (size.width != cur.width || size.height != cur.height) {
+          /* resize_and_replace (blit.c:244-283): stretch keeping the aspect, then centre on a new sheet */
+          const float hr = (float)size.width / (float)cur.width, vr = (float)size.height / (float)cur.height;
+          RectangleSize ss;
+          if (hr < vr) ss = (RectangleSize){size.width, cur.height * hr};
+          else if (vr < hr) ss = (RectangleSize){cur.width * vr, size.height};
+          else ss = size;
+          if (ss.width != cur.width || ss.height != cur.height) { steps[ns++] = (GeoStep){GS_STRETCH, 0, GEO(ss.width, ss.height)}; cur = ss; }
+          if (size.width != ss.width || size.height != ss.height) { steps[ns++] = (GeoStep){GS_CENTER, 0, GEO(size.width, size.height)}; cur = size; }
+        }
+      }
+      if (stage) e->n_post = ns; else e->n_pre = ns;
+      if (cur.width <= 0 || cur.height <= 0) { b200_set_error("engine: a size option gives an empty sheet"); free(e); return NULL; }
+      if (!stage) { e->sheet_w = cur.width; e->sheet_h = cur.height; }
+    }
+    e->g_out = GEO(cur.width, cur.height);
+#undef GEO
+  }
+  e->sheet_row = e->sheet_w * e->bpp;
   e->out_count = cfg->output_count == 2 ? 2 : 1;
-  e->out_w = e->sheet_w / e->out_count;          /* sheet_stages.c:612 */
+  e->out_w = e->g_out.w / e->out_count;          /* sheet_stages.c:612 */
   e->out_dfmt = e->dfmt; e->out_row = e->out_w * e->bpp;
   e->sheet_pitch = (e->sheet_row + 15) & ~15;
-  e->sheet_stride = (((size_t)e->sheet_pitch * e->sheet_h + 64) + 255) & ~(size_t)255;
-  e->page_bytes = (size_t)e->page_row * page_h;
+  {
+    size_t big = (size_t)e->g_in.pitch * e->g_in.h;
+    for (int i = 0; i < e->n_pre; i++) { size_t b = (size_t)e->pre_steps[i].to.pitch * e->pre_steps[i].to.h; if (b > big) big = b; }
+    for (int i = 0; i < e->n_post; i++) { size_t b = (size_t)e->post_steps[i].to.pitch * e->post_steps[i].to.h; if (b > big) big = b; }
+    e->sheet_stride = ((big + 64) + 255) & ~(size_t)255;
+  }
+  /* the upload can be the decode stage's centre copy when a page IS the decoded sheet */
+  e->direct_upload = cfg->input_count == 1 && !e->pre_rot_dir && e->g_in.w == page_w && e->g_in.h == page_h &&
+                     e->g_in.pitch == e->page_row && e->page_dfmt == e->dfmt;
   int W = e->sheet_w, H = e->sheet_h;
 
   /* layout-derived points, mask maxima, border-scan areas (sheet_stages.c:232-279) */
@@ -401,6 +467,7 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
     size_t ink_stride = ((size_t)ink_cells + 255) & ~(size_t)255;
     ln->ink = (uint8_t *)b200_dev_alloc(ink_stride * P);
     ln->page_stage = (uint8_t *)b200_dev_alloc(e->page_bytes * cfg->input_count * P + 64);
+    if (e->pre_rot_dir) ln->page_stage2 = (uint8_t *)b200_dev_alloc(e->rp_bytes * cfg->input_count * P + 64);
     ln->pages_dev = (DPage *)b200_dev_alloc(sizeof(DPage) * P);
     if (!cfg->no_deskew && e->rot.host_tail) {
       ln->rot_pull = (DPage *)b200_pinned_alloc(sizeof(DPage) * P);
@@ -420,7 +487,7 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
     DFillJob *dfill = (DFillJob *)calloc((size_t)P, sizeof(DFillJob));
     for (int p = 0; p < P; p++) {
       DPage *pg = &ln->pages_tmpl[p];
-      pg->img = (DImg){ln->sheets + e->sheet_stride * p, W, H, e->sheet_pitch, e->dfmt, cfg->abs_black_threshold,
+      pg->img = (DImg){ln->sheets + e->sheet_stride * p, e->g_in.w, e->g_in.h, e->g_in.pitch, e->dfmt, cfg->abs_black_threshold,
                        {cfg->sheet_background.r, cfg->sheet_background.g, cfg->sheet_background.b}};
       pg->buf[0] = pg->img.data; pg->buf[1] = ln->sheets2 + e->sheet_stride * p;
       pg->other = pg->buf[1];
@@ -439,15 +506,21 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
       /* decode: create_image(fill) + center_image per input (sheet_stages.c:150-165).
        * Pages have the slot's size here, so center_image never wipes and the
        * fill is only needed when the sheet pitch has padding columns (none read). */
-      dfill[p].img = pg->img; dfill[p].r = (DRect){0, 0, W - 1, H - 1};
+      dfill[p].img = pg->img; dfill[p].r = (DRect){0, 0, e->g_in.w - 1, e->g_in.h - 1};
       dfill[p].c[0] = cfg->sheet_background.r; dfill[p].c[1] = cfg->sheet_background.g; dfill[p].c[2] = cfg->sheet_background.b;
-      dfill[p].enabled = 0;
+      /* create_image(fill): only visible where the pages do not cover the sheet */
+      dfill[p].enabled = e->rp_w * cfg->input_count != e->g_in.w || e->rp_h != e->g_in.h;
       for (int j = 0; j < cfg->input_count; j++) {
         DCopyJob *cj = &ln->decode_copy_host_tmpl[(size_t)p * cfg->input_count + j];
-        cj->src = (DImg){NULL, page_w, page_h, e->page_row, e->page_dfmt, cfg->abs_black_threshold, {255, 255, 255}};
+        cj->src = (DImg){NULL, e->rp_w, e->rp_h, e->rp_row, e->page_dfmt, cfg->abs_black_threshold, {255, 255, 255}};
         cj->dst = pg->img;
-        cj->area = (DRect){0, 0, page_w - 1, page_h - 1};
-        cj->tx = W * j / cfg->input_count; cj->ty = 0;
+        /* center_image(page, sheet, cell origin, cell size) (blit.c:175-207; sheet_stages.c:160-164) */
+        int cw = e->g_in.w / cfg->input_count, chh = e->g_in.h;
+        int sx = 0, sy = 0, sw2 = e->rp_w, sh2 = e->rp_h, tx = e->g_in.w * j / cfg->input_count, ty = 0;
+        if (sw2 <= cw) tx += (cw - sw2) / 2; else { sx += (sw2 - cw) / 2; sw2 = cw; }
+        if (sh2 <= chh) ty += (chh - sh2) / 2; else { sy += (sh2 - chh) / 2; sh2 = chh; }
+        cj->area = (DRect){sx, sy, sx + sw2 - 1, sy + sh2 - 1};
+        cj->tx = tx; cj->ty = ty;
         cj->enabled = 1;
       }
     }
@@ -481,20 +554,23 @@ static void mark(B200Engine *e, Lane *ln, int stage_boundary) {
 
 /* apply pre-masks first (sheet_stages.c:211-214), then wipes (:282-285), then
  * border (:288-291) — same order for the mid and post slots */
-static void run_static(B200Engine *e, Lane *ln, StageCtx *c, int slot, int n, unsigned skip) {
+/* part 0: everything; 1: only the pre-masks (they come before the pre-stage stretch, :210-214); 2: the rest */
+static void run_static(B200Engine *e, Lane *ln, StageCtx *c, int slot, int n, unsigned skip, int part) {
   int P = e->group;
   int q = 0;
   bool has_masks = slot == 0 && e->cfg.pre_mask_count > 0;
+  if (part == 1 && !has_masks) return;
   /* the tables were built for buffer 0; aim them at the buffer that holds the sheet now */
   if (ln->static_fill_n[slot] > 0 || e->n_static_mask_jobs[slot] > 0) {
     b200k_retarget_jobs(c->st, c->pages, n, ln->static_fill[slot], ln->static_fill_n[slot] * P,
                         ln->static_mask[slot], e->n_static_mask_jobs[slot] * P, P);
     c->launches++;
   }
-  if (has_masks) { b200k_apply_masks(c->st, ln->static_mask[slot] + (size_t)q * P, n, e->sheet_w, e->sheet_h); q++; c->launches++; }
+  if (has_masks) { if (part != 2) { b200k_apply_masks(c->st, ln->static_mask[slot] + (size_t)q * P, n, c->w, c->h); c->launches++; } q++; }
+  if (part == 1) return;
   if (!(skip >> SW_WIPE & 1))
-    for (int k = 0; k < ln->static_fill_n[slot]; k++) { b200k_fill_jobs(c->st, ln->static_fill[slot] + (size_t)k * P, n, e->sheet_w, e->sheet_h); c->launches++; }
-  if (q < e->n_static_mask_jobs[slot] && !(skip >> SW_BORDER & 1)) { b200k_apply_masks(c->st, ln->static_mask[slot] + (size_t)q * P, n, e->sheet_w, e->sheet_h); c->launches++; }
+    for (int k = 0; k < ln->static_fill_n[slot]; k++) { b200k_fill_jobs(c->st, ln->static_fill[slot] + (size_t)k * P, n, c->w, c->h); c->launches++; }
+  if (q < e->n_static_mask_jobs[slot] && !(skip >> SW_BORDER & 1)) { b200k_apply_masks(c->st, ln->static_mask[slot] + (size_t)q * P, n, c->w, c->h); c->launches++; }
 }
 
 /* isExcluded(sheet_nr, no_<stage>_multi_index, ignore_multi_index) (parse.h:30-34) for every stage switch */
@@ -511,10 +587,25 @@ void unpaper_b200_engine_set_first_sheet_nr(B200Engine *e, int sheet_nr) { if (e
 /* mirror() then shift_image() on every sheet of the group (sheet_stages.c:200-208, :499-508) */
 static void run_geometry(B200Engine *e, Lane *ln, StageCtx *c, int k, int n) {
   Direction m = k == 0 ? e->cfg.pre_mirror : e->cfg.post_mirror;
-  if (m.horizontal || m.vertical) { b200k_mirror_pages(c->st, c->pages, n, e->sheet_w, e->sheet_h, m.horizontal, m.vertical); c->launches++; }
+  if (m.horizontal || m.vertical) { b200k_mirror_pages(c->st, c->pages, n, c->w, c->h, m.horizontal, m.vertical); c->launches++; }
   Delta d = k == 0 ? e->cfg.pre_shift : e->cfg.post_shift;
   (void)ln;
   if (d.horizontal != 0 || d.vertical != 0) stage_shift_pass(c, d);   /* shift_image (blit.c:360-368) */
+}
+
+/* the size-changing passes of the pre / post stage: img -> other with a new geometry */
+static void run_geo_steps(B200Engine *e, StageCtx *c, const GeoStep *steps, int ns, int n) {
+  for (int i = 0; i < ns; i++) {
+    const GeoStep *g = &steps[i];
+    if (g->op == GS_ROT90) b200k_rotate90_pages(c->st, c->pages, n, c->w, c->h, g->dir, g->to.pitch);
+    else if (g->op == GS_STRETCH) b200k_stretch_pages(c->st, c->pages, n, c->w, c->h, g->to.w, g->to.h, g->to.pitch, e->cfg.interpolate_type);
+    else b200k_center_pages(c->st, c->pages, n, g->to.w, g->to.h, g->to.pitch);
+    b200k_swap_sheets(c->st, c->pages, n);
+    b200k_set_geometry(c->st, c->pages, n, g->to.w, g->to.h, g->to.pitch);
+    c->parity ^= 1; c->w = g->to.w; c->h = g->to.h;
+    c->rows_aligned16 = 1;
+    c->launches += 3;
+  }
 }
 
 static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, int n, unsigned skip) {
@@ -528,7 +619,7 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
 #undef OFF
   StageCtx c;
   memset(&c, 0, sizeof(c));
-  c.st = ln->st; c.npages = n; c.pages = ln->pages_dev; c.w = e->sheet_w; c.h = e->sheet_h; c.fmt = e->dfmt;
+  c.st = ln->st; c.npages = n; c.pages = ln->pages_dev; c.w = e->g_in.w; c.h = e->g_in.h; c.fmt = e->dfmt;
   c.rows_aligned16 = (e->sheet_pitch & 15) == 0;   /* slabs are 256-byte aligned, strides multiples of 256 */
   c.fillA = ln->fillA; c.fillB = ln->fillB; c.fillC = ln->fillC; c.copyA = ln->copyA; c.copyB = ln->copyB; c.maskJ = ln->maskJ;
   if (ln->rot_pull) { c.rot_jobs = ln->rot_jobs[ln->slot]; c.rot_pull = ln->rot_pull; c.rot_tab_host = ln->rot_tab_host; c.rot_tab_dev = ln->rot_tab_dev; }
@@ -537,19 +628,33 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
 
   mark(e, ln, STG_DECODE);
   b200k_page_reset(c.st, c.pages, n);
+  if (e->n_pre || e->n_post) { b200k_set_geometry(c.st, c.pages, n, e->g_in.w, e->g_in.h, e->g_in.pitch); c.launches++; }
   /* decode stage: page(s) -> sheet (pages_dev_in == NULL: the upload already placed them) */
   if (pages_dev_in) {
+    const uint8_t *psrc = pages_dev_in;
+    size_t pbytes = e->page_bytes;
+    if (e->pre_rot_dir) {
+      /* flip_rotate_90 of every input page (sheet_stages.c:134-137) */
+      DImg rs = {(uint8_t *)pages_dev_in, e->page_w, e->page_h, e->page_row, e->page_dfmt, cfg->abs_black_threshold, {255, 255, 255}};
+      DImg rd = {ln->page_stage2, e->rp_w, e->rp_h, e->rp_row, e->page_dfmt, cfg->abs_black_threshold, {255, 255, 255}};
+      b200k_rotate90_batch(c.st, rs, rd, e->pre_rot_dir, n * ic, e->page_bytes, e->rp_bytes);
+      psrc = ln->page_stage2; pbytes = e->rp_bytes;
+      c.launches += 1;
+    }
     for (int p = 0; p < n; p++)
       for (int j = 0; j < ic; j++)
-        ln->decode_copy_host_tmpl[(size_t)p * ic + j].src.data = (uint8_t *)pages_dev_in + e->page_bytes * ((size_t)p * ic + j);
+        ln->decode_copy_host_tmpl[(size_t)p * ic + j].src.data = (uint8_t *)psrc + pbytes * ((size_t)p * ic + j);
     /* job records are tiny; one pageable H2D per group */
     CUDA_OK(cudaMemcpyAsync(ln->decode_copy, ln->decode_copy_host_tmpl, sizeof(DCopyJob) * n * ic, cudaMemcpyHostToDevice, c.st));
-    b200k_copy_jobs(c.st, ln->decode_copy, n * ic, e->page_row, e->page_h);
-    c.launches += 1;
+    b200k_fill_jobs(c.st, ln->decode_fill, n, e->g_in.w, e->g_in.h);   /* jobs disabled unless the pages leave part of the sheet uncovered */
+    b200k_copy_jobs(c.st, ln->decode_copy, n * ic, e->rp_row, e->rp_h);
+    c.launches += 2;
   }
   c.launches += 1;
   run_geometry(e, ln, &c, 0, n);
-  run_static(e, ln, &c, 0, n, skip);
+  run_static(e, ln, &c, 0, n, skip, 1);                       /* pre-masks */
+  run_geo_steps(e, &c, e->pre_steps, e->n_pre, n);          /* stretch, resize */
+  run_static(e, ln, &c, 0, n, skip, 2);                       /* pre-wipes, pre-border */
 
   mark(e, ln, STG_BLACK);
   if (!no_blackfilter) stage_blackfilter(&c, &e->bf);
@@ -580,7 +685,7 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
     if (!no_mask_scan) stage_detect_masks(&c, &e->mask);
     stage_center_masks_pass(&c, nm);
   }
-  run_static(e, ln, &c, 1, n, skip);
+  run_static(e, ln, &c, 1, n, skip, 0);
   mark(e, ln, STG_BORDER);
   if (!no_border_scan) {
     stage_detect_border(&c, &e->border);
@@ -588,11 +693,13 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
     if (!no_border_align && e->noutside > 0) stage_align_masks_pass(&c, &cfg->mask_alignment, e->noutside, cfg->mask_color);
     else stage_apply_border_masks(&c, cfg->mask_color);
   }
-  run_static(e, ln, &c, 2, n, skip);
+  run_static(e, ln, &c, 2, n, skip, 0);
   run_geometry(e, ln, &c, 1, n);
+  run_geo_steps(e, &c, e->post_steps, e->n_post, n);         /* rotate, stretch, resize */
   mark(e, ln, STG_OUTPUT);
   /* output stage (sheet_stages.c:536-631): sheet -> caller, tight rows, + the decisions */
-  size_t img_bytes = (size_t)e->out_row * e->sheet_h, out_sheet = img_bytes * e->out_count;
+  const int osheet_row = e->g_out.w * e->bpp;
+  size_t img_bytes = (size_t)e->out_row * e->g_out.h, out_sheet = img_bytes * e->out_count;
   const uint8_t *cur = c.parity ? ln->sheets2 : ln->sheets;   /* the buffer that holds the finished sheets */
   if (e->out_fmt >= 0 || e->out_count > 1) {
     /* per output image: the sheet split of :606-621 (copy_rectangle of the j-th
@@ -601,14 +708,14 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
     for (int j = 0; j < e->out_count; j++) {
       DImg sv;
       memset(&sv, 0, sizeof(sv));
-      sv.data = (uint8_t *)cur + (size_t)j * e->out_w * e->bpp; sv.w = e->out_w; sv.h = e->sheet_h; sv.pitch = e->sheet_pitch;
+      sv.data = (uint8_t *)cur + (size_t)j * e->out_w * e->bpp; sv.w = e->out_w; sv.h = e->g_out.h; sv.pitch = e->g_out.pitch;
       sv.fmt = e->dfmt; sv.abt = cfg->abs_black_threshold;
       if (e->out_fmt >= 0) {
         DImg dv = sv;
         dv.data = dst + img_bytes * j; dv.pitch = e->out_row; dv.fmt = e->out_dfmt;
         b200k_convert_out(c.st, sv, dv, n, e->sheet_stride, out_sheet);
       } else {
-        b200k_pack_rows(c.st, sv.data, e->sheet_pitch, dst + img_bytes * j, e->out_row, e->out_row, e->sheet_h, n,
+        b200k_pack_rows(c.st, sv.data, e->g_out.pitch, dst + img_bytes * j, e->out_row, e->out_row, e->g_out.h, n,
                         e->sheet_stride, out_sheet);
       }
       c.launches++;
@@ -616,20 +723,20 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
     if (ln->host_mode)
       CUDA_OK(cudaMemcpyAsync(ln->out_host, ln->out_stage, out_sheet * n, cudaMemcpyDeviceToHost, c.st));
   } else if (ln->host_mode) {
-    size_t sheet_bytes = (size_t)e->sheet_row * e->sheet_h;
-    if (e->sheet_pitch == e->sheet_row) {
+    size_t sheet_bytes = (size_t)osheet_row * e->g_out.h;
+    if (e->g_out.pitch == osheet_row) {
       /* rows are tight, sheets are `sheet_stride` apart: one 2-D copy with one "row" per sheet */
       CUDA_OK(cudaMemcpy2DAsync(ln->out_host, sheet_bytes, cur, e->sheet_stride, sheet_bytes, (size_t)n,
                                 cudaMemcpyDeviceToHost, c.st));
     } else {
       for (int p = 0; p < n; p++)
-        CUDA_OK(cudaMemcpy2DAsync(ln->out_host + sheet_bytes * p, (size_t)e->sheet_row,
-                                  cur + e->sheet_stride * p, (size_t)e->sheet_pitch, (size_t)e->sheet_row,
-                                  (size_t)e->sheet_h, cudaMemcpyDeviceToHost, c.st));
+        CUDA_OK(cudaMemcpy2DAsync(ln->out_host + sheet_bytes * p, (size_t)osheet_row,
+                                  cur + e->sheet_stride * p, (size_t)e->g_out.pitch, (size_t)osheet_row,
+                                  (size_t)e->g_out.h, cudaMemcpyDeviceToHost, c.st));
     }
   } else {
-    b200k_pack_rows(c.st, cur, e->sheet_pitch, ln->out_dev, e->sheet_row, e->sheet_row, e->sheet_h, n,
-                    e->sheet_stride, (size_t)e->sheet_row * e->sheet_h);
+    b200k_pack_rows(c.st, cur, e->g_out.pitch, ln->out_dev, osheet_row, osheet_row, e->g_out.h, n,
+                    e->sheet_stride, (size_t)osheet_row * e->g_out.h);
     c.launches++;
   }
   CUDA_OK(cudaMemcpyAsync(ln->fl[ln->slot].pages_res, ln->pages_dev, sizeof(DPage) * n, cudaMemcpyDeviceToHost, c.st));
@@ -665,7 +772,7 @@ static void collect(B200Engine *e, Lane *ln) {
       B200SheetResult *r = results ? &results[p] : &local;
       memset(r, 0, sizeof(*r));
       r->status = pg->error ? -(int)pg->error : 0;
-      r->sheet_width = e->sheet_w; r->sheet_height = e->sheet_h;
+      r->sheet_width = e->g_out.w; r->sheet_height = e->g_out.h;
       int nm = pg->mask_count < B200_TRACE_MAX_MASKS ? pg->mask_count : B200_TRACE_MAX_MASKS;
       /* the deskew-stage masks are overwritten by the post-stage detection in
        * the device record; rotation[] belongs to the former, masks[] to the latter */
@@ -764,7 +871,7 @@ static int stream_feed(B200Engine *e, const uint8_t *pages, uint8_t *out, int n_
     fl->out = out + out_sheet * first;
     if (host_mode) {
       ln->out_host = out + out_sheet * first;
-      if (ic == 1 && e->sheet_pitch == e->page_row && e->page_dfmt == e->dfmt) {
+      if (e->direct_upload) {
         /* page == sheet geometry: the upload IS the decode stage's centre copy
          * (one 2-D copy, one "row" per sheet slot) */
         CUDA_OK(cudaMemcpy2DAsync(ln->sheets, e->sheet_stride, src, e->page_bytes, e->page_bytes, (size_t)n,

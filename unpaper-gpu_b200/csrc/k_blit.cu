@@ -307,9 +307,70 @@ __global__ void k_rotate90(DImg src, DImg dst, int dir) {
   }
 }
 
+// ---- sheet-engine forms of the size-changing operations (one launch per group) ---------
+// flip_rotate_90 of nimages equally sized images stored `*_stride` bytes apart (the input
+// pages of a group: options->pre_rotate, sheet_stages.c:134-137)
+__global__ void k_rotate90_batch(DImg src, DImg dst, int dir, size_t src_stride, size_t dst_stride) {
+  src.data += (size_t)blockIdx.z * src_stride;
+  dst.data += (size_t)blockIdx.z * dst_stride;
+  for (int y = blockIdx.y; y < src.h; y += gridDim.y) {
+    int xx = ((dir > 0) ? src.h - 1 : 0) - y * dir;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < src.w; x += gridDim.x * blockDim.x) {
+      int yy = ((dir < 0) ? src.w - 1 : 0) + x * dir;
+      Px p = px_load(src, x, y);
+      px_set(dst, xx, yy, p.r, p.g, p.b);
+    }
+  }
+}
+// flip_rotate_90 of every page's working sheet into its other buffer (options->post_rotate, :511-514)
+__global__ void k_rotate90_pages(DPage *pages, int dir, int dw, int dh, int dpitch) {
+  const DPage &pg = pages[blockIdx.z];
+  DImg src = pg.img, dst = pg.img;
+  dst.data = pg.other; dst.w = dw; dst.h = dh; dst.pitch = dpitch;
+  for (int y = blockIdx.y; y < src.h; y += gridDim.y) {
+    int xx = ((dir > 0) ? src.h - 1 : 0) - y * dir;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < src.w; x += gridDim.x * blockDim.x) {
+      int yy = ((dir < 0) ? src.w - 1 : 0) + x * dir;
+      Px p = px_load(src, x, y);
+      px_set(dst, xx, yy, p.r, p.g, p.b);
+    }
+  }
+}
+// resize_and_replace's second half (blit.c:279-281): a background sheet of the new size with the
+// (already stretched) working sheet centred on it — center_image, blit.c:175-207
+__global__ void k_center_pages(DPage *pages, int dw, int dh, int dpitch) {
+  const DPage &pg = pages[blockIdx.z];
+  DImg src = pg.img, dst = pg.img;
+  dst.data = pg.other; dst.w = dw; dst.h = dh; dst.pitch = dpitch;
+  int sx0 = 0, sy0 = 0, sw = src.w, sh = src.h, tx0 = 0, ty0 = 0;
+  if (sw <= dw) tx0 = (dw - sw) / 2; else { sx0 = (sw - dw) / 2; sw = dw; }
+  if (sh <= dh) ty0 = (dh - sh) / 2; else { sy0 = (sh - dh) / 2; sh = dh; }
+  for (int y = blockIdx.y; y < dh; y += gridDim.y)
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < dw; x += gridDim.x * blockDim.x) {
+      int u = x - tx0, v = y - ty0;
+      if (u >= 0 && u < sw && v >= 0 && v < sh) { Px p = px_load(src, sx0 + u, sy0 + v); px_store(dst, x, y, p.r, p.g, p.b); }
+      else px_store(dst, x, y, dst.bg[0], dst.bg[1], dst.bg[2]);
+    }
+}
+
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
 extern "C" {
+void b200k_rotate90_batch(cudaStream_t st, DImg src, DImg dst, int dir, int nimages, size_t src_stride, size_t dst_stride) {
+  if (nimages <= 0 || src.w <= 0 || src.h <= 0) return;
+  dim3 g(min(cdiv(src.w, 256), 16u), min((unsigned)src.h, 1024u), nimages);
+  k_rotate90_batch<<<g, 256, 0, st>>>(src, dst, dir, src_stride, dst_stride);
+}
+void b200k_rotate90_pages(cudaStream_t st, DPage *pages, int npages, int sw, int sh, int dir, int dpitch) {
+  if (npages <= 0 || sw <= 0 || sh <= 0) return;
+  dim3 g(min(cdiv(sw, 256), 16u), min((unsigned)sh, 1024u), npages);
+  k_rotate90_pages<<<g, 256, 0, st>>>(pages, dir, sh, sw, dpitch);
+}
+void b200k_center_pages(cudaStream_t st, DPage *pages, int npages, int dw, int dh, int dpitch) {
+  if (npages <= 0 || dw <= 0 || dh <= 0) return;
+  dim3 g(min(cdiv(dw, 256), 16u), min((unsigned)dh, 1024u), npages);
+  k_center_pages<<<g, 256, 0, st>>>(pages, dw, dh, dpitch);
+}
 void b200k_fill_jobs(cudaStream_t st, const DFillJob *jobs, int njobs, int maxw, int maxh) {
   if (njobs <= 0 || maxw <= 0 || maxh <= 0) return;
   // one 256-thread block covers a row (16 B per thread per step); ~8 rows per block

@@ -714,6 +714,44 @@ __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) 
   }
 }
 
+// ---- packed fp32x2 arithmetic (sm_100a FMUL2 / FADD2): two IEEE single operations per issue
+// slot, each rounded exactly like the scalar instruction.  Separate mul and add instructions
+// with explicit .rn: nothing here may be contracted into an FMA (checked in the SASS: no FFMA2).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(unsigned lo, unsigned hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void upk2(u64 v, unsigned &lo, unsigned &hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+// ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false, which would
+// round once instead of twice.  The product therefore passes through an integer XOR with a
+// run-time zero (kernel argument): one LOP3 per packed multiplication keeps the two roundings.
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b, unsigned zero) {
+  u64 r;
+  asm volatile("{\n\t.reg .b32 lo, hi;\n\tmul.rn.f32x2 %0, %1, %2;\n\tmov.b64 {lo, hi}, %0;\n\txor.b32 lo, lo, %3;\n\tmov.b64 %0, {lo, hi};\n\t}"
+               : "=l"(r) : "l"(a), "l"(b), "r"(zero));
+  return r;
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 r; asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fadd2_rz(u64 a, u64 b) { u64 r; asm volatile("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned dp4(unsigned taps, int weights) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(taps), "r"(weights), "r"(0x4B400000));
+  return (unsigned)d;
+}
+// cubic_scale_w for two independent tap words at once: (f.lo, ta) and (f.hi, tb)
+__device__ __forceinline__ void cubic_scale_w2(u64 f2, u64 hf2, unsigned ta, unsigned tb, unsigned &oa, unsigned &ob, unsigned zero) {
+  const u64 M = pk2(0xCB400000u, 0xCB400000u);            // -1.5 * 2^23 twice
+  u64 R = fadd2(pk2(dp4(ta, 0x000100FF), dp4(tb, 0x000100FF)), M);                    // c - a
+  u64 P = fadd2(pk2(dp4(ta, (int)0xFF04FB02u), dp4(tb, (int)0xFF04FB02u)), M);        // 2a - 5b + 4c - d
+  u64 Q = fadd2(pk2(dp4(ta, 0x01FD03FF), dp4(tb, 0x01FD03FF)), M);                    // -a + 3b - 3c + d
+  u64 B = fadd2(pk2(dp4(ta, 0x00000100), dp4(tb, 0x00000100)), M);                    // b
+  u64 v = fadd2(B, fmul2(hf2, fadd2(R, fmul2(f2, fadd2(P, fmul2(f2, Q, zero)), zero)), zero));
+  unsigned va, vb;
+  upk2(v, va, vb);
+  float ca = fminf(fmaxf(__uint_as_float(va), 0.0f), 255.0f), cb = fminf(fmaxf(__uint_as_float(vb), 0.0f), 255.0f);
+  u64 t = fadd2_rz(pk2(__float_as_uint(ca), __float_as_uint(cb)), pk2(0x4B000000u, 0x4B000000u));   // + 2^23, toward zero
+  upk2(t, va, vb);
+  oa = va & 0xFFu; ob = vb & 0xFFu;
+}
+
 // Sheet-engine form of deskew() (deskew.c:276-290) for mask `mi` of every page: ONE sweep
 // over the whole sheet from the working buffer into the slot's other buffer,
 //     dst(X,Y) = (X,Y) inside the pasted rectangle [mask.vertex[0], + size) ? rotate(...) : src(X,Y)
@@ -724,9 +762,32 @@ __global__ void k_rotate(DPage *pages, int mi, int interp, DCopyJob *back_jobs) 
 // taps" identities are exact, so computing the formula gives the same value) — the only
 // branch is warp-uniform: a warp whose 32 pixels all sit on constant 4x4 neighbourhoods
 // skips the arithmetic.  Divergent per-row shortcuts cost more issue slots than they save.
-__global__ void __launch_bounds__(128) k_rotate_sheet(DPage *pages, int mi, int interp) {
-  DPage &pg = pages[blockIdx.z];
-  const DImg &im = pg.img;
+// true when the source footprint (plus the interpolation taps) of the target tile
+// [xa..xb] x [ya..yb] (coordinates of the rotated image) only touches pure-white ink cells or lies
+// outside the image.  Warp-collective.  The footprint is the bounding box of the four
+// rotated corners, with two pixels of slack for float rounding.
+__device__ __forceinline__ bool tile_white(const uint8_t *ink, int ink_ncx, int W, int H, int xa, int xb, int ya, int yb,
+                                           float scx, float scy, float tcx, float tcy, float sinval, float cosval, int lane) {
+  float ax = (xa - tcx) * cosval, bx = (xb - tcx) * cosval, ay = (ya - tcy) * sinval, by = (yb - tcy) * sinval;
+  float cy = (ya - tcy) * cosval, dy = (yb - tcy) * cosval, cx = (xa - tcx) * sinval, dx = (xb - tcx) * sinval;
+  float mnx = scx + fminf(ax, bx) + fminf(ay, by), mxx = scx + fmaxf(ax, bx) + fmaxf(ay, by);
+  float mny = scy + fminf(cy, dy) - fmaxf(cx, dx), mxy = scy + fmaxf(cy, dy) - fminf(cx, dx);
+  if (!(fabsf(mnx) < 1e7f && fabsf(mxx) < 1e7f && fabsf(mny) < 1e7f && fabsf(mxy) < 1e7f)) return false;
+  // taps reach from (int)src - 1 to (int)src + 2
+  int bx0 = (int)floorf(mnx) - 3, bx1 = (int)floorf(mxx) + 4, by0 = (int)floorf(mny) - 3, by1 = (int)floorf(mxy) + 4;
+  if (bx1 < 0 || by1 < 0 || bx0 >= W || by0 >= H) return true;   // entirely outside: reads as white
+  int cx0 = max(bx0, 0) / INK_CELL, cx1 = min(bx1, W - 1) / INK_CELL;
+  int cy0 = max(by0, 0) / INK_CELL, cy1 = min(by1, H - 1) / INK_CELL;
+  int nx = cx1 - cx0 + 1, n = nx * (cy1 - cy0 + 1);
+  if (n > 32) return false;
+  bool wh = true;
+  if (lane < n) wh = ink[(cy0 + lane / nx) * ink_ncx + cx0 + lane % nx] != 0;
+  return __all_sync(0xffffffffu, wh);
+}
+
+__global__ void __launch_bounds__(128) k_rotate_sheet(DPage *pages, int mi, int interp, unsigned zero) {
+  const DPage &pg = pages[blockIdx.z];
+  const DImg im = pg.img;                 // by value: no reloads of the descriptor behind the stores below
   DImg out = im;
   out.data = pg.other;
   const int W = im.w, H = im.h, bpp = bytes_pp(im.fmt);
@@ -761,66 +822,99 @@ __global__ void __launch_bounds__(128) k_rotate_sheet(DPage *pages, int mi, int 
   const bool gray = im.fmt != DF_RGB24;
   const bool fast = im.fmt == DF_GRAY8 && interp == 2 && (im.pitch & 3) == 0 && ((uintptr_t)im.data & 3) == 0;
   const bool can_skip = pg.ink_ok && interp == 2 && (im.fmt == DF_GRAY8 || im.fmt == DF_RGB24);
+  const uint8_t *const ink = pg.ink;
+  const int ink_ncx = pg.ink_ncx;
   const int lane = threadIdx.x & 31;
   const int Xw = X0 + (threadIdx.x & ~31);          // this warp's 32 sheet columns
   if (Xw >= W) return;                              // whole warp (warp-uniform)
   const int X = Xw + lane;
   const int x = X - ox;                             // column in the rotated image
   const bool colin = X < W && x >= 0 && x < w;
-  const int wpitch = im.pitch >> 2;
+  const int pitch = im.pitch;
+  const uint8_t *const src = im.data;
+  // the x-dependent halves of the source coordinates: srcX = (scx + (x - tcx) cos) + (y - tcy) sin,
+  // srcY = (scy + (y - tcy) cos) - (x - tcx) sin — evaluated in the reference's order below
+  const float xr = u8f((unsigned)(colin ? x : 0)) - tcx;      // (float)x - tcx
+  const float xc = xr * cosval, xs = xr * sinval;
   for (int Yt = Y0; Yt <= Y1; Yt += ROT_TILE) {
     const int Yte = min(Yt + ROT_TILE - 1, Y1);
     // the warp's tile entirely inside the pasted rectangle and its source footprint pure white?
-    bool tile_in = Xw >= ox && min(Xw + 31, W - 1) < ox + w && Yt >= oy && Yte < oy + h;
+    const int Xwe = min(Xw + 31, W - 1);
+    const bool tile_in = Xw >= ox && Xwe < ox + w && Yt >= oy && Yte < oy + h;
     if (can_skip && tile_in &&
-        rot_tile_white(pg, im, Xw - ox, min(Xw + 31, W - 1) - ox, Yt - oy, Yte - oy, scx, scy, tcx, tcy, sinval, cosval, lane)) {
-      if (X < W)
-        for (int Y = Yt; Y <= Yte; Y++) {
-          uint8_t *o = out.data + (size_t)Y * out.pitch + (size_t)X * bpp;
-          o[0] = 255; if (bpp == 3) { o[1] = 255; o[2] = 255; }
-        }
+        tile_white(ink, ink_ncx, W, H, Xw - ox, Xwe - ox, Yt - oy, Yte - oy, scx, scy, tcx, tcy, sinval, cosval, lane)) {
+      if (X < W) {
+        uint8_t *o = out.data + (size_t)Yt * pitch + (size_t)X * bpp;
+        for (int Y = Yt; Y <= Yte; Y++, o += pitch) { o[0] = 255; if (bpp == 3) { o[1] = 255; o[2] = 255; } }
+      }
       continue;
     }
+    if (fast && tile_in && Yte == Yt + ROT_TILE - 1) {
+      // ---- GRAY8 + cubic, every pixel of the 32 x 8 tile inside the rotated image: two rows per step
+      uint8_t *orow = out.data + (size_t)Yt * pitch + X;
+#pragma unroll 1
+      for (int Ya = Yt; Ya < Yt + ROT_TILE; Ya += 2, orow += 2 * (size_t)pitch) {
+        float srcX[2], srcY[2], tX[2], tY[2];
+        unsigned rw[2][4];
+        bool ok[2];
+        bool need = false;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const float yr = u8f((unsigned)(Ya + k - oy)) - tcy;        // (float)y - tcy
+          srcX[k] = (scx + xc) + yr * sinval;
+          srcY[k] = (scy + yr * cosval) - xs;
+          // (int)srcX for 1 <= srcX < 2^23 by the 2^23 trick (anything else fails the range test)
+          tX[k] = __fadd_rz(srcX[k], 8388608.0f); tY[k] = __fadd_rz(srcY[k], 8388608.0f);
+          const int px = __float_as_int(tX[k]) - 0x4B000000, py = __float_as_int(tY[k]) - 0x4B000000;
+          ok[k] = (unsigned)(px - 1) < (unsigned)(W - 3) && (unsigned)(py - 1) < (unsigned)(H - 3);
+          const int off = ok[k] ? (py - 1) * pitch + (px - 1) : 0;
+          const unsigned sh = ((unsigned)off & 3u) * 8u;
+          const uint8_t *p0 = src + (off & ~3);
+#pragma unroll
+          for (int i = 0; i < 4; i++, p0 += pitch) {
+            const unsigned *wp = (const unsigned *)p0;
+            rw[k][i] = __funnelshift_r(wp[0], wp[1], sh);
+          }
+          const unsigned b0 = rw[k][0] & 0xFFu;
+          const bool uni = rw[k][0] == b0 * 0x01010101u && rw[k][1] == rw[k][0] && rw[k][2] == rw[k][0] && rw[k][3] == rw[k][0];
+          need = need || (ok[k] && !uni);
+        }
+        unsigned o0 = rw[0][0] & 0xFFu, o1 = rw[1][0] & 0xFFu;   // all 16 taps equal: every cubic term cancels exactly
+        if (__any_sync(0xffffffffu, need)) {
+          // srcX - (float)px; the four rows of a pixel share fx, the two pixels' vertical passes pair up
+          float fx0 = srcX[0] - (tX[0] - 8388608.0f), fy0 = srcY[0] - (tY[0] - 8388608.0f);
+          float fx1 = srcX[1] - (tX[1] - 8388608.0f), fy1 = srcY[1] - (tY[1] - 8388608.0f);
+          u64 f2a = pk2(__float_as_uint(fx0), __float_as_uint(fx0)), h2a = pk2(__float_as_uint(0.5f * fx0), __float_as_uint(0.5f * fx0));
+          u64 f2b = pk2(__float_as_uint(fx1), __float_as_uint(fx1)), h2b = pk2(__float_as_uint(0.5f * fx1), __float_as_uint(0.5f * fx1));
+          unsigned a0, a1, a2, a3, b0, b1, b2, b3;
+          cubic_scale_w2(f2a, h2a, rw[0][0], rw[0][1], a0, a1, zero);
+          cubic_scale_w2(f2a, h2a, rw[0][2], rw[0][3], a2, a3, zero);
+          cubic_scale_w2(f2b, h2b, rw[1][0], rw[1][1], b0, b1, zero);
+          cubic_scale_w2(f2b, h2b, rw[1][2], rw[1][3], b2, b3, zero);
+          unsigned ca = __byte_perm(__byte_perm(a0, a1, 0x0040), __byte_perm(a2, a3, 0x0040), 0x5410);
+          unsigned cb = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+          u64 fy2 = pk2(__float_as_uint(fy0), __float_as_uint(fy1)), hy2 = pk2(__float_as_uint(0.5f * fy0), __float_as_uint(0.5f * fy1));
+          cubic_scale_w2(fy2, hy2, ca, cb, o0, o1, zero);
+        }
+        if (ok[0] && ok[1]) { orow[0] = (uint8_t)o0; orow[pitch] = (uint8_t)o1; continue; }
+        // taps reaching outside the image: the general path (reads outside = white)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          if (ok[k]) { orow[(size_t)k * pitch] = (uint8_t)(k ? o1 : o0); continue; }
+          Px q = interp_any(im, srcX[k], srcY[k], interp, gray);
+          px_store(out, X, Ya + k, q.r, q.g, q.b);
+        }
+      }
+      continue;
+    }
+    // ---- tiles on the rectangle's edge, other formats / interpolations: pixel by pixel
     for (int Y = Yt; Y <= Yte; Y++) {
       const int y = Y - oy;
-      const bool inside = colin && y >= 0 && y < h;
-      float srcX = 0.0f, srcY = 0.0f;
-      if (inside) {
+      if (colin && y >= 0 && y < h) {
         float xf = u8f((unsigned)x), yf = u8f((unsigned)y);   // == (float)x, (float)y for 0 <= v < 2^23
-        srcX = scx + (xf - tcx) * cosval + (yf - tcy) * sinval;
-        srcY = scy + (yf - tcy) * cosval - (xf - tcx) * sinval;
-      }
-      bool fastok = false;
-      unsigned rw[4] = {0, 0, 0, 0};
-      float tX = 0.0f, tY = 0.0f;
-      if (fast && inside) {
-        // (int)srcX for 1 <= srcX < 2^23 by the 2^23 trick (anything else fails the range test)
-        tX = __fadd_rz(srcX, 8388608.0f); tY = __fadd_rz(srcY, 8388608.0f);
-        int px = __float_as_int(tX) - 0x4B000000, py = __float_as_int(tY) - 0x4B000000;
-        fastok = (unsigned)(px - 1) < (unsigned)(W - 3) && (unsigned)(py - 1) < (unsigned)(H - 3);
-        if (fastok) {
-          const uint8_t *p0 = im.data + (size_t)(py - 1) * im.pitch + (px - 1);
-          const unsigned *wp = (const unsigned *)((uintptr_t)p0 & ~(uintptr_t)3);
-          unsigned sh = ((unsigned)(uintptr_t)p0 & 3u) * 8u;
-#pragma unroll
-          for (int i = 0; i < 4; i++) rw[i] = __funnelshift_r(wp[i * wpitch], wp[i * wpitch + 1], sh);
-        }
-      }
-      unsigned o = rw[0] & 0xFFu;
-      bool uni = rw[0] == o * 0x01010101u && rw[1] == rw[0] && rw[2] == rw[0] && rw[3] == rw[0];
-      if (__any_sync(0xffffffffu, fastok && !uni)) {
-        if (fastok) {
-          float fx = srcX - (tX - 8388608.0f), fy = srcY - (tY - 8388608.0f);   // srcX - (float)px
-          float hfx = 0.5f * fx;
-          unsigned r0 = cubic_scale_w(fx, hfx, rw[0]), r1 = cubic_scale_w(fx, hfx, rw[1]);
-          unsigned r2 = cubic_scale_w(fx, hfx, rw[2]), r3 = cubic_scale_w(fx, hfx, rw[3]);
-          unsigned lo = __byte_perm(r0, r1, 0x0040), hi = __byte_perm(r2, r3, 0x0040);
-          o = cubic_scale_w(fy, 0.5f * fy, __byte_perm(lo, hi, 0x5410));
-        }
-      }
-      if (fastok) { out.data[(size_t)Y * out.pitch + X] = (uint8_t)o; continue; }
-      if (inside) {
-        Px q = interp_any(im, srcX, srcY, interp, gray);
+        float sX = scx + (xf - tcx) * cosval + (yf - tcy) * sinval;
+        float sY = scy + (yf - tcy) * cosval - (xf - tcx) * sinval;
+        Px q = interp_any(im, sX, sY, interp, gray);
         px_store(out, X, Y, q.r, q.g, q.b);
       } else if (X < W) {
         Px q = px_load(im, X, Y);
@@ -841,7 +935,26 @@ __global__ void k_stretch(DImg src, DImg dst, float hr, float vr, int interp) {
   }
 }
 
+// stretch_and_replace of every page's working sheet into its other buffer (sheet_stages.c:216-222, :516-522)
+__global__ void k_stretch_pages(DPage *pages, int dw, int dh, int dpitch, float hr, float vr, int interp) {
+  const DPage &pg = pages[blockIdx.z];
+  DImg src = pg.img, dst = pg.img;
+  dst.data = pg.other; dst.w = dw; dst.h = dh; dst.pitch = dpitch;
+  bool gray = src.fmt != DF_RGB24;
+  for (int y = blockIdx.y; y < dh; y += gridDim.y)
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < dw; x += gridDim.x * blockDim.x) {
+      Px o = interp_any(src, x * hr, y * vr, interp, gray);
+      px_store(dst, x, y, o.r, o.g, o.b);
+    }
+}
+
 extern "C" {
+void b200k_stretch_pages(cudaStream_t st, DPage *pages, int npages, int sw, int sh, int dw, int dh, int dpitch, int interp) {
+  if (npages <= 0 || dw <= 0 || dh <= 0) return;
+  float hr = (float)sw / (float)dw, vr = (float)sh / (float)dh;   /* blit.c:213-216 */
+  dim3 g(min(cdiv(dw, 128), 32u), min((unsigned)dh, 2048u), npages);
+  k_stretch_pages<<<g, 128, 0, st>>>(pages, dw, dh, dpitch, hr, vr, interp);
+}
 int b200k_rot_peaks(cudaStream_t st, DPage *pages, int npages, int mi_first, int mi_count, const float *tan_tab_dev,
                     int nangles, int scan_size_param, float scan_depth, const int edges[4],
                     int peak_off, int scan_cap, int maxw, int use_prefix, int run_cap) {
@@ -900,7 +1013,7 @@ void b200k_rotate_sheet(cudaStream_t st, DPage *pages, int npages, int mi, int i
   if (npages <= 0 || maxw <= 0 || maxh <= 0) return;
   if (interp == 2) k_inkmap<<<dim3(min(cdiv(maxh, INK_CELL), 256u), npages), 128, 0, st>>>(pages);
   dim3 g(cdiv(maxw, 128), cdiv(maxh, ROT_ROWS), npages);
-  k_rotate_sheet<<<g, 128, 0, st>>>(pages, mi, interp);
+  k_rotate_sheet<<<g, 128, 0, st>>>(pages, mi, interp, 0u);
 }
 void b200k_stretch(cudaStream_t st, DImg src, DImg dst, float hr, float vr, int interp) {
   if (dst.w <= 0 || dst.h <= 0) return;

@@ -28,12 +28,20 @@ __global__ void k_swap_sheets(DPage *pages, int npages) {
   uint8_t *t = pg.img.data; pg.img.data = pg.other; pg.other = t;
 }
 
+// the working sheet of every page now has this geometry (after a size-changing pass, or back to
+// the decoded size at the start of a sheet)
+__global__ void k_set_geometry(DPage *pages, int npages, int w, int h, int pitch) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npages) return;
+  pages[p].img.w = w; pages[p].img.h = h; pages[p].img.pitch = pitch;
+}
+
 // static job tables (wipes, borders, pre-masks: geometry known at engine creation) carry an
 // image descriptor per page; point them at the page's CURRENT working buffer
 __global__ void k_retarget_jobs(const DPage *pages, int npages, DFillJob *fills, int nfill, DMaskJob *masks, int nmask, int stride) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nfill) { int p = i % stride; if (p < npages) fills[i].img.data = pages[p].img.data; }
-  if (i < nmask) { int p = i % stride; if (p < npages) masks[i].img.data = pages[p].img.data; }
+  if (i < nfill) { int p = i % stride; if (p < npages) fills[i].img = pages[p].img; }
+  if (i < nmask) { int p = i % stride; if (p < npages) masks[i].img = pages[p].img; }
 }
 
 // Strided row copy between packed host-layout images and pitched device
@@ -106,6 +114,10 @@ void b200k_convert_out(cudaStream_t st, DImg src, DImg dst, int nimages, size_t 
 void b200k_swap_sheets(cudaStream_t st, DPage *pages, int npages) {
   if (npages <= 0) return;
   k_swap_sheets<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages);
+}
+void b200k_set_geometry(cudaStream_t st, DPage *pages, int npages, int w, int h, int pitch) {
+  if (npages <= 0) return;
+  k_set_geometry<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages, w, h, pitch);
 }
 void b200k_retarget_jobs(cudaStream_t st, const DPage *pages, int npages, DFillJob *fills, int nfill,
                          DMaskJob *masks, int nmask, int stride) {

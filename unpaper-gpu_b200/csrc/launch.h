@@ -72,6 +72,12 @@ void b200k_stretch(cudaStream_t st, DImg src, DImg dst, float hr, float vr, int 
 void b200k_swap_sheets(cudaStream_t st, DPage *pages, int npages);
 void b200k_retarget_jobs(cudaStream_t st, const DPage *pages, int npages, DFillJob *fills, int nfill,
                          DMaskJob *masks, int nmask, int stride);
+void b200k_set_geometry(cudaStream_t st, DPage *pages, int npages, int w, int h, int pitch);
+/* size-changing operations for a group (k_blit.cu / k_deskew.cu): img -> other with a new geometry */
+void b200k_rotate90_batch(cudaStream_t st, DImg src, DImg dst, int dir, int nimages, size_t src_stride, size_t dst_stride);
+void b200k_rotate90_pages(cudaStream_t st, DPage *pages, int npages, int sw, int sh, int dir, int dpitch);
+void b200k_center_pages(cudaStream_t st, DPage *pages, int npages, int dw, int dh, int dpitch);
+void b200k_stretch_pages(cudaStream_t st, DPage *pages, int npages, int sw, int sh, int dw, int dh, int dpitch, int interp);
 /* one-sweep rectangle move img -> other of every page's DPage.move (k_blit.cu) */
 void b200k_move_pass(cudaStream_t st, DPage *pages, int npages, int maxw_bytes, int maxh, int mc_r, int mc_g, int mc_b);
 /* k_masks.cu: fill DPage.move for center_mask(i) / align_mask(i) / shift_image */
