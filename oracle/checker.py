@@ -45,19 +45,20 @@ def load_oracle():
     return lib
 
 
-def process_sheets_cpu(lib, prefix, cfg, pages, page_w, page_h, fmt, threads=1, want_out=True):
+def process_sheets_cpu(lib, prefix, cfg, pages, page_w, page_h, fmt, threads=1, want_out=True, out_size=None):
     """Run ``n`` sheets through a CPU library's process_sheet() equivalent.
 
-    ``pages``: uint8 array holding n*input_count tightly packed pages.
+    ``pages``: uint8 array holding n*input_count tightly packed pages.  ``out_size``: (w, h) of
+    the finished sheets when size-changing options are set (default: pages side by side).
     Returns (out array [n, sheet_h, sheet_row_bytes] or None, list of SheetResult)."""
     row = bytes_per_row(fmt, page_w)
     per_sheet = row * page_h * cfg.input_count
     pages = np.ascontiguousarray(pages, dtype=np.uint8).reshape(-1)
     n = pages.size // per_sheet
-    sw, sh = page_w * cfg.input_count, page_h
+    sw, sh = out_size if out_size else (page_w * cfg.input_count, page_h)
     out = np.empty((n, sh, bytes_per_row(fmt, sw)), dtype=np.uint8) if want_out else None
     res = (SheetResult * n)()
-    w, h = C.c_int(), C.c_int()
+    w, h = C.c_int(sw), C.c_int(sh)
     rc = getattr(lib, prefix + "process_sheets")(
         C.byref(cfg), pages.ctypes.data, page_w, page_h, fmt, n,
         out.ctypes.data if want_out else None, res, threads, C.byref(w), C.byref(h))

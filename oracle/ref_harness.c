@@ -463,6 +463,12 @@ static void options_from_cfg(Options *o, Rectangle *bf_excl, const B200SheetConf
   o->pre_wipes.count = (size_t)c->pre_wipe_count;
   o->wipes.count = (size_t)c->wipe_count;
   o->post_wipes.count = (size_t)c->post_wipe_count;
+  /* size-changing options (sheet_stages.c:134-145, :216-230, :511-531) */
+  o->pre_rotate = c->pre_rotate; o->post_rotate = c->post_rotate;
+  o->sheet_size = c->sheet_size; o->stretch_size = c->stretch_size; o->page_size = c->page_size;
+  o->post_stretch_size = c->post_stretch_size; o->post_page_size = c->post_page_size;
+  if (c->pre_zoom_factor != 0.0f) o->pre_zoom_factor = c->pre_zoom_factor;
+  if (c->post_zoom_factor != 0.0f) o->post_zoom_factor = c->post_zoom_factor;
   o->pre_mirror = c->pre_mirror; o->post_mirror = c->post_mirror;
   o->pre_shift = c->pre_shift; o->post_shift = c->post_shift;
   for (int i = 0; i < 8; i++) {
@@ -475,7 +481,8 @@ static void options_from_cfg(Options *o, Rectangle *bf_excl, const B200SheetConf
 /* One sheet: pages -> reference process_sheet() -> sheet in the page format. */
 static int run_one_sheet(const B200SheetConfig *cfg, const Options *opt,
                          const uint8_t *pages, int page_w, int page_h, int page_fmt,
-                         uint8_t *out, B200SheetResult *res, char **out_files, int out_count, int sheet_nr) {
+                         uint8_t *out, B200SheetResult *res, char **out_files, int out_count, int sheet_nr,
+                         int out_w, int out_h) {
   int row = av_shim_row_bytes(page_fmt, page_w);
   if (row < 0) return -1;
   size_t page_bytes = (size_t)row * page_h;
@@ -520,7 +527,10 @@ static int run_one_sheet(const B200SheetConfig *cfg, const Options *opt,
   if (ok) {
     res->sheet_width = st.sheet.frame->width;
     res->sheet_height = st.sheet.frame->height;
-    if (out) {
+    if (out && (res->sheet_width != out_w || res->sheet_height != out_h)) {
+      ok = false;                        /* the caller's buffer was sized for another geometry */
+      res->status = -5;
+    } else if (out) {
       /* what saveImage() would hand to the writer (file.c:211-262) */
       B200HostImage o = {.data = out, .width = res->sheet_width, .height = res->sheet_height,
                          .linesize = av_shim_row_bytes(page_fmt, res->sheet_width),
@@ -545,6 +555,7 @@ typedef struct {
   B200SheetResult *results;
   const char *out_dir; int out_count;   /* write_output runs: files <dir>/s<sheet>_<page>.pnm */
   int page_w, page_h, page_fmt, n_sheets;
+  int out_w, out_h;                      /* size of the buffers behind `out` */
   size_t sheet_in_bytes, sheet_out_bytes;
   atomic_int next;
   atomic_int failed;
@@ -571,7 +582,7 @@ static void *worker(void *arg) {
                            jb->page_w, jb->page_h, jb->page_fmt,
                            jb->out ? jb->out + (size_t)i * jb->sheet_out_bytes : NULL,
                            jb->results ? &jb->results[i] : NULL, jb->out_dir ? files : NULL, jb->out_count,
-                           (jb->cfg->first_sheet_nr > 0 ? jb->cfg->first_sheet_nr : 1) + i);
+                           (jb->cfg->first_sheet_nr > 0 ? jb->cfg->first_sheet_nr : 1) + i, jb->out_w, jb->out_h);
     if (rc != 0) atomic_fetch_add(&jb->failed, 1);
 #ifdef REF_DROPIN
     if (stream) {   /* lib/batch_worker.c:253-255 */
@@ -598,11 +609,15 @@ int ref_process_sheets(const B200SheetConfig *cfg, const uint8_t *pages, int pag
   options_from_cfg(&opt, bf_excl, cfg);
   int row = av_shim_row_bytes(page_fmt, page_w);
   if (row < 0) return -1;
-  int sw = page_w * cfg->input_count, sh = page_h;
+  /* in: the expected size of the finished sheets when the options change it (the caller sizes
+   * `out` with it; every sheet's actual size comes back in results[].sheet_width/height) */
+  int sw = (sheet_w && *sheet_w > 0) ? *sheet_w : page_w * cfg->input_count;
+  int sh = (sheet_h && *sheet_h > 0) ? *sheet_h : page_h;
   if (sheet_w) *sheet_w = sw;
   if (sheet_h) *sheet_h = sh;
   Job jb = {.cfg = cfg, .opt = &opt, .pages = pages, .out = out, .results = results,
             .page_w = page_w, .page_h = page_h, .page_fmt = page_fmt, .n_sheets = n_sheets,
+            .out_w = sw, .out_h = sh,
             .sheet_in_bytes = (size_t)row * page_h * cfg->input_count,
             .sheet_out_bytes = (size_t)av_shim_row_bytes(page_fmt, sw) * sh};
   atomic_init(&jb.next, 0);

@@ -17,8 +17,9 @@ def _compare(cfg, pages, w, h, fmt, ref_lib, group=4, lanes=2):
     from unpaper_gpu_b200.lib import Engine
     eng = Engine(cfg, w, h, fmt, group_pages=group, lanes=lanes)
     out, res = eng.process_numpy(pages)
+    size = (eng.sheet_w, eng.sheet_h)
     eng.close()
-    rout, rres = checker.process_sheets_cpu(ref_lib, "ref_", cfg, pages, w, h, fmt, threads=8)
+    rout, rres = checker.process_sheets_cpu(ref_lib, "ref_", cfg, pages, w, h, fmt, threads=8, out_size=size)
     for i, (a, b) in enumerate(zip(res, rres)):
         assert a.status == 0 and b.status == 0
         assert a.deskew_mask_count == b.deskew_mask_count, f"sheet {i}"
@@ -425,3 +426,61 @@ def test_engine_double_600dpi_vs_reference(ref_lib):
         assert U.border_tuple(a.borders[k]) == U.border_tuple(b.borders[k])
         assert files[0][k][:3] == (U.FMT_GRAY8, w // 2, h)
         assert np.array_equal(out[0, k], files[0][k][3]), f"page {k}: {int((out[0, k] != files[0][k][3]).sum())} differing bytes"
+
+
+def _size_cases():
+    """name -> (config edits, page format, input_count): the size-changing options of the decode, pre and
+    post stages (sheet_stages.c:134-145, :216-230, :511-531)."""
+    RS = U.RectangleSize
+    return {
+        "pre_rotate_cw": (dict(pre_rotate=90), U.FMT_GRAY8, 1),
+        "pre_rotate_ccw_two_pages": (dict(pre_rotate=-90, layout=U.LAYOUT_DOUBLE), U.FMT_GRAY8, 2),
+        "post_rotate": (dict(post_rotate=-90), U.FMT_GRAY8, 1),
+        "stretch": (dict(stretch_size=RS(700, 940)), U.FMT_GRAY8, 1),
+        "stretch_width_only_linear": (dict(stretch_size=RS(560, -1), interpolate_type=U.INTERP_LINEAR), U.FMT_GRAY8, 1),
+        "pre_zoom": (dict(pre_zoom_factor=1.25), U.FMT_GRAY8, 1),
+        "post_zoom_and_post_stretch": (dict(post_zoom_factor=0.5, post_stretch_size=RS(900, 1000)), U.FMT_GRAY8, 1),
+        "page_size_wider": (dict(page_size=RS(900, 877)), U.FMT_GRAY8, 1),
+        "page_size_smaller": (dict(page_size=RS(500, 800)), U.FMT_GRAY8, 1),
+        "post_page_size": (dict(post_page_size=RS(640, 640)), U.FMT_GRAY8, 1),
+        "sheet_size_larger": (dict(sheet_size=RS(700, 1000)), U.FMT_GRAY8, 1),
+        "sheet_size_crops": (dict(sheet_size=RS(600, 850)), U.FMT_GRAY8, 1),
+        "everything_rgb": (dict(pre_rotate=90, stretch_size=RS(940, 700), post_rotate=90, post_page_size=RS(720, 960),
+                                no_blackfilter=1, no_noisefilter=1), U.FMT_RGB24, 1),
+        "mono_pages_rotated": (dict(pre_rotate=90, post_rotate=-90), U.FMT_MONOBLACK, 1),
+    }
+
+
+def _size_case(name):
+    edits, fmt, ic = _size_cases()[name]
+    cfg = U.default_sheet_config()
+    cfg.input_count = ic
+    for k, v in edits.items():
+        setattr(cfg, k, v)
+    w, h = (620, 877) if fmt != U.FMT_MONOBLACK else (624, 880)
+    n = 2 * ic
+    if fmt == U.FMT_RGB24:
+        pages = np.stack([synth.color_page(600 + i, w, h) for i in range(n)])
+    else:
+        pages = np.stack([synth.gray_page(600 + i, w, h, box=SMALL_BOX) for i in range(n)])
+        if fmt == U.FMT_MONOBLACK:
+            pages = np.stack([np.packbits(p >= 128, axis=1) for p in pages])
+    return cfg, pages, w, h, fmt
+
+
+@pytest.mark.parametrize("name", sorted(_size_cases()))
+def test_engine_size_changing_options(ref_lib, name):
+    cfg, pages, w, h, fmt = _size_case(name)
+    if fmt == U.FMT_MONOBLACK:
+        from unpaper_gpu_b200.lib import Engine
+        eng = Engine(cfg, w, h, fmt, group_pages=2, lanes=1)
+        out, res = eng.process_numpy(pages)
+        size = (eng.sheet_w, eng.sheet_h)
+        eng.close()
+        rout, rres = checker.process_sheets_cpu(ref_lib, "ref_", cfg, pages, w, h, fmt, threads=4, out_size=size)
+        assert all(r.status == 0 for r in res) and all(r.status == 0 for r in rres)
+        assert size[0] % 8 == 0
+        assert np.array_equal(out, rout ^ 0xFF)      # the harness hands back MONOBLACK; saveImage() writes MONOWHITE
+        return
+    out, res = _compare(cfg, pages, w, h, fmt, ref_lib, group=2, lanes=2)
+    assert (res[0].sheet_width, res[0].sheet_height) == (out.shape[2] // (3 if fmt == U.FMT_RGB24 else 1), out.shape[1])
