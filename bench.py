@@ -178,6 +178,9 @@ def main():
                     help="distinct synthetic pages per rank (per-page seeds); the step's pages cycle through them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-iso", action="store_true", help="skip the isolated per-stage pass (profiling runs)")
+    ap.add_argument("--iso-group", type=int, default=int(os.environ.get("BENCH_ISO_GROUP", "296")),
+                    help="sheets per launch sequence of the isolated per-stage pass: 2 x 148 SMs, so that the kernels "
+                         "that give one CTA to a page (flood fill, noise resolve, gray cascade) fill the machine")
     ap.add_argument("--out-format", default="page", choices=["page", "mono"],
                     help="sheet_stage_output format: 'page' (GRAY8, the headline config) or 'mono' (pbm, 1 bit/px D2H)")
     args = ap.parse_args()
@@ -302,8 +305,8 @@ def main():
     if rank == 0 and args.no_iso:
         iso = (prof, args.group)
     elif rank == 0:
-        ie = Engine(cfg, W, H, U.FMT_GRAY8, group_pages=min(args.group, 64), lanes=1, device=local)
-        n_iso = min(args.group, 64)
+        n_iso = max(1, min(args.iso_group, args.pages))
+        ie = Engine(cfg, W, H, U.FMT_GRAY8, group_pages=n_iso, lanes=1, device=local)
         for _ in range(2):
             ie.process_ptr(dev_in.data_ptr(), dev_out.data_ptr(), n_iso, False, None)
         ie.set_profiling(True)

@@ -219,3 +219,15 @@ def test_deskew(cuda_ops, ref_ops, fmt, interp):
         d = np.abs(a[:, :n].astype(int) - b[:, :n].astype(int))
         assert d.max() <= 1 and (d > 0).mean() <= 0.001, f"deskew: max diff {d.max()}, frac {(d > 0).mean()}"
         assert_same(a, b, fmt, w, f"deskew exact {U.rect_tuple(mask)} {rad}")
+
+
+def test_noisefilter_dense_page_high_intensity(cuda_ops, ref_ops):
+    """intensity > 15: every dark pixel is decided in raster order; a page with far more than a
+    quarter of its pixels dark must not overflow the list (the reference just processes it)."""
+    from util import noise_image, run_inplace, assert_same
+    w, h = 320, 200
+    img = noise_image(77, w, h, U.FMT_GRAY8, dark=0.6, lo=0, hi=120)
+    for inten in (16, 40):
+        a = run_inplace(cuda_ops, "noisefilter", img, U.FMT_GRAY8, w, inten, 229)
+        b = run_inplace(ref_ops, "noisefilter", img, U.FMT_GRAY8, w, inten, 229)
+        assert_same(a, b, U.FMT_GRAY8, w, f"noisefilter intensity {inten} on a dense page")

@@ -408,6 +408,7 @@ static void noisefilter_b200(Image image, uint64_t intensity, uint8_t min_white_
   if (!image.frame) return;
   ScratchNeed n;
   scratch_need_all(&n, image.frame->width, image.frame->height, 0);
+  n.list_cap = nf_list_cap(image.frame->width, image.frame->height, intensity);
   Op o; op_begin(&o, &image, 0, n.list_cap, 0, 0);
   op_push(&o);
   if (stage_noisefilter(&o.sc, intensity, min_white_level)) b200_fatal("%s", unpaper_b200_last_error());

@@ -117,6 +117,7 @@ struct B200Engine {
   uint64_t stage_groups[STG_COUNT];
   /* stream state: groups [g_done, g) are in flight, at most two per lane */
   int streaming, host_mode, g, g_done, fed;
+  int issue_failed;   /* a stage launcher refused (limits are checked at creation, so this is a bug trap) */
 };
 
 static int imax(int a, int b) { return a > b ? a : b; }
@@ -437,6 +438,7 @@ B200Engine *unpaper_b200_engine_create(const B200SheetConfig *cfg, int device, i
   if (rc) { unpaper_b200_engine_destroy(e); return NULL; }
 
   scratch_need_all(&e->need, W, H, e->dfmt);
+  if (!cfg->no_noisefilter) e->need.list_cap = nf_list_cap(W, H, cfg->noisefilter_intensity);
   int u32 = 64;
   u32 = imax(u32, e->bf.u32_need); u32 = imax(u32, e->blur.u32_need); u32 = imax(u32, e->gray.u32_need);
   u32 = imax(u32, e->mask.u32_need); u32 = imax(u32, e->border.u32_need); u32 = imax(u32, e->rot.u32_need);
@@ -659,13 +661,13 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
   mark(e, ln, STG_BLACK);
   if (!no_blackfilter) stage_blackfilter(&c, &e->bf);
   mark(e, ln, STG_NOISE);
-  if (!no_noisefilter) stage_noisefilter(&c, cfg->noisefilter_intensity, cfg->abs_white_threshold);
+  if (!no_noisefilter && stage_noisefilter(&c, cfg->noisefilter_intensity, cfg->abs_white_threshold)) e->issue_failed++;
   mark(e, ln, STG_BLUR);
   if (!no_blurfilter) stage_blurfilter(&c, &e->blur);
   mark(e, ln, STG_GRAY);
   /* masks stage: the reference's first detect_masks() result is discarded
    * (sheet_stages.c:368-372) and has no side effect -> not run */
-  if (!no_grayfilter) stage_grayfilter(&c, &e->gray);
+  if (!no_grayfilter && stage_grayfilter(&c, &e->gray)) e->issue_failed++;
   mark(e, ln, STG_MASKS);
   int nm = e->npoints;
   if (!no_deskew) {
@@ -674,7 +676,7 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
     /* mask by mask like sheet_stages.c:406-413: detect_rotation(mask i+1) sees the
      * sheet with mask i already deskewed (the masks may share pixels) */
     for (int mi = 0; mi < nm; mi++) {
-      stage_detect_rotation_mask(&c, &e->rot, mi);
+      if (stage_detect_rotation_mask(&c, &e->rot, mi)) e->issue_failed++;
       if (mi == nm - 1) mark(e, ln, STG_DESKEW);   /* profile split: exact for one mask */
       stage_deskew_mask_pass(&c, cfg->interpolate_type, mi);
     }
@@ -918,6 +920,11 @@ int unpaper_b200_engine_stream_end(B200Engine *e) {
     float ms = 0;
     if (e->lanes[i].ran && cudaEventElapsedTime(&ms, e->ev_begin, e->lanes[i].last_done_t) == cudaSuccess && ms > e->last_device_ms)
       e->last_device_ms = ms;
+  }
+  if (e->issue_failed) {
+    e->issue_failed = 0; e->done_failed = 0; e->bad_sheets = 0; e->bad_flags = 0;
+    b200_set_error("engine: a stage could not be launched: %s", unpaper_b200_last_error());
+    return -5;
   }
   if (e->done_failed) {
     int nf = e->done_failed;

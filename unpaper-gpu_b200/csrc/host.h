@@ -128,6 +128,7 @@ void stage_shift_pass(StageCtx *c, Delta d);
 /* scratch sizing for one page of w x h in device format fmt */
 typedef struct { size_t aux_bytes; int aux_pitch, aux_h; size_t cls_bytes; int list_cap, u32_cap, stack_cap; long long pre_cap; } ScratchNeed;
 void scratch_need_all(ScratchNeed *n, int w, int h, int fmt);
+int nf_list_cap(int w, int h, uint64_t intensity);   /* noisefilter list entries for this intensity */
 
 void *blob_upload(const void *host, size_t bytes);   /* synchronous H2D into cached device memory */
 

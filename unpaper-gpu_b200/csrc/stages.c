@@ -51,9 +51,19 @@ void scratch_need_all(ScratchNeed *n, int w, int h, int fmt) {
   n->aux_h = ah;
   n->aux_bytes = (size_t)n->aux_pitch * ah + 64;
   n->cls_bytes = (size_t)w * h + 64;
-  n->list_cap = imax(4096, (w * h) / 4);
+  n->list_cap = imax(4096, (w * h) / 4);   /* noisefilter: see nf_list_cap() */
   n->u32_cap = 0;
   n->stack_cap = 1 << 16;
+}
+
+/* Entries of the noisefilter's list of pixels that are decided in raster order.  Up to
+ * intensity 15 only pixels of small clusters and of the left/top band land there (a quarter
+ * of the image is far more than a scan holds); above that every dark pixel does
+ * (k_filters.cu: all_mutable), so the list must be able to hold the whole image. */
+int nf_list_cap(int w, int h, uint64_t intensity) {
+  long long px = (long long)w * h;
+  if (intensity > 15) return (int)(px < 0x7fffffffLL ? px : 0x7fffffffLL);
+  return imax(4096, (int)(px / 4));
 }
 
 /* ---- blackfilter plan: reference filters.c:49-127 loop structure ---------- */
@@ -206,6 +216,8 @@ int gray_plan_build(GrayPlan *pl, int w, int h, const GrayfilterParameters *p, i
   pl->u32_need = (int)(4 * nc) + nwx * nwy + nwx + skew * (nwy - 1) + 4;
   pl->dark_max = abt;
   pl->ok = 1;
+  /* k_cellstats keeps two counters per cell of a cell row in shared memory */
+  if ((size_t)ncx * 2 * sizeof(unsigned) > 200 * 1024) { b200_set_error("grayfilter: cell row too wide for this scan size/step"); return -1; }
   return 0;
 }
 
