@@ -20,6 +20,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <time.h>
 
 #include "host.h"
 
@@ -816,6 +817,21 @@ static void collect_next(B200Engine *e) {
   int k = e->g_done++;
   Lane *ln = &e->lanes[k % e->nlanes];
   ln->slot = (k / e->nlanes) & 1;
+  static int trace = -1;
+  if (trace < 0) trace = getenv("UNPAPER_B200_ENGINE_TRACE") != NULL;
+  if (trace) {
+    struct timespec a, b;
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    CUDA_OK(cudaEventSynchronize(ln->fl[ln->slot].done));
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    int ready = 0;
+    for (int j = e->g_done; j < e->g; j++) {
+      Lane *o = &e->lanes[j % e->nlanes];
+      if (cudaEventQuery(o->fl[(j / e->nlanes) & 1].done) == cudaSuccess) ready |= 1 << (j - e->g_done);
+    }
+    fprintf(stderr, "[engine] group %d lane %d waited %.2f ms; later groups already done: 0x%x\n", k, k % e->nlanes,
+            (b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) / 1e6, ready);
+  }
   collect(e, ln);
 }
 

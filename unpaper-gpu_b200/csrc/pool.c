@@ -18,7 +18,14 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+#include <time.h>
+
 #include "host.h"
+
+static int g_trace = -1;
+static double now_ms(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec / 1e6; }
+#define TRACE(...) do { if (g_trace < 0) g_trace = getenv("UNPAPER_B200_POOL_TRACE") != NULL; if (g_trace) { fprintf(stderr, "[pool %9.3f] ", now_ms()); fprintf(stderr, __VA_ARGS__); fputc('\n', stderr); } } while (0)
 
 typedef struct {
   uint8_t *in, *out;     /* pinned */
@@ -133,6 +140,7 @@ static void *producer_main(void *arg) {
         break;
       }
     }
+    TRACE("dev %d produced slot %d first %d got %d", d->device, k, first, got);
     pthread_mutex_lock(&d->mu);
     if (got > 0) {
       d->slots[k].first = first; d->slots[k].n = got; d->slots[k].reported = 0; d->slots[k].state = 2;
@@ -183,12 +191,14 @@ static void *feeder_main(void *arg) {
     }
     pthread_mutex_unlock(&d->mu);
     if (finished) break;
-    if (k < 0) { unpaper_b200_engine_stream_poll(d->eng); continue; }
+    if (k < 0) { TRACE("dev %d poll (nothing ready)", d->device); unpaper_b200_engine_stream_poll(d->eng); TRACE("dev %d poll done", d->device); continue; }
     Slot *s = &d->slots[k];
     pthread_mutex_lock(&d->mu);
     s->state = 3;
     pthread_mutex_unlock(&d->mu);
+    TRACE("dev %d feed slot %d first %d n %d in flight %d", d->device, k, s->first, s->n, unpaper_b200_engine_stream_in_flight(d->eng));
     if (unpaper_b200_engine_stream_feed(d->eng, s->in, s->out, s->n, p->results ? p->results + s->first : NULL, s->first)) { d->rc = -1; break; }
+    TRACE("dev %d fed", d->device);
   }
   int rc = unpaper_b200_engine_stream_end(d->eng);
   if (rc && !d->rc) d->rc = rc;
