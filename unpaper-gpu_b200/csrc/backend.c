@@ -267,12 +267,17 @@ static void apply_masks_b200(Image image, const Rectangle masks[], size_t masks_
 static void apply_wipes_b200(Image image, Wipes wipes, Pixel color) {
   if (!image.frame || wipes.count == 0) return;
   Op o; op_begin(&o, &image, 0, 0, 0, 0);
+  /* all rectangles in one launch (same colour, so their order does not matter) */
+  DFillJob *h = (DFillJob *)calloc(wipes.count, sizeof(DFillJob));
   for (size_t i = 0; i < wipes.count; i++) {
-    push_fill(&o, o.sc.fillA, o.hp.img, drect(wipes.areas[i]), color);
-    b200k_fill_jobs(o.sc.st, o.sc.fillA, 1, o.hp.img.w, o.hp.img.h);
-    CUDA_OK(cudaStreamSynchronize(o.sc.st));   /* the job slot is reused */
+    h[i].img = o.hp.img; h[i].r = drect(wipes.areas[i]);
+    h[i].c[0] = color.r; h[i].c[1] = color.g; h[i].c[2] = color.b; h[i].enabled = 1;
   }
+  DFillJob *d = (DFillJob *)blob_upload(h, wipes.count * sizeof(DFillJob));
+  free(h);
+  b200k_fill_jobs(o.sc.st, d, (int)wipes.count, o.hp.img.w, o.hp.img.h);
   op_end(&o, &image, true);
+  b200_dev_free(d);
 }
 
 static void apply_border_b200(Image image, const Border border, Pixel color) {   /* masks.c:370-382 */

@@ -778,10 +778,12 @@ __device__ __forceinline__ bool tile_white(const uint8_t *ink, int ink_ncx, int 
   if (bx1 < 0 || by1 < 0 || bx0 >= W || by0 >= H) return true;   // entirely outside: reads as white
   int cx0 = max(bx0, 0) / INK_CELL, cx1 = min(bx1, W - 1) / INK_CELL;
   int cy0 = max(by0, 0) / INK_CELL, cy1 = min(by1, H - 1) / INK_CELL;
-  int nx = cx1 - cx0 + 1, n = nx * (cy1 - cy0 + 1);
-  if (n > 32) return false;
+  // lanes form an 8 x 4 grid of cells (a 32 x 8 tile rotated by a few degrees touches 6-7 x 3-4 cells)
+  int nx = cx1 - cx0 + 1, ny = cy1 - cy0 + 1;
+  if (nx > 8 || ny > 4) return false;
+  int lx = lane & 7, ly = lane >> 3;
   bool wh = true;
-  if (lane < n) wh = ink[(cy0 + lane / nx) * ink_ncx + cx0 + lane % nx] != 0;
+  if (lx < nx && ly < ny) wh = ink[(cy0 + ly) * ink_ncx + cx0 + lx] != 0;
   return __all_sync(0xffffffffu, wh);
 }
 

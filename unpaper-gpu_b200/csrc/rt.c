@@ -104,11 +104,13 @@ void unpaper_b200_thread_sync(void) { CUDA_OK(cudaStreamSynchronize(b200_rt_stre
 /* ---- bucketed caches ------------------------------------------------------ */
 
 #define NBUCKET 112
+#define LIVE_SLOTS 4096   /* open-addressing table of the blocks handed out (power of two) */
 typedef struct Block { struct Block *next; void *ptr; size_t bytes; int dev; int bucket; } Block;
 typedef struct {
   pthread_mutex_t mu;
   Block *free_list[B200_MAX_DEVICES + 1][NBUCKET];
-  Block *live;   /* blocks handed out */
+  Block *live[LIVE_SLOTS];   /* pointer -> block, linear probing; overflow falls back to the chain below */
+  Block *live_overflow;
 } Cache;
 static Cache g_dev_cache = {PTHREAD_MUTEX_INITIALIZER};
 static Cache g_pin_cache = {PTHREAD_MUTEX_INITIALIZER};
@@ -126,6 +128,32 @@ static int bucket_of(size_t bytes, size_t *rounded) {
   return -1;
 }
 
+static unsigned live_hash(const void *p) { return (unsigned)(((uintptr_t)p >> 9) * 2654435761u) & (LIVE_SLOTS - 1); }
+/* both with c->mu held */
+static void live_put(Cache *c, Block *b) {
+  unsigned h = live_hash(b->ptr);
+  for (int i = 0; i < 64; i++, h = (h + 1) & (LIVE_SLOTS - 1))
+    if (!c->live[h]) { c->live[h] = b; return; }
+  b->next = c->live_overflow; c->live_overflow = b;
+}
+static Block *live_take(Cache *c, const void *p) {
+  unsigned h = live_hash(p);
+  for (int i = 0; i < 64; i++, h = (h + 1) & (LIVE_SLOTS - 1)) {
+    Block *b = c->live[h];
+    if (b && b->ptr == p) {
+      /* keep probe chains intact: re-insert the run that follows */
+      c->live[h] = NULL;
+      unsigned j = (h + 1) & (LIVE_SLOTS - 1);
+      while (c->live[j]) { Block *m = c->live[j]; c->live[j] = NULL; live_put(c, m); j = (j + 1) & (LIVE_SLOTS - 1); }
+      return b;
+    }
+    if (!b) break;
+  }
+  for (Block **pp = &c->live_overflow; *pp; pp = &(*pp)->next)
+    if ((*pp)->ptr == p) { Block *b = *pp; *pp = b->next; return b; }
+  return NULL;
+}
+
 static void *cache_alloc(Cache *c, size_t bytes, int dev, bool pinned) {
   size_t rounded;
   int k = bucket_of(bytes, &rounded);
@@ -134,7 +162,8 @@ static void *cache_alloc(Cache *c, size_t bytes, int dev, bool pinned) {
     Block *b = c->free_list[dev][k];
     if (b) {
       c->free_list[dev][k] = b->next;
-      b->next = c->live; c->live = b;
+      b->next = NULL;
+      live_put(c, b);
       pthread_mutex_unlock(&c->mu);
       return b->ptr;
     }
@@ -146,7 +175,7 @@ static void *cache_alloc(Cache *c, size_t bytes, int dev, bool pinned) {
   Block *b = (Block *)calloc(1, sizeof(*b));
   b->ptr = p; b->bytes = rounded; b->dev = dev; b->bucket = k;
   pthread_mutex_lock(&c->mu);
-  b->next = c->live; c->live = b;
+  live_put(c, b);
   pthread_mutex_unlock(&c->mu);
   return p;
 }
@@ -154,11 +183,8 @@ static void *cache_alloc(Cache *c, size_t bytes, int dev, bool pinned) {
 static void cache_free(Cache *c, void *p, bool pinned) {
   if (!p) return;
   pthread_mutex_lock(&c->mu);
-  Block **pp = &c->live;
-  while (*pp && (*pp)->ptr != p) pp = &(*pp)->next;
-  Block *b = *pp;
+  Block *b = live_take(c, p);
   if (!b) { pthread_mutex_unlock(&c->mu); b200_fatal("free of unknown block %p", p); }
-  *pp = b->next;
   if (b->bucket >= 0) {
     b->next = c->free_list[b->dev][b->bucket];
     c->free_list[b->dev][b->bucket] = b;
