@@ -231,3 +231,24 @@ def test_noisefilter_dense_page_high_intensity(cuda_ops, ref_ops):
         a = run_inplace(cuda_ops, "noisefilter", img, U.FMT_GRAY8, w, inten, 229)
         b = run_inplace(ref_ops, "noisefilter", img, U.FMT_GRAY8, w, inten, 229)
         assert_same(a, b, U.FMT_GRAY8, w, f"noisefilter intensity {inten} on a dense page")
+
+
+def test_detect_rotation_beyond_depth_cap(cuda_ops, ref_ops):
+    """The column-prefix table of the rotation scan covers the first 256 columns from each scanned
+    edge; a page on which a scan line has not reached deskew.c:67's total by then is redone over the
+    full width.  Faint ink (the running total grows slowly) and a wide white margin inside the mask
+    both need that second pass; the mixed case needs it for one edge only."""
+    w, h = 1800, 1200
+    base = synth.gray_page(91, w, h, dark_edges=False, box=(0.5, 0.8))       # text box: the middle half of the width
+    faint = base.copy()
+    faint[base < 128] = 254
+    mixed = base.copy()
+    mixed[:, :w // 2][base[:, :w // 2] < 128] = 254                           # left half faint, right half dark
+    mask = U.rect(0, 0, w - 1, h - 1)                                          # the edges start 450 px away from the text
+    for name, g in (("wide margin", base), ("faint", faint), ("mixed", mixed)):
+        for size in (1500, 700):
+            p = _deskew_params((True, False, True, False), size)
+            ra, rb = C.c_float(), C.c_float()
+            cuda_ops.call("detect_rotation", C.byref(himg(g, U.FMT_GRAY8, w)), C.byref(mask), C.byref(p), C.byref(ra))
+            ref_ops.call("detect_rotation", C.byref(himg(g, U.FMT_GRAY8, w)), C.byref(mask), C.byref(p), C.byref(rb))
+            assert ra.value == rb.value, f"{name} size {size}: cuda {ra.value} ref {rb.value}"

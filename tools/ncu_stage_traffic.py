@@ -41,12 +41,28 @@ def main():
         return v * {"ms": 1e3, "msecond": 1e3, "us": 1.0, "usecond": 1.0, "ns": 1e-3, "nsecond": 1e-3, "s": 1e6, "second": 1e6,
                     "Mbyte": 1.0, "Kbyte": 1e-3, "Gbyte": 1e3, "byte": 1e-6}.get(u, 1.0)
 
+    # the capture may start in the middle of a group and run into the next one: rotate it so that it
+    # starts at the group's first launch (k_page_reset) and keep one full group
+    body = rows[2:]
+    first = next((i for i, r in enumerate(body) if r[col["Kernel Name"]].startswith("k_page_reset")), 0)
+    head = body[:first]                      # the tail of the previous group
+    body = body[first:]
+    nxt = next((i for i, r in enumerate(body[1:], 1) if r[col["Kernel Name"]].startswith("k_page_reset")), len(body))
+    body = body[:nxt]
+    # what the capture did not reach of this group (e.g. the output stage) is taken from the previous group's tail
+    names_main = [r[col["Kernel Name"]].split("(")[0] for r in body]
+    last_stage = max((i for i, (_, ks) in enumerate(STAGES) if any(k in names_main for k in ks[-1:])), default=-1)
+    for r in head:
+        nm = r[col["Kernel Name"]].split("(")[0]
+        st = max((i for i, (_, ks) in enumerate(STAGES) if nm in ks), default=-1)
+        if st > last_stage and all(nm not in ks for _, ks in STAGES[:last_stage + 1]):
+            body.append(r)
     si, seen_in_stage = 0, False
     per_stage = {}
     print(f"| capture | stage | kernel | time (us) | per sheet (us) | DRAM read (MB) | DRAM write (MB) | traffic / sheet (MB) | "
           f"warp inst (M) | issue active % | warps active % |")
     print("|---|---|---|---|---|---|---|---|---|---|---|")
-    for r in rows[2:]:
+    for r in body:
         name = r[col["Kernel Name"]].split("(")[0]
         # advance to the first stage (from the current one on) that knows this kernel; a kernel that
         # belongs to the current stage keeps it
@@ -54,7 +70,11 @@ def main():
         while j < len(STAGES) and name not in STAGES[j][1]:
             j += 1
         if j == len(STAGES):
-            continue          # not part of the sheet pipeline (e.g. a second group started)
+            j = 0             # the capture ran into the next group: start over at decode
+            while j < len(STAGES) and name not in STAGES[j][1]:
+                j += 1
+            if j == len(STAGES):
+                continue
         if j != si:
             si = j
         # the first kernel of a later stage that also exists in the current one (k_zero_u32 ...) starts the next stage

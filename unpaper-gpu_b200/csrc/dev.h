@@ -95,6 +95,7 @@ typedef struct DPage {
   float rotation[D_MAX_MASKS];
   float rot_sin[D_MAX_MASKS], rot_cos[D_MAX_MASKS];  /* of -rotation */
   int32_t rot_apply[D_MAX_MASKS];
+  int32_t rot_more[D_MAX_MASKS];         /* a scan line of this mask did not end within the depth-limited prefix table */
   int32_t centered[D_MAX_MASKS];
   DBorder border[D_MAX_BORDERS];
   DRect border_mask[D_MAX_BORDERS];

@@ -134,6 +134,7 @@ __global__ void k_rot_peaks(DPage *pages, const float *tan_tab, RotParams rp, in
  * reads 32 consecutive prefix entries per run.
  * ------------------------------------------------------------------------ */
 #define RP_SEG 32
+#define ROT_DEPTH_CAP 256   // columns from each scanned edge covered by phase 1 of the prefix table
 
 __device__ __forceinline__ void rot_line_geometry(const DRect &mask, int scan_param, int &scan, int &Y0) {
   int sh = abs(mask.y0 - mask.y1) + 1;
@@ -144,12 +145,18 @@ __device__ __forceinline__ void rot_line_geometry(const DRect &mask, int scan_pa
   Y0 = mask.y0 + mid - half;
 }
 
-__global__ void __launch_bounds__(32 * RP_SEG, 2) k_rot_colprefix(DPage *pages, int mi, int scan_param) {
+// Two phases (the blackness of a scan line is only needed until the running total reaches
+// deskew.c:67's limit, a few dozen columns past the first ink): phase 1 builds the table for the
+// columns within `depth_cap` of the two scanned edges only; a page on which some scan line did not
+// stop within that depth is flagged (DPage.rot_more) and redone over the full width in phase 2,
+// whose kernels return at once for every other page.
+__global__ void __launch_bounds__(32 * RP_SEG, 2) k_rot_colprefix(DPage *pages, int mi, int scan_param, int depth_cap, int outer_max, int phase) {
   // block = 32 lanes x RP_SEG row segments; a lane owns 4 adjacent columns (one
   // 32-bit load per row, one 16-byte store of four running sums)
   __shared__ uint4 tot[RP_SEG][32];
   DPage &pg = pages[blockIdx.y];
   if (mi >= pg.mask_count) return;
+  if (phase == 2 && !pg.rot_more[mi]) return;
   const DImg &im = pg.img;
   DRect mask = pg.masks[mi];
   int scan, Y0;
@@ -157,6 +164,17 @@ __global__ void __launch_bounds__(32 * RP_SEG, 2) k_rot_colprefix(DPage *pages, 
   if (scan <= 0) return;
   if ((long long)(scan + 1) * im.w > pg.pre_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&pg.error, DERR_UNSUPPORTED); return; }
   int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  // columns the peak kernels can read: run x in [x0 - 2 outer, x0] + depth (left edge), mirrored for the right edge
+  int need_l1, need_r0;
+  {
+    int mx0 = min(mask.x0, mask.x1), mx1 = max(mask.x0, mask.x1);
+    bool limited = phase == 1 && depth_cap < (mx1 - mx0 + 1) / 2;
+    need_l1 = limited ? mx0 + depth_cap + 1 : 0x7fffffff;
+    need_r0 = limited ? mx1 - depth_cap - 1 : -0x7fffffff;
+    (void)outer_max;
+    int bx0 = blockIdx.x * 128, bx1 = bx0 + 127;
+    if (bx0 > need_l1 && bx1 < need_r0) return;     // whole block outside both strips (block-uniform)
+  }
   int x = (blockIdx.x * 32 + lane) * 4;
   int my0 = min(mask.y0, mask.y1), my1 = max(mask.y0, mask.y1);
   int vy0 = max(my0, 0), vy1 = min(my1, im.h - 1);
@@ -168,6 +186,7 @@ __global__ void __launch_bounds__(32 * RP_SEG, 2) k_rot_colprefix(DPage *pages, 
   {   // only the mask's columns are ever read back (k_rot_peaks_*: vx0..vx1)
     int mx0 = min(mask.x0, mask.x1), mx1 = max(mask.x0, mask.x1);
     if (x + 3 < max(mx0, 0) || x > min(mx1, im.w - 1)) ncol = 0;
+    if (x > need_l1 && x + 3 < need_r0) ncol = 0;
   }
   uint4 t = make_uint4(0, 0, 0, 0);
   if (ncol > 0)
@@ -289,7 +308,7 @@ __global__ void k_rot_peaks_h(DPage *pages, const float *tan_tab, RotParams rp, 
 // and the max-difference tracking become a warp prefix sum and a ballot, so
 // there is no block barrier and no single-thread scan inside the depth loop.
 #define RW_ANG 8
-__global__ void __launch_bounds__(32 * RW_ANG) k_rot_peaks_w(DPage *pages, const float *tan_tab, RotParams rp, int mi, int rstride) {
+__global__ void __launch_bounds__(32 * RW_ANG) k_rot_peaks_w(DPage *pages, const float *tan_tab, RotParams rp, int mi, int rstride, int depth_cap, int phase) {
   extern __shared__ int rsm[];          // [RW_ANG][rstride] run x | [RW_ANG][rstride] run start k
   __shared__ int rn[RW_ANG];
   int *rx = rsm, *rk = rsm + RW_ANG * rstride;
@@ -297,6 +316,7 @@ __global__ void __launch_bounds__(32 * RW_ANG) k_rot_peaks_w(DPage *pages, const
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int e = blockIdx.y ? 2 : 0;
   if (mi >= pg.mask_count || !rp.edges[e]) return;
+  if (phase == 2 && !pg.rot_more[mi]) return;
   const DImg &im = pg.img;
   DRect mask = pg.masks[mi];
   int sw = abs(mask.x0 - mask.x1) + 1;
@@ -305,6 +325,7 @@ __global__ void __launch_bounds__(32 * RW_ANG) k_rot_peaks_w(DPage *pages, const
   rot_line_geometry(mask, rp.scan_size, scan, Y0);
   int maxDepth = sw / 2;
   int maxAbs = (int)(255 * rp.scan_size * rp.scan_depth);
+  const int depthLimit = phase == 1 ? min(maxDepth, depth_cap) : maxDepth;   // phase 1 looks at the first depth_cap columns only
   if (threadIdx.x < RW_ANG) {
     int t = threadIdx.x, a = blockIdx.x * RW_ANG + t;
     int n = 0;
@@ -340,7 +361,8 @@ __global__ void __launch_bounds__(32 * RW_ANG) k_rot_peaks_w(DPage *pages, const
   const unsigned *C = pg.pre;
   bool have = (long long)(scan + 1) * im.w <= pg.pre_cap && scan > 0;
   int last = 0, maxDiff = 0, acc = 0, dep = 0;
-  for (int base = 0; base < maxDepth; base += 32) {
+  bool stopped = false;     // the reference's loop ended: total reached, or all depths seen
+  for (int base = 0; base < depthLimit; base += 32) {
     int ox = (base + lane) * shx;
     int b = 0;
     if (have)
@@ -353,7 +375,7 @@ __global__ void __launch_bounds__(32 * RW_ANG) k_rot_peaks_w(DPage *pages, const
     int incl = b;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    bool proc = (acc + incl - b < maxAbs) && (base + lane < maxDepth);
+    bool proc = (acc + incl - b < maxAbs) && (base + lane < depthLimit);
     unsigned pm = __ballot_sync(0xffffffffu, proc);
     int nproc = __popc(pm);            // the processed steps are a prefix: blackness >= 0
     int prevb = __shfl_up_sync(0xffffffffu, b, 1);
@@ -369,7 +391,9 @@ __global__ void __launch_bounds__(32 * RW_ANG) k_rot_peaks_w(DPage *pages, const
     }
     if (nproc < 32) break;
   }
+  stopped = acc >= maxAbs || dep >= maxDepth;     // deskew.c:119 would have left its loop here too
   if (lane == 0) {
+    if (phase == 1 && !stopped) atomicOr((unsigned *)&pg.rot_more[mi], 1u);   // did not end within depth_cap: redo in phase 2
     int peak = (dep < maxDepth) ? maxDiff : 0;   // deskew.c:137-141
     pg.u32[rp.peak_off + ((size_t)mi * 4 + e) * rp.nangles + a] = (unsigned)peak;
   }
@@ -973,12 +997,15 @@ int b200k_rot_peaks(cudaStream_t st, DPage *pages, int npages, int mi_first, int
   bool horiz = edges[0] || edges[2], vert = edges[1] || edges[3];
   if (use_prefix && horiz) {
     for (int mi = mi_first; mi < mi_first + mi_count; mi++) {
-      k_rot_colprefix<<<dim3(cdiv(maxw, 128), npages), 32 * RP_SEG, 0, st>>>(pages, mi, scan_size_param);
       if (run_cap > 0) {
         int rstride = run_cap | 1;   // odd stride: the lanes of phase A hit different banks
         size_t smw = (size_t)(2 * RW_ANG * rstride) * sizeof(int);
-        k_rot_peaks_w<<<dim3(cdiv(nangles, RW_ANG), 2, npages), 32 * RW_ANG, smw, st>>>(pages, tan_tab_dev, rp, mi, rstride);
+        for (int phase = 1; phase <= 2; phase++) {
+          k_rot_colprefix<<<dim3(cdiv(maxw, 128), npages), 32 * RP_SEG, 0, st>>>(pages, mi, scan_size_param, ROT_DEPTH_CAP, 0, phase);
+          k_rot_peaks_w<<<dim3(cdiv(nangles, RW_ANG), 2, npages), 32 * RW_ANG, smw, st>>>(pages, tan_tab_dev, rp, mi, rstride, ROT_DEPTH_CAP, phase);
+        }
       } else {
+        k_rot_colprefix<<<dim3(cdiv(maxw, 128), npages), 32 * RP_SEG, 0, st>>>(pages, mi, scan_size_param, 0, 0, 0);
         k_rot_peaks_h<<<dim3(nangles, 2, npages), 64, sm, st>>>(pages, tan_tab_dev, rp, mi);
       }
     }

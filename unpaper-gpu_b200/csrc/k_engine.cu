@@ -14,7 +14,7 @@ __global__ void k_page_reset(DPage *pages, int npages) {
   pg.move.enabled = 0; pg.move.use_masks = 0; pg.move.nseg = 0;
   pg.mask_count = 0; pg.mask_count_deskew = 0; pg.ink_ok = 0;
   for (int i = 0; i < D_MAX_MASKS; i++) {
-    pg.rotation[i] = 0.0f; pg.rot_sin[i] = 0.0f; pg.rot_cos[i] = 1.0f; pg.rot_apply[i] = 0; pg.centered[i] = 0;
+    pg.rotation[i] = 0.0f; pg.rot_sin[i] = 0.0f; pg.rot_cos[i] = 1.0f; pg.rot_apply[i] = 0; pg.centered[i] = 0; pg.rot_more[i] = 0;
     pg.mask_valid[i] = 0;
     for (int e = 0; e < 4; e++) { pg.edge_count[i][e] = 0; pg.rot_angle_idx[i][e] = -1; }
   }
