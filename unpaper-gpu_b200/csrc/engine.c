@@ -672,7 +672,9 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
   mark(e, ln, STG_MASKS);
   int nm = e->npoints;
   if (!no_deskew) {
+    c.want_ink = cfg->interpolate_type == 2;      /* the cubic rotation skips white tiles through the ink map */
     if (!no_mask_scan) stage_detect_masks(&c, &e->mask);
+    c.want_ink = 0;
     mark(e, ln, STG_ROTDET);
     /* mask by mask like sheet_stages.c:406-413: detect_rotation(mask i+1) sees the
      * sheet with mask i already deskewed (the masks may share pixels) */

@@ -102,6 +102,7 @@ typedef struct {
   RotHostJob *rot_jobs;       /* host memory, D_MAX_MASKS entries that stay valid until the group is done */
   DPage *rot_pull;            /* pinned, npages records */
   float *rot_tab_host, *rot_tab_dev;   /* pinned / device, 4 floats per page */
+  int want_ink, ink_fresh;    /* engine: let detect_masks' pass over the sheet also build the ink map; it is current */
   int parity;                 /* engine: which of the slot's two sheet buffers is the working image (same for the whole group) */
   uint64_t launches;
 } StageCtx;

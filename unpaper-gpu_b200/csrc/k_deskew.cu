@@ -1038,9 +1038,9 @@ void b200k_rotate(cudaStream_t st, DPage *pages, int npages, int mi, int interp,
   dim3 g(min(cdiv(maxw, 128), 64u), cdiv(maxh, ROT_ROWS), npages);
   k_rotate<<<g, 128, 0, st>>>(pages, mi, interp, back_jobs);
 }
-void b200k_rotate_sheet(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int maxw, int maxh) {
+void b200k_rotate_sheet(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int maxw, int maxh, int ink_fresh) {
   if (npages <= 0 || maxw <= 0 || maxh <= 0) return;
-  if (interp == 2) k_inkmap<<<dim3(min(cdiv(maxh, INK_CELL), 256u), npages), 128, 0, st>>>(pages);
+  if (interp == 2 && !ink_fresh) k_inkmap<<<dim3(min(cdiv(maxh, INK_CELL), 256u), npages), 128, 0, st>>>(pages);
   dim3 g(cdiv(maxw, 128), cdiv(maxh, ROT_ROWS), npages);
   k_rotate_sheet<<<g, 128, 0, st>>>(pages, mi, interp, 0u);
 }

@@ -71,6 +71,90 @@ __global__ void k_linesum_cols(DPage *pages, const DLineJob *jobs, int njobs, in
   atomicAdd(pages[page].u32 + j.out_off + (x - j.xa), acc);
 }
 
+// GRAY8 column sums, four adjacent columns per thread (one aligned 32-bit load per row), for jobs
+// whose columns start on a 4-byte boundary.  With make_ink (the job covers the whole image, whose
+// width is a multiple of 8) the pass also leaves the page's ink map behind — which 8 x 8 cells
+// are pure white (see k_inkmap in k_deskew.cu) — so that the rotation that follows needs no pass
+// of its own over the sheet.
+__global__ void __launch_bounds__(128) k_linesum_cols4(DPage *pages, const DLineJob *jobs, int njobs, int make_ink) {
+  int page = blockIdx.z / njobs, job = blockIdx.z % njobs;
+  const DLineJob j = jobs[job];
+  if (j.axis != 0 || j.xa > j.xb || j.ya > j.yb) return;
+  DPage &pg = pages[page];
+  const DImg im = pg.img;
+  int x = j.xa + 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  int y0 = j.ya + blockIdx.y * LS_ROWS;
+  if (y0 > j.yb) return;
+  int y1 = min(y0 + LS_ROWS - 1, j.yb);
+  const int ncx = (im.w + 7) >> 3, ncy = (im.h + 7) >> 3;
+  bool ink = make_ink && pg.ink && ncx * ncy <= pg.ink_cap;
+  if (ink && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { pg.ink_ncx = ncx; pg.ink_ncy = ncy; pg.ink_ok = 1; }
+  bool live = x <= j.xb;                         // the job's width is a multiple of 4
+  unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0, all = 0xFFFFFFFFu;
+  const uint8_t *p = im.data + (size_t)y0 * im.pitch + (live ? x : j.xa);
+  for (int y = y0; y <= y1; y++, p += im.pitch) {
+    unsigned w = *(const unsigned *)p;
+    a0 += w & 0xFFu; a1 += (w >> 8) & 0xFFu; a2 += (w >> 16) & 0xFFu; a3 += w >> 24;
+    if (ink) {
+      all &= w;
+      if ((y & 7) == 7 || y == y1) {
+        // a cell = 8 columns = this thread and its neighbour (x is a multiple of 4, cells start at multiples of 8)
+        unsigned mine = all == 0xFFFFFFFFu, other = __shfl_xor_sync(0xffffffffu, mine, 1);
+        if (live && !(threadIdx.x & 1)) pg.ink[(y >> 3) * ncx + (x >> 3)] = (uint8_t)(mine & other);
+        all = 0xFFFFFFFFu;
+      }
+    }
+  }
+  if (live) {
+    unsigned *o = pg.u32 + j.out_off + (x - j.xa);
+    atomicAdd(o, a0); atomicAdd(o + 1, a1); atomicAdd(o + 2, a2); atomicAdd(o + 3, a3);
+  }
+}
+
+// The same with sixteen columns per thread (one aligned 16-byte load per row; two 16-bit partial sums per
+// register: LS_ROWS * 255 < 65536), for jobs whose columns start on a 16-byte boundary.  A thread owns two
+// ink cells, so no exchange is needed.
+__global__ void __launch_bounds__(64) k_linesum_cols16(DPage *pages, const DLineJob *jobs, int njobs, int make_ink) {
+  int page = blockIdx.z / njobs, job = blockIdx.z % njobs;
+  const DLineJob j = jobs[job];
+  if (j.axis != 0 || j.xa > j.xb || j.ya > j.yb) return;
+  DPage &pg = pages[page];
+  const DImg im = pg.img;
+  int x = j.xa + 16 * (blockIdx.x * blockDim.x + threadIdx.x);
+  int y0 = j.ya + blockIdx.y * LS_ROWS;
+  if (y0 > j.yb || x > j.xb) return;
+  int y1 = min(y0 + LS_ROWS - 1, j.yb);
+  const int ncx = (im.w + 7) >> 3, ncy = (im.h + 7) >> 3;
+  bool ink = make_ink && pg.ink && ncx * ncy <= pg.ink_cap;
+  if (ink && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { pg.ink_ncx = ncx; pg.ink_ncy = ncy; pg.ink_ok = 1; }
+  unsigned lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};      // lo[k]: bytes 0 and 2 of word k, hi[k]: bytes 1 and 3
+  uint4 all = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  const uint8_t *p = im.data + (size_t)y0 * im.pitch + x;
+#pragma unroll 4
+  for (int y = y0; y <= y1; y++, p += im.pitch) {
+    uint4 w = *(const uint4 *)p;
+    lo[0] += w.x & 0x00FF00FFu; hi[0] += (w.x >> 8) & 0x00FF00FFu;
+    lo[1] += w.y & 0x00FF00FFu; hi[1] += (w.y >> 8) & 0x00FF00FFu;
+    lo[2] += w.z & 0x00FF00FFu; hi[2] += (w.z >> 8) & 0x00FF00FFu;
+    lo[3] += w.w & 0x00FF00FFu; hi[3] += (w.w >> 8) & 0x00FF00FFu;
+    if (ink) {
+      all.x &= w.x; all.y &= w.y; all.z &= w.z; all.w &= w.w;
+      if ((y & 7) == 7 || y == y1) {
+        uint8_t *c = pg.ink + (y >> 3) * ncx + (x >> 3);
+        c[0] = (uint8_t)((all.x & all.y) == 0xFFFFFFFFu);
+        c[1] = (uint8_t)((all.z & all.w) == 0xFFFFFFFFu);
+        all = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      }
+    }
+  }
+  unsigned *o = pg.u32 + j.out_off + (x - j.xa);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    atomicAdd(o + 4 * k + 0, lo[k] & 0xFFFFu); atomicAdd(o + 4 * k + 1, hi[k] & 0xFFFFu);
+    atomicAdd(o + 4 * k + 2, lo[k] >> 16); atomicAdd(o + 4 * k + 3, hi[k] >> 16);
+  }
+}
+
 // Row sums: one warp per row.
 __global__ void k_linesum_rows(DPage *pages, const DLineJob *jobs, int njobs, int stat, int lo, int hi) {
   int page = blockIdx.z / njobs, job = blockIdx.z % njobs;
@@ -240,9 +324,11 @@ void b200k_zero_u32(cudaStream_t st, DPage *pages, int npages, int off, int n) {
   dim3 g(min(cdiv(n, 256), 256u), npages);
   k_zero_u32<<<g, 256, 0, st>>>(pages, off, n);
 }
-void b200k_linesums(cudaStream_t st, DPage *pages, int npages, const DLineJob *jobs_dev,
-                    const DLineJob *jobs_host, int njobs, int stat, int lo, int hi) {
-  if (njobs <= 0 || npages <= 0) return;
+int b200k_linesums(cudaStream_t st, DPage *pages, int npages, const DLineJob *jobs_dev,
+                   const DLineJob *jobs_host, int njobs, int stat, int lo, int hi, int gray8_aligned, int img_w, int img_h,
+                   int want_ink) {
+  if (njobs <= 0 || npages <= 0) return 0;
+  int made_ink = 0;
   int maxc = 0, maxr = 0, rows_len = 0, rows_any = 0, cols_any = 0;
   for (int i = 0; i < njobs; i++) {
     const DLineJob *j = &jobs_host[i];
@@ -251,13 +337,42 @@ void b200k_linesums(cudaStream_t st, DPage *pages, int npages, const DLineJob *j
     else { rows_any = 1; rows_len = max(rows_len, j->yb - j->ya + 1); }
   }
   if (cols_any) {
-    dim3 g(cdiv(maxc, 256), cdiv(maxr, LS_ROWS), npages * njobs);
-    k_linesum_cols<<<g, 256, 0, st>>>(pages, jobs_dev, njobs, stat, lo, hi);
+    /* every column job starts and ends on a 4-byte boundary of a GRAY8 image with aligned rows: four columns per thread */
+    bool vec = gray8_aligned && stat != ST_COUNT_GRAY_RANGE;
+    int full = -1;
+    for (int i = 0; i < njobs && vec; i++) {
+      const DLineJob *j = &jobs_host[i];
+      if (j->axis != 0 || j->xa > j->xb || j->ya > j->yb) continue;
+      if ((j->xa & 3) || ((j->xb - j->xa + 1) & 3)) vec = false;
+      if (j->xa == 0 && j->ya == 0 && j->xb == img_w - 1 && j->yb == img_h - 1) full = i;
+    }
+    bool vec16 = vec;
+    for (int i = 0; i < njobs && vec16; i++) {
+      const DLineJob *j = &jobs_host[i];
+      if (j->axis != 0 || j->xa > j->xb || j->ya > j->yb) continue;
+      if ((j->xa & 15) || ((j->xb - j->xa + 1) & 15)) vec16 = false;
+    }
+    if (vec) {
+      /* the ink map rides along when ONE job covers the whole image (and nothing else would write it twice) */
+      int ink = want_ink && full >= 0 && njobs == 1 && (img_w & 7) == 0 && stat == ST_GRAY;
+      if (vec16) {
+        dim3 g(cdiv(maxc, 1024), cdiv(maxr, LS_ROWS), npages * njobs);
+        k_linesum_cols16<<<g, 64, 0, st>>>(pages, jobs_dev, njobs, ink);
+      } else {
+        dim3 g(cdiv(maxc, 512), cdiv(maxr, LS_ROWS), npages * njobs);
+        k_linesum_cols4<<<g, 128, 0, st>>>(pages, jobs_dev, njobs, ink);
+      }
+      made_ink = ink;
+    } else {
+      dim3 g(cdiv(maxc, 256), cdiv(maxr, LS_ROWS), npages * njobs);
+      k_linesum_cols<<<g, 256, 0, st>>>(pages, jobs_dev, njobs, stat, lo, hi);
+    }
   }
   if (rows_any) {
     dim3 g(1, cdiv(rows_len, 8), npages * njobs);
     k_linesum_rows<<<g, 256, 0, st>>>(pages, jobs_dev, njobs, stat, lo, hi);
   }
+  return made_ink;
 }
 void b200k_rect_count(cudaStream_t st, DPage *pages, int npages, const DRect *rects_dev, int nrects,
                       int lo, int hi, int out_off) {

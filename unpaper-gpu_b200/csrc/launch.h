@@ -21,8 +21,11 @@ void b200k_rotate90(cudaStream_t st, DImg src, DImg dst, int dir);
 
 /* k_stats.cu */
 void b200k_zero_u32(cudaStream_t st, DPage *pages, int npages, int off, int n);
-void b200k_linesums(cudaStream_t st, DPage *pages, int npages, const DLineJob *jobs_dev,
-                    const DLineJob *jobs_host, int njobs, int stat, int lo, int hi);
+/* gray8_aligned: every page is GRAY8 with 16-byte aligned rows (vector path); want_ink: also leave the
+ * ink map of k_inkmap behind when one job covers the whole img_w x img_h image; returns 1 if it did */
+int b200k_linesums(cudaStream_t st, DPage *pages, int npages, const DLineJob *jobs_dev,
+                   const DLineJob *jobs_host, int njobs, int stat, int lo, int hi, int gray8_aligned, int img_w, int img_h,
+                   int want_ink);
 void b200k_rect_count(cudaStream_t st, DPage *pages, int npages, const DRect *rects_dev, int nrects,
                       int lo, int hi, int out_off);
 int b200k_cellstats(cudaStream_t st, DPage *pages, int npages, int gx, int gy, int ncx, int ncy,
@@ -86,7 +89,8 @@ void b200k_prep_align_move(cudaStream_t st, DPage *pages, int npages, int i, int
                            int bottom, int margin_h, int margin_v, int use_masks);
 void b200k_prep_shift_move(cudaStream_t st, DPage *pages, int npages, int dx, int dy);
 /* k_deskew.cu: deskew() of mask `mi` as one full-sheet pass img -> other */
-void b200k_rotate_sheet(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int maxw, int maxh);
+void b200k_rotate_sheet(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int maxw, int maxh,
+                        int ink_fresh /* the ink map of the current sheet contents already exists */);
 void b200k_page_reset(cudaStream_t st, DPage *pages, int npages);
 void b200k_pack_rows(cudaStream_t st, const uint8_t *src, int src_pitch, uint8_t *dst, int dst_pitch,
                      int row_bytes, int rows, int nimages, size_t src_stride, size_t dst_stride);

@@ -376,7 +376,8 @@ static int bppf(int fmt) { return fmt == DF_GRAY8 ? 1 : fmt == DF_Y400A ? 2 : fm
 void stage_blackfilter(StageCtx *c, const BfPlan *pl) {
   if (pl->npos <= 0) return;
   b200k_zero_u32(c->st, c->pages, c->npages, 0, pl->sums_len);
-  b200k_linesums(c->st, c->pages, c->npages, pl->jobs_dev, pl->jobs_host, pl->njobs, ST_MAXCH, 0, 0);
+  b200k_linesums(c->st, c->pages, c->npages, pl->jobs_dev, pl->jobs_host, pl->njobs, ST_MAXCH, 0, 0,
+                 c->fmt == DF_GRAY8 && c->rows_aligned16, c->w, c->h, 0);
   b200k_bf_scan(c->st, c->pages, c->npages, pl->pos_dev, pl->npos, pl->abs_threshold, pl->intensity, 0,
                 pl->mask_hi, pl->flag_off, c->h);
   c->launches += 4;
@@ -412,7 +413,9 @@ void stage_detect_masks(StageCtx *c, const MaskPlan *pl) {
   const MaskDetectionParameters *p = &pl->p;
   if (pl->njobs > 0) {
     b200k_zero_u32(c->st, c->pages, c->npages, 0, pl->u32_need);
-    b200k_linesums(c->st, c->pages, c->npages, pl->jobs_dev, pl->jobs_host, pl->njobs, ST_GRAY, 0, 0);
+    /* the pass over the sheet also leaves the ink map the next rotation wants (engine only) */
+    c->ink_fresh = b200k_linesums(c->st, c->pages, c->npages, pl->jobs_dev, pl->jobs_host, pl->njobs, ST_GRAY, 0, 0,
+                                  c->fmt == DF_GRAY8 && c->rows_aligned16, c->w, c->h, c->want_ink);
     c->launches += 3;
   }
   int size[2] = {p->scan_size.width, p->scan_size.height};
@@ -481,10 +484,11 @@ void stage_deskew(StageCtx *c, int interp, int max_masks) {
 /* ---- sheet-engine forms: one sweep img -> other, then the buffers change roles ---- */
 
 void stage_deskew_mask_pass(StageCtx *c, int interp, int mi) {
-  b200k_rotate_sheet(c->st, c->pages, c->npages, mi, interp, c->w, c->h);
+  b200k_rotate_sheet(c->st, c->pages, c->npages, mi, interp, c->w, c->h, c->ink_fresh);
   b200k_swap_sheets(c->st, c->pages, c->npages);
   c->parity ^= 1;
-  c->launches += 2 + (interp == 2);
+  c->launches += 2 + (interp == 2 && !c->ink_fresh);
+  c->ink_fresh = 0;            /* the sheet has changed */
 }
 
 static void move_pass(StageCtx *c, Pixel mask_color) {
@@ -543,7 +547,8 @@ void stage_detect_border(StageCtx *c, const BorderPlan *pl) {
   const BorderScanParameters *p = &pl->p;
   if (pl->njobs > 0) {
     b200k_zero_u32(c->st, c->pages, c->npages, 0, pl->u32_need);
-    b200k_linesums(c->st, c->pages, c->npages, pl->jobs_dev, pl->jobs_host, pl->njobs, ST_COUNT_GRAY_RANGE, 0, pl->abt);
+    b200k_linesums(c->st, c->pages, c->npages, pl->jobs_dev, pl->jobs_host, pl->njobs, ST_COUNT_GRAY_RANGE, 0, pl->abt,
+                   c->fmt == DF_GRAY8 && c->rows_aligned16, c->w, c->h, 0);
     c->launches += 3;
   }
   b200k_detect_border(c->st, c->pages, c->npages, p->scan_size.width, p->scan_size.height,
