@@ -950,6 +950,217 @@ __global__ void __launch_bounds__(128) k_rotate_sheet(DPage *pages, int mi, int 
   }
 }
 
+// ---- GRAY8 + bicubic form of the sweep above: four target pixels per lane --------------------
+// A warp owns a 128 x 8 tile of the sheet (lane = four consecutive columns, one aligned 32-bit
+// store per row), a CTA four such tiles stacked (128 x 32).  Per tile, once:
+//   * the lane's four columns give the x-halves of the source coordinates,
+//       srcX = (scx + (x - tcx) cos) + (y - tcy) sin,  srcY = (scy + (y - tcy) cos) - (x - tcx) sin
+//     (the reference's evaluation order, deskew.c:263-268); a row then costs one add per coordinate;
+//   * the source bounding box of (tile ∩ pasted rectangle) decides whether every tap of every
+//     pixel lies inside the image (then no pixel needs a range test; otherwise the tile takes
+//     the general per-pixel path) — columns of the tile outside the rectangle are evaluated at
+//     the nearest column inside it and replaced by the sheet's own pixel afterwards, so tiles on
+//     the rectangle's edge run the same code;
+//   * the ink map decides whether the source footprint is pure white: lane = one column of ink
+//     cells, which only looks at the cell rows the tile's rows can reach at that source column
+//     (srcY = scy + (y - tcy) / cos - tan * (srcX - scx)), not at the whole bounding box.
+// Per row and pixel: two aligned loads + a funnel shift per tap row, "all 16 taps equal" (every
+// cubic term cancels exactly) decides per warp row whether the arithmetic runs at all.
+#define RS_TW 128
+#define RS_TH 8
+__global__ void __launch_bounds__(128) k_rotate_sheet_g8c(DPage *pages, int mi, unsigned zero) {
+  const DPage &pg = pages[blockIdx.z];
+  const DImg im = pg.img;                 // by value: no reloads of the descriptor behind the stores below
+  DImg out = im;
+  out.data = pg.other;
+  const int W = im.w, H = im.h, pitch = im.pitch;
+  const int X0 = blockIdx.x * RS_TW, Yb0 = blockIdx.y * (4 * RS_TH);
+  if (X0 >= W || Yb0 >= H) return;
+  const bool active = mi < pg.mask_count && pg.rot_apply[mi];
+  const DRect mask = pg.masks[mi];
+  const int w = abs(mask.x0 - mask.x1) + 1, h = abs(mask.y0 - mask.y1) + 1;
+  const int ox = mask.x0, oy = mask.y0;   // copy_rectangle(rotated, source, full, mask.vertex[0]) (deskew.c:283)
+  const int X1 = min(X0 + RS_TW - 1, W - 1), Yb1 = min(Yb0 + 4 * RS_TH - 1, H - 1);
+  const uint8_t *const src = im.data;
+  uint8_t *const dst = out.data;
+  __builtin_assume(__isGlobal(src));      // LDG / STG instead of generic accesses
+  __builtin_assume(__isGlobal(dst));
+  const bool aligned = im.fmt == DF_GRAY8 && (pitch & 15) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+  const bool touches = active && X1 >= ox && X0 < ox + w && Yb1 >= oy && Yb0 < oy + h;
+  if (!touches && aligned) {              // the CTA's 128 x 32 pixels are copied, 16 bytes per thread
+    const int rows = Yb1 - Yb0 + 1, nch = (X1 - X0 + 16) >> 4;   // a row's pitch padding may be copied along
+    for (int i = threadIdx.x; i < nch * rows; i += blockDim.x) {
+      const int r = i / nch, c = i - r * nch;
+      const size_t off = (size_t)(Yb0 + r) * pitch + (size_t)X0 + ((size_t)c << 4);
+      *(uint4 *)(dst + off) = *(const uint4 *)(src + off);
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int Yt = Yb0 + wid * RS_TH;
+  if (Yt > Yb1) return;                   // whole warp
+  const int Yte = min(Yt + RS_TH - 1, Yb1);
+  const int X = X0 + 4 * lane;            // the lane's columns X .. X + 3
+  const bool lane_on = X < pitch;         // its word lies inside the row (pitch is a multiple of 16)
+  // center_of_rectangle (primitives.c:136-145) of the (normalised) mask / of the target
+  const int nx0 = min(mask.x0, mask.x1), ny0 = min(mask.y0, mask.y1);
+  const float scx = nx0 + w / 2.0f, scy = ny0 + h / 2.0f;
+  const float tcx = 0 + w / 2.0f, tcy = 0 + h / 2.0f;
+  const float sinval = pg.rot_sin[mi], cosval = pg.rot_cos[mi];
+  enum { M_COPY, M_WHITE, M_FAST, M_SLOW };
+  int mode = M_SLOW;
+  int xa = 0, xb = 0;
+  const bool t_touch = touches && Yte >= oy && Yt < oy + h;
+  const bool tile_in = X0 >= ox && X0 + RS_TW - 1 < ox + w && X0 + RS_TW - 1 < W && Yt >= oy && Yte < oy + h;
+  if (aligned && !t_touch) mode = M_COPY;
+  else if (aligned) {
+    // the part of the tile inside the pasted rectangle, in coordinates of the rotated image
+    xa = max(X0, ox) - ox; xb = min(X1, ox + w - 1) - ox;
+    const int ya = max(Yt, oy) - oy, yb = min(Yte, oy + h - 1) - oy;
+    const float fxa = xa - tcx, fxb = xb - tcx, fya = ya - tcy, fyb = yb - tcy;
+    const float ax = fxa * cosval, bx = fxb * cosval, ay = fya * sinval, by = fyb * sinval;
+    const float cy = fya * cosval, dy = fyb * cosval, cx = fxa * sinval, dx = fxb * sinval;
+    const float mnx = scx + fminf(ax, bx) + fminf(ay, by), mxx = scx + fmaxf(ax, bx) + fmaxf(ay, by);
+    const float mny = scy + fminf(cy, dy) - fmaxf(cx, dx), mxy = scy + fmaxf(cy, dy) - fminf(cx, dx);
+    if (fabsf(mnx) < 1e7f && fabsf(mxx) < 1e7f && fabsf(mny) < 1e7f && fabsf(mxy) < 1e7f) {
+      // taps reach from (int)src - 1 to (int)src + 2; two pixels of slack for float rounding
+      const int bx0 = (int)floorf(mnx) - 3, bx1 = (int)floorf(mxx) + 4, by0 = (int)floorf(mny) - 3, by1 = (int)floorf(mxy) + 4;
+      const bool safe = bx0 >= 0 && by0 >= 0 && bx1 < W && by1 < H;
+      bool white = false;
+      if (pg.ink_ok && fabsf(cosval) > 0.5f) {
+        if (bx1 < 0 || by1 < 0 || bx0 >= W || by0 >= H) white = true;   // entirely outside: reads as white
+        else {
+          const int cx0 = max(bx0, 0) >> 3, cx1 = min(bx1, W - 1) >> 3;
+          static_assert(D_INK_CELL == 8, "cell index = coordinate >> 3");
+          if (cx1 - cx0 < 32) {
+            bool wh = true;
+            if (cx0 + lane <= cx1) {
+              // pixels whose taps touch cell column c have (int)srcX in [8c - 2, 8c + 8]
+              const int c = cx0 + lane;
+              const float sxl = fmaxf((float)(8 * c - 4), mnx), sxh = fminf((float)(8 * c + 11), mxx);
+              const float icos = 1.0f / cosval, tanv = sinval * icos;
+              const float e0 = scy + fya * icos, e1 = scy + fyb * icos;
+              const float t0 = tanv * (sxl - scx), t1 = tanv * (sxh - scx);
+              const float sylo = fminf(e0, e1) - fmaxf(t0, t1), syhi = fmaxf(e0, e1) - fminf(t0, t1);
+              const int ry0 = max((int)floorf(sylo) - 3, by0), ry1 = min((int)floorf(syhi) + 4, by1);
+              if (ry1 >= 0 && ry0 < H && ry0 <= ry1) {
+                const int cyl = max(ry0, 0) >> 3, cyh = min(ry1, H - 1) >> 3;
+                if (cyh - cyl > 7) wh = false;
+                else {
+                  const uint8_t *q = pg.ink + (size_t)cyl * pg.ink_ncx + c;
+                  for (int cc = cyl; cc <= cyh; cc++, q += pg.ink_ncx) wh = wh && (*q != 0);
+                }
+              }
+            }
+            white = __all_sync(0xffffffffu, wh);
+          }
+        }
+      }
+      if (white) mode = M_WHITE;
+      else if (safe) mode = M_FAST;
+    }
+  }
+  if (mode == M_COPY) {
+    if (lane_on)
+      for (int Y = Yt; Y <= Yte; Y++) {
+        const size_t off = (size_t)Y * pitch + X;
+        *(unsigned *)(dst + off) = *(const unsigned *)(src + off);
+      }
+    return;
+  }
+  if (mode == M_SLOW) {
+    // taps outside the image (reads = white), unaligned buffers: pixel by pixel
+    for (int Y = Yt; Y <= Yte; Y++) {
+      const int y = Y - oy;
+      for (int j = 0; j < 4; j++) {
+        const int Xj = X + j, x = Xj - ox;
+        if (Xj >= W) break;
+        if (active && x >= 0 && x < w && y >= 0 && y < h) {
+          const float xf = u8f((unsigned)x), yf = u8f((unsigned)y);   // == (float)x, (float)y for 0 <= v < 2^23
+          const float sX = scx + (xf - tcx) * cosval + (yf - tcy) * sinval;
+          const float sY = scy + (yf - tcy) * cosval - (xf - tcx) * sinval;
+          const Px q = interp_cubic<true>(im, sX, sY);
+          px_store(out, Xj, Y, q.r, q.g, q.b);
+        } else {
+          const Px q = px_load(im, Xj, Y);
+          px_store(out, Xj, Y, q.r, q.g, q.b);
+        }
+      }
+    }
+    return;
+  }
+  // ---- M_WHITE / M_FAST
+  unsigned xmask = 0;                     // bytes of the lane's word that lie inside the pasted rectangle
+  float bX[4], xs[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int Xj = X + j, xj = Xj - ox;
+    if (Xj < W && xj >= 0 && xj < w) xmask |= 0xFFu << (8 * j);
+    const float xr = u8f((unsigned)min(max(xj, xa), xb)) - tcx;      // (float)x - tcx
+    bX[j] = scx + xr * cosval;
+    xs[j] = xr * sinval;
+  }
+  for (int Y = Yt; Y <= Yte; Y++) {
+    const size_t rowoff = (size_t)Y * pitch + X;
+    const int y = Y - oy;
+    if (y < 0 || y >= h) {                // warp-uniform: a row of the tile outside the rectangle
+      if (lane_on) *(unsigned *)(dst + rowoff) = *(const unsigned *)(src + rowoff);
+      continue;
+    }
+    unsigned vals = 0xFFFFFFFFu;
+    if (mode == M_FAST) {
+      const float yr = u8f((unsigned)y) - tcy;                        // (float)y - tcy
+      const float ysin = yr * sinval, ycos = scy + yr * cosval;
+      unsigned rw[4][4], o[4];
+      float fx[4], fy[4];
+      bool need = false;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float sX = bX[j] + ysin, sY = ycos - xs[j];
+        // (int)srcX for 1 <= srcX < 2^23 by the 2^23 trick (the tile's bounding box guarantees the range)
+        const float tX = __fadd_rz(sX, 8388608.0f), tY = __fadd_rz(sY, 8388608.0f);
+        const int px = __float_as_int(tX) - 0x4B000000, py = __float_as_int(tY) - 0x4B000000;
+        fx[j] = sX - (tX - 8388608.0f); fy[j] = sY - (tY - 8388608.0f);   // srcX - (float)px
+        const int off = (py - 1) * pitch + (px - 1);
+        const unsigned sh = ((unsigned)off & 3u) * 8u;
+        const uint8_t *p0 = src + (off & ~3);
+#pragma unroll
+        for (int i = 0; i < 4; i++, p0 += pitch) {
+          const unsigned *wp = (const unsigned *)p0;
+          rw[j][i] = __funnelshift_r(wp[0], wp[1], sh);
+        }
+        o[j] = rw[j][0] & 0xFFu;          // all 16 taps equal: every cubic term cancels exactly
+        need = need || !(rw[j][0] == o[j] * 0x01010101u && rw[j][1] == rw[j][0] && rw[j][2] == rw[j][0] && rw[j][3] == rw[j][0]);
+      }
+      if (__any_sync(0xffffffffu, need)) {
+        unsigned c4[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const unsigned fb = __float_as_uint(fx[j]), hb = __float_as_uint(0.5f * fx[j]);
+          const u64 f2 = pk2(fb, fb), h2 = pk2(hb, hb);
+          unsigned a0, a1, a2, a3;
+          cubic_scale_w2(f2, h2, rw[j][0], rw[j][1], a0, a1, zero);
+          cubic_scale_w2(f2, h2, rw[j][2], rw[j][3], a2, a3, zero);
+          c4[j] = __byte_perm(__byte_perm(a0, a1, 0x0040), __byte_perm(a2, a3, 0x0040), 0x5410);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+          const u64 fy2 = pk2(__float_as_uint(fy[j]), __float_as_uint(fy[j + 1]));
+          const u64 hy2 = pk2(__float_as_uint(0.5f * fy[j]), __float_as_uint(0.5f * fy[j + 1]));
+          cubic_scale_w2(fy2, hy2, c4[j], c4[j + 1], o[j], o[j + 1], zero);
+        }
+      }
+      vals = __byte_perm(__byte_perm(o[0], o[1], 0x0040), __byte_perm(o[2], o[3], 0x0040), 0x5410);
+    }
+    if (!lane_on) continue;
+    if (!tile_in) {
+      const unsigned sw = *(const unsigned *)(src + rowoff);
+      vals = (vals & xmask) | (sw & ~xmask);
+    }
+    *(unsigned *)(dst + rowoff) = vals;
+  }
+}
+
 // stretch_frame (blit.c:209-228)
 __global__ void k_stretch(DImg src, DImg dst, float hr, float vr, int interp) {
   int y = blockIdx.y;
@@ -1038,9 +1249,13 @@ void b200k_rotate(cudaStream_t st, DPage *pages, int npages, int mi, int interp,
   dim3 g(min(cdiv(maxw, 128), 64u), cdiv(maxh, ROT_ROWS), npages);
   k_rotate<<<g, 128, 0, st>>>(pages, mi, interp, back_jobs);
 }
-void b200k_rotate_sheet(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int maxw, int maxh, int ink_fresh) {
+void b200k_rotate_sheet(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int fmt, int maxw, int maxh, int ink_fresh) {
   if (npages <= 0 || maxw <= 0 || maxh <= 0) return;
   if (interp == 2 && !ink_fresh) k_inkmap<<<dim3(min(cdiv(maxh, INK_CELL), 256u), npages), 128, 0, st>>>(pages);
+  if (interp == 2 && fmt == DF_GRAY8) {
+    k_rotate_sheet_g8c<<<dim3(cdiv(maxw, RS_TW), cdiv(maxh, 4 * RS_TH), npages), 128, 0, st>>>(pages, mi, 0u);
+    return;
+  }
   dim3 g(cdiv(maxw, 128), cdiv(maxh, ROT_ROWS), npages);
   k_rotate_sheet<<<g, 128, 0, st>>>(pages, mi, interp, 0u);
 }

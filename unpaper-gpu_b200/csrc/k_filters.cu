@@ -762,23 +762,25 @@ __global__ void __launch_bounds__(256, 8) k_nf_classify_bits(DPage *pages, int i
   if (y >= im.h || bx + lx0 >= im.w) continue;
   int k = 1 + (lx0 >> 5), sh = lx0 & 31;
   unsigned dark8 = (s_dark[r][k] >> sh) & 0xFFu, nb8 = (s_nb[r][k] >> sh) & 0xFFu, big8 = (s_big[r][k] >> sh) & 0xFFu;
-  unsigned lo = 0, hi = 0;   // eight class bytes
-  unsigned todo = dark8;
-  while (todo) {
-    int i = __ffs(todo) - 1;
-    todo &= todo - 1;
-    bool mut;
-    if (!((nb8 >> i) & 1u)) mut = true;                               // in the left/top band
-    else if ((big8 >> i) & 1u) mut = false;
-    else mut = nfb_small_component(s_nb, rows, 32 + lx0 + i, r, need);
-    unsigned c = NF_LIVE | NF_TRIG;
-    if (mut) {
-      c |= NF_MUT | NF_UNDEC;
-      unsigned idx = atomicAdd(&pg.list_n, 1u);
-      if (idx < (unsigned)pg.list_cap) pg.list[idx] = ((unsigned)y << 16) | (unsigned)(bx + lx0 + i);
+  // mutable = dark inside the left/top band, or dark outside it, not settled by the bit planes and
+  // found small by the exact walk (rare); no per-pixel loop for the rest
+  unsigned mut8 = dark8 & ~nb8;
+  unsigned open8 = nb8 & ~big8;
+  while (open8) {
+    int i = __ffs(open8) - 1;
+    open8 &= open8 - 1;
+    if (nfb_small_component(s_nb, rows, 32 + lx0 + i, r, need)) mut8 |= 1u << i;
+  }
+  // four bits -> four bytes (bit i -> bit 0 of byte i), then the class codes
+  unsigned dl = ((dark8 & 0xFu) * 0x00204081u) & 0x01010101u, dh = ((dark8 >> 4) * 0x00204081u) & 0x01010101u;
+  unsigned ml = ((mut8 & 0xFu) * 0x00204081u) & 0x01010101u, mh = ((mut8 >> 4) * 0x00204081u) & 0x01010101u;
+  unsigned lo = dl * (NF_LIVE | NF_TRIG) + ml * (NF_MUT | NF_UNDEC), hi = dh * (NF_LIVE | NF_TRIG) + mh * (NF_MUT | NF_UNDEC);
+  if (mut8) {
+    unsigned idx = atomicAdd(&pg.list_n, (unsigned)__popc(mut8));
+    for (unsigned m = mut8; m; m &= m - 1, idx++) {
+      if (idx < (unsigned)pg.list_cap) pg.list[idx] = ((unsigned)y << 16) | (unsigned)(bx + lx0 + __ffs(m) - 1);
       else atomicOr(&pg.error, DERR_LIST_OVERFLOW);
     }
-    if (i < 4) lo |= c << (8 * i); else hi |= c << (8 * (i - 4));
   }
   size_t o = (size_t)y * im.w + bx + lx0;
   if ((im.w & 7) == 0 && ((uintptr_t)pg.cls & 7) == 0) *(uint2 *)(pg.cls + o) = make_uint2(lo, hi);

@@ -89,7 +89,7 @@ void b200k_prep_align_move(cudaStream_t st, DPage *pages, int npages, int i, int
                            int bottom, int margin_h, int margin_v, int use_masks);
 void b200k_prep_shift_move(cudaStream_t st, DPage *pages, int npages, int dx, int dy);
 /* k_deskew.cu: deskew() of mask `mi` as one full-sheet pass img -> other */
-void b200k_rotate_sheet(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int maxw, int maxh,
+void b200k_rotate_sheet(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int fmt, int maxw, int maxh,
                         int ink_fresh /* the ink map of the current sheet contents already exists */);
 void b200k_page_reset(cudaStream_t st, DPage *pages, int npages);
 void b200k_pack_rows(cudaStream_t st, const uint8_t *src, int src_pitch, uint8_t *dst, int dst_pitch,

@@ -484,7 +484,7 @@ void stage_deskew(StageCtx *c, int interp, int max_masks) {
 /* ---- sheet-engine forms: one sweep img -> other, then the buffers change roles ---- */
 
 void stage_deskew_mask_pass(StageCtx *c, int interp, int mi) {
-  b200k_rotate_sheet(c->st, c->pages, c->npages, mi, interp, c->w, c->h, c->ink_fresh);
+  b200k_rotate_sheet(c->st, c->pages, c->npages, mi, interp, c->fmt, c->w, c->h, c->ink_fresh);
   b200k_swap_sheets(c->st, c->pages, c->npages);
   c->parity ^= 1;
   c->launches += 2 + (interp == 2 && !c->ink_fresh);
