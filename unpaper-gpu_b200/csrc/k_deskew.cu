@@ -776,6 +776,27 @@ __device__ __forceinline__ void cubic_scale_w2(u64 f2, u64 hf2, unsigned ta, uns
   oa = va & 0xFFu; ob = vb & 0xFFu;
 }
 
+// cubic_scale_w2 with the two results clipped to 0..255 in the two 16-bit halves of one word.
+//  * each product is fma(a, b, -0.0) == mul.rn(a, b) (same single rounding, same signed zeros): an FMA
+//    cannot be contracted with the addition that follows, so no integer fence is needed.  `nz2` holds
+//    -0.0 twice and comes from a kernel argument so that ptxas cannot fold the addend away;
+//  * (int)v then av_clip_uint8: v + 1.5 * 2^23 rounded toward zero leaves floor(v) as a two's complement
+//    number in the low mantissa bits (floor(v) == (int)v for v >= 0; below zero both clip to 0), and one
+//    packed min-with-relu clips both halves.
+__device__ __forceinline__ u64 fmul2z(u64 a, u64 b, u64 nz2) { u64 r; asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz2)); return r; }
+__device__ __forceinline__ unsigned cubic_scale_w2p(u64 f2, u64 hf2, unsigned ta, unsigned tb, u64 nz2) {
+  const u64 M = pk2(0xCB400000u, 0xCB400000u);            // -1.5 * 2^23 twice
+  u64 R = fadd2(pk2(dp4(ta, 0x000100FF), dp4(tb, 0x000100FF)), M);                    // c - a
+  u64 P = fadd2(pk2(dp4(ta, (int)0xFF04FB02u), dp4(tb, (int)0xFF04FB02u)), M);        // 2a - 5b + 4c - d
+  u64 Q = fadd2(pk2(dp4(ta, 0x01FD03FF), dp4(tb, 0x01FD03FF)), M);                    // -a + 3b - 3c + d
+  u64 B = fadd2(pk2(__byte_perm(ta, 0x4B400000u, 0x7651), __byte_perm(tb, 0x4B400000u, 0x7651)), M);   // b (byte 1 under the bias)
+  u64 v = fadd2(B, fmul2z(hf2, fadd2(R, fmul2z(f2, fadd2(P, fmul2z(f2, Q, nz2)), nz2)), nz2));
+  u64 t = fadd2_rz(v, pk2(0x4B400000u, 0x4B400000u));
+  unsigned lo, hi;
+  upk2(t, lo, hi);
+  return __vimin_s16x2_relu(__byte_perm(lo, hi, 0x5410), 0x00FF00FFu);
+}
+
 // Sheet-engine form of deskew() (deskew.c:276-290) for mask `mi` of every page: ONE sweep
 // over the whole sheet from the working buffer into the slot's other buffer,
 //     dst(X,Y) = (X,Y) inside the pasted rectangle [mask.vertex[0], + size) ? rotate(...) : src(X,Y)
@@ -1007,6 +1028,7 @@ __global__ void __launch_bounds__(128) k_rotate_sheet_g8c(DPage *pages, int mi, 
   const float scx = nx0 + w / 2.0f, scy = ny0 + h / 2.0f;
   const float tcx = 0 + w / 2.0f, tcy = 0 + h / 2.0f;
   const float sinval = pg.rot_sin[mi], cosval = pg.rot_cos[mi];
+  const u64 nz2 = pk2(0x80000000u | zero, 0x80000000u | zero);      // -0.0 twice (`zero` is 0 at run time)
   enum { M_COPY, M_WHITE, M_FAST, M_SLOW };
   int mode = M_SLOW;
   int xa = 0, xb = 0;
@@ -1132,25 +1154,22 @@ __global__ void __launch_bounds__(128) k_rotate_sheet_g8c(DPage *pages, int mi, 
         o[j] = rw[j][0] & 0xFFu;          // all 16 taps equal: every cubic term cancels exactly
         need = need || !(rw[j][0] == o[j] * 0x01010101u && rw[j][1] == rw[j][0] && rw[j][2] == rw[j][0] && rw[j][3] == rw[j][0]);
       }
+      unsigned v01 = o[0] | (o[1] << 16), v23 = o[2] | (o[3] << 16);
       if (__any_sync(0xffffffffu, need)) {
         unsigned c4[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const unsigned fb = __float_as_uint(fx[j]), hb = __float_as_uint(0.5f * fx[j]);
           const u64 f2 = pk2(fb, fb), h2 = pk2(hb, hb);
-          unsigned a0, a1, a2, a3;
-          cubic_scale_w2(f2, h2, rw[j][0], rw[j][1], a0, a1, zero);
-          cubic_scale_w2(f2, h2, rw[j][2], rw[j][3], a2, a3, zero);
-          c4[j] = __byte_perm(__byte_perm(a0, a1, 0x0040), __byte_perm(a2, a3, 0x0040), 0x5410);
+          const unsigned r01 = cubic_scale_w2p(f2, h2, rw[j][0], rw[j][1], nz2), r23 = cubic_scale_w2p(f2, h2, rw[j][2], rw[j][3], nz2);
+          c4[j] = __byte_perm(r01, r23, 0x6420);            // the four row results as one tap word
         }
-#pragma unroll
-        for (int j = 0; j < 4; j += 2) {
-          const u64 fy2 = pk2(__float_as_uint(fy[j]), __float_as_uint(fy[j + 1]));
-          const u64 hy2 = pk2(__float_as_uint(0.5f * fy[j]), __float_as_uint(0.5f * fy[j + 1]));
-          cubic_scale_w2(fy2, hy2, c4[j], c4[j + 1], o[j], o[j + 1], zero);
-        }
+        v01 = cubic_scale_w2p(pk2(__float_as_uint(fy[0]), __float_as_uint(fy[1])),
+                              pk2(__float_as_uint(0.5f * fy[0]), __float_as_uint(0.5f * fy[1])), c4[0], c4[1], nz2);
+        v23 = cubic_scale_w2p(pk2(__float_as_uint(fy[2]), __float_as_uint(fy[3])),
+                              pk2(__float_as_uint(0.5f * fy[2]), __float_as_uint(0.5f * fy[3])), c4[2], c4[3], nz2);
       }
-      vals = __byte_perm(__byte_perm(o[0], o[1], 0x0040), __byte_perm(o[2], o[3], 0x0040), 0x5410);
+      vals = __byte_perm(v01, v23, 0x6420);
     }
     if (!lane_on) continue;
     if (!tile_in) {
