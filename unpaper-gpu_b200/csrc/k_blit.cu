@@ -35,21 +35,6 @@ __device__ __forceinline__ void fill_run(uint8_t *dst, int n, const uint8_t pat[
   for (int i = head + (nvec << 4) + tid; i < n; i += nthreads) dst[i] = pat[(phase + i) % 3];
 }
 
-// 16 bytes of a byte stream that starts `wq` words and `sh` bits into the aligned chunk pair (a, b)
-__device__ __forceinline__ uint4 take16(uint4 a, uint4 b, unsigned wq, unsigned sh) {
-  unsigned w0, w1, w2, w3, w4;
-  switch (wq) {                      // uniform over a run
-  case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
-  case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
-  case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
-  default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
-  }
-  return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-}
-
-// dst[0..n) = src[0..n): 16-byte stores on the aligned body of dst.  An unaligned source is read as aligned
-// 16-byte chunks (every store takes its bytes from two of them) — one wavefront per 128 bytes instead of
-// the four that word loads 16 bytes apart cost — and several independent loads are in flight per thread.
 __device__ __forceinline__ void copy_run(uint8_t *dst, const uint8_t *src, int n, int tid, int nthreads) {
   int head = (int)((16u - ((unsigned)(uintptr_t)dst & 15u)) & 15u);
   if (head > n) head = n;
@@ -57,33 +42,22 @@ __device__ __forceinline__ void copy_run(uint8_t *dst, const uint8_t *src, int n
   int nvec = (n - head) >> 4;
   uint4 *d4 = (uint4 *)(dst + head);
   const uint8_t *sb = src + head;
-  const unsigned m16 = (unsigned)(uintptr_t)sb & 15u;
-  int i = tid;
-  if (m16 == 0) {
+  unsigned mis = (unsigned)(uintptr_t)sb & 3u;
+  if (((uintptr_t)sb & 15u) == 0) {
     const uint4 *s4 = (const uint4 *)sb;
-    for (; i + 3 * nthreads < nvec; i += 4 * nthreads) {
-      uint4 a = s4[i], b = s4[i + nthreads], c = s4[i + 2 * nthreads], d = s4[i + 3 * nthreads];
-      d4[i] = a; d4[i + nthreads] = b; d4[i + 2 * nthreads] = c; d4[i + 3 * nthreads] = d;
-    }
-    for (; i < nvec; i += nthreads) d4[i] = s4[i];
+    for (int i = tid; i < nvec; i += nthreads) d4[i] = s4[i];
+  } else if (mis == 0) {
+    const unsigned *sw = (const unsigned *)sb;
+    for (int i = tid; i < nvec; i += nthreads) d4[i] = make_uint4(sw[4 * i], sw[4 * i + 1], sw[4 * i + 2], sw[4 * i + 3]);
   } else {
-    const uint4 *s4 = (const uint4 *)(sb - m16);   // chunk k covers source bytes [16 k - m16, 16 k - m16 + 16)
-    const unsigned wq = m16 >> 2, sh = (m16 & 3u) * 8u;
-    // chunk i + 1 of the last two vectors can end behind the run: those go word by word below
-    const int nfast = nvec - 2;
-    for (; i + nthreads < nfast; i += 2 * nthreads) {
-      uint4 a0 = s4[i], b0 = s4[i + 1], a1 = s4[i + nthreads], b1 = s4[i + nthreads + 1];
-      d4[i] = take16(a0, b0, wq, sh);
-      d4[i + nthreads] = take16(a1, b1, wq, sh);
-    }
-    for (; i < nfast; i += nthreads) d4[i] = take16(s4[i], s4[i + 1], wq, sh);
-    const unsigned *sw = (const unsigned *)(sb - (m16 & 3u));   // aligned words straddling the source bytes
-    for (; i < nvec; i += nthreads) {
-      unsigned a = sw[4 * i], b = sw[4 * i + 1], c = sw[4 * i + 2], d = sw[4 * i + 3], e = (m16 & 3u) ? sw[4 * i + 4] : 0u;
+    const unsigned *sw = (const unsigned *)(sb - mis);   // aligned words straddling the source bytes
+    unsigned sh = mis * 8;
+    for (int i = tid; i < nvec; i += nthreads) {
+      unsigned a = sw[4 * i], b = sw[4 * i + 1], c = sw[4 * i + 2], d = sw[4 * i + 3], e = sw[4 * i + 4];
       d4[i] = make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh), __funnelshift_r(c, d, sh), __funnelshift_r(d, e, sh));
     }
   }
-  for (int k = head + (nvec << 4) + tid; k < n; k += nthreads) dst[k] = src[k];
+  for (int i = head + (nvec << 4) + tid; i < n; i += nthreads) dst[i] = src[i];
 }
 
 __global__ void __launch_bounds__(256, 8) k_fill_jobs(const DFillJob *jobs) {

@@ -241,9 +241,8 @@ __global__ void __launch_bounds__(256, 8) k_rect_count(DPage *pages, const DRect
         if (end < 4) keep &= 0xFFFFFFFFu >> (8 * (4 - end));
         const unsigned *p = base + i;
         unsigned acc = 0;
-#pragma unroll 8
         for (int r = 0; r < rows; r++, p += wpitch) {
-          unsigned wd = __ldg(p);
+          unsigned wd = *p;
           acc += (unsigned)__popc(__vcmpgeu4(wd, lo4) & __vcmpleu4(wd, hi4) & keep);
         }
         cnt += acc >> 3;
