@@ -18,6 +18,13 @@ def _compare(cfg, pages, w, h, fmt, ref_lib, group=4, lanes=2):
     eng = Engine(cfg, w, h, fmt, group_pages=group, lanes=lanes)
     out, res = eng.process_numpy(pages)
     size = (eng.sheet_w, eng.sheet_h)
+    # the device-resident entry point (sheets rendered straight into the caller's device buffer when
+    # the layout allows it) returns the same bytes as the host-buffer one
+    import torch
+    d_in = torch.from_numpy(np.ascontiguousarray(pages).reshape(-1)).cuda()
+    d_out = torch.zeros(out.size, dtype=torch.uint8, device="cuda")
+    eng.process_ptr(d_in.data_ptr(), d_out.data_ptr(), len(res), False, None)
+    assert np.array_equal(d_out.cpu().numpy().reshape(out.shape), out), "device-resident output differs from the host-buffer output"
     eng.close()
     rout, rres = checker.process_sheets_cpu(ref_lib, "ref_", cfg, pages, w, h, fmt, threads=8, out_size=size)
     for i, (a, b) in enumerate(zip(res, rres)):
@@ -73,6 +80,30 @@ def test_engine_stage_switches(ref_lib):
         for f in flags:
             setattr(cfg, f, 1)
         _compare(cfg, pages, w, h, U.FMT_GRAY8, ref_lib, group=2, lanes=1)
+
+
+def _textured_page(index, w, h, box=SMALL_BOX):
+    """A page with a light paper texture (a quarter of the background pixels at 253 / 254): no tile of the
+    rotation can be skipped as white and most 4x4 neighbourhoods are not constant.  (A heavier texture keeps
+    the reference's detect_edge() from ever seeing a light bar: masks.c:88-97 never returns then.)"""
+    page = synth.gray_page(index, w, h, speckle=0, dark_edges=False, box=box)
+    rng = np.random.Generator(np.random.PCG64(977 + index))
+    tex = rng.integers(1, 3, size=page.shape, dtype=np.uint8) * (rng.random(page.shape) < 0.25)
+    return np.where(page == 255, 255 - tex, page).astype(np.uint8)
+
+
+@pytest.mark.parametrize("w,h,box", [(701, 903, SMALL_BOX), (1000, 1300, SMALL_BOX), (1111, 1403, SMALL_BOX), (800, 1000, (0.9, 0.72))])
+def test_engine_deskew_textured_pages(ref_lib, w, h, box):
+    """Sheet rotation (GRAY8, cubic) with every pixel computed, on widths that are no multiple of the
+    rotation tile (128 x 8), of 16 or of 4: tiles that straddle the mask's edges and the sheet's right edge.
+    The masks found here run from the top to the bottom row of the sheet (the last one covers the whole sheet
+    and one column more), so the rotated rectangle's source footprint leaves the image (reads outside = white):
+    the tiles along those edges take the general per-pixel path while the interior keeps the fast one."""
+    pages = np.stack([_textured_page(300 + i, w, h, box=box) for i in range(3)])
+    cfg = U.default_sheet_config()
+    cfg.no_blackfilter = cfg.no_noisefilter = cfg.no_blurfilter = cfg.no_grayfilter = 1
+    out, res = _compare(cfg, pages, w, h, U.FMT_GRAY8, ref_lib, group=3, lanes=1)
+    assert any(r.rotation[0] != 0.0 for r in res)
 
 
 def test_engine_full_a4(ref_lib):

@@ -9,8 +9,8 @@ typedef unsigned long long u64;
 #define CH 8
 template <int OP>
 __global__ void __launch_bounds__(256) k(unsigned *out, unsigned seed, float fs, u64 ps) {
-  unsigned a[CH]; float f[CH]; u64 p[CH];
-  for (int i = 0; i < CH; i++) { a[i] = seed + threadIdx.x * 7 + i; f[i] = fs + i; p[i] = ps + i; }
+  unsigned a[CH], seedv[CH]; float f[CH]; u64 p[CH];
+  for (int i = 0; i < CH; i++) { a[i] = seed + threadIdx.x * 7 + i; seedv[i] = a[i] * 3; f[i] = fs + i; p[i] = ps + i; }
 #pragma unroll 1
   for (int it = 0; it < ITER; it++) {
 #pragma unroll
@@ -36,11 +36,16 @@ __global__ void __launch_bounds__(256) k(unsigned *out, unsigned seed, float fs,
       if (OP == 18) { asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(a[i]) : "r"(seed)); asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(fs)); }
       if (OP == 19) { asm volatile("lop3.b32 %0, %0, %1, %1, 0x96;" : "+r"(a[i]) : "r"(seed)); asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(fs)); }
       if (OP == 20) { asm volatile("lop3.b32 %0, %0, %1, %1, 0x96;" : "+r"(a[i]) : "r"(seed)); asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(ps)); }
-      if (OP == 21) asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(f[i]) : "r"(a[i] + it));
+      if (OP == 21) asm volatile("{\n\t.reg .f32 t;\n\tcvt.rn.f32.s32 t, %0;\n\tmov.b32 %0, t;\n\t}" : "+r"(a[i]));
+      if (OP == 22) { asm volatile("{\n\t.reg .f32 t;\n\tcvt.rn.f32.s32 t, %0;\n\tmov.b32 %0, t;\n\t}" : "+r"(a[i])); asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(ps)); }
+      if (OP == 23) { asm volatile("{\n\t.reg .f32 t;\n\tcvt.rn.f32.s32 t, %0;\n\tmov.b32 %0, t;\n\t}" : "+r"(a[i])); asm volatile("lop3.b32 %0, %0, %1, %1, 0x96;" : "+r"(seedv[i]) : "r"(seed)); }
+      if (OP == 24) { asm volatile("{\n\t.reg .f32 t;\n\tcvt.rn.f32.s32 t, %0;\n\tmov.b32 %0, t;\n\t}" : "+r"(a[i])); asm volatile("dp4a.u32.s32 %0, %0, %1, %0;" : "+r"(seedv[i]) : "r"(seed)); }
+      if (OP == 25) { asm volatile("{\n\t.reg .s32 t;\n\tcvt.rzi.s32.f32 t, %0;\n\tmov.b32 %0, t;\n\t}" : "+f"(f[i])); }
+      if (OP == 26) { asm volatile("dp4a.u32.s32 %0, %0, %1, %0;" : "+r"(a[i]) : "r"(seed)); asm volatile("prmt.b32 %0, %0, %1, 0x7651;" : "+r"(seedv[i]) : "r"(seed)); asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(ps)); }
     }
   }
   unsigned r = 0;
-  for (int i = 0; i < CH; i++) r += a[i] + __float_as_uint(f[i]) + (unsigned)p[i] + (unsigned)(p[i] >> 32);
+  for (int i = 0; i < CH; i++) r += a[i] + seedv[i] + __float_as_uint(f[i]) + (unsigned)p[i] + (unsigned)(p[i] >> 32);
   if (r == 0x12345678u) out[0] = r;
 }
 template <int OP> void run(const char *name, int per_iter) {
@@ -64,8 +69,9 @@ template <int OP> void run(const char *name, int per_iter) {
 int main() {
   run<0>("FADD", 1); run<1>("FADD2", 1); run<2>("FFMA", 1); run<3>("FFMA2", 1); run<11>("FMUL", 1); run<16>("FADD.RZ", 1);
   run<4>("IDP.4A", 1); run<5>("PRMT", 1); run<6>("LOP3", 1); run<7>("IMAD", 1); run<17>("IADD", 1); run<8>("FMNMX", 1);
-  run<9>("VIMNMX.S16x2.RELU", 1); run<10>("SHF", 1); run<21>("I2FP", 1);
+  run<9>("VIMNMX.S16x2.RELU", 1); run<10>("SHF", 1); run<21>("I2FP", 1); run<25>("F2I", 1);
   run<12>("IDP.4A + FADD2", 2); run<13>("IDP.4A + FADD", 2); run<14>("PRMT + FADD2", 2); run<15>("FADD + FADD2", 2);
+  run<22>("I2FP + FADD2", 2); run<23>("I2FP + LOP3", 2); run<24>("I2FP + IDP.4A", 2); run<26>("IDP.4A + PRMT + FADD2", 3);
   run<18>("IMAD + FADD", 2); run<19>("LOP3 + FADD", 2); run<20>("LOP3 + FADD2", 2);
   return 0;
 }

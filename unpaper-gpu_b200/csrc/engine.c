@@ -621,6 +621,7 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
   const bool no_border_align = OFF(SW_BORDER_ALIGN, no_border_align);
 #undef OFF
   StageCtx c;
+  bool direct_out = false;
   memset(&c, 0, sizeof(c));
   c.st = ln->st; c.npages = n; c.pages = ln->pages_dev; c.w = e->g_in.w; c.h = e->g_in.h; c.fmt = e->dfmt;
   c.rows_aligned16 = (e->sheet_pitch & 15) == 0;   /* slabs are 256-byte aligned, strides multiples of 256 */
@@ -695,8 +696,16 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
   if (!no_border_scan) {
     stage_detect_border(&c, &e->border);
     /* apply_masks(border masks) is fused into the first align_mask sweep */
-    if (!no_border_align && e->noutside > 0) stage_align_masks_pass(&c, &cfg->mask_alignment, e->noutside, cfg->mask_color);
-    else stage_apply_border_masks(&c, cfg->mask_color);
+    if (!no_border_align && e->noutside > 0) {
+      /* nothing touches the sheet after this sweep and the caller's device buffer has the sheet's own
+       * layout: render the last sweep straight into it */
+      direct_out = !ln->host_mode && e->out_fmt < 0 && e->out_count == 1 && e->n_post == 0 &&
+                   e->g_out.pitch == e->g_out.w * e->bpp && ln->static_fill_n[2] == 0 && e->n_static_mask_jobs[2] == 0 &&
+                   !cfg->post_mirror.horizontal && !cfg->post_mirror.vertical && cfg->post_shift.horizontal == 0 &&
+                   cfg->post_shift.vertical == 0;
+      stage_align_masks_pass(&c, &cfg->mask_alignment, e->noutside, cfg->mask_color, direct_out ? ln->out_dev : NULL,
+                             (size_t)e->g_out.pitch * e->g_out.h);
+    } else stage_apply_border_masks(&c, cfg->mask_color);
   }
   run_static(e, ln, &c, 2, n, skip, 0);
   run_geometry(e, ln, &c, 1, n);
@@ -739,7 +748,7 @@ static void issue_group(B200Engine *e, Lane *ln, const uint8_t *pages_dev_in, in
                                   cur + e->sheet_stride * p, (size_t)e->g_out.pitch, (size_t)osheet_row,
                                   (size_t)e->g_out.h, cudaMemcpyDeviceToHost, c.st));
     }
-  } else {
+  } else if (!direct_out) {
     b200k_pack_rows(c.st, cur, e->g_out.pitch, ln->out_dev, osheet_row, osheet_row, e->g_out.h, n,
                     e->sheet_stride, (size_t)osheet_row * e->g_out.h);
     c.launches++;

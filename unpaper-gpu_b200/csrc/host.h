@@ -123,7 +123,8 @@ void stage_align_masks(StageCtx *c, const MaskAlignmentParameters *p, int n_outs
 /* sheet-engine forms (two sheet buffers per slot, one sweep per move, see dev.h DPage.other) */
 void stage_deskew_mask_pass(StageCtx *c, int interp, int mi);
 void stage_center_masks_pass(StageCtx *c, int max_masks);
-void stage_align_masks_pass(StageCtx *c, const MaskAlignmentParameters *p, int n_outside, Pixel mask_color);
+void stage_align_masks_pass(StageCtx *c, const MaskAlignmentParameters *p, int n_outside, Pixel mask_color,
+                            uint8_t *final_dst, size_t final_stride);
 void stage_shift_pass(StageCtx *c, Delta d);
 
 /* scratch sizing for one page of w x h in device format fmt */

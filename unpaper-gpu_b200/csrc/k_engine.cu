@@ -28,6 +28,13 @@ __global__ void k_swap_sheets(DPage *pages, int npages) {
   uint8_t *t = pg.img.data; pg.img.data = pg.other; pg.other = t;
 }
 
+// the next pass img -> other renders sheet p straight into base + p * stride (the caller's output)
+__global__ void k_set_other(DPage *pages, int npages, uint8_t *base, size_t stride) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npages) return;
+  pages[p].other = base + (size_t)p * stride;
+}
+
 // the working sheet of every page now has this geometry (after a size-changing pass, or back to
 // the decoded size at the start of a sheet)
 __global__ void k_set_geometry(DPage *pages, int npages, int w, int h, int pitch) {
@@ -114,6 +121,10 @@ void b200k_convert_out(cudaStream_t st, DImg src, DImg dst, int nimages, size_t 
 void b200k_swap_sheets(cudaStream_t st, DPage *pages, int npages) {
   if (npages <= 0) return;
   k_swap_sheets<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages);
+}
+void b200k_set_other(cudaStream_t st, DPage *pages, int npages, uint8_t *base, size_t stride) {
+  if (npages <= 0) return;
+  k_set_other<<<cdiv(npages, 64), 64, 0, st>>>(pages, npages, base, stride);
 }
 void b200k_set_geometry(cudaStream_t st, DPage *pages, int npages, int w, int h, int pitch) {
   if (npages <= 0) return;

@@ -755,36 +755,55 @@ __global__ void __launch_bounds__(256, 8) k_nf_classify_bits(DPage *pages, int i
     s_big[r][k] = s_nb[r][k] & D;
   }
   __syncthreads();
-  // phase 3: eight pixels per item
-  for (int it = threadIdx.x; it < (NFB_TW / 8) * NFB_TH; it += blockDim.x) {
-  int ly = it / (NFB_TW / 8), lx0 = (it % (NFB_TW / 8)) * 8;
-  int y = by + ly, r = ly + halo;
-  if (y >= im.h || bx + lx0 >= im.w) continue;
-  int k = 1 + (lx0 >> 5), sh = lx0 & 31;
-  unsigned dark8 = (s_dark[r][k] >> sh) & 0xFFu, nb8 = (s_nb[r][k] >> sh) & 0xFFu, big8 = (s_big[r][k] >> sh) & 0xFFu;
-  // mutable = dark inside the left/top band, or dark outside it, not settled by the bit planes and
-  // found small by the exact walk (rare); no per-pixel loop for the rest
-  unsigned mut8 = dark8 & ~nb8;
-  unsigned open8 = nb8 & ~big8;
-  while (open8) {
-    int i = __ffs(open8) - 1;
-    open8 &= open8 - 1;
-    if (nfb_small_component(s_nb, rows, 32 + lx0 + i, r, need)) mut8 |= 1u << i;
-  }
-  // four bits -> four bytes (bit i -> bit 0 of byte i), then the class codes
-  unsigned dl = ((dark8 & 0xFu) * 0x00204081u) & 0x01010101u, dh = ((dark8 >> 4) * 0x00204081u) & 0x01010101u;
-  unsigned ml = ((mut8 & 0xFu) * 0x00204081u) & 0x01010101u, mh = ((mut8 >> 4) * 0x00204081u) & 0x01010101u;
-  unsigned lo = dl * (NF_LIVE | NF_TRIG) + ml * (NF_MUT | NF_UNDEC), hi = dh * (NF_LIVE | NF_TRIG) + mh * (NF_MUT | NF_UNDEC);
-  if (mut8) {
-    unsigned idx = atomicAdd(&pg.list_n, (unsigned)__popc(mut8));
-    for (unsigned m = mut8; m; m &= m - 1, idx++) {
-      if (idx < (unsigned)pg.list_cap) pg.list[idx] = ((unsigned)y << 16) | (unsigned)(bx + lx0 + __ffs(m) - 1);
-      else atomicOr(&pg.error, DERR_LIST_OVERFLOW);
+  // phase 3: class bytes.  An item is one 32-pixel word of the bit planes (two 16-byte stores) when the
+  // class map allows it, else eight pixels.
+  const bool wide = (im.w & 15) == 0 && ((uintptr_t)pg.cls & 15) == 0;
+  const int ppi = wide ? 32 : 8;                       // pixels per item
+  const int ipr = NFB_TW / ppi;                        // items per tile row
+  for (int it = threadIdx.x; it < ipr * NFB_TH; it += blockDim.x) {
+    const int ly = it / ipr, lx0 = (it - ly * ipr) * ppi;
+    const int y = by + ly, r = ly + halo;
+    if (y >= im.h || bx + lx0 >= im.w) continue;
+    const int k = 1 + (lx0 >> 5), sh = lx0 & 31;
+    const unsigned pm = wide ? 0xFFFFFFFFu : 0xFFu;
+    const unsigned darkw = (s_dark[r][k] >> sh) & pm, nbw = (s_nb[r][k] >> sh) & pm, bigw = (s_big[r][k] >> sh) & pm;
+    // mutable = dark inside the left/top band, or dark outside it, not settled by the bit planes and
+    // found small by the exact walk (rare); no per-pixel loop for the rest
+    unsigned mutw = darkw & ~nbw;
+    unsigned openw = nbw & ~bigw;
+    while (openw) {
+      const int i = __ffs(openw) - 1;
+      openw &= openw - 1;
+      if (nfb_small_component(s_nb, rows, 32 + lx0 + i, r, need)) mutw |= 1u << i;
     }
-  }
-  size_t o = (size_t)y * im.w + bx + lx0;
-  if ((im.w & 7) == 0 && ((uintptr_t)pg.cls & 7) == 0) *(uint2 *)(pg.cls + o) = make_uint2(lo, hi);
-  else for (int i = 0; i < 8 && bx + lx0 + i < im.w; i++) pg.cls[o + i] = (uint8_t)((i < 4 ? lo >> (8 * i) : hi >> (8 * (i - 4))) & 0xFFu);
+    if (mutw) {
+      unsigned idx = atomicAdd(&pg.list_n, (unsigned)__popc(mutw));
+      for (unsigned m = mutw; m; m &= m - 1, idx++) {
+        if (idx < (unsigned)pg.list_cap) pg.list[idx] = ((unsigned)y << 16) | (unsigned)(bx + lx0 + __ffs(m) - 1);
+        else atomicOr(&pg.error, DERR_LIST_OVERFLOW);
+      }
+    }
+    // four bits -> four bytes (bit i -> bit 0 of byte i), then the class codes
+    const size_t o = (size_t)y * im.w + bx + lx0;
+    if (wide) {
+      unsigned cw[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const unsigned d4 = (((darkw >> (4 * q)) & 0xFu) * 0x00204081u) & 0x01010101u, m4 = (((mutw >> (4 * q)) & 0xFu) * 0x00204081u) & 0x01010101u;
+        cw[q] = d4 * (NF_LIVE | NF_TRIG) + m4 * (NF_MUT | NF_UNDEC);
+      }
+      uint4 *o4 = (uint4 *)(pg.cls + o);
+      if (bx + lx0 + 31 < im.w) { o4[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]); o4[1] = make_uint4(cw[4], cw[5], cw[6], cw[7]); }
+      else {   // the image ends inside this word (its width is a multiple of 16)
+        if (bx + lx0 + 15 < im.w) o4[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+      }
+    } else {
+      const unsigned dl = ((darkw & 0xFu) * 0x00204081u) & 0x01010101u, dh = ((darkw >> 4) * 0x00204081u) & 0x01010101u;
+      const unsigned ml = ((mutw & 0xFu) * 0x00204081u) & 0x01010101u, mh = ((mutw >> 4) * 0x00204081u) & 0x01010101u;
+      const unsigned lo = dl * (NF_LIVE | NF_TRIG) + ml * (NF_MUT | NF_UNDEC), hi = dh * (NF_LIVE | NF_TRIG) + mh * (NF_MUT | NF_UNDEC);
+      if ((im.w & 7) == 0 && ((uintptr_t)pg.cls & 7) == 0) *(uint2 *)(pg.cls + o) = make_uint2(lo, hi);
+      else for (int i = 0; i < 8 && bx + lx0 + i < im.w; i++) pg.cls[o + i] = (uint8_t)((i < 4 ? lo >> (8 * i) : hi >> (8 * (i - 4))) & 0xFFu);
+    }
   }
 }
 

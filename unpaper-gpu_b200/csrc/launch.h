@@ -92,6 +92,8 @@ void b200k_prep_shift_move(cudaStream_t st, DPage *pages, int npages, int dx, in
 void b200k_rotate_sheet(cudaStream_t st, DPage *pages, int npages, int mi, int interp, int fmt, int maxw, int maxh,
                         int ink_fresh /* the ink map of the current sheet contents already exists */);
 void b200k_page_reset(cudaStream_t st, DPage *pages, int npages);
+/* the next pass img -> other of sheet p writes to base + p * stride instead of the slot's other buffer */
+void b200k_set_other(cudaStream_t st, DPage *pages, int npages, uint8_t *base, size_t stride);
 void b200k_pack_rows(cudaStream_t st, const uint8_t *src, int src_pitch, uint8_t *dst, int dst_pitch,
                      int row_bytes, int rows, int nimages, size_t src_stride, size_t dst_stride);
 

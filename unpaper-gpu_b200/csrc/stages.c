@@ -509,11 +509,15 @@ void stage_center_masks_pass(StageCtx *c, int max_masks) {
 
 /* apply_masks(border masks) + align_mask() per outside area (sheet_stages.c:474-483); the
  * mask painting rides on the first move */
-void stage_align_masks_pass(StageCtx *c, const MaskAlignmentParameters *p, int n_outside, Pixel mask_color) {
+/* final_dst != NULL: the last sweep renders sheet p into final_dst + p * final_stride (tight rows equal to
+ * the sheet's pitch) — the output stage then has nothing left to copy */
+void stage_align_masks_pass(StageCtx *c, const MaskAlignmentParameters *p, int n_outside, Pixel mask_color,
+                            uint8_t *final_dst, size_t final_stride) {
   for (int i = 0; i < n_outside; i++) {
     b200k_prep_align_move(c->st, c->pages, c->npages, i, p->alignment.left, p->alignment.top, p->alignment.right,
                           p->alignment.bottom, p->margin.horizontal, p->margin.vertical, i == 0);
     c->launches += 1;
+    if (final_dst && i == n_outside - 1) { b200k_set_other(c->st, c->pages, c->npages, final_dst, final_stride); c->launches += 1; }
     move_pass(c, mask_color);
   }
 }
