@@ -1045,26 +1045,28 @@ __global__ void __launch_bounds__(128) k_rotate_sheet_g8c(DPage *pages, int mi, 
     const float mnx = scx + fminf(ax, bx) + fminf(ay, by), mxx = scx + fmaxf(ax, bx) + fmaxf(ay, by);
     const float mny = scy + fminf(cy, dy) - fmaxf(cx, dx), mxy = scy + fmaxf(cy, dy) - fminf(cx, dx);
     if (fabsf(mnx) < 1e7f && fabsf(mxx) < 1e7f && fabsf(mny) < 1e7f && fabsf(mxy) < 1e7f) {
-      // taps reach from (int)src - 1 to (int)src + 2; two pixels of slack for float rounding
+      // taps reach from (int)src - 1 to (int)src + 2.  The bounding box is evaluated in another order than the
+      // pixels' coordinates (differences of the order of 1e-3 pixels): two pixels of slack for the range guarantee,
+      // one for the white test
       const int bx0 = (int)floorf(mnx) - 3, bx1 = (int)floorf(mxx) + 4, by0 = (int)floorf(mny) - 3, by1 = (int)floorf(mxy) + 4;
       const bool safe = bx0 >= 0 && by0 >= 0 && bx1 < W && by1 < H;
       bool white = false;
       if (pg.ink_ok && fabsf(cosval) > 0.5f) {
         if (bx1 < 0 || by1 < 0 || bx0 >= W || by0 >= H) white = true;   // entirely outside: reads as white
         else {
-          const int cx0 = max(bx0, 0) >> 3, cx1 = min(bx1, W - 1) >> 3;
+          const int cx0 = max(bx0 + 1, 0) >> 3, cx1 = min(bx1 - 1, W - 1) >> 3;
           static_assert(D_INK_CELL == 8, "cell index = coordinate >> 3");
           if (cx1 - cx0 < 32) {
             bool wh = true;
             if (cx0 + lane <= cx1) {
               // pixels whose taps touch cell column c have (int)srcX in [8c - 2, 8c + 8]
               const int c = cx0 + lane;
-              const float sxl = fmaxf((float)(8 * c - 4), mnx), sxh = fminf((float)(8 * c + 11), mxx);
+              const float sxl = fmaxf((float)(8 * c - 3), mnx), sxh = fminf((float)(8 * c + 10), mxx);
               const float icos = 1.0f / cosval, tanv = sinval * icos;
               const float e0 = scy + fya * icos, e1 = scy + fyb * icos;
               const float t0 = tanv * (sxl - scx), t1 = tanv * (sxh - scx);
               const float sylo = fminf(e0, e1) - fmaxf(t0, t1), syhi = fmaxf(e0, e1) - fminf(t0, t1);
-              const int ry0 = max((int)floorf(sylo) - 3, by0), ry1 = min((int)floorf(syhi) + 4, by1);
+              const int ry0 = max((int)floorf(sylo) - 2, by0), ry1 = min((int)floorf(syhi) + 3, by1);
               if (ry1 >= 0 && ry0 < H && ry0 <= ry1) {
                 const int cyl = max(ry0, 0) >> 3, cyh = min(ry1, H - 1) >> 3;
                 if (cyh - cyl > 7) wh = false;

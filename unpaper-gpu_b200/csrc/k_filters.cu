@@ -635,9 +635,9 @@ __global__ void k_nf_classify_g8(DPage *pages, int intensity, int white) {
  * touches one belongs to a component of >= need pixels (all members of a core
  * pixel's block touch it) — settled for 32 pixels per instruction.  Only the
  * few dark pixels that this test leaves open run the exact bounded walk. */
-#define NFB_NW 8                      /* words per plane row: one halo word each side */
+#define NFB_NW 12                     /* words per plane row: one halo word each side */
 #define NFB_TW (32 * (NFB_NW - 2))
-#define NFB_TH 32
+#define NFB_TH 64
 #define NFB_ROWS (NFB_TH + 2 * 8)
 
 __device__ __forceinline__ bool nfb_bit(const unsigned (*nb)[NFB_NW], int x, int y) { return (nb[y][x >> 5] >> (x & 31)) & 1u; }
