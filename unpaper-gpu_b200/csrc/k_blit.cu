@@ -211,8 +211,8 @@ __device__ __forceinline__ bool px_in_masks(const DPage &pg, int x, int y) {
   return false;
 }
 
-__global__ void __launch_bounds__(256) k_move_pass(DPage *pages, uint8_t c0, uint8_t c1, uint8_t c2) {
-  const DPage &pg = pages[blockIdx.z];
+// The segment form (a warp per row): layouts whose rows or buffers are not 16-byte aligned.
+__device__ __noinline__ void move_rows_segments(const DPage &pg, int y0, int yend, uint8_t c0, uint8_t c1, uint8_t c2) {
   const DImg &im = pg.img;
   uint8_t *dstb = pg.other;
   const int W = im.w, H = im.h;
@@ -236,9 +236,8 @@ __global__ void __launch_bounds__(256) k_move_pass(DPage *pages, uint8_t c0, uin
     mcp[0] = rgb ? c0 : mcg; mcp[1] = rgb ? c1 : mcg; mcp[2] = rgb ? c2 : mcg;
   }
   const int tb0 = tx * bpp, tb1 = (tx + w) * bpp, tsv = tb0 + (have_src ? wc : 0) * bpp, ab0 = ax0 * bpp, ab1 = (ax1 + 1) * bpp;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int yend = min(H, (int)(blockIdx.y + 1) * MOVE_ROWS);
-  for (int y = blockIdx.y * MOVE_ROWS + warp; y < yend; y += 8) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int y = y0 + warp; y < yend; y += nwarps) {
     const uint8_t *srow = im.data + (size_t)y * im.pitch;
     uint8_t *drow = dstb + (size_t)y * im.pitch;
     const bool rowT = en && y >= ty && y < ty + h;
@@ -260,6 +259,181 @@ __global__ void __launch_bounds__(256) k_move_pass(DPage *pages, uint8_t c0, uin
       else copy_run(drow + p, sp + p, q - p, lane, 32);
     }
   }
+}
+
+// 16 source bytes at any alignment from two aligned 16-byte loads (`mis` = address & 15 is the same for
+// every chunk of a page: rows are a multiple of 16 bytes apart)
+__device__ __forceinline__ uint4 sel16_shifted(uint4 A, uint4 B, unsigned wsel, unsigned sh) {
+  switch (wsel) {
+    case 0: return make_uint4(__funnelshift_r(A.x, A.y, sh), __funnelshift_r(A.y, A.z, sh), __funnelshift_r(A.z, A.w, sh), __funnelshift_r(A.w, B.x, sh));
+    case 1: return make_uint4(__funnelshift_r(A.y, A.z, sh), __funnelshift_r(A.z, A.w, sh), __funnelshift_r(A.w, B.x, sh), __funnelshift_r(B.x, B.y, sh));
+    case 2: return make_uint4(__funnelshift_r(A.z, A.w, sh), __funnelshift_r(A.w, B.x, sh), __funnelshift_r(B.x, B.y, sh), __funnelshift_r(B.y, B.z, sh));
+    default: return make_uint4(__funnelshift_r(A.w, B.x, sh), __funnelshift_r(B.x, B.y, sh), __funnelshift_r(B.y, B.z, sh), __funnelshift_r(B.z, B.w, sh));
+  }
+}
+__device__ __forceinline__ uint4 ld16_shifted(const uint8_t *s, unsigned mis) {
+  const uint4 *a = (const uint4 *)(s - mis);
+  const uint4 A = __ldg(a);
+  if (mis == 0) return A;
+  return sel16_shifted(A, __ldg(a + 1), mis >> 2, (mis & 3u) * 8u);
+}
+
+// The sweep for 16-byte aligned rows (every sheet buffer of the engine): a thread owns one 16-byte chunk
+// column of MOVE_VROWS rows.  What a chunk column can be along x (inside T, inside the part of T that has a
+// source, inside area', inside / outside the masks) is decided once, the row-dependent part is a few
+// warp-uniform comparisons per row, and every byte moves as one 16-byte load (two aligned loads + funnel
+// shifts for the pasted pixels) and one 16-byte store.  The few chunk columns that contain a boundary of
+// DMove.bnd (or the ragged end of the row) are rendered afterwards byte by byte, all threads of the block
+// sharing them, from the per-byte definition of the gather above.
+#define MOVE_VROWS 16
+#define MOVE_VTHREADS 160
+__global__ void __launch_bounds__(MOVE_VTHREADS) k_move_pass(DPage *pages, uint8_t c0, uint8_t c1, uint8_t c2) {
+  const DPage &pg = pages[blockIdx.z];
+  const DImg im = pg.img;                 // by value: no reloads of the descriptor behind the stores below
+  uint8_t *const dstb = pg.other;
+  const int W = im.w, H = im.h, pitch = im.pitch;
+  const int y0 = blockIdx.y * MOVE_VROWS, yend = min(H, y0 + MOVE_VROWS);
+  if (y0 >= H) return;
+  const bool rgb = im.fmt == DF_RGB24;
+  if ((pitch & 15) != 0 || (((uintptr_t)im.data | (uintptr_t)dstb) & 15) != 0 || !(rgb || im.fmt == DF_GRAY8)) {
+    move_rows_segments(pg, y0, yend, c0, c1, c2);
+    return;
+  }
+  const int bpp = rgb ? 3 : 1, rowbytes = W * bpp;
+  const DMove &mv = pg.move;
+  const DRect area = mv.area;
+  const int nseg = mv.nseg;
+  const int nx0 = min(area.x0, area.x1), nx1 = max(area.x0, area.x1);
+  const int ny0 = min(area.y0, area.y1), ny1 = max(area.y0, area.y1);
+  const int w = nx1 - nx0 + 1, h = ny1 - ny0 + 1;
+  const int ax0 = max(nx0, 0), ax1 = min(nx1, W - 1), ay0 = max(ny0, 0), ay1 = min(ny1, H - 1);   // clip_rectangle
+  const int wc = ax1 - ax0 + 1, hc = ay1 - ay0 + 1;
+  const bool have_src = wc > 0 && hc > 0;
+  const bool en = mv.enabled != 0;
+  const int nmask = mv.use_masks != 0 ? min(pg.outside_count, D_MAX_BORDERS) : 0;   // apply_masks paints nothing without masks (masks.c:313-315)
+  static_assert(D_MAX_BORDERS == 2, "the two border masks live in registers");
+  // normalised like point_in_rectangle; an unused slot is empty
+  const DRect r0 = pg.border_mask[0], r1 = pg.border_mask[1];
+  const int m0xa = nmask > 0 ? min(r0.x0, r0.x1) : 1, m0xb = nmask > 0 ? max(r0.x0, r0.x1) : 0, m0ya = min(r0.y0, r0.y1), m0yb = max(r0.y0, r0.y1);
+  const int m1xa = nmask > 1 ? min(r1.x0, r1.x1) : 1, m1xb = nmask > 1 ? max(r1.x0, r1.x1) : 0, m1ya = min(r1.y0, r1.y1), m1yb = max(r1.y0, r1.y1);
+#define MV_IN_MASKS(x, y) (((x) >= m0xa && (x) <= m0xb && (y) >= m0ya && (y) <= m0yb) || ((x) >= m1xa && (x) <= m1xb && (y) >= m1ya && (y) <= m1yb))
+  const int tx = mv.tx, ty = mv.ty;
+  const unsigned bgg = (unsigned)((im.bg[0] + im.bg[1] + im.bg[2]) / 3) & 0xFFu, mcg = (unsigned)((c0 + c1 + c2) / 3) & 0xFFu;
+  const unsigned bg0 = rgb ? im.bg[0] : bgg, bg1 = rgb ? im.bg[1] : bgg, bg2 = rgb ? im.bg[2] : bgg;
+  const unsigned mc0 = rgb ? c0 : mcg, mc1 = rgb ? c1 : mcg, mc2 = rgb ? c2 : mcg;
+  const int tb0 = tx * bpp, tb1 = (tx + w) * bpp, tsv = tb0 + (have_src ? wc : 0) * bpp, ab0 = ax0 * bpp, ab1 = (ax1 + 1) * bpp;
+  const unsigned misT = (unsigned)(ab0 - tb0) & 15u;   // alignment of a pasted chunk's source
+  // rows at which the kind of a chunk column can change: the block's rows all behave alike when none lies inside it
+  bool rows_same = true;
+  {
+#define MV_BRK(yb) rows_same = rows_same && ((yb) <= y0 || (yb) >= yend)
+    if (en) { MV_BRK(ty); MV_BRK(ty + h); if (have_src) { MV_BRK(ty + hc); MV_BRK(ay0); MV_BRK(ay1 + 1); } }
+    if (nmask > 0) { MV_BRK(m0ya); MV_BRK(m0yb + 1); if (en) { MV_BRK(m0ya + ty - ay0); MV_BRK(m0yb + 1 + ty - ay0); } }
+    if (nmask > 1) { MV_BRK(m1ya); MV_BRK(m1yb + 1); if (en) { MV_BRK(m1ya + ty - ay0); MV_BRK(m1yb + 1 + ty - ay0); } }
+#undef MV_BRK
+  }
+  __shared__ int s_nb, s_bc[20];
+  if (threadIdx.x == 0) s_nb = 0;
+  __syncthreads();
+  const int nch = (rowbytes + 15) >> 4;
+  for (int c = threadIdx.x; c < nch; c += MOVE_VTHREADS) {
+    const int p = c << 4;
+    bool uni = p + 16 <= rowbytes;
+    for (int s = 1; s < nseg; s++) { const int bs = mv.bnd[s]; uni = uni && !(bs > p && bs < p + 16); }
+    if (!uni) { s_bc[atomicAdd(&s_nb, 1)] = c; continue; }
+    const bool inT = en && p >= tb0 && p < tb1, inTs = p < tsv;
+    const bool inA = en && have_src && p >= ab0 && p < ab1;
+    // the 16 bytes of a 3-periodic pattern that start at byte p (p % 3 == c % 3)
+    const int ph = c % 3;
+    uint4 bgv, mcv;
+    {
+      const unsigned b0 = bg0 | (bg1 << 8) | (bg2 << 16) | (bg0 << 24), b1 = bg1 | (bg2 << 8) | (bg0 << 16) | (bg1 << 24), b2 = bg2 | (bg0 << 8) | (bg1 << 16) | (bg2 << 24);
+      const unsigned m0 = mc0 | (mc1 << 8) | (mc2 << 16) | (mc0 << 24), m1 = mc1 | (mc2 << 8) | (mc0 << 16) | (mc1 << 24), m2 = mc2 | (mc0 << 8) | (mc1 << 16) | (mc2 << 24);
+      bgv = ph == 0 ? make_uint4(b0, b1, b2, b0) : ph == 1 ? make_uint4(b1, b2, b0, b1) : make_uint4(b2, b0, b1, b2);
+      mcv = ph == 0 ? make_uint4(m0, m1, m2, m0) : ph == 1 ? make_uint4(m1, m2, m0, m1) : make_uint4(m2, m0, m1, m2);
+    }
+    const int sxT = (p - tb0) / bpp + ax0, sxO = p / bpp;
+    const uint8_t *sown = im.data + (size_t)y0 * pitch + p;
+    const uint8_t *spst = im.data + ((ptrdiff_t)(ay0 + y0 - ty) * pitch + ab0 - tb0 + p);
+    uint8_t *d = dstb + (size_t)y0 * pitch + p;
+    if (rows_same) {
+      // no row of this block changes what a chunk column is: decide at y0, then move the rows with the loads of
+      // eight rows in flight
+      const int v = y0 - ty;
+      int kind;                               // 0 fill, 1 own pixels, 2 pasted pixels
+      int sx, sy;
+      if (inT && y0 >= ty && v < h) {
+        if (inTs && have_src && v < hc) { kind = 2; sx = sxT; sy = ay0 + v; } else { kind = 0; sx = sy = 0; }
+      } else if (inA && y0 >= ay0 && y0 <= ay1) { kind = 0; sx = sy = 0; }
+      else { kind = 1; sx = sxO; sy = y0; }
+      uint4 fv = bgv;
+      if (kind != 0 && nmask > 0 && !MV_IN_MASKS(sx, sy)) { kind = 0; fv = mcv; }
+      const int rows = yend - y0;
+      if (kind == 0) {
+        for (int r = 0; r < rows; r++, d += pitch) *(uint4 *)d = fv;
+      } else if (kind == 1 || misT == 0) {
+        const uint8_t *sp = kind == 1 ? sown : spst;
+        int r = 0;
+        for (; r + 8 <= rows; r += 8, sp += 8 * (size_t)pitch, d += 8 * (size_t)pitch) {
+          uint4 t[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) t[k] = __ldg((const uint4 *)(sp + (size_t)k * pitch));
+#pragma unroll
+          for (int k = 0; k < 8; k++) *(uint4 *)(d + (size_t)k * pitch) = t[k];
+        }
+        for (; r < rows; r++, sp += pitch, d += pitch) *(uint4 *)d = __ldg((const uint4 *)sp);
+      } else {
+        const uint8_t *sp = spst - misT;      // the aligned chunk that holds the first source byte
+        const unsigned sh = (misT & 3u) * 8u, wsel = misT >> 2;
+        int r = 0;
+        for (; r + 4 <= rows; r += 4, sp += 4 * (size_t)pitch, d += 4 * (size_t)pitch) {
+          uint4 A[4], B[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) { A[k] = __ldg((const uint4 *)(sp + (size_t)k * pitch)); B[k] = __ldg((const uint4 *)(sp + (size_t)k * pitch) + 1); }
+#pragma unroll
+          for (int k = 0; k < 4; k++) *(uint4 *)(d + (size_t)k * pitch) = sel16_shifted(A[k], B[k], wsel, sh);
+        }
+        for (; r < rows; r++, sp += pitch, d += pitch) *(uint4 *)d = sel16_shifted(__ldg((const uint4 *)sp), __ldg((const uint4 *)sp + 1), wsel, sh);
+      }
+      continue;
+    }
+    for (int y = y0; y < yend; y++, sown += pitch, spst += pitch, d += pitch) {
+      const int v = y - ty;
+      const bool rowT = y >= ty && v < h;
+      uint4 val;
+      int sx, sy;
+      bool fill = false;
+      if (inT && rowT) {
+        if (inTs && have_src && v < hc) { val = ld16_shifted(spst, misT); sx = sxT; sy = ay0 + v; }
+        else fill = true;
+      } else if (inA && y >= ay0 && y <= ay1) fill = true;
+      else { val = __ldg((const uint4 *)sown); sx = sxO; sy = y; }
+      if (fill) val = bgv;
+      else if (nmask > 0 && !MV_IN_MASKS(sx, sy)) val = mcv;
+      *(uint4 *)d = val;
+    }
+  }
+  __syncthreads();
+  // chunk columns with a boundary inside: byte b of row y straight from the definition
+  const int nb = s_nb, rows = yend - y0;
+  for (int i = threadIdx.x; i < nb * rows * 16; i += MOVE_VTHREADS) {
+    const int b = (s_bc[i / (rows * 16)] << 4) + (i & 15), y = y0 + (i >> 4) % rows;
+    if (b >= rowbytes) continue;
+    const int v = y - ty;
+    const uint8_t *sp = NULL;
+    int sx = 0, sy = 0;
+    if (en && y >= ty && v < h && b >= tb0 && b < tb1) {
+      if (have_src && v < hc && b < tsv) { sp = im.data + ((ptrdiff_t)(ay0 + v) * pitch + ab0 - tb0 + b); sx = (b - tb0) / bpp + ax0; sy = ay0 + v; }
+    } else if (!(en && have_src && y >= ay0 && y <= ay1 && b >= ab0 && b < ab1)) { sp = im.data + (size_t)y * pitch + b; sx = b / bpp; sy = y; }
+    const int ph = b % 3;
+    unsigned val;
+    if (!sp) val = ph == 0 ? bg0 : ph == 1 ? bg1 : bg2;
+    else {
+      val = (nmask == 0 || MV_IN_MASKS(sx, sy)) ? *sp : ph == 0 ? mc0 : ph == 1 ? mc1 : mc2;
+    }
+    dstb[(size_t)y * pitch + b] = (uint8_t)val;
+  }
+#undef MV_IN_MASKS
 }
 
 // ---- mirror (blit.c:320-354): disjoint pixel pairs swapped in place --------
@@ -385,8 +559,8 @@ void b200k_copy_jobs(cudaStream_t st, const DCopyJob *jobs, int njobs, int maxw_
 }
 void b200k_move_pass(cudaStream_t st, DPage *pages, int npages, int maxw_bytes, int maxh, int mc_r, int mc_g, int mc_b) {
   if (npages <= 0 || maxw_bytes <= 0 || maxh <= 0) return;
-  dim3 g(1, cdiv(maxh, MOVE_ROWS), npages);
-  k_move_pass<<<g, 256, 0, st>>>(pages, (uint8_t)mc_r, (uint8_t)mc_g, (uint8_t)mc_b);
+  dim3 g(1, cdiv(maxh, MOVE_VROWS), npages);
+  k_move_pass<<<g, MOVE_VTHREADS, 0, st>>>(pages, (uint8_t)mc_r, (uint8_t)mc_g, (uint8_t)mc_b);
 }
 void b200k_apply_masks(cudaStream_t st, const DMaskJob *jobs, int njobs, int maxw, int maxh) {
   if (njobs <= 0 || maxw <= 0 || maxh <= 0) return;

@@ -978,6 +978,18 @@ __global__ void k_blur_wipe(DPage *pages, int n, int bw, int bh, int flag_off) {
   if (!pg.u32[flag_off + (size_t)r * n + b]) return;
   const DImg &im = pg.img;
   int x0 = b * bw, y0 = r * bh;
+  if (im.fmt == DF_GRAY8 && (bw & 3) == 0 && (im.pitch & 3) == 0 && ((uintptr_t)im.data & 3) == 0) {
+    // a warp per row, 32-bit stores (x0 is a multiple of 4); what lies outside the image is dropped like set_pixel does
+    const int xe = min(x0 + bw, im.w), ye = min(y0 + bh, im.h);
+    const int nw = max(xe - x0, 0) >> 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int y = y0 + warp; y < ye; y += nwarps) {
+      uint8_t *row = im.data + (size_t)y * im.pitch + x0;
+      for (int i = lane; i < nw; i += 32) ((unsigned *)row)[i] = 0xFFFFFFFFu;
+      for (int x = x0 + 4 * nw + lane; x < xe; x += 32) row[x - x0] = 255;
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < bw * bh; i += blockDim.x) {
     int x = x0 + i % bw, y = y0 + i / bw;
     px_set(im, x, y, 255, 255, 255);
@@ -1100,19 +1112,29 @@ __global__ void k_gray_prewhite(DPage *pages, GrayParams gp, int white_off) {
   }
 }
 
-__global__ void k_gray_wipe(DPage *pages, GrayParams gp, int white_off) {
+// A thread per cell: wiped cells that were not pure white before are rare, so the pass is a scan of the
+// cell flags; the lanes of a warp then paint each flagged cell of their 32 together.
+__global__ void __launch_bounds__(256) k_gray_wipe(DPage *pages, GrayParams gp, int white_off) {
   DPage &pg = pages[blockIdx.y];
   const DImg &im = pg.img;
-  int nc = gp.ncx * gp.ncy;
-  int cy = blockIdx.x;
-  const unsigned *wiped = pg.u32 + gp.off + 2 * nc + (size_t)cy * gp.ncx;
-  const unsigned *white = pg.u32 + white_off + (size_t)cy * gp.ncx;
-  bool skip_white = im.fmt != DF_Y400A;
-  int y0 = cy * gp.gy, y1 = min(y0 + gp.gy - 1, im.h - 1);
-  for (int x = threadIdx.x; x < im.w; x += blockDim.x) {
-    int cx = x / gp.gx;
-    if (cx >= gp.ncx || !wiped[cx] || (skip_white && white[cx])) continue;
-    for (int y = y0; y <= y1; y++) px_store(im, x, y, 255, 255, 255);
+  const int nc = gp.ncx * gp.ncy;
+  const unsigned *wiped = pg.u32 + gp.off + 2 * nc;
+  const unsigned *white = pg.u32 + white_off;
+  const bool skip_white = im.fmt != DF_Y400A;
+  const int lane = threadIdx.x & 31;
+  for (int c0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; c0 < nc; c0 += gridDim.x * blockDim.x) {   // warp-uniform trip count
+    const int c = c0 + lane;
+    const bool f = c < nc && wiped[c] && !(skip_white && white[c]);
+    unsigned m = __ballot_sync(0xffffffffu, f);
+    while (m) {
+      const int cc = c0 + __ffs(m) - 1;
+      m &= m - 1;
+      const int cx = cc % gp.ncx, cy = cc / gp.ncx;
+      const int x0 = cx * gp.gx, y0 = cy * gp.gy;
+      const int w = min(x0 + gp.gx, im.w) - x0, h = min(y0 + gp.gy, im.h) - y0;
+      if (w <= 0 || h <= 0) continue;
+      for (int i = lane; i < w * h; i += 32) px_store(im, x0 + i % w, y0 + i / w, 255, 255, 255);
+    }
   }
 }
 
@@ -1184,7 +1206,7 @@ void b200k_gray_cascade(cudaStream_t st, DPage *pages, int npages, const int *gp
   k_zero_range<<<dim3(min(cdiv(nc + nwave, 256), 128u), npages), 256, 0, st>>>(pages, gp.off + 2 * nc, nc, wave_off, nwave);
   k_gray_windows<<<dim3(min(cdiv(nw, 128), 256u), npages), 128, 0, st>>>(pages, gp, white_off, wflag_off, wave_off);
   k_gray_cascade<<<npages, 256, 0, st>>>(pages, gp, wflag_off, wave_off);
-  dim3 g2(gp.ncy, npages);
+  dim3 g2(min(cdiv(nc, 256), 256u), npages);
   k_gray_wipe<<<g2, 256, 0, st>>>(pages, gp, white_off);
 }
 }

@@ -26,6 +26,26 @@ __device__ __forceinline__ unsigned count4_range(unsigned w, unsigned lo4, unsig
   unsigned ge = __vcmpgeu4(w, lo4), le = __vcmpleu4(w, hi4);
   return (unsigned)__popc(ge & le) >> 3;
 }
+// The same test as three integer instructions per bound instead of the six the byte-compare
+// intrinsics expand to: bit 7 of every byte of lt4() is set where the byte of w is < T.
+//   (w & 0x7F7F7F7F) + (0x80 - (T & 0x7F)) per byte never carries into the next byte and has
+//   bit 7 set iff the low seven bits of the byte are >= those of T; with the top bit of the byte:
+//   byte >= T  <=>  T < 128 ? (top | low_ge) : (top & low_ge).
+struct Lt4 { unsigned addv, both; };       // both: all ones for T >= 128 (top & low_ge), zero for T < 128 (top | low_ge)
+__device__ __forceinline__ Lt4 lt4_make(int T) {
+  Lt4 r;
+  T = T < 0 ? 0 : T;                        // nothing is below 0: the sum always has bit 7 set, every byte is ">= T"
+  r.both = T >= 128 ? 0xFFFFFFFFu : 0u;
+  r.addv = T >= 256 ? 0u : (0x80u - ((unsigned)T & 0x7Fu)) * 0x01010101u;   // T >= 256: bit 7 of the sum never set, no byte is ">= T"
+  return r;
+}
+__device__ __forceinline__ unsigned lt4(unsigned w, Lt4 t) {
+  const unsigned s = (w & 0x7F7F7F7Fu) + t.addv;
+  const unsigned ge = (w & s) | ((w | s) & ~t.both);
+  return ~ge & 0x80808080u;
+}
+// bit 7 of every byte set where lo <= byte <= hi (hiT = lt4_make(hi + 1), loT = lt4_make(lo))
+__device__ __forceinline__ unsigned range4_bit7(unsigned w, Lt4 loT, Lt4 hiT) { return lt4(w, hiT) & ~lt4(w, loT); }
 // Applies f(word, nvalid_mask) over the bytes [p, p+n): aligned 32-bit loads,
 // `keep` has 0xFF in the byte lanes that belong to the run.
 template <typename F>
@@ -171,7 +191,7 @@ __global__ void k_linesum_rows(DPage *pages, const DLineJob *jobs, int njobs, in
     const uint4 *r4 = (const uint4 *)(im.data + (size_t)y * im.pitch);
     const int c0 = j.xa >> 4, c1 = j.xb >> 4;
     const bool cnt = stat == ST_COUNT_GRAY_RANGE;
-    const unsigned lo4 = (unsigned)lo * 0x01010101u, hi4 = (unsigned)hi * 0x01010101u;
+    const Lt4 loT = lt4_make(lo), hiT = lt4_make(hi + 1);
 #pragma unroll 4
     for (int c = c0 + lane; c <= c1; c += 32) {
       const uint4 v = __ldg(r4 + c);
@@ -186,7 +206,7 @@ __global__ void k_linesum_rows(DPage *pages, const DLineJob *jobs, int njobs, in
       }
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        if (cnt) acc += (unsigned)__popc(__vcmpgeu4(wv[k], lo4) & __vcmpleu4(wv[k], hi4) & keep[k]) >> 3;
+        if (cnt) acc += (unsigned)__popc(range4_bit7(wv[k], loT, hiT) & keep[k]);
         else acc += sum4(wv[k] & keep[k]);
       }
     }
@@ -230,7 +250,7 @@ __global__ void __launch_bounds__(256, 8) k_rect_count(DPage *pages, const DRect
     if (im.fmt == DF_GRAY8 && (im.pitch & 3) == 0 && ((uintptr_t)im.data & 3) == 0) {
       // every row of the rectangle has the same word alignment: a lane owns one
       // word column and walks down the rows
-      unsigned lo4 = (unsigned)lo * 0x01010101u, hi4 = (unsigned)hi * 0x01010101u;
+      const Lt4 loT = lt4_make(lo), hiT = lt4_make(hi + 1);
       int lead = x0 & 3, nw = (lead + w + 3) >> 2;
       const unsigned *base = (const unsigned *)(im.data + (size_t)y0 * im.pitch + (x0 - lead));
       int wpitch = im.pitch >> 2, rows = y1 - y0 + 1;
@@ -243,9 +263,9 @@ __global__ void __launch_bounds__(256, 8) k_rect_count(DPage *pages, const DRect
         unsigned acc = 0;
         for (int r = 0; r < rows; r++, p += wpitch) {
           unsigned wd = *p;
-          acc += (unsigned)__popc(__vcmpgeu4(wd, lo4) & __vcmpleu4(wd, hi4) & keep);
+          acc += (unsigned)__popc(range4_bit7(wd, loT, hiT) & keep);
         }
-        cnt += acc >> 3;
+        cnt += acc;
       }
     } else if (im.fmt == DF_GRAY8) {
       unsigned lo4 = (unsigned)lo * 0x01010101u, hi4 = (unsigned)hi * 0x01010101u;
