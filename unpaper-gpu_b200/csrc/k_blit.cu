@@ -279,13 +279,13 @@ __device__ __forceinline__ uint4 ld16_shifted(const uint8_t *s, unsigned mis) {
 }
 
 // The sweep for 16-byte aligned rows (every sheet buffer of the engine): a thread owns one 16-byte chunk
-// column of MOVE_VROWS rows.  What a chunk column can be along x (inside T, inside the part of T that has a
+// column of MOVE_VROWS rows, in batches of eight.  What a chunk column can be along x (inside T, inside the part of T that has a
 // source, inside area', inside / outside the masks) is decided once, the row-dependent part is a few
 // warp-uniform comparisons per row, and every byte moves as one 16-byte load (two aligned loads + funnel
 // shifts for the pasted pixels) and one 16-byte store.  The few chunk columns that contain a boundary of
 // DMove.bnd (or the ragged end of the row) are rendered afterwards byte by byte, all threads of the block
 // sharing them, from the per-byte definition of the gather above.
-#define MOVE_VROWS 16
+#define MOVE_VROWS 64
 #define MOVE_VTHREADS 160
 __global__ void __launch_bounds__(MOVE_VTHREADS) k_move_pass(DPage *pages, uint8_t c0, uint8_t c1, uint8_t c2) {
   const DPage &pg = pages[blockIdx.z];
@@ -323,15 +323,20 @@ __global__ void __launch_bounds__(MOVE_VTHREADS) k_move_pass(DPage *pages, uint8
   const unsigned mc0 = rgb ? c0 : mcg, mc1 = rgb ? c1 : mcg, mc2 = rgb ? c2 : mcg;
   const int tb0 = tx * bpp, tb1 = (tx + w) * bpp, tsv = tb0 + (have_src ? wc : 0) * bpp, ab0 = ax0 * bpp, ab1 = (ax1 + 1) * bpp;
   const unsigned misT = (unsigned)(ab0 - tb0) & 15u;   // alignment of a pasted chunk's source
-  // rows at which the kind of a chunk column can change: the block's rows all behave alike when none lies inside it
-  bool rows_same = true;
-  {
-#define MV_BRK(yb) rows_same = rows_same && ((yb) <= y0 || (yb) >= yend)
+  // rows at which the kind of a chunk column can change: the eight rows of a batch all behave alike when none of
+  // them lies inside the batch (one bit per batch)
+  unsigned same_mask = 0;
+  for (int bi = 0, ya = y0; ya < yend; bi++, ya += 8) {
+    const int yb = min(ya + 8, yend);
+    bool sm = true;
+#define MV_BRK(yy) sm = sm && ((yy) <= ya || (yy) >= yb)
     if (en) { MV_BRK(ty); MV_BRK(ty + h); if (have_src) { MV_BRK(ty + hc); MV_BRK(ay0); MV_BRK(ay1 + 1); } }
     if (nmask > 0) { MV_BRK(m0ya); MV_BRK(m0yb + 1); if (en) { MV_BRK(m0ya + ty - ay0); MV_BRK(m0yb + 1 + ty - ay0); } }
     if (nmask > 1) { MV_BRK(m1ya); MV_BRK(m1yb + 1); if (en) { MV_BRK(m1ya + ty - ay0); MV_BRK(m1yb + 1 + ty - ay0); } }
 #undef MV_BRK
+    same_mask |= (sm ? 1u : 0u) << bi;
   }
+  static_assert(MOVE_VROWS <= 8 * 32, "one bit per batch of eight rows");
   __shared__ int s_nb, s_bc[20];
   if (threadIdx.x == 0) s_nb = 0;
   __syncthreads();
@@ -353,64 +358,65 @@ __global__ void __launch_bounds__(MOVE_VTHREADS) k_move_pass(DPage *pages, uint8
       mcv = ph == 0 ? make_uint4(m0, m1, m2, m0) : ph == 1 ? make_uint4(m1, m2, m0, m1) : make_uint4(m2, m0, m1, m2);
     }
     const int sxT = (p - tb0) / bpp + ax0, sxO = p / bpp;
-    const uint8_t *sown = im.data + (size_t)y0 * pitch + p;
-    const uint8_t *spst = im.data + ((ptrdiff_t)(ay0 + y0 - ty) * pitch + ab0 - tb0 + p);
-    uint8_t *d = dstb + (size_t)y0 * pitch + p;
-    if (rows_same) {
-      // no row of this block changes what a chunk column is: decide at y0, then move the rows with the loads of
-      // eight rows in flight
-      const int v = y0 - ty;
-      int kind;                               // 0 fill, 1 own pixels, 2 pasted pixels
-      int sx, sy;
-      if (inT && y0 >= ty && v < h) {
-        if (inTs && have_src && v < hc) { kind = 2; sx = sxT; sy = ay0 + v; } else { kind = 0; sx = sy = 0; }
-      } else if (inA && y0 >= ay0 && y0 <= ay1) { kind = 0; sx = sy = 0; }
-      else { kind = 1; sx = sxO; sy = y0; }
-      uint4 fv = bgv;
-      if (kind != 0 && nmask > 0 && !MV_IN_MASKS(sx, sy)) { kind = 0; fv = mcv; }
-      const int rows = yend - y0;
-      if (kind == 0) {
-        for (int r = 0; r < rows; r++, d += pitch) *(uint4 *)d = fv;
-      } else if (kind == 1 || misT == 0) {
-        const uint8_t *sp = kind == 1 ? sown : spst;
-        int r = 0;
-        for (; r + 8 <= rows; r += 8, sp += 8 * (size_t)pitch, d += 8 * (size_t)pitch) {
-          uint4 t[8];
+    for (int bi = 0, ya = y0; ya < yend; bi++, ya += 8) {
+      const int rows = min(8, yend - ya);
+      const uint8_t *sown = im.data + (size_t)ya * pitch + p;
+      const uint8_t *spst = im.data + ((ptrdiff_t)(ay0 + ya - ty) * pitch + ab0 - tb0 + p);
+      uint8_t *d = dstb + (size_t)ya * pitch + p;
+      if ((same_mask >> bi) & 1u) {
+        // no row of this batch changes what a chunk column is: decide at its first row, then move the rows with
+        // all their loads in flight
+        const int v = ya - ty;
+        int kind;                               // 0 fill, 1 own pixels, 2 pasted pixels
+        int sx, sy;
+        if (inT && ya >= ty && v < h) {
+          if (inTs && have_src && v < hc) { kind = 2; sx = sxT; sy = ay0 + v; } else { kind = 0; sx = sy = 0; }
+        } else if (inA && ya >= ay0 && ya <= ay1) { kind = 0; sx = sy = 0; }
+        else { kind = 1; sx = sxO; sy = ya; }
+        uint4 fv = bgv;
+        if (kind != 0 && nmask > 0 && !MV_IN_MASKS(sx, sy)) { kind = 0; fv = mcv; }
+        if (kind == 0) {
+          for (int r = 0; r < rows; r++, d += pitch) *(uint4 *)d = fv;
+        } else if (kind == 1 || misT == 0) {
+          const uint8_t *sp = kind == 1 ? sown : spst;
+          if (rows == 8) {
+            uint4 t[8];
 #pragma unroll
-          for (int k = 0; k < 8; k++) t[k] = __ldg((const uint4 *)(sp + (size_t)k * pitch));
+            for (int k = 0; k < 8; k++) t[k] = __ldg((const uint4 *)(sp + (size_t)k * pitch));
 #pragma unroll
-          for (int k = 0; k < 8; k++) *(uint4 *)(d + (size_t)k * pitch) = t[k];
+            for (int k = 0; k < 8; k++) *(uint4 *)(d + (size_t)k * pitch) = t[k];
+          } else
+            for (int r = 0; r < rows; r++, sp += pitch, d += pitch) *(uint4 *)d = __ldg((const uint4 *)sp);
+        } else {
+          const uint8_t *sp = spst - misT;      // the aligned chunk that holds the first source byte
+          const unsigned sh = (misT & 3u) * 8u, wsel = misT >> 2;
+          int r = 0;
+          for (; r + 4 <= rows; r += 4, sp += 4 * (size_t)pitch, d += 4 * (size_t)pitch) {
+            uint4 A[4], B[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { A[k] = __ldg((const uint4 *)(sp + (size_t)k * pitch)); B[k] = __ldg((const uint4 *)(sp + (size_t)k * pitch) + 1); }
+#pragma unroll
+            for (int k = 0; k < 4; k++) *(uint4 *)(d + (size_t)k * pitch) = sel16_shifted(A[k], B[k], wsel, sh);
+          }
+          for (; r < rows; r++, sp += pitch, d += pitch) *(uint4 *)d = sel16_shifted(__ldg((const uint4 *)sp), __ldg((const uint4 *)sp + 1), wsel, sh);
         }
-        for (; r < rows; r++, sp += pitch, d += pitch) *(uint4 *)d = __ldg((const uint4 *)sp);
-      } else {
-        const uint8_t *sp = spst - misT;      // the aligned chunk that holds the first source byte
-        const unsigned sh = (misT & 3u) * 8u, wsel = misT >> 2;
-        int r = 0;
-        for (; r + 4 <= rows; r += 4, sp += 4 * (size_t)pitch, d += 4 * (size_t)pitch) {
-          uint4 A[4], B[4];
-#pragma unroll
-          for (int k = 0; k < 4; k++) { A[k] = __ldg((const uint4 *)(sp + (size_t)k * pitch)); B[k] = __ldg((const uint4 *)(sp + (size_t)k * pitch) + 1); }
-#pragma unroll
-          for (int k = 0; k < 4; k++) *(uint4 *)(d + (size_t)k * pitch) = sel16_shifted(A[k], B[k], wsel, sh);
-        }
-        for (; r < rows; r++, sp += pitch, d += pitch) *(uint4 *)d = sel16_shifted(__ldg((const uint4 *)sp), __ldg((const uint4 *)sp + 1), wsel, sh);
+        continue;
       }
-      continue;
-    }
-    for (int y = y0; y < yend; y++, sown += pitch, spst += pitch, d += pitch) {
-      const int v = y - ty;
-      const bool rowT = y >= ty && v < h;
-      uint4 val;
-      int sx, sy;
-      bool fill = false;
-      if (inT && rowT) {
-        if (inTs && have_src && v < hc) { val = ld16_shifted(spst, misT); sx = sxT; sy = ay0 + v; }
-        else fill = true;
-      } else if (inA && y >= ay0 && y <= ay1) fill = true;
-      else { val = __ldg((const uint4 *)sown); sx = sxO; sy = y; }
-      if (fill) val = bgv;
-      else if (nmask > 0 && !MV_IN_MASKS(sx, sy)) val = mcv;
-      *(uint4 *)d = val;
+      for (int y = ya; y < ya + rows; y++, sown += pitch, spst += pitch, d += pitch) {
+        const int v = y - ty;
+        const bool rowT = y >= ty && v < h;
+        uint4 val;
+        int sx, sy;
+        bool fill = false;
+        if (inT && rowT) {
+          if (inTs && have_src && v < hc) { val = ld16_shifted(spst, misT); sx = sxT; sy = ay0 + v; }
+          else fill = true;
+        } else if (inA && y >= ay0 && y <= ay1) fill = true;
+        else { val = __ldg((const uint4 *)sown); sx = sxO; sy = y; }
+        if (fill) val = bgv;
+        else if (nmask > 0 && !MV_IN_MASKS(sx, sy)) val = mcv;
+        *(uint4 *)d = val;
+      }
     }
   }
   __syncthreads();
