@@ -664,13 +664,23 @@ __device__ __noinline__ bool nfb_small_component(const unsigned (*nb)[NFB_NW], i
 }
 
 __global__ void __launch_bounds__(256, 8) k_nf_classify_bits(DPage *pages, int intensity, int white) {
-  __shared__ unsigned s_dark[NFB_ROWS][NFB_NW], s_nb[NFB_ROWS][NFB_NW], s_h0[NFB_ROWS][NFB_NW], s_h1[NFB_ROWS][NFB_NW],
-      s_core[NFB_ROWS][NFB_NW], s_big[NFB_ROWS][NFB_NW];
+  // six bit planes, each with one guard word before and after: the word left of word 0 of a row is the last word
+  // of the row above (and the other way round), whose bit next to the row boundary is always clear — a halo word
+  // only carries the eight pixels next to the interior, a word that leaves the image none beyond it — so the
+  // neighbour exchanges below need no edge cases
+  __shared__ unsigned s_planes[6][NFB_ROWS * NFB_NW + 2];
+  unsigned (*const s_dark)[NFB_NW] = (unsigned (*)[NFB_NW])(&s_planes[0][1]);
+  unsigned (*const s_nb)[NFB_NW] = (unsigned (*)[NFB_NW])(&s_planes[1][1]);
+  unsigned *const f_nb = &s_planes[1][1], *const f_h0 = &s_planes[2][1], *const f_h1 = &s_planes[3][1];
+  unsigned *const f_core = &s_planes[4][1], *const f_big = &s_planes[5][1];
+  unsigned (*const s_big)[NFB_NW] = (unsigned (*)[NFB_NW])f_big;
   DPage &pg = pages[blockIdx.z];
   const DImg &im = pg.img;
+  uint8_t *const cls = pg.cls;
   int halo = intensity + 1, rows = NFB_TH + 2 * halo, need = intensity + 1, band = 2 * intensity;
   int bx = blockIdx.x * NFB_TW, by = blockIdx.y * NFB_TH;
   if (bx >= im.w || by >= im.h) return;
+  if (threadIdx.x == 0) { f_nb[-1] = 0u; f_nb[rows * NFB_NW] = 0u; f_core[-1] = 0u; f_core[rows * NFB_NW] = 0u; }   // the words next to the planes in use
   int x_org = bx - 32, y_org = by - halo;
   unsigned white4 = white > 255 ? 0xFFFFFFFFu : (unsigned)max(white, 0) * 0x01010101u;
   // phase 1: bit planes
@@ -709,59 +719,62 @@ __global__ void __launch_bounds__(256, 8) k_nf_classify_bits(DPage *pages, int i
   }
   __syncthreads();
   // phase 2a: per row, how many of (left, self, right) are set: h1:h0
-  for (int item = threadIdx.x; item < rows * NFB_NW; item += blockDim.x) {
-    int r = item / NFB_NW, k = item % NFB_NW;
-    unsigned C = s_nb[r][k], P = k > 0 ? s_nb[r][k - 1] : 0u, N = k < NFB_NW - 1 ? s_nb[r][k + 1] : 0u;
-    unsigned L = (C << 1) | (P >> 31), R = (C >> 1) | (N << 31);
-    s_h0[r][k] = L ^ C ^ R;
-    s_h1[r][k] = (L & C) | (C & R) | (L & R);
+  const int nitems = rows * NFB_NW;
+  for (int i = threadIdx.x; i < nitems; i += blockDim.x) {
+    const unsigned C = f_nb[i], P = f_nb[i - 1], N = f_nb[i + 1];
+    const unsigned L = __funnelshift_l(P, C, 1), R = __funnelshift_r(C, N, 1);   // (C << 1) | (P >> 31), (C >> 1) | (N << 31)
+    f_h0[i] = L ^ C ^ R;
+    f_h1[i] = (L & C) | (C & R) | (L & R);
   }
   __syncthreads();
   // phase 2b: 3x3 population (bit-sliced) >= need, centred on an nb pixel
-  for (int item = threadIdx.x; item < rows * NFB_NW; item += blockDim.x) {
-    int r = item / NFB_NW, k = item % NFB_NW;
-    unsigned core = 0;
-    if (r >= 1 && r + 1 < rows) {
-      unsigned a0 = s_h0[r - 1][k], a1 = s_h1[r - 1][k], b0 = s_h0[r][k], b1 = s_h1[r][k], c0 = s_h0[r + 1][k], c1 = s_h1[r + 1][k];
-      unsigned s0 = a0 ^ b0 ^ c0, k0 = (a0 & b0) | (b0 & c0) | (a0 & c0);      // weight 1, carry (weight 2)
-      unsigned t1 = a1 ^ b1 ^ c1, k1 = (a1 & b1) | (b1 & c1) | (a1 & c1);      // weight 2, carry (weight 4)
-      unsigned u1 = t1 ^ k0, c2 = t1 & k0;                                      // weight 2, carry (weight 4)
-      unsigned v2 = k1 ^ c2, v3 = k1 & c2;                                      // weight 4, weight 8
-      unsigned bits[4] = {s0, u1, v2, v3};
-      unsigned gt = 0, eq = 0xFFFFFFFFu;
+  {
+    unsigned kb[4];
 #pragma unroll
-      for (int b = 3; b >= 0; b--) {
-        unsigned kb = ((need >> b) & 1) ? 0xFFFFFFFFu : 0u;
-        gt |= eq & bits[b] & ~kb;
-        eq &= ~(bits[b] ^ kb);
+    for (int b = 0; b < 4; b++) kb[b] = ((need >> b) & 1) ? 0xFFFFFFFFu : 0u;
+    const unsigned live = need > 9 ? 0u : 0xFFFFFFFFu;
+    for (int i = threadIdx.x; i < nitems; i += blockDim.x) {
+      unsigned core = 0;
+      if (i >= NFB_NW && i < nitems - NFB_NW) {        // rows 1 .. rows - 2
+        const unsigned a0 = f_h0[i - NFB_NW], a1 = f_h1[i - NFB_NW], b0 = f_h0[i], b1 = f_h1[i], c0 = f_h0[i + NFB_NW], c1 = f_h1[i + NFB_NW];
+        const unsigned s0 = a0 ^ b0 ^ c0, k0 = (a0 & b0) | (b0 & c0) | (a0 & c0);      // weight 1, carry (weight 2)
+        const unsigned t1 = a1 ^ b1 ^ c1, k1 = (a1 & b1) | (b1 & c1) | (a1 & c1);      // weight 2, carry (weight 4)
+        const unsigned u1 = t1 ^ k0, c2 = t1 & k0;                                      // weight 2, carry (weight 4)
+        const unsigned v2 = k1 ^ c2, v3 = k1 & c2;                                      // weight 4, weight 8
+        const unsigned bits[4] = {s0, u1, v2, v3};
+        unsigned gt = 0, eq = 0xFFFFFFFFu;
+#pragma unroll
+        for (int b = 3; b >= 0; b--) {
+          gt |= eq & bits[b] & ~kb[b];
+          eq &= ~(bits[b] ^ kb[b]);
+        }
+        core = (gt | eq) & f_nb[i] & live;
       }
-      core = (gt | eq) & s_nb[r][k];
-      if (need > 9) core = 0;
+      f_core[i] = core;
     }
-    s_core[r][k] = core;
   }
   __syncthreads();
   // phase 2c: nb pixels that are a core pixel or touch one
-  for (int item = threadIdx.x; item < rows * NFB_NW; item += blockDim.x) {
-    int r = item / NFB_NW, k = item % NFB_NW;
+  for (int i = threadIdx.x; i < nitems; i += blockDim.x) {
     unsigned D = 0;
-    if (r >= 1 && r + 1 < rows) {
+    if (i >= NFB_NW && i < nitems - NFB_NW) {
 #pragma unroll
       for (int rr = -1; rr <= 1; rr++) {
-        unsigned C = s_core[r + rr][k], P = k > 0 ? s_core[r + rr][k - 1] : 0u, N = k < NFB_NW - 1 ? s_core[r + rr][k + 1] : 0u;
-        D |= C | (C << 1) | (P >> 31) | (C >> 1) | (N << 31);
+        const int j = i + rr * NFB_NW;
+        const unsigned C = f_core[j], P = f_core[j - 1], N = f_core[j + 1];
+        D |= C | __funnelshift_l(P, C, 1) | __funnelshift_r(C, N, 1);
       }
     }
-    s_big[r][k] = s_nb[r][k] & D;
+    f_big[i] = f_nb[i] & D;
   }
   __syncthreads();
   // phase 3: class bytes.  An item is one 32-pixel word of the bit planes (two 16-byte stores) when the
   // class map allows it, else eight pixels.
-  const bool wide = (im.w & 15) == 0 && ((uintptr_t)pg.cls & 15) == 0;
+  const bool wide = (im.w & 15) == 0 && ((uintptr_t)cls & 15) == 0;
   const int ppi = wide ? 32 : 8;                       // pixels per item
   const int ipr = NFB_TW / ppi;                        // items per tile row
   for (int it = threadIdx.x; it < ipr * NFB_TH; it += blockDim.x) {
-    const int ly = it / ipr, lx0 = (it - ly * ipr) * ppi;
+    const int ly = wide ? it / (NFB_TW / 32) : it / (NFB_TW / 8), lx0 = (it - ly * ipr) * ppi;   // divisions by constants
     const int y = by + ly, r = ly + halo;
     if (y >= im.h || bx + lx0 >= im.w) continue;
     const int k = 1 + (lx0 >> 5), sh = lx0 & 31;
@@ -792,7 +805,7 @@ __global__ void __launch_bounds__(256, 8) k_nf_classify_bits(DPage *pages, int i
         const unsigned d4 = (((darkw >> (4 * q)) & 0xFu) * 0x00204081u) & 0x01010101u, m4 = (((mutw >> (4 * q)) & 0xFu) * 0x00204081u) & 0x01010101u;
         cw[q] = d4 * (NF_LIVE | NF_TRIG) + m4 * (NF_MUT | NF_UNDEC);
       }
-      uint4 *o4 = (uint4 *)(pg.cls + o);
+      uint4 *o4 = (uint4 *)(cls + o);
       if (bx + lx0 + 31 < im.w) { o4[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]); o4[1] = make_uint4(cw[4], cw[5], cw[6], cw[7]); }
       else {   // the image ends inside this word (its width is a multiple of 16)
         if (bx + lx0 + 15 < im.w) o4[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
@@ -801,8 +814,8 @@ __global__ void __launch_bounds__(256, 8) k_nf_classify_bits(DPage *pages, int i
       const unsigned dl = ((darkw & 0xFu) * 0x00204081u) & 0x01010101u, dh = ((darkw >> 4) * 0x00204081u) & 0x01010101u;
       const unsigned ml = ((mutw & 0xFu) * 0x00204081u) & 0x01010101u, mh = ((mutw >> 4) * 0x00204081u) & 0x01010101u;
       const unsigned lo = dl * (NF_LIVE | NF_TRIG) + ml * (NF_MUT | NF_UNDEC), hi = dh * (NF_LIVE | NF_TRIG) + mh * (NF_MUT | NF_UNDEC);
-      if ((im.w & 7) == 0 && ((uintptr_t)pg.cls & 7) == 0) *(uint2 *)(pg.cls + o) = make_uint2(lo, hi);
-      else for (int i = 0; i < 8 && bx + lx0 + i < im.w; i++) pg.cls[o + i] = (uint8_t)((i < 4 ? lo >> (8 * i) : hi >> (8 * (i - 4))) & 0xFFu);
+      if ((im.w & 7) == 0 && ((uintptr_t)cls & 7) == 0) *(uint2 *)(cls + o) = make_uint2(lo, hi);
+      else for (int i = 0; i < 8 && bx + lx0 + i < im.w; i++) cls[o + i] = (uint8_t)((i < 4 ? lo >> (8 * i) : hi >> (8 * (i - 4))) & 0xFFu);
     }
   }
 }
