@@ -13,17 +13,17 @@ import sys
 
 STAGES = [
     ("decode", ["k_page_reset", "k_fill_jobs", "k_copy_jobs"]),
-    ("blackfilter", ["k_zero_u32", "k_linesum_cols", "k_linesum_rows", "k_bf_scan"]),
+    ("blackfilter", ["k_zero_u32", "k_linesum_cols", "k_linesum_cols4", "k_linesum_cols16", "k_linesum_rows", "k_bf_scan"]),
     ("noisefilter", ["k_nf_classify_bits", "k_nf_classify_g8", "k_nf_classify", "k_nf_resolve"]),
     ("blurfilter", ["k_rect_count", "k_blur_decide_sm", "k_blur_decide", "k_blur_wipe"]),
     ("grayfilter", ["k_cellstats", "k_zero_range", "k_gray_prewhite", "k_gray_windows", "k_gray_cascade", "k_gray_wipe"]),
-    ("detect_masks", ["k_zero_u32", "k_linesum_cols", "k_linesum_rows", "k_detect_edges", "k_assemble_masks2"]),
+    ("detect_masks", ["k_zero_u32", "k_linesum_cols", "k_linesum_cols4", "k_linesum_cols16", "k_linesum_rows", "k_detect_edges", "k_assemble_masks2"]),
     ("detect_rotation", ["k_rot_colprefix", "k_rot_peaks_w", "k_rot_peaks_h", "k_rot_peaks", "k_rot_finalize", "k_rot_set"]),
-    ("deskew", ["k_inkmap", "k_rotate_sheet", "k_swap_sheets"]),
-    ("center_mask", ["k_zero_u32", "k_linesum_cols", "k_linesum_rows", "k_detect_edges", "k_assemble_masks2", "k_prep_center_move",
+    ("deskew", ["k_inkmap", "k_rotate_sheet", "k_rotate_sheet_g8c", "k_swap_sheets"]),
+    ("center_mask", ["k_zero_u32", "k_linesum_cols", "k_linesum_cols4", "k_linesum_cols16", "k_linesum_rows", "k_detect_edges", "k_assemble_masks2", "k_prep_center_move",
                      "k_move_pass", "k_swap_sheets"]),
-    ("border", ["k_zero_u32", "k_linesum_cols", "k_linesum_rows", "k_detect_border", "k_border_to_mask", "k_prep_align_move",
-                "k_prep_border_maskjob", "k_apply_masks", "k_move_pass", "k_swap_sheets"]),
+    ("border", ["k_zero_u32", "k_linesum_cols", "k_linesum_cols4", "k_linesum_cols16", "k_linesum_rows", "k_detect_border", "k_border_to_mask", "k_prep_align_move",
+                "k_prep_border_maskjob", "k_apply_masks", "k_set_other", "k_move_pass", "k_swap_sheets"]),
     ("output", ["k_pack_rows", "k_convert_out"]),
 ]
 

@@ -287,7 +287,7 @@ __device__ __forceinline__ uint4 ld16_shifted(const uint8_t *s, unsigned mis) {
 // sharing them, from the per-byte definition of the gather above.
 #define MOVE_VROWS 64
 #define MOVE_VTHREADS 160
-__global__ void __launch_bounds__(MOVE_VTHREADS) k_move_pass(DPage *pages, uint8_t c0, uint8_t c1, uint8_t c2) {
+__global__ void __launch_bounds__(MOVE_VTHREADS, 6) k_move_pass(DPage *pages, uint8_t c0, uint8_t c1, uint8_t c2) {
   const DPage &pg = pages[blockIdx.z];
   const DImg im = pg.img;                 // by value: no reloads of the descriptor behind the stores below
   uint8_t *const dstb = pg.other;

@@ -46,6 +46,9 @@ __device__ __forceinline__ unsigned lt4(unsigned w, Lt4 t) {
 }
 // bit 7 of every byte set where lo <= byte <= hi (hiT = lt4_make(hi + 1), loT = lt4_make(lo))
 __device__ __forceinline__ unsigned range4_bit7(unsigned w, Lt4 loT, Lt4 hiT) { return lt4(w, hiT) & ~lt4(w, loT); }
+// LO0: the lower bound is 0 (every caller on the sheet path: "dark" = gray in [0, threshold]) and costs nothing
+template <bool LO0>
+__device__ __forceinline__ unsigned range4_bit7_t(unsigned w, Lt4 loT, Lt4 hiT) { return LO0 ? lt4(w, hiT) : range4_bit7(w, loT, hiT); }
 // Applies f(word, nvalid_mask) over the bytes [p, p+n): aligned 32-bit loads,
 // `keep` has 0xFF in the byte lanes that belong to the run.
 template <typename F>
@@ -134,6 +137,7 @@ __global__ void __launch_bounds__(128) k_linesum_cols4(DPage *pages, const DLine
 // The same with sixteen columns per thread (one aligned 16-byte load per row; two 16-bit partial sums per
 // register: LS_ROWS * 255 < 65536), for jobs whose columns start on a 16-byte boundary.  A thread owns two
 // ink cells, so no exchange is needed.
+#define LS_ROWS16 128  /* rows per block (32 measured slower: four times the atomics on the same 2480 sums) */
 __global__ void __launch_bounds__(64) k_linesum_cols16(DPage *pages, const DLineJob *jobs, int njobs, int make_ink) {
   int page = blockIdx.z / njobs, job = blockIdx.z % njobs;
   const DLineJob j = jobs[job];
@@ -141,9 +145,10 @@ __global__ void __launch_bounds__(64) k_linesum_cols16(DPage *pages, const DLine
   DPage &pg = pages[page];
   const DImg im = pg.img;
   int x = j.xa + 16 * (blockIdx.x * blockDim.x + threadIdx.x);
-  int y0 = j.ya + blockIdx.y * LS_ROWS;
+  int y0 = j.ya + blockIdx.y * LS_ROWS16;
   if (y0 > j.yb || x > j.xb) return;
-  int y1 = min(y0 + LS_ROWS - 1, j.yb);
+  int y1 = min(y0 + LS_ROWS16 - 1, j.yb);
+  static_assert(LS_ROWS16 % 8 == 0 && LS_ROWS16 * 255 < 65536, "whole ink cells per block, 16-bit partial sums");
   const int ncx = (im.w + 7) >> 3, ncy = (im.h + 7) >> 3;
   bool ink = make_ink && pg.ink && ncx * ncy <= pg.ink_cap;
   if (ink && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { pg.ink_ncx = ncx; pg.ink_ncy = ncy; pg.ink_ok = 1; }
@@ -175,6 +180,34 @@ __global__ void __launch_bounds__(64) k_linesum_cols16(DPage *pages, const DLine
   }
 }
 
+// A lane's share of row [xa, xb] of an aligned GRAY8 row: 16 bytes per load, a row's loads independent of each
+// other (a 2480-pixel row is five of them per lane, all in flight); only the two chunks holding xa and xb mask
+// bytes off.  MODE 0: sum of the bytes, 1: bytes <= hi, 2: bytes in [lo, hi].
+template <int MODE>
+__device__ __forceinline__ unsigned row_words(const uint4 *r4, int xa, int xb, int lane, Lt4 loT, Lt4 hiT) {
+  const int c0 = xa >> 4, c1 = xb >> 4;
+  unsigned acc = 0;
+#pragma unroll 4
+  for (int c = c0 + lane; c <= c1; c += 32) {
+    const uint4 v = __ldg(r4 + c);
+    unsigned wv[4] = {v.x, v.y, v.z, v.w}, keep[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (c == c0 || c == c1) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int x0 = 16 * c + 4 * k;
+        const int dl = min(max(xa - x0, 0), 4), dh = min(max(x0 + 3 - xb, 0), 4);   // bytes to drop at either end
+        keep[k] = (dl + dh >= 4) ? 0u : ((0xFFFFFFFFu << (8 * dl)) & (0xFFFFFFFFu >> (8 * dh)));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (MODE == 0) acc += sum4(wv[k] & keep[k]);
+      else acc += (unsigned)__popc(range4_bit7_t<MODE == 1>(wv[k], loT, hiT) & keep[k]);
+    }
+  }
+  return acc;
+}
+
 // Row sums: one warp per row.
 __global__ void k_linesum_rows(DPage *pages, const DLineJob *jobs, int njobs, int stat, int lo, int hi) {
   int page = blockIdx.z / njobs, job = blockIdx.z % njobs;
@@ -189,27 +222,9 @@ __global__ void k_linesum_rows(DPage *pages, const DLineJob *jobs, int njobs, in
     // aligned rows: 16 bytes per lane and load, a row's loads independent of each other (a 2480-pixel row
     // is five of them per lane, all in flight); only the two chunks holding xa and xb mask bytes off
     const uint4 *r4 = (const uint4 *)(im.data + (size_t)y * im.pitch);
-    const int c0 = j.xa >> 4, c1 = j.xb >> 4;
-    const bool cnt = stat == ST_COUNT_GRAY_RANGE;
     const Lt4 loT = lt4_make(lo), hiT = lt4_make(hi + 1);
-#pragma unroll 4
-    for (int c = c0 + lane; c <= c1; c += 32) {
-      const uint4 v = __ldg(r4 + c);
-      unsigned wv[4] = {v.x, v.y, v.z, v.w}, keep[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-      if (c == c0 || c == c1) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int x0 = 16 * c + 4 * k;
-          const int dl = min(max(j.xa - x0, 0), 4), dh = min(max(x0 + 3 - j.xb, 0), 4);   // bytes to drop at either end
-          keep[k] = (dl + dh >= 4) ? 0u : ((0xFFFFFFFFu << (8 * dl)) & (0xFFFFFFFFu >> (8 * dh)));
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if (cnt) acc += (unsigned)__popc(range4_bit7(wv[k], loT, hiT) & keep[k]);
-        else acc += sum4(wv[k] & keep[k]);
-      }
-    }
+    acc = stat != ST_COUNT_GRAY_RANGE ? row_words<0>(r4, j.xa, j.xb, lane, loT, hiT)
+          : lo <= 0 ? row_words<1>(r4, j.xa, j.xb, lane, loT, hiT) : row_words<2>(r4, j.xa, j.xb, lane, loT, hiT);
   } else if (im.fmt == DF_GRAY8) {
     const uint8_t *row = im.data + (size_t)y * im.pitch + j.xa;
     int n = j.xb - j.xa + 1;
@@ -261,10 +276,10 @@ __global__ void __launch_bounds__(256, 8) k_rect_count(DPage *pages, const DRect
         if (end < 4) keep &= 0xFFFFFFFFu >> (8 * (4 - end));
         const unsigned *p = base + i;
         unsigned acc = 0;
-        for (int r = 0; r < rows; r++, p += wpitch) {
-          unsigned wd = *p;
-          acc += (unsigned)__popc(range4_bit7(wd, loT, hiT) & keep);
-        }
+        if (lo <= 0)
+          for (int r = 0; r < rows; r++, p += wpitch) acc += (unsigned)__popc(range4_bit7_t<true>(*p, loT, hiT) & keep);
+        else
+          for (int r = 0; r < rows; r++, p += wpitch) acc += (unsigned)__popc(range4_bit7_t<false>(*p, loT, hiT) & keep);
         cnt += acc;
       }
     } else if (im.fmt == DF_GRAY8) {
@@ -294,7 +309,7 @@ __global__ void __launch_bounds__(256, 8) k_rect_count(DPage *pages, const DRect
 //   light[c] = sum of min-channel over the in-image pixels
 // One block per cell row; columns accumulate in registers over the g rows and
 // merge into shared per-cell counters.  Layout in u32: [dark ncx*ncy][light ncx*ncy].
-__global__ void __launch_bounds__(256, 8) k_cellstats(DPage *pages, int gx, int gy, int ncx, int ncy, int dark_max, int out_off) {
+__global__ void __launch_bounds__(256, 4) k_cellstats(DPage *pages, int gx, int gy, int ncx, int ncy, int dark_max, int out_off) {
   extern __shared__ unsigned sm[];
   unsigned *sd = sm, *sl = sm + ncx;
   int page = blockIdx.y, cy = blockIdx.x;
@@ -303,7 +318,47 @@ __global__ void __launch_bounds__(256, 8) k_cellstats(DPage *pages, int gx, int 
   __syncthreads();
   int y0 = cy * gy, y1 = min(y0 + gy - 1, im.h - 1);
   int xlim = min(ncx * gx, im.w);
-  if (im.fmt == DF_GRAY8 && gx >= 4 && (im.pitch & 3) == 0 && ((uintptr_t)im.data & 3) == 0) {
+  if (im.fmt == DF_GRAY8 && gx >= 4 && (im.pitch & 15) == 0 && ((uintptr_t)im.data & 15) == 0) {
+    // sixteen pixels per load: the four words of a chunk are four instances of the word form below, with the
+    // loads of a chunk column's rows in flight together
+    const Lt4 dmT = lt4_make(min(max(dark_max, -1) + 1, 256));   // v <= dark_max  <=>  v < dark_max + 1
+    const uint8_t *const base = im.data;
+    const int pitch = im.pitch;
+    for (int x = 16 * threadIdx.x; x < xlim; x += 16 * blockDim.x) {
+      int c[4];
+      unsigned m0[4], m1[4];
+      unsigned d0[4] = {0, 0, 0, 0}, d1[4] = {0, 0, 0, 0}, l0[4] = {0, 0, 0, 0}, l1[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int xk = x + 4 * k;
+        c[k] = xk / gx;
+        const int nb = min((c[k] + 1) * gx - xk, 4);           // bytes of this word in cell c
+        const int nv = min(max(xlim - xk, 0), 4);              // bytes of this word inside the grid
+        const unsigned mv = nv >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nv)) - 1u);
+        m0[k] = (nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u)) & mv;
+        m1[k] = mv & ~m0[k];
+      }
+      const uint8_t *p = base + (size_t)y0 * pitch + x;
+#pragma unroll 5
+      for (int y = y0; y <= y1; y++, p += pitch) {
+        const uint4 q = __ldg((const uint4 *)p);
+        const unsigned v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const unsigned dk = lt4(v[k], dmT);                  // bit 7 of every dark byte
+          d0[k] += __popc(dk & m0[k]); d1[k] += __popc(dk & m1[k]);
+          l0[k] += __vsadu4(v[k] & m0[k], 0u); l1[k] += __vsadu4(v[k] & m1[k], 0u);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (!(m0[k] | m1[k])) continue;
+        if (d0[k]) atomicAdd(&sd[c[k]], d0[k]);
+        if (m0[k]) atomicAdd(&sl[c[k]], l0[k]);
+        if (m1[k]) { if (d1[k]) atomicAdd(&sd[c[k] + 1], d1[k]); atomicAdd(&sl[c[k] + 1], l1[k]); }
+      }
+    }
+  } else if (im.fmt == DF_GRAY8 && gx >= 4 && (im.pitch & 3) == 0 && ((uintptr_t)im.data & 3) == 0) {
     // four pixels per 32-bit load; a word touches at most two cells (gx >= 4): the first
     // `nb` bytes belong to cell c, the rest to cell c + 1.  Packed-byte compare / SAD do
     // the counting and the sum.
@@ -402,7 +457,7 @@ int b200k_linesums(cudaStream_t st, DPage *pages, int npages, const DLineJob *jo
       /* the ink map rides along when ONE job covers the whole image (and nothing else would write it twice) */
       int ink = want_ink && full >= 0 && njobs == 1 && (img_w & 7) == 0 && stat == ST_GRAY;
       if (vec16) {
-        dim3 g(cdiv(maxc, 1024), cdiv(maxr, LS_ROWS), npages * njobs);
+        dim3 g(cdiv(maxc, 1024), cdiv(maxr, LS_ROWS16), npages * njobs);
         k_linesum_cols16<<<g, 64, 0, st>>>(pages, jobs_dev, njobs, ink);
       } else {
         dim3 g(cdiv(maxc, 512), cdiv(maxr, LS_ROWS), npages * njobs);
@@ -433,7 +488,10 @@ int b200k_cellstats(cudaStream_t st, DPage *pages, int npages, int gx, int gy, i
   if (sm > 200 * 1024) return -1;
   if (sm > 48 * 1024) cudaFuncSetAttribute(k_cellstats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   dim3 gr(ncy, npages);
-  k_cellstats<<<gr, 256, sm, st>>>(pages, gx, gy, ncx, ncy, dark_max, out_off);
+  // a thread takes 16 pixels of a cell row at a time (aligned GRAY8 sheets): no more threads than chunks
+  unsigned chunks = cdiv((unsigned)ncx * (unsigned)gx, 16u);
+  unsigned threads = min(256u, max(64u, cdiv(chunks, 32u) * 32u));
+  k_cellstats<<<gr, threads, sm, st>>>(pages, gx, gy, ncx, ncy, dark_max, out_off);
   return 0;
 }
 }
