@@ -157,11 +157,15 @@ def run_reference(args, rank, world):
 
 
 # algorithmic (compulsory) bytes per sheet of each stage, S = working-sheet bytes,
-# M = mask-rectangle bytes (bpp = 1 for the gray working sheet)
-def stage_bytes(S, M):
+# M = mask-rectangle bytes (bpp = 1 for the gray working sheet).
+# deskew: SURVEY's "2 S if fused into a fresh sheet" (it is: one sweep into the slot's other buffer);
+# center_mask / border: the mask scan's read of the sheet + the one sweep that replaces SURVEY's five
+# blits of 5 M (the blits are not compulsory, and counting them would put `alg_gbs` above the HBM peak);
+# output: nothing is moved when the last sweep already wrote the caller's buffer.
+def stage_bytes(S, M, direct_out=True):
     return {"decode": 2 * S, "blackfilter": S, "noisefilter": S, "blurfilter": S, "grayfilter": S,
-            "detect_masks": S, "detect_rotation": 0.25 * S, "deskew": 4 * M, "center_mask": S + 5 * M,
-            "border": 2 * S + 5 * M, "output": 2 * S}
+            "detect_masks": S, "detect_rotation": 0.25 * S, "deskew": 2 * S, "center_mask": S + 2 * S,
+            "border": S + 2 * S, "output": 0 if direct_out else 2 * S}
 
 
 def main():
@@ -319,7 +323,7 @@ def main():
         peaks, peak_src = measured_peaks()
         S = W * H
         M = S * 0.82        # typical detected mask share of the sheet on these pages
-        sb = stage_bytes(S, M)
+        sb = stage_bytes(S, M, direct_out=(args.out_format == "page"))
 
         def table(profile, pages_per_group):
             out, dom, dom_ms = {}, None, 0.0
@@ -358,7 +362,8 @@ def main():
                                 "frac": round(sum(sb.values()) * value / world / 1e9 / peaks["hbm_gbs"], 4),
                                 "note": "all stages: sum of the per-stage algorithmic bytes x measured sheets/s per GPU "
                                         "(the throughput arm, all lanes overlapping)"},
-                "note": "algorithmic bytes per SURVEY 8(d) with the 1 B/px working sheet; the dominant stage is "
+                "note": "algorithmic bytes per SURVEY 8(d) with the 1 B/px working sheet, fused forms (deskew 2 S, mask moves one "
+                        "sweep of 2 S each, no output copy); the dominant stage is "
                         "the one with the largest share of the isolated per-sheet time. The stages are not HBM-bound "
                         "in this implementation: the limits are instruction issue (rotate, noise classification) "
                         "and chains of dependent steps (flood fill, cascades) - see DESIGN.md section 5"}

@@ -155,8 +155,30 @@ __global__ void __launch_bounds__(64) k_linesum_cols16(DPage *pages, const DLine
   unsigned lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};      // lo[k]: bytes 0 and 2 of word k, hi[k]: bytes 1 and 3
   uint4 all = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
   const uint8_t *p = im.data + (size_t)y0 * im.pitch + x;
-#pragma unroll 4
-  for (int y = y0; y <= y1; y++, p += im.pitch) {
+  // a block's rows are one dependent chain per thread (every block of the grid is resident at once), so the time
+  // is rows / loads in flight x DRAM latency: eight rows (= one row of ink cells) per batch, loads first
+  int y = y0;
+  if (!ink || (y0 & 7) == 0)
+    for (; y + 7 <= y1; y += 8, p += 8 * (size_t)im.pitch) {
+      uint4 w[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) w[k] = __ldg((const uint4 *)(p + (size_t)k * im.pitch));
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        lo[0] += w[k].x & 0x00FF00FFu; hi[0] += (w[k].x >> 8) & 0x00FF00FFu;
+        lo[1] += w[k].y & 0x00FF00FFu; hi[1] += (w[k].y >> 8) & 0x00FF00FFu;
+        lo[2] += w[k].z & 0x00FF00FFu; hi[2] += (w[k].z >> 8) & 0x00FF00FFu;
+        lo[3] += w[k].w & 0x00FF00FFu; hi[3] += (w[k].w >> 8) & 0x00FF00FFu;
+        all.x &= w[k].x; all.y &= w[k].y; all.z &= w[k].z; all.w &= w[k].w;
+      }
+      if (ink) {
+        uint8_t *c = pg.ink + (y >> 3) * ncx + (x >> 3);
+        c[0] = (uint8_t)((all.x & all.y) == 0xFFFFFFFFu);
+        c[1] = (uint8_t)((all.z & all.w) == 0xFFFFFFFFu);
+      }
+      all = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    }
+  for (; y <= y1; y++, p += im.pitch) {     // what is left (and jobs whose blocks do not start on a cell row)
     uint4 w = *(const uint4 *)p;
     lo[0] += w.x & 0x00FF00FFu; hi[0] += (w.x >> 8) & 0x00FF00FFu;
     lo[1] += w.y & 0x00FF00FFu; hi[1] += (w.y >> 8) & 0x00FF00FFu;
