@@ -122,3 +122,40 @@ def test_library_carries_sm_100a_code_with_line_info():
     elfs = subprocess.run([cuobjdump, "-lelf", so], capture_output=True, text=True).stdout
     kernels = [l for l in elfs.splitlines() if "sm_100a" in l]
     assert len(kernels) >= 6, elfs          # one cubin per k_*.cu
+
+
+def test_swar_byte_compare(tmp_path):
+    """csrc/swar.h (the byte compares of the row / rectangle / cell statistics kernels) compiled as C:
+    every (lo, hi) pair over every byte value, four different bytes per word, against the plain
+    comparison — and no bit other than bit 7 of a byte is ever set."""
+    src = tmp_path / "swar_check.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "swar.h"
+int main(void) {
+  long bad = 0;
+  for (int lo = -3; lo <= 300; lo++)
+    for (int hi = -3; hi <= 300; hi++) {
+      Lt4 a = lt4_make(lo), b = lt4_make(hi + 1);
+      for (int v = 0; v < 256; v++) {
+        unsigned w = (unsigned)v | ((unsigned)(255 - v) << 8) | ((unsigned)((v * 7 + 3) & 255) << 16) | ((unsigned)((v * 13 + 101) & 255) << 24);
+        unsigned m = range4_bit7(w, a, b), l = lt4(w, b);
+        for (int k = 0; k < 4; k++) {
+          int byte = (w >> (8 * k)) & 255;
+          if (((m >> (8 * k + 7)) & 1) != (byte >= lo && byte <= hi)) bad++;
+          if (((l >> (8 * k + 7)) & 1) != (byte <= hi)) bad++;
+          if (((m | l) >> (8 * k)) & 0x7F) bad++;
+        }
+      }
+    }
+  printf("%ld\n", bad);
+  return bad != 0;
+}
+''')
+    exe = tmp_path / "swar_check"
+    csrc = os.path.join(os.path.dirname(U.__file__), "csrc")
+    if not os.path.isdir(csrc):
+        csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "unpaper-gpu_b200", "csrc")
+    subprocess.run(["gcc", "-O2", "-std=gnu11", "-I", csrc, "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "0", out.stdout

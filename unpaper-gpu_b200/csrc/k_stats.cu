@@ -10,6 +10,7 @@
 // and the NPP integral images (npp_integral.c).
 #include "common.cuh"
 #include "launch.h"
+#include "swar.h"
 
 __device__ __forceinline__ unsigned stat_of(Px p, int stat, int lo, int hi) {
   if (stat == ST_GRAY) return (unsigned)px_gray(p);
@@ -26,26 +27,7 @@ __device__ __forceinline__ unsigned count4_range(unsigned w, unsigned lo4, unsig
   unsigned ge = __vcmpgeu4(w, lo4), le = __vcmpleu4(w, hi4);
   return (unsigned)__popc(ge & le) >> 3;
 }
-// The same test as three integer instructions per bound instead of the six the byte-compare
-// intrinsics expand to: bit 7 of every byte of lt4() is set where the byte of w is < T.
-//   (w & 0x7F7F7F7F) + (0x80 - (T & 0x7F)) per byte never carries into the next byte and has
-//   bit 7 set iff the low seven bits of the byte are >= those of T; with the top bit of the byte:
-//   byte >= T  <=>  T < 128 ? (top | low_ge) : (top & low_ge).
-struct Lt4 { unsigned addv, both; };       // both: all ones for T >= 128 (top & low_ge), zero for T < 128 (top | low_ge)
-__device__ __forceinline__ Lt4 lt4_make(int T) {
-  Lt4 r;
-  T = T < 0 ? 0 : T;                        // nothing is below 0: the sum always has bit 7 set, every byte is ">= T"
-  r.both = T >= 128 ? 0xFFFFFFFFu : 0u;
-  r.addv = T >= 256 ? 0u : (0x80u - ((unsigned)T & 0x7Fu)) * 0x01010101u;   // T >= 256: bit 7 of the sum never set, no byte is ">= T"
-  return r;
-}
-__device__ __forceinline__ unsigned lt4(unsigned w, Lt4 t) {
-  const unsigned s = (w & 0x7F7F7F7Fu) + t.addv;
-  const unsigned ge = (w & s) | ((w | s) & ~t.both);
-  return ~ge & 0x80808080u;
-}
-// bit 7 of every byte set where lo <= byte <= hi (hiT = lt4_make(hi + 1), loT = lt4_make(lo))
-__device__ __forceinline__ unsigned range4_bit7(unsigned w, Lt4 loT, Lt4 hiT) { return lt4(w, hiT) & ~lt4(w, loT); }
+// three-instruction byte compares: lt4 / range4_bit7 (swar.h)
 // LO0: the lower bound is 0 (every caller on the sheet path: "dark" = gray in [0, threshold]) and costs nothing
 template <bool LO0>
 __device__ __forceinline__ unsigned range4_bit7_t(unsigned w, Lt4 loT, Lt4 hiT) { return LO0 ? lt4(w, hiT) : range4_bit7(w, loT, hiT); }
